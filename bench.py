@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — headline metric of BASELINE.json: utterances/s (2 s @ 16 kHz) embedding extraction.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (fbank -> CMN -> model forward) over one batch of synthetic utterances
+per GPU.  Default workload = BASELINE.json configs[1]: ECAPA-TDNN-1024, bf16 tensor-core path, batch 256 of
+2.02 s utterances (32320 samples -> 200 frames, the "256 x 200-frame" case).  `value` is measured with the
+waveforms already resident in HBM; `e2e` is the same metric through the public host-buffer API
+(B200SpeakerModel.extract_from_wav on pinned host int16 PCM: H2D + kernels + D2H inside the timed region).
+Multi-GPU: one rank per GPU, utterances sharded with no data-path collective (weak scaling), ONE NCCL all-gather
+of the embeddings at the end of the job, inside the timed region.  `--impl reference` times the oracle port of
+the reference's CPU PyTorch path (torch fp32 on all host cores) on the same config, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model, precision, batch per GPU, samples per utterance, GFLOP/utt of conv+linear layers at that T)
+    "ecapa1024_bf16_b256": ("ECAPA_TDNN_c1024", "bf16", 256, 32320, 5.141),
+    "ecapa512_bf16_b256": ("ECAPA_TDNN_c512", "bf16", 256, 32320, 1.917),
+    "ecapa512_fp32_b16": ("ECAPA_TDNN_c512", "fp32", 16, 32000, 1.898),
+    "resnet34_fp16_b64": ("ResNet34", "fp16", 64, 32320, 9.056),
+    "campplus_bf16_b64": ("CAMPPlus", "bf16", 64, 32320, 2.252),
+}
+DEFAULT_WORKLOAD = "ecapa1024_bf16_b256"
+METRIC = "utterances/s (2s@16kHz) embedding extraction"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(model_name, nsamples, batch, budget_s, max_batches):
+    """Oracle port of the reference CPU path (numpy fbank+CMN, torch-CPU fp32 forward, all host threads)."""
+    from oracle import fbank_np, models_torch
+    from wespeaker_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in syn.make_state_dict(model_name, 0).items()}
+    wavs = syn.make_wavs(batch, nsamples, seed=0)
+
+    def one():
+        feats = np.stack([fbank_np.cmn(fbank_np.fbank(w)) for w in wavs])
+        return models_torch.forward(model_name, sd, torch.from_numpy(feats))
+
+    one()  # warm-up
+    t0, nb = time.perf_counter(), 0
+    while nb < max_batches and (time.perf_counter() - t0 < budget_s or nb == 0):
+        one(); nb += 1
+    dt = time.perf_counter() - t0
+    return nb * batch / dt, cores, nb, dt
+
+
+def run_reference(args, wl):
+    model, _, _, nsamples, _ = WORKLOADS[wl]
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    batch = 16
+    # each "step" = one bounded sample (16 utterances) of the same workload
+    from oracle import fbank_np, models_torch
+    from wespeaker_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in syn.make_state_dict(model, 0).items()}
+    wavs = syn.make_wavs(batch, nsamples, seed=0)
+
+    def one():
+        feats = np.stack([fbank_np.cmn(fbank_np.fbank(w)) for w in wavs])
+        return models_torch.forward(model, sd, torch.from_numpy(feats))
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = time.perf_counter() - t0
+    v = args.steps * batch / dt
+    sample = f"{args.steps} steps x {batch} utts of {nsamples} samples, oracle port (numpy fbank + torch-CPU fp32), {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl, "model": model, "batch_per_step": batch, "samples_per_utt": nsamples},
+        "cpu_baseline": {"value": v, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def time_dominant_kernel(model, prec, B, T, iters=10):
+    """Roofline leg: the dominant launch of the step — ECAPA's 1x1 conv 3C->1536 over B*T positions
+    (ecapa_tdnn.py:200,218; 47-49% of the model's MACs) — timed live with CUDA events on the launching stream
+    through ws_conv.  Algorithmic FLOPs per launch = 2 * B*T * 3C * 1536."""
+    import ctypes as C
+    from wespeaker_b200 import lib
+    if not model.startswith("ECAPA"):
+        return None
+    Cc = 1024 if "1024" in model else 512
+    cin, cout = 3 * Cc, 1536
+    code, tdt = {"fp32": (0, torch.float32), "tf32": (0, torch.float32), "bf16": (1, torch.bfloat16),
+                 "fp16": (2, torch.float16)}[prec]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    # rotate over enough (x, out) pairs that every launch reads operands not left in L2 by the previous one
+    per = B * T * (cin + cout) * (2 if code else 4)
+    nbuf = max(2, int(2 * 126e6 // per) + 1)
+    xs = [torch.randn(B, 1, T, cin, device=dev).to(tdt) for _ in range(nbuf)]
+    outs = [torch.empty(B, 1, T, cout, device=dev, dtype=tdt) for _ in range(nbuf)]
+    w = (torch.randn(cout, cin, device=dev) / cin ** 0.5).to(tdt)
+    bias = torch.zeros(cout, device=dev)
+    L = lib.load()
+    descs = []
+    for x, o in zip(xs, outs):
+        d = lib.ConvDesc()
+        d.x, d.B, d.F, d.T, d.Cin, d.x_ld = x.data_ptr(), B, 1, T, cin, cin
+        d.w, d.Cout, d.kf, d.kt = w.data_ptr(), cout, 1, 1
+        d.dil_f = d.dil_t = d.stride_f = d.stride_t = 1
+        d.bias, d.act1, d.out, d.out_ld, d.dtype, d.use_tc = bias.data_ptr(), 1, o.data_ptr(), cout, code, int(prec != "fp32")
+        descs.append(d)
+    st = lib.cur_stream_ptr()
+    for i in range(3):
+        lib.check(L.ws_conv(C.byref(descs[i % nbuf]), st), "ws_conv")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        lib.check(L.ws_conv(C.byref(descs[i % nbuf]), st), "ws_conv")
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * B * T * cin * cout
+    return dict(ms=ms, tflops=flops / (ms * 1e-3) / 1e12, flops=flops, nbuf=nbuf,
+                kernel=f"ws_conv_gemm_tc_kernel 1x1 {cin}->{cout} over {B * T} positions")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = args.workload
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+    model_name, prec, B, nsamples, gflop_utt = WORKLOADS[wl]
+
+    from wespeaker_b200 import parallel
+    from wespeaker_b200.models import from_synthetic
+    from wespeaker_b200 import synthetic as syn
+    rank, world, local = parallel.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    peaks = measured_peaks()
+
+    model = from_synthetic(model_name, 0, precision=prec).to(dev)
+    L_frames = 1 + (nsamples - 400) // 160
+    # rotate over distinct input batches; the per-step working set (activations) is >> the 126 MB L2 anyway
+    nrot = 4
+    base = syn.make_wavs(B, nsamples, seed=100 + rank)
+    wav_dev = [torch.from_numpy(np.roll(base, i, axis=0)).to(dev) for i in range(nrot)]
+    wav_pin = [torch.from_numpy(np.roll(base, i, axis=0).astype(np.int16)).pin_memory() for i in range(nrot)]
+    emb = None
+    for i in range(max(3, args.warmup)):
+        emb = model.extract_from_wav(wav_dev[i % nrot])
+    torch.cuda.synchronize()
+    launches_per_step = model.last_launches()
+
+    # ---------------- device-resident throughput (`value`)
+    sampler = ClockSampler(local)
+    parallel.barrier(); torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    local_embs = []
+    for i in range(args.steps):
+        local_embs.append(model.extract_from_wav(wav_dev[i % nrot]))
+    allemb = torch.cat(local_embs, 0)
+    gathered = parallel.gather_embeddings(allemb, allemb.shape[0] * world)  # the one NCCL all-gather of the job
+    e1.record()
+    torch.cuda.synchronize(); parallel.barrier()
+    ms_total = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+    clocks = sampler.stop() if rank == 0 else None
+    assert gathered.shape[0] == args.steps * B * world and torch.isfinite(gathered).all()
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---------------- end-to-end through the public host-buffer API (`e2e`)
+    for i in range(2):
+        model.extract_from_wav(wav_pin[i % nrot])
+    parallel.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out_h = model.extract_from_wav(wav_pin[i % nrot])  # H2D + kernels + D2H + sync inside the C ABI
+    torch.cuda.synchronize()
+    dt = parallel.max_over_ranks(time.perf_counter() - t0, dev)
+    parallel.barrier()
+    e2e_value = world * B * args.steps / dt
+    assert torch.isfinite(out_h).all()
+
+    if rank != 0:
+        return
+    # ---------------- roofline for the dominant kernel + whole-step tensor utilisation
+    dom = time_dominant_kernel(model_name, prec, B, L_frames)
+    step_tf = value / world * gflop_utt / 1e3  # TFLOP/s per GPU, algorithmic
+    if dom is not None:
+        roof = {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                "frac": dom["tflops"] / peaks["tf_burst"], "traffic": None, "kernel": dom["kernel"],
+                "kernel_ms": dom["ms"], "flops_per_launch": dom["flops"], "peak_source": peaks["src"] + " (burst, kernel timed alone)",
+                "step_tflops_per_gpu": step_tf, "step_frac_of_sustained": step_tf / peaks["tf_sustained"]}
+    else:
+        roof = {"bound": "tensor", "achieved": step_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": step_tf / peaks["tf_sustained"], "traffic": None, "kernel": "whole step (conv GEMMs)",
+                "peak_source": peaks["src"] + " (sustained, whole step)"}
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, cores, nb, cdt = cpu_reference_run(model_name, nsamples, 16, budget_s=12.0, max_batches=40)
+        cpu = {"value": v, "unit": "utt/s", "cores": cores, "kind": "port",
+               "sample": f"{nb} batches x 16 utts of {nsamples} samples in {cdt:.1f}s: numpy fbank+CMN + torch-CPU fp32 forward (oracle port of the reference path)"}
+    act_mb = B * L_frames * (1536 * 2 + 128 + (1024 if '1024' in model_name else 512) * 7) * (4 if prec in ("fp32", "tf32") else 2) / 1e6
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16", "fp16": "f16"}[prec], "data": "synthetic",
+        "config": {"workload": wl, "model": model_name, "batch_per_gpu": B, "samples_per_utt": nsamples,
+                   "frames": L_frames, "precision": prec, "gflop_per_utt": gflop_utt,
+                   "l2": f"inputs rotate over {nrot} batches; per-step activation working set ~{act_mb:.0f} MB > 126 MB L2",
+                   "collective": "one all_gather_into_tensor of embeddings at job end (inside timed region)" if world > 1 else "none"},
+        "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": B * nsamples * 2, "d2h_bytes_per_step": B * model.embed_dim * 4,
+                "api": "B200SpeakerModel.extract_from_wav(pinned int16 PCM host tensor)"},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+    }))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,107 @@
+/* wespeaker_b200 — C ABI of the B200-native speaker-embedding extraction + PLDA scoring engine.
+ *
+ * The reference (wenet-e2e/wespeaker) has no FFI layer for this path; the seams this library sits behind are
+ * Python call signatures and one C++ virtual.  Each entry point below cites the reference
+ * interface it replaces.  Conventions: plain pointers and sizes, no torch types; every function returns 0 on
+ * success and non-zero on failure with a message in ws_last_error() (thread-local); no exceptions cross the ABI.
+ * "dev" pointers are CUDA device pointers owned by the caller (e.g. torch tensors' data_ptr()); `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Handles are bound to one device and are not
+ * internally thread-safe (same contract as the reference's single-threaded callers, extract.py:109-139).
+ */
+#ifndef WESPEAKER_B200_H_
+#define WESPEAKER_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ws_engine ws_engine;
+typedef struct ws_plda ws_plda;
+
+int ws_version(void);
+const char* ws_last_error(void);
+
+/* ---- model engine: replaces `get_speaker_model(name)(**model_args)` + `load_checkpoint` + `model(features)`
+ *      (wespeaker/models/speaker_model.py:31-62, wespeaker/utils/checkpoint.py:20-85, wespeaker/bin/extract.py:68-79,133)
+ *      and is the B200 back-end for `SpeakerModel::ExtractEmbedding` (runtime/core/speaker/speaker_model.h:25-32).
+ * model_name: ECAPA_TDNN_c512 | ECAPA_TDNN_GLOB_c512 | ECAPA_TDNN_c1024 | ECAPA_TDNN_GLOB_c1024 | ResNet18 |
+ *             ResNet34 | CAMPPlus.
+ * precision:  "fp32" (exact IEEE fp32 FFMA path, parity <= 1e-4), "tf32", "bf16", "fp16" (tcgen05 tensor cores). */
+int ws_engine_create(const char* model_name, const char* precision, int feat_dim, int embed_dim, int device,
+                     ws_engine** out);
+/* options: "two_emb_layer", "emb_bn" (model_args), "cuda_graph" (default 1), "force_simt" (debug cross-check) */
+int ws_engine_set_option(ws_engine* e, const char* key, long long value);
+/* one reference state_dict entry (fp32 host data, reference key names). */
+int ws_engine_set_tensor(ws_engine* e, const char* key, const float* host_data, const long long* shape, int ndim);
+/* packs / folds / converts weights once; errors if a required key is missing (strict for the forward path). */
+int ws_engine_finalize(ws_engine* e);
+int ws_engine_embed_dim(const ws_engine* e);
+/* feats_dev: fp32 (B,T,feat_dim) already mean-normalised by the caller, as `model(features)` receives them
+ * (extract.py:125-133); embs_dev: fp32 (B,embed_dim). */
+int ws_engine_forward(ws_engine* e, const float* feats_dev, int B, int T, float* embs_dev, void* stream);
+/* same with HOST buffers (pinned or pageable): H2D + forward + D2H + stream sync; mirrors
+ * `features.to(device)` ... `embeds.cpu()` (extract.py:116,135). */
+int ws_engine_forward_host(ws_engine* e, const float* feats_host, int B, int T, float* embs_host);
+/* waveform -> embedding on device: fbank (80 bins, 25/10 ms, dither 0) + CMN + forward.  Replaces
+ * compute_fbank + apply_cmvn + model() (processor.py:496-526, dataset_utils.py:19-26, cli/speaker.py:130-167).
+ * wav: (B, wav_ld) samples in int16 range — float32 (`wav * (1<<15)`) or int16 PCM; feats_out_dev optional. */
+int ws_engine_extract_wav(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples, int B,
+                          const char* window_type, float* embs_dev, float* feats_out_dev, void* stream);
+int ws_engine_extract_wav_host(ws_engine* e, const void* wav_host, int wav_is_i16, int nsamples, int B,
+                               const char* window_type, float* embs_host);
+/* number of this library's kernels launched by the most recent forward/extract call */
+long long ws_engine_last_launches(const ws_engine* e);
+void ws_engine_destroy(ws_engine* e);
+
+/* ---- fbank + CMN: replaces torchaudio.compliance.kaldi.fbank as called at processor.py:518-525 /
+ *      cli/speaker.py:92-99 and Fbank::Compute (runtime/core/frontend/fbank.h:138-198). */
+int ws_fbank_num_frames(int nsamples);
+int ws_fbank(const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples, int B, const char* window_type,
+             int apply_cmn, float* feats_dev, void* stream);
+
+/* ---- generic fused conv operator (channels-last), the building block of the engine; exported for parity tests
+ *      against torch conv1d/conv2d.  Replaces Conv1dReluBn (ecapa_tdnn.py:85-106), BasicBlock convs
+ *      (resnet.py:35-69), TDNNLayer (campplus.py:55-83). */
+typedef struct {
+    const void* x;            /* [B][F][T][x_ld] activations, dtype below, channels [0,Cin) used */
+    int B, F, T, Cin;
+    long long x_ld;
+    const void* w;            /* [Cout][kf*kt*Cin], tap-major (tap = jf*kt + jt), dtype below */
+    int Cout, kf, kt, dil_f, dil_t, pad_f, pad_t, stride_f, stride_t;
+    const float* bias;        /* added before act1 (or NULL) */
+    int act1;                 /* 0 none 1 relu 2 tanh 3 sigmoid */
+    const float* scale;       /* per-channel affine after act1 (or NULL) */
+    const float* shift;
+    const void* res;          /* residual added after the affine (or NULL), [positions][res_ld] */
+    long long res_ld;
+    int act2;
+    void* out;                /* [B][Fo][To][out_ld] */
+    long long out_ld;
+    int dtype;                /* 0 fp32 (tf32 MMA when use_tc), 1 bf16, 2 fp16 */
+    int use_tc;               /* 1: tcgen05 kernel, 0: fp32 FFMA kernel */
+} ws_conv_desc;
+int ws_conv(const ws_conv_desc* d, void* stream);
+
+/* ---- two-covariance PLDA scorer: replaces TwoCovPLDA.transform_embedding / log_likelihood_ratio / the trial
+ *      loop of eval_sv (wespeaker/utils/plda/two_cov_plda.py:156-184,186-256), fp64 like the reference. */
+int ws_plda_create(int dim, const double* mu, const double* transform, const double* psi, const double* offset,
+                   int normalize_length, int device, ws_plda** out);
+/* y = transform_embedding(pre(x - mean_vec)); pre = sqrt(D)-length-norm (norm_embeddings, plda_utils.py:46-58) iff
+ * pre_norm != 0 — eval_sv (:225-241) pre-normalises exactly when normalize_length is set.
+ * x_dev fp32 (N,D); mean_vec_host fp64 (D) or NULL; y_dev fp64 (N,D). */
+int ws_plda_transform(ws_plda* p, const float* x_dev, long long N, const double* mean_vec_host, int pre_norm,
+                      double* y_dev, void* stream);
+/* all-pairs LLR: out[i*out_ld + j] = log_likelihood_ratio(enroll_t[i], test_t[j], n_i);  n_i = counts_dev[i] or const_n */
+int ws_plda_score_matrix(ws_plda* p, const double* enroll_t_dev, const int* counts_dev, int const_n, long long N,
+                         const double* test_t_dev, long long M, void* out_dev, int out_is_f64, long long out_ld,
+                         void* stream);
+/* listed trials only (eval_sv :248-256): out[k] = LLR(enroll_t[ei[k]], test_t[ti[k]], n_{ei[k]}) */
+int ws_plda_score_trials(ws_plda* p, const double* enroll_t_dev, const int* counts_dev, int const_n, long long N,
+                         const double* test_t_dev, long long M, const long long* ei_dev, const long long* ti_dev,
+                         long long ntrials, double* out_dev, void* stream);
+void ws_plda_destroy(ws_plda* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WESPEAKER_B200_H_ */

@@ -1,0 +1,283 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Everything goes through the C ABI
+(wespeaker_b200/lib.py -> libwespeaker_b200.so); the oracle is only the checker.
+
+Tolerances (stated per SURVEY.md §7/§8d):
+  * fp32 precision  : embeddings rel-L2 <= 1e-4 vs the reference goldens and the oracle (north_star bar)
+  * tf32/bf16/fp16  : tensor-core input rounding; the reference itself drifts 4.1e-3 under bf16 autocast
+                       so the bar is rel-L2 <= 3e-2 (bf16) / 1e-2 (fp16, tf32), reported separately
+  * fbank           : |log-mel error| <= 2e-3 max, 5e-5 mean vs torchaudio goldens (fp32 FFT rounding only)
+  * PLDA            : |s - s_ref| <= 1e-5 * max(1, |s_ref|) vs the fp64 reference
+"""
+import ctypes as C
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fbank_np, models_torch, plda_np
+from wespeaker_b200 import frontend, lib, synthetic as syn
+from wespeaker_b200.models import from_synthetic
+from wespeaker_b200.plda import TwoCovPLDA
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+G_MODELS = np.load(os.path.join(HERE, "golden", "models.npz"))
+G_FBANK = np.load(os.path.join(HERE, "golden", "fbank.npz"))
+G_PLDA = np.load(os.path.join(HERE, "golden", "plda.npz"))
+DEV = "cuda:0"
+DT = {"fp32": (0, torch.float32), "tf32": (0, torch.float32), "bf16": (1, torch.bfloat16), "fp16": (2, torch.float16)}
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b, axis=-1) / np.linalg.norm(b, axis=-1)
+
+
+# ------------------------------------------------------------------------------------------ fused conv operator
+def run_conv(x_cl, w, bias, scale, shift, res, prec, use_tc, kf, kt, dil, pad, stride, act1=1, act2=0):
+    """x_cl (B,F,T,Cin) float32 channels-last; w torch layout (Cout,Cin,kf,kt)."""
+    code, tdt = DT[prec]
+    B, F, T, Cin = x_cl.shape
+    Cout = w.shape[0]
+    Fo = (F + 2 * pad[0] - dil[0] * (kf - 1) - 1) // stride[0] + 1
+    To = (T + 2 * pad[1] - dil[1] * (kt - 1) - 1) // stride[1] + 1
+    xd = x_cl.to(DEV, tdt).contiguous()
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, kf * kt * Cin).to(DEV, tdt).contiguous()
+    out = torch.zeros((B, Fo, To, Cout), dtype=tdt, device=DEV)
+    keep = [xd, wp, out]
+    d = lib.ConvDesc()
+    d.x, d.B, d.F, d.T, d.Cin, d.x_ld = xd.data_ptr(), B, F, T, Cin, Cin
+    d.w, d.Cout, d.kf, d.kt = wp.data_ptr(), Cout, kf, kt
+    d.dil_f, d.dil_t, d.pad_f, d.pad_t, d.stride_f, d.stride_t = dil[0], dil[1], pad[0], pad[1], stride[0], stride[1]
+    for name, v in (("bias", bias), ("scale", scale), ("shift", shift)):
+        if v is not None:
+            t = v.to(DEV, torch.float32).contiguous()
+            keep.append(t)
+            setattr(d, name, t.data_ptr())
+    if res is not None:
+        r = res.to(DEV, tdt).contiguous()
+        keep.append(r)
+        d.res, d.res_ld = r.data_ptr(), Cout
+    d.act1, d.act2, d.out, d.out_ld, d.dtype, d.use_tc = act1, act2, out.data_ptr(), Cout, code, int(use_tc)
+    lib.check(lib.load().ws_conv(C.byref(d), None), "ws_conv")
+    torch.cuda.synchronize()
+    return out.float().cpu()
+
+
+def ref_conv(x_cl, w, bias, scale, shift, res, tdt, kf, kt, dil, pad, stride, act1=1, act2=0):
+    # reference in fp64 on inputs rounded to the operand dtype (isolates kernel error from input rounding)
+    x = x_cl.to(tdt).double().permute(0, 3, 1, 2)
+    wq = w.to(tdt).double()
+    y = torch.nn.functional.conv2d(x, wq, None if bias is None else bias.double(), stride=stride, padding=pad, dilation=dil)
+    if act1 == 1:
+        y = torch.relu(y)
+    elif act1 == 2:
+        y = torch.tanh(y)
+    if scale is not None:
+        y = y * scale.double()[None, :, None, None] + shift.double()[None, :, None, None]
+    y = y.permute(0, 2, 3, 1)
+    if res is not None:
+        y = y + res.to(tdt).double()
+    if act2 == 1:
+        y = torch.relu(y)
+    return y
+
+
+CONV_CASES = [
+    # name, B, F, T, Cin, Cout, kf, kt, dil, pad, stride
+    ("pw512", 3, 1, 198, 512, 512, 1, 1, (1, 1), (0, 0), (1, 1)),
+    ("k5_80", 4, 1, 198, 80, 512, 1, 5, (1, 1), (0, 2), (1, 1)),
+    ("k3_d3_w64", 5, 1, 61, 64, 64, 1, 3, (1, 3), (0, 3), (1, 1)),
+    ("c3x3_32", 2, 20, 37, 32, 32, 3, 3, (1, 1), (1, 1), (1, 1)),
+    ("c3x3_s2", 2, 20, 37, 32, 64, 3, 3, (1, 1), (1, 1), (2, 2)),
+    ("c3x3_s21", 2, 10, 45, 32, 32, 3, 3, (1, 1), (1, 1), (2, 1)),
+    ("pw_s2", 2, 20, 37, 64, 128, 1, 1, (1, 1), (0, 0), (2, 2)),
+    ("k3_d2_128_32", 2, 1, 100, 128, 32, 1, 3, (1, 2), (0, 2), (1, 1)),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("mode", ["fp32-simt", "tf32-tc", "bf16-tc", "fp16-tc", "bf16-simt"])
+def test_conv_operator(case, mode):
+    name, B, F, T, Cin, Cout, kf, kt, dil, pad, stride = case
+    prec, path = mode.split("-")
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)
+    x = torch.randn(B, F, T, Cin, generator=g)
+    w = torch.randn(Cout, Cin, kf, kt, generator=g) / np.sqrt(Cin * kf * kt)
+    bias = 0.1 * torch.randn(Cout, generator=g)
+    scale = 0.5 + torch.rand(Cout, generator=g)
+    shift = 0.1 * torch.randn(Cout, generator=g)
+    Fo = (F + 2 * pad[0] - dil[0] * (kf - 1) - 1) // stride[0] + 1
+    To = (T + 2 * pad[1] - dil[1] * (kt - 1) - 1) // stride[1] + 1
+    res = torch.randn(B, Fo, To, Cout, generator=g)
+    out = run_conv(x, w, bias, scale, shift, res, prec, path == "tc", kf, kt, dil, pad, stride, 1, 1)
+    tdt = DT[prec][1]
+    ref = ref_conv(x, w, bias, scale, shift, res, tdt, kf, kt, dil, pad, stride, 1, 1)
+    err = (out.double() - ref).abs().max().item()
+    scale_ref = ref.abs().max().item()
+    # fp32 FFMA: accumulation rounding only.  tf32: 10-bit operand mantissa.  16-bit: inputs pre-rounded, so the
+    # error left is fp32 accumulation + the 16-bit output rounding.
+    tol = {"fp32": 2e-5, "tf32": 4e-3, "bf16": 1.2e-2, "fp16": 2e-3}[prec] * max(1.0, scale_ref)
+    print(f"{name} {mode}: max|err|={err:.3e} (ref max {scale_ref:.2f}, tol {tol:.1e})")
+    assert err <= tol, (name, mode, err, tol)
+
+
+# ------------------------------------------------------------------------------------------ fbank + CMN
+@pytest.mark.parametrize("wt", ["hamming", "povey"])
+def test_fbank_matches_torchaudio_golden(wt):
+    wavs = torch.from_numpy(syn.make_wavs(3, 32000, seed=0)).to(DEV)
+    out = frontend.fbank_batch(wavs, window_type=wt).cpu().numpy()
+    ref = G_FBANK[f"fbank_{wt}"]
+    d = np.abs(out - ref)
+    print(f"fbank {wt}: max {d.max():.3e} mean {d.mean():.3e}")
+    assert out.shape == ref.shape and d.max() < 2e-3 and d.mean() < 5e-5
+    # int16 PCM input is bit-identical to the float path (samples are integers)
+    out16 = frontend.fbank_batch(wavs.to(torch.int16), window_type=wt).cpu().numpy()
+    assert np.array_equal(out16, out)
+
+
+def test_fbank_cmn_short_ragged_and_oracle():
+    short = syn.make_wavs(1, 16000 + 77, seed=5)
+    out = frontend.fbank_batch(torch.from_numpy(short).to(DEV)).cpu().numpy()[0]
+    assert out.shape == (98, 80) and np.abs(out - G_FBANK["fbank_hamming_short"]).max() < 2e-3
+    assert np.abs(out - fbank_np.fbank(short[0])).max() < 2e-3
+    cm = frontend.fbank_batch(torch.from_numpy(syn.make_wavs(3, 32000, seed=0)).to(DEV), cmn=True).cpu().numpy()
+    assert np.abs(cm - G_FBANK["cmvn_hamming"]).max() < 2e-3
+    assert np.abs(cm.mean(axis=1)).max() < 1e-4
+    # edge cases: shorter than one frame -> zero frames; exactly one frame
+    assert frontend.fbank_batch(torch.zeros(2, 399, device=DEV)).shape == (2, 0, 80)
+    one = frontend.fbank_batch(torch.from_numpy(syn.make_wavs(1, 400, seed=1)).to(DEV)).cpu().numpy()
+    assert one.shape == (1, 1, 80) and np.abs(one[0] - fbank_np.fbank(syn.make_wavs(1, 400, seed=1)[0])).max() < 2e-3
+    # CMN'd features are invariant to the input gain (log-mel gain is additive): property at full size
+    w = torch.from_numpy(syn.make_wavs(8, 32000, seed=7)).to(DEV)
+    a = frontend.fbank_batch(w, cmn=True)
+    b = frontend.fbank_batch(w * 0.5, cmn=True)
+    assert (a - b).abs().max().item() < 2e-3
+
+
+# ------------------------------------------------------------------------------------------ model parity
+def parse_case(key):
+    name, rest = key.split("__")
+    s, b, t = rest.split("_")
+    return name, int(s[1:]), int(b[1:]), int(t[1:])
+
+
+@pytest.mark.parametrize("key", list(G_MODELS.files))
+def test_model_fp32_matches_reference_golden(key):
+    name, seed, B, T = parse_case(key)
+    m = from_synthetic(name, seed, precision="fp32")
+    feats = torch.from_numpy(syn.make_feats(B, T, 80, seed=seed + 17 * T)).to(DEV)
+    out = m(feats)
+    emb = (out[-1] if isinstance(out, tuple) else out).cpu().numpy()
+    rel = rel_l2(emb, G_MODELS[key])
+    print(f"{key} fp32: rel-L2 max {rel.max():.3e}, launches {m.last_launches()}")
+    assert rel.max() <= 1e-4, (key, rel)
+    # second call replays the CUDA graph: must be bit-identical
+    emb2 = m(feats)
+    emb2 = (emb2[-1] if isinstance(emb2, tuple) else emb2).cpu().numpy()
+    assert np.array_equal(emb, emb2)
+
+
+TC_TOL = {"tf32": 1e-2, "bf16": 3e-2, "fp16": 1e-2}
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16", "fp16"])
+@pytest.mark.parametrize("key", ["ECAPA_TDNN_c512__s0_B4_T198", "ECAPA_TDNN_GLOB_c1024__s1_B2_T200",
+                                 "ResNet34__s0_B2_T99", "CAMPPlus__s0_B2_T455"])
+def test_model_tensor_core_precisions(key, prec):
+    name, seed, B, T = parse_case(key)
+    m = from_synthetic(name, seed, precision=prec)
+    feats = torch.from_numpy(syn.make_feats(B, T, 80, seed=seed + 17 * T)).to(DEV)
+    out = m(feats)
+    emb = (out[-1] if isinstance(out, tuple) else out).cpu().numpy()
+    rel = rel_l2(emb, G_MODELS[key])
+    print(f"{key} {prec}: rel-L2 max {rel.max():.3e}")
+    assert np.isfinite(emb).all() and rel.max() <= TC_TOL[prec], (key, prec, rel)
+
+
+def test_config1_ecapa512_16utts_wav_to_embedding():
+    """BASELINE.json configs[0]: ECAPA-TDNN-512, 16 synthetic 2 s utterances, fbank -> CMN -> forward.
+    Parity on identical fbank inputs (<=1e-4) and end-to-end from the waveform (fbank rounding included)."""
+    name = "ECAPA_TDNN_c512"
+    m = from_synthetic(name, 0, precision="fp32")
+    sd = syn.make_state_dict(name, 0)
+    wavs = syn.make_wavs(16, 32000, seed=0)
+    emb, feats = m.extract_from_wav(torch.from_numpy(wavs).to(DEV), return_feats=True)
+    emb, feats = emb.cpu().numpy(), feats.cpu()
+    ref_same_feats = models_torch.forward(name, sd, feats).numpy()
+    rel = rel_l2(emb, ref_same_feats)
+    print(f"config1 identical-fbank rel-L2 max {rel.max():.3e}")
+    assert rel.max() <= 1e-4
+    of = np.stack([fbank_np.cmn(fbank_np.fbank(w)) for w in wavs])
+    ref_e2e = models_torch.forward(name, sd, torch.from_numpy(of)).numpy()
+    rel2 = rel_l2(emb, ref_e2e)
+    print(f"config1 wav->emb rel-L2 max {rel2.max():.3e}")
+    assert rel2.max() <= 1e-3
+    # host-buffer entry point == device entry point
+    emb_h = m.extract_from_wav(torch.from_numpy(wavs)).numpy()
+    assert np.array_equal(emb_h, emb)
+    emb_i16 = m.extract_from_wav(torch.from_numpy(wavs).to(torch.int16)).numpy()
+    assert np.array_equal(emb_i16, emb)
+
+
+@pytest.mark.parametrize("name,prec", [("ECAPA_TDNN_c1024", "bf16"), ("ResNet34", "fp16"), ("CAMPPlus", "bf16")])
+def test_batch_invariance_at_bench_size(name, prec):
+    """Size-independent property at BASELINE sizes: an utterance's embedding does not depend on its batch
+    (no cross-utterance leakage through tiles / padding), and the host-buffer ABI equals the device ABI."""
+    B, T = (256, 200) if name.startswith("ECAPA") else (64, 200)
+    m = from_synthetic(name, 0, precision=prec)
+    feats = torch.from_numpy(syn.make_feats(B, T, 80, seed=11)).to(DEV)
+    full = m.embed(feats).cpu().numpy()
+    sub = m.embed(feats[5:8].contiguous()).cpu().numpy()
+    assert np.isfinite(full).all()
+    assert rel_l2(sub, full[5:8]).max() < 1e-6
+    host = m.embed(feats.cpu()).numpy()
+    assert np.array_equal(host, full)
+
+
+# ------------------------------------------------------------------------------------------ PLDA
+def _tol_ok(s, ref):
+    return np.abs(s - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref))
+
+
+@pytest.mark.parametrize("tag", ["norm", "raw"])
+def test_plda_matches_reference_golden(tag):
+    nl = tag == "norm"
+    p = TwoCovPLDA.from_arrays(**syn.make_plda(256, seed=3, normalize_length=nl))
+    enroll, test = syn.make_embeddings(48, 256, seed=3), syn.make_embeddings(40, 256, seed=4)
+    e_t, t_t = p.transform_batch(enroll), p.transform_batch(test)
+    assert np.abs(e_t.cpu().numpy() - G_PLDA[f"enroll_t_{tag}"]).max() < 1e-10
+    assert np.abs(t_t.cpu().numpy() - G_PLDA[f"test_t_{tag}"]).max() < 1e-10
+    s1 = p.score_matrix(e_t, t_t, 1, out_dtype=torch.float64).cpu().numpy()
+    counts = ((np.arange(48) % 5) + 1).astype(np.int32)
+    sn = p.score_matrix(e_t, t_t, counts, out_dtype=torch.float64).cpu().numpy()
+    print(f"plda {tag}: max err n1 {np.abs(s1 - G_PLDA[f'scores_n1_{tag}']).max():.2e} nvar {np.abs(sn - G_PLDA[f'scores_nvar_{tag}']).max():.2e}")
+    assert _tol_ok(s1, G_PLDA[f"scores_n1_{tag}"]).all() and _tol_ok(sn, G_PLDA[f"scores_nvar_{tag}"]).all()
+    s1f = p.score_matrix(e_t, t_t, 1).cpu().numpy()  # fp32 output buffer (the bench configuration)
+    assert _tol_ok(s1f.astype(np.float64), G_PLDA[f"scores_n1_{tag}"]).all()
+    ei, ti = np.array([0, 5, 47, 13]), np.array([0, 7, 39, 2])
+    tr = p.score_trials(e_t, t_t, ei, ti, counts).cpu().numpy()
+    assert _tol_ok(tr, G_PLDA[f"scores_nvar_{tag}"][ei, ti]).all()
+    one = p.log_likelihood_ratio(G_PLDA[f"enroll_t_{tag}"][5], G_PLDA[f"test_t_{tag}"][7], 1)
+    assert abs(one - G_PLDA[f"scores_n1_{tag}"][5, 7]) <= 1e-5 * max(1, abs(one))
+
+
+def test_plda_4096_block_vs_oracle_and_symmetry():
+    """SURVEY §8d config 5 parity block (4096 x 4096) vs the fp64 oracle; n=1 scores are symmetric."""
+    pm = syn.make_plda(256, seed=3, normalize_length=True)
+    p = TwoCovPLDA.from_arrays(**pm)
+    a, b = syn.make_embeddings(4096, 256, seed=21), syn.make_embeddings(4096, 256, seed=22)
+    a_t, b_t = p.transform_batch(a), p.transform_batch(b)
+    s = p.score_matrix(a_t, b_t, 1).cpu().numpy().astype(np.float64)
+    ref = plda_np.llr_matrix(pm, plda_np.prepare_test(pm, a.astype(np.float64))[:512],
+                             plda_np.prepare_test(pm, b.astype(np.float64)), 1)
+    assert _tol_ok(s[:512], ref).all(), np.abs(s[:512] - ref).max()
+    st = p.score_matrix(b_t, a_t, 1).cpu().numpy().astype(np.float64)
+    assert np.abs(s - st.T).max() < 1e-5
+    # ragged sizes (not multiples of the 128x64 tile) and empty inputs
+    s2 = p.score_matrix(a_t[:130], b_t[:67], 3, out_dtype=torch.float64).cpu().numpy()
+    ref2 = plda_np.llr_matrix(pm, a_t[:130].cpu().numpy(), b_t[:67].cpu().numpy(), 3)
+    assert _tol_ok(s2, ref2).all()
+    assert p.score_matrix(a_t[:0], b_t[:5], 1).shape == (0, 5)

@@ -1,0 +1,118 @@
+"""CPU: host logic, the C-ABI library (loads, exports every declared symbol, fails loudly without a GPU),
+Kaldi IO, the nn.Module-shaped wrapper, and the world_size-2 gloo path of the multi-GPU gather."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from wespeaker_b200 import kaldi_io, lib, parallel, synthetic as syn
+from wespeaker_b200.models import B200SpeakerModel, from_synthetic, get_speaker_model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = lib.load()
+    hdr = open(os.path.join(ROOT, "include", "wespeaker_b200.h")).read()
+    declared = set(re.findall(r"\b(ws_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(lib.EXPORTED_SYMBOLS), declared ^ set(lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.ws_version() >= 100
+    assert L.ws_fbank_num_frames(32000) == 198 and L.ws_fbank_num_frames(399) == 0 and L.ws_fbank_num_frames(400) == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    m = from_synthetic("ECAPA_TDNN_c512")
+    with pytest.raises(lib.B200Error):
+        m(torch.zeros(1, 200, 80))
+    from wespeaker_b200.plda import TwoCovPLDA
+    p = TwoCovPLDA.from_arrays(**syn.make_plda(256))
+    with pytest.raises(lib.B200Error):
+        p.transform_batch(np.zeros((2, 256), np.float32))
+
+
+def test_wrapper_state_dict_contract():
+    ctor = get_speaker_model("ResNet34")
+    m = ctor(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False)
+    assert isinstance(m, torch.nn.Module) and isinstance(m, B200SpeakerModel)
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in syn.make_state_dict("ResNet34", 0).items()}
+    r = m.load_state_dict(sd)
+    assert r.missing_keys == [] and r.unexpected_keys == []
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    bad = dict(sd)
+    bad["projection.weight"] = torch.zeros(10, 256)
+    del bad["seg_1.bias"]
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad, strict=True)
+    r = m.load_state_dict(bad, strict=False)  # checkpoint.py:66-85 semantics
+    assert r.missing_keys == ["seg_1.bias"] and r.unexpected_keys == ["projection.weight"]
+    bad2 = dict(sd)
+    bad2["seg_1.weight"] = torch.zeros(3, 3)
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad2, strict=False)
+    assert m.to("cpu").eval() is m
+    with pytest.raises(ValueError):
+        get_speaker_model("XVEC")
+
+
+def test_kaldi_vector_roundtrip(tmp_path):
+    ark, scp = str(tmp_path / "xvector.ark"), str(tmp_path / "xvector.scp")
+    rng = np.random.default_rng(0)
+    vecs = {f"utt{i}": rng.standard_normal(192).astype(np.float32) for i in range(5)}
+    with kaldi_io.VectorWriter(ark, scp) as w:
+        for k, v in vecs.items():
+            w(k, v)
+    back = kaldi_io.read_vec_scp_file(scp)
+    assert list(back) == list(vecs)
+    for k in vecs:
+        assert np.array_equal(back[k], vecs[k])
+    assert [k for k, _ in kaldi_io.load_ark(ark)] == list(vecs)
+    raw = open(ark, "rb").read()
+    assert raw.startswith(b"utt0 \0BFV \4" + (192).to_bytes(4, "little"))
+
+
+def test_shard_helpers():
+    assert parallel.shard_indices(10, 1, 4) == [1, 5, 9]
+    assert parallel.shard_rows(10, 3, 4) == (9, 10) and parallel.shard_rows(10, 0, 4) == (0, 3)
+    x = torch.arange(6.0).view(3, 2)
+    assert parallel.gather_embeddings(x, 3) is x  # world size 1: identity
+
+
+_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, {root!r})
+from wespeaker_b200 import parallel
+import torch.distributed as dist
+rank, world, _ = parallel.init_from_env("gloo")
+N, E = 7, 4
+full = torch.arange(N * E, dtype=torch.float32).view(N, E)
+mine = full[parallel.shard_indices(N, rank, world)]
+out = parallel.gather_embeddings(mine, N)
+assert torch.equal(out, full), (rank, out)
+lo, hi = parallel.shard_rows(N, rank, world)
+tot = torch.tensor([float(hi - lo)]); dist.all_reduce(tot); assert tot.item() == N
+assert parallel.max_over_ranks(float(rank)) == world - 1
+parallel.barrier()
+print("OK", rank)
+"""
+
+
+def test_gather_embeddings_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT="29533")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "OK" in o, o

@@ -1,0 +1,222 @@
+// Shared device/host definitions for the wespeaker_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+enum WsDType : int { WS_F32 = 0, WS_BF16 = 1, WS_F16 = 2 };
+enum WsAct : int { WS_ACT_NONE = 0, WS_ACT_RELU = 1, WS_ACT_TANH = 2, WS_ACT_SIGMOID = 3 };
+
+__host__ __device__ inline int ws_esize(int dt) { return dt == WS_F32 ? 4 : 2; }
+
+// Fused epilogue of every conv/GEMM launch (applied on the fp32 accumulator, in this order):
+//   v  = acc + bias[c] + rowbias[b][c]
+//   v  = act1(v)
+//   v  = v * scale[c] + shift[c]
+//   v *= gate[b][t / gate_seg][c]
+//   v += res[pos][c]
+//   v  = act2(v)
+//   out[pos][c] = v ;  out2[pos][c] = v + add2[pos][c]
+// ECAPA's conv->relu->bn (ecapa_tdnn.py:105-106) is {bias, relu, scale/shift}; folded-BN conv->bn->relu
+// (resnet.py:64-69, campplus.py:65-83) is {scale/shift folded into W, shift as bias, relu}.
+struct WsEpi {
+    const float* bias;
+    const float* rowbias;
+    int rowbias_ld;
+    int act1;
+    const float* scale;
+    const float* shift;
+    const float* gate;
+    int gate_ld, gate_seg, gate_nseg;
+    const void* res;
+    long long res_ld;
+    int act2;
+    void* out;
+    long long out_ld;
+    void* out2;
+    long long out2_ld;
+    const void* add2;
+    long long add2_ld;
+    int dtype;  // dtype of res/out/out2/add2 (activation dtype)
+    int FT;     // F*T of the output tensor (pos / FT = b)
+    int T;      // T of the output tensor   (pos % T = t)
+};
+
+__device__ __forceinline__ float ws_act(float v, int act) {
+    switch (act) {
+        case WS_ACT_RELU: return fmaxf(v, 0.f);
+        case WS_ACT_TANH: return tanhf(v);
+        case WS_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ float ws_bf16_bits_to_f(uint32_t u16) { return __uint_as_float(u16 << 16); }
+__device__ __forceinline__ float ws_f16_bits_to_f(uint32_t u16) {
+    return __half2float(__ushort_as_half((unsigned short)u16));
+}
+__device__ __forceinline__ uint32_t ws_f_to_16(float v, int dt) {
+    return dt == WS_BF16 ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v))
+                         : (uint32_t)__half_as_ushort(__float2half_rn(v));
+}
+__device__ __forceinline__ float ws_16_to_f(uint32_t u, int dt) {
+    return dt == WS_BF16 ? ws_bf16_bits_to_f(u) : ws_f16_bits_to_f(u);
+}
+
+// scalar typed load/store (any alignment)
+__device__ __forceinline__ float ws_ld(const void* p, int dt, long long i) {
+    if (dt == WS_F32) return ((const float*)p)[i];
+    return ws_16_to_f(((const unsigned short*)p)[i], dt);
+}
+__device__ __forceinline__ void ws_st(void* p, int dt, long long i, float v) {
+    if (dt == WS_F32) ((float*)p)[i] = v;
+    else ((unsigned short*)p)[i] = (unsigned short)ws_f_to_16(v, dt);
+}
+
+// NV consecutive elements starting at element offset `off` (off % 4 == 0, base 16B aligned).
+template <int NV>
+__device__ __forceinline__ void ws_ldv(const void* p, int dt, long long off, float* v) {
+    static_assert(NV % 4 == 0, "NV % 4");
+    if (dt == WS_F32) {
+        const float4* q = reinterpret_cast<const float4*>((const float*)p + off);
+#pragma unroll
+        for (int i = 0; i < NV / 4; ++i) {
+            float4 x = q[i];
+            v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+        }
+    } else {
+        const uint2* q = reinterpret_cast<const uint2*>((const unsigned short*)p + off);
+#pragma unroll
+        for (int i = 0; i < NV / 4; ++i) {
+            uint2 x = q[i];
+            v[4 * i] = ws_16_to_f(x.x & 0xffffu, dt); v[4 * i + 1] = ws_16_to_f(x.x >> 16, dt);
+            v[4 * i + 2] = ws_16_to_f(x.y & 0xffffu, dt); v[4 * i + 3] = ws_16_to_f(x.y >> 16, dt);
+        }
+    }
+}
+template <int NV>
+__device__ __forceinline__ void ws_stv(void* p, int dt, long long off, const float* v) {
+    static_assert(NV % 4 == 0, "NV % 4");
+    if (dt == WS_F32) {
+        float4* q = reinterpret_cast<float4*>((float*)p + off);
+#pragma unroll
+        for (int i = 0; i < NV / 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+        uint2* q = reinterpret_cast<uint2*>((unsigned short*)p + off);
+#pragma unroll
+        for (int i = 0; i < NV / 4; ++i) {
+            uint2 x;
+            x.x = ws_f_to_16(v[4 * i], dt) | (ws_f_to_16(v[4 * i + 1], dt) << 16);
+            x.y = ws_f_to_16(v[4 * i + 2], dt) | (ws_f_to_16(v[4 * i + 3], dt) << 16);
+            q[i] = x;
+        }
+    }
+}
+
+// Apply the fused epilogue to NV consecutive output channels [col0, col0+NV) of output position `pos`.
+template <int NV>
+__device__ __forceinline__ void ws_epilogue(const WsEpi& e, long long pos, int col0, float* v) {
+    int b = 0, t = 0;
+    if (e.rowbias != nullptr || e.gate != nullptr) {
+        b = (int)(pos / e.FT);
+        t = (int)(pos % e.T);
+    }
+    if (e.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] += __ldg(e.bias + col0 + j);
+    }
+    if (e.rowbias != nullptr) {
+        const float* rb = e.rowbias + (long long)b * e.rowbias_ld + col0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] += __ldg(rb + j);
+    }
+    if (e.act1 != WS_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = ws_act(v[j], e.act1);
+    }
+    if (e.scale != nullptr) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = fmaf(v[j], __ldg(e.scale + col0 + j), __ldg(e.shift + col0 + j));
+    }
+    if (e.gate != nullptr) {
+        const float* g = e.gate + ((long long)b * e.gate_nseg + t / e.gate_seg) * e.gate_ld + col0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] *= __ldg(g + j);
+    }
+    if (e.res != nullptr) {
+        float r[NV];
+        ws_ldv<NV>(e.res, e.dtype, pos * e.res_ld + col0, r);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] += r[j];
+    }
+    if (e.act2 != WS_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = ws_act(v[j], e.act2);
+    }
+    ws_stv<NV>(e.out, e.dtype, pos * e.out_ld + col0, v);
+    if (e.out2 != nullptr) {
+        float r[NV];
+        ws_ldv<NV>(e.add2, e.dtype, pos * e.add2_ld + col0, r);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) r[j] += v[j];
+        ws_stv<NV>(e.out2, e.dtype, pos * e.out2_ld + col0, r);
+    }
+}
+
+// ------------------------------------------------------------------ conv-as-GEMM description
+// Activations are channels-last [B][F][T][C]; one "tap" contributes  sum_c X_src[b, f+df, t+dt, c0+c] * W[co][wk+c]
+// for c in [0, nch).  Strided convs use parity-plane source views so taps stay unit-stride.
+#define WS_MAX_SRC 4
+#define WS_MAX_TAPS 64
+
+struct WsSrc {
+    const void* ptr;
+    int B, F, T, C;          // extents of the (possibly strided) view; reads outside are zero (conv padding)
+    long long sB, sF, sT;    // element strides
+};
+struct WsTap {
+    int src, c0, dt, df, wk, nch;
+};
+
+struct WsSimtParams {
+    WsSrc src[WS_MAX_SRC];
+    WsTap taps[WS_MAX_TAPS];
+    int ntaps;
+    const void* W;  // [Cout][Ktot], activation dtype
+    int Ktot, Cout;
+    int B, F, T;    // output extents
+    int dtype;
+    WsEpi epi;
+};
+
+#define WS_TC_MAX_STAGES 8
+struct WsTcTap {
+    int map, c0, dt, df, wk, nkb;
+};
+struct WsTcParams {
+    CUtensorMap amap[WS_MAX_SRC];
+    CUtensorMap wmap;
+    WsTcTap taps[WS_MAX_TAPS];
+    int ntaps, nk_total;
+    int bk_bytes;                       // 128 / 64 / 32 : k-block row bytes == TMA/UMMA swizzle span
+    int bt_log2, bf_log2, bb_log2;      // output tile = 2^bt x 2^bf x 2^bb = 128 positions
+    int tiles_t, tiles_f, tiles_b, tiles_n;
+    int B, F, T;                        // output extents
+    int bn;                             // N tile (output channels per CTA) == UMMA N == TMEM columns
+    int nstages;
+    uint32_t idesc;                     // tcgen05 instruction descriptor
+    int kind;                           // 0 = tf32, 1 = f16/bf16
+    WsEpi epi;
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+const char* ws_tc_init(void);
+const char* ws_tc_launch(const WsTcParams* p, cudaStream_t s);
+const char* ws_simt_launch(const WsSimtParams* p, cudaStream_t s);
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,261 @@
+// Host side of the fused conv operator: tap generation (incl. parity planes for strided convs), TMA tensor-map
+// construction, tile-shape selection and the launch closures for the tcgen05 and FFMA kernels.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+
+#include "../../include/wespeaker_b200.h"
+#include "ws_host.h"
+
+namespace ws {
+
+static thread_local std::string g_err;
+void set_err(const std::string& msg) { g_err = msg; }
+const std::string& get_err() { return g_err; }
+
+void fill_epi_out(WsEpi& e, const View& out) {
+    e.out = out.p;
+    e.out_ld = out.ld;
+    e.dtype = out.dt;
+    e.FT = out.F * out.T;
+    e.T = out.T;
+}
+
+static int find_or_add_src(ConvSpec& s, const WsSrc& v) {
+    for (int i = 0; i < s.nsrc; ++i)
+        if (s.src[i].ptr == v.ptr && s.src[i].sT == v.sT && s.src[i].sF == v.sF && s.src[i].T == v.T &&
+            s.src[i].F == v.F && s.src[i].C == v.C)
+            return i;
+    if (s.nsrc >= WS_MAX_SRC) return -1;
+    s.src[s.nsrc] = v;
+    return s.nsrc++;
+}
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+int add_conv_taps(ConvSpec& spec, const View& x, int kf, int kt, int dil_f, int dil_t, int pad_f, int pad_t,
+                  int stride_f, int stride_t, int wk0, int* Fo, int* To) {
+    const int es = ws_esize(x.dt);
+    *Fo = (x.F + 2 * pad_f - dil_f * (kf - 1) - 1) / stride_f + 1;
+    *To = (x.T + 2 * pad_t - dil_t * (kt - 1) - 1) / stride_t + 1;
+    const long long sT = x.ld, sF = (long long)x.T * x.ld, sB = (long long)x.F * x.T * x.ld;
+    for (int jf = 0; jf < kf; ++jf)
+        for (int jt = 0; jt < kt; ++jt) {
+            const int offf = jf * dil_f - pad_f, offt = jt * dil_t - pad_t;
+            const int pf = ((offf % stride_f) + stride_f) % stride_f, pt = ((offt % stride_t) + stride_t) % stride_t;
+            WsSrc v;
+            v.ptr = (const char*)x.p + ((size_t)pf * sF + (size_t)pt * sT) * es;
+            v.B = x.B;
+            v.F = (x.F - pf + stride_f - 1) / stride_f;
+            v.T = (x.T - pt + stride_t - 1) / stride_t;
+            v.C = x.C;
+            v.sB = sB;
+            v.sF = sF * stride_f;
+            v.sT = sT * stride_t;
+            const int si = find_or_add_src(spec, v);
+            if (si < 0) return -1;
+            WsTap tap;
+            tap.src = si;
+            tap.c0 = 0;
+            tap.df = floordiv(offf - pf, stride_f);
+            tap.dt = floordiv(offt - pt, stride_t);
+            tap.wk = wk0 + (jf * kt + jt) * x.C;
+            tap.nch = x.C;
+            spec.taps.push_back(tap);
+        }
+    return kf * kt * x.C;
+}
+
+// ------------------------------------------------------------------------------------------------ TMA maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+static bool encode_map(CUtensorMap* m, int dt, const void* ptr, int rank, const cuuint64_t* dims,
+                       const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes) {
+    EncodeTiledFn fn = get_encode();
+    if (fn == nullptr) {
+        set_err("cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)");
+        return false;
+    }
+    const CUtensorMapDataType t = dt == WS_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                               : (dt == WS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                                : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                       : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                              : CU_TENSOR_MAP_SWIZZLE_32B);
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, t, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[256];
+        snprintf(buf, sizeof buf,
+                 "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u] sw %d", (int)r,
+                 rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                 (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                 rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, swizzle_bytes);
+        set_err(buf);
+        return false;
+    }
+    return true;
+}
+
+static int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+static bool build_tc(const ConvSpec& s, WsTcParams* p) {
+    memset(p, 0, sizeof(*p));
+    const int es = ws_esize(s.dt);
+    p->kind = s.dt == WS_F32 ? 0 : 1;
+    if (s.Cout % 16 != 0) { set_err("tc conv: Cout must be a multiple of 16"); return false; }
+    if ((int)s.taps.size() > WS_MAX_TAPS) { set_err("tc conv: too many taps"); return false; }
+    int minb = 1 << 30;
+    for (const WsTap& t : s.taps) minb = std::min(minb, t.nch * es);
+    p->bk_bytes = minb >= 128 ? 128 : (minb >= 64 ? 64 : 32);
+    if (minb < 32) { set_err("tc conv: fewer than 32 bytes of channels per tap"); return false; }
+    const int bk_elems = p->bk_bytes / es;
+    p->ntaps = (int)s.taps.size();
+    p->nk_total = 0;
+    for (int i = 0; i < p->ntaps; ++i) {
+        const WsTap& t = s.taps[i];
+        WsTcTap& o = p->taps[i];
+        o.map = t.src; o.c0 = t.c0; o.dt = t.dt; o.df = t.df; o.wk = t.wk;
+        o.nkb = (t.nch + bk_elems - 1) / bk_elems;
+        if (t.nch % bk_elems != 0 && t.c0 + t.nch != s.src[t.src].C) {
+            set_err("tc conv: ragged k-block needs the tap to end at the source view's last channel");
+            return false;
+        }
+        p->nk_total += o.nkb;
+    }
+    // ---- output tile shape
+    int B = s.B, F = s.F, T = s.T;
+    bool flat = s.dense_pointwise;
+    int bt = 128, bf = 1, bb = 1;
+    if (flat) {
+        T = s.B * s.F * s.T; F = 1; B = 1;
+    } else {
+        long long best = -1;
+        for (int t = 1; t <= 128; t <<= 1)
+            for (int f = 1; t * f <= 128; f <<= 1) {
+                const int b = 128 / (t * f);
+                if (F == 1 && f != 1) continue;
+                const long long cost = (long long)((T + t - 1) / t) * t * ((F + f - 1) / f) * f * ((B + b - 1) / b) * b;
+                if (best < 0 || cost < best || (cost == best && t > bt)) { best = cost; bt = t; bf = f; bb = b; }
+            }
+    }
+    p->bt_log2 = ilog2(bt); p->bf_log2 = ilog2(bf); p->bb_log2 = ilog2(bb);
+    p->tiles_t = (T + bt - 1) / bt; p->tiles_f = (F + bf - 1) / bf; p->tiles_b = (B + bb - 1) / bb;
+    p->B = B; p->F = F; p->T = T;
+    p->bn = s.Cout % 128 == 0 ? 128 : (s.Cout % 64 == 0 ? 64 : (s.Cout % 32 == 0 ? 32 : 16));
+    p->tiles_n = s.Cout / p->bn;
+    const int stage_bytes = (128 + p->bn) * p->bk_bytes;
+    int ns = (96 * 1024) / stage_bytes;
+    p->nstages = ns < 2 ? 2 : (ns > WS_TC_MAX_STAGES ? WS_TC_MAX_STAGES : ns);
+    const uint32_t fmt = s.dt == WS_F32 ? 2u : (s.dt == WS_BF16 ? 1u : 0u);
+    // cute::UMMA::InstrDescriptor: c_format f32 @4, a_format @7, b_format @10, K-major both, N>>3 @17, M>>4 @24
+    p->idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p->bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // ---- tensor maps
+    for (int i = 0; i < s.nsrc; ++i) {
+        const WsSrc& v = s.src[i];
+        cuuint64_t dims[4], str[3];
+        cuuint32_t box[4];
+        if (flat) {
+            dims[0] = (cuuint64_t)v.C; dims[1] = (cuuint64_t)T; dims[2] = 1; dims[3] = 1;
+            str[0] = (cuuint64_t)v.sT * es; str[1] = (cuuint64_t)T * v.sT * es; str[2] = str[1];
+        } else {
+            dims[0] = (cuuint64_t)v.C; dims[1] = (cuuint64_t)v.T; dims[2] = (cuuint64_t)v.F; dims[3] = (cuuint64_t)v.B;
+            str[0] = (cuuint64_t)v.sT * es; str[1] = (cuuint64_t)v.sF * es; str[2] = (cuuint64_t)v.sB * es;
+        }
+        box[0] = (cuuint32_t)bk_elems; box[1] = (cuuint32_t)bt; box[2] = (cuuint32_t)bf; box[3] = (cuuint32_t)bb;
+        if (!encode_map(&p->amap[i], s.dt, v.ptr, 4, dims, str, box, p->bk_bytes)) return false;
+    }
+    for (int i = s.nsrc; i < WS_MAX_SRC; ++i) p->amap[i] = p->amap[0];
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)s.Ktot, (cuuint64_t)s.Cout};
+        cuuint64_t str[1] = {(cuuint64_t)s.Ktot * es};
+        cuuint32_t box[2] = {(cuuint32_t)bk_elems, (cuuint32_t)p->bn};
+        if (!encode_map(&p->wmap, s.dt, s.W, 2, dims, str, box, p->bk_bytes)) return false;
+    }
+    p->epi = s.epi;
+    return true;
+}
+
+static bool build_simt(const ConvSpec& s, WsSimtParams* p) {
+    memset(p, 0, sizeof(*p));
+    if ((int)s.taps.size() > WS_MAX_TAPS) { set_err("conv: too many taps"); return false; }
+    if (s.Cout % 4 != 0) { set_err("conv: Cout must be a multiple of 4"); return false; }
+    for (int i = 0; i < s.nsrc; ++i) p->src[i] = s.src[i];
+    p->ntaps = (int)s.taps.size();
+    for (int i = 0; i < p->ntaps; ++i) p->taps[i] = s.taps[i];
+    p->W = s.W; p->Ktot = s.Ktot; p->Cout = s.Cout;
+    p->B = s.B; p->F = s.F; p->T = s.T;
+    p->dtype = s.dt;
+    p->epi = s.epi;
+    return true;
+}
+
+bool make_conv_op(const ConvSpec& spec, bool use_tc, Op* out) {
+    if (use_tc) {
+        auto p = std::make_shared<WsTcParams>();
+        if (!build_tc(spec, p.get())) return false;
+        *out = [p](cudaStream_t s) { return ws_tc_launch(p.get(), s); };
+    } else {
+        auto p = std::make_shared<WsSimtParams>();
+        if (!build_simt(spec, p.get())) return false;
+        *out = [p](cudaStream_t s) { return ws_simt_launch(p.get(), s); };
+    }
+    return true;
+}
+
+}  // namespace ws
+
+// ------------------------------------------------------------------------------------------------ C ABI: ws_conv
+extern "C" int ws_conv(const ws_conv_desc* d, void* stream) {
+    using namespace ws;
+    if (d == nullptr) { set_err("ws_conv: null descriptor"); return 1; }
+    View x;
+    x.p = const_cast<void*>(d->x); x.B = d->B; x.F = d->F; x.T = d->T; x.C = d->Cin; x.ld = d->x_ld; x.dt = d->dtype;
+    ConvSpec s;
+    s.dt = d->dtype;
+    int Fo = 0, To = 0;
+    const int K = add_conv_taps(s, x, d->kf, d->kt, d->dil_f, d->dil_t, d->pad_f, d->pad_t, d->stride_f, d->stride_t, 0,
+                                &Fo, &To);
+    if (K < 0) { set_err("ws_conv: too many source planes"); return 1; }
+    s.W = d->w; s.Ktot = K; s.Cout = d->Cout;
+    s.B = d->B; s.F = Fo; s.T = To;
+    s.dense_pointwise = (d->kf == 1 && d->kt == 1 && d->stride_f == 1 && d->stride_t == 1 && d->pad_f == 0 &&
+                         d->pad_t == 0);
+    View o;
+    o.p = d->out; o.B = d->B; o.F = Fo; o.T = To; o.C = d->Cout; o.ld = d->out_ld; o.dt = d->dtype;
+    fill_epi_out(s.epi, o);
+    s.epi.bias = d->bias; s.epi.act1 = d->act1; s.epi.scale = d->scale; s.epi.shift = d->shift;
+    s.epi.res = d->res; s.epi.res_ld = d->res_ld; s.epi.act2 = d->act2;
+    Op op;
+    if (d->use_tc) WS_CKS(ws_tc_init());
+    if (!make_conv_op(s, d->use_tc != 0, &op)) return 1;
+    const char* m = op((cudaStream_t)stream);
+    if (m != nullptr) { set_err(std::string("ws_conv launch: ") + m); return 1; }
+    return 0;
+}
+
+extern "C" const char* ws_last_error(void) { return ws::get_err().c_str(); }
+extern "C" int ws_version(void) { return 100; }

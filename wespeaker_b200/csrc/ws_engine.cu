@@ -1,0 +1,994 @@
+// B200 speaker-embedding engine: weight ingest (reference state_dict keys), per-(B,T) launch plans for
+// ECAPA-TDNN / ResNet / CAM++ built from the fused conv operator + bandwidth kernels, CUDA-graph replay, fbank
+// frontend tables, and the C ABI declared in include/wespeaker_b200.h.
+//
+// Reference behaviour being reproduced (file:line in /root/reference/wespeaker):
+//   models/ecapa_tdnn.py:29-234, models/pooling_layers.py:67-148, models/resnet.py:35-204,
+//   models/campplus.py:55-413, utils/checkpoint.py:20-85, bin/extract.py:109-139.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+
+#include "../../include/wespeaker_b200.h"
+#include "ws_host.h"
+
+using namespace ws;
+
+namespace {
+
+struct HostT {
+    std::vector<float> v;
+    std::vector<long long> shape;
+    long long numel() const {
+        long long n = 1;
+        for (long long d : shape) n *= d;
+        return n;
+    }
+};
+
+struct FbankTables {
+    float* window = nullptr;
+    float* melw = nullptr;
+    int* melstart = nullptr;
+    int* mellen = nullptr;
+    int maxlen = 0;
+};
+
+struct Plan {
+    int B = 0, T = 0;
+    std::vector<Op> ops;
+    std::vector<void*> bufs;
+    float* feats_in = nullptr;  // fp32 [B][T][feat_dim]
+    float* emb = nullptr;       // fp32 [B][embed_dim]
+    cudaGraphExec_t gexec = nullptr;
+    bool graph_failed = false;
+    ~Plan() {
+        if (gexec) cudaGraphExecDestroy(gexec);
+        for (void* p : bufs) cudaFree(p);
+    }
+};
+
+}  // namespace
+
+struct ws_engine {
+    std::string model, prec;
+    int feat_dim = 80, embed_dim = 0, device = 0;
+    int act_dt = WS_F32;
+    bool use_tc = false;
+    std::map<std::string, long long> opts;
+    std::map<std::string, HostT> sd;
+    bool finalized = false;
+    std::map<std::string, void*> wcache;  // packed device weights by id
+    std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+    long long last_launches = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    std::map<std::string, FbankTables> fb;
+    void* wav_dev = nullptr;
+    size_t wav_bytes = 0;
+    // model hyper-parameters
+    int channels = 512;
+    bool glob = false;
+    std::vector<int> num_blocks;
+    ~ws_engine() {
+        plans.clear();
+        for (auto& kv : wcache) cudaFree(kv.second);
+        for (auto& kv : fb) {
+            cudaFree(kv.second.window); cudaFree(kv.second.melw); cudaFree(kv.second.melstart); cudaFree(kv.second.mellen);
+        }
+        if (wav_dev) cudaFree(wav_dev);
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_out) cudaEventDestroy(ev_out);
+        if (st) cudaStreamDestroy(st);
+    }
+    long long opt(const char* k, long long dflt) const {
+        auto it = opts.find(k);
+        return it == opts.end() ? dflt : it->second;
+    }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ weights
+struct Weights {
+    ws_engine& e;
+    bool ok = true;
+    explicit Weights(ws_engine& eng) : e(eng) {}
+
+    const HostT* get(const std::string& key) {
+        auto it = e.sd.find(key);
+        if (it == e.sd.end()) {
+            if (ok) set_err("missing tensor in state_dict: " + key);
+            ok = false;
+            return nullptr;
+        }
+        return &it->second;
+    }
+    void* upload(const std::string& id, const void* host, size_t bytes) {
+        auto it = e.wcache.find(id);
+        if (it != e.wcache.end()) return it->second;
+        void* d = nullptr;
+        if (cudaMalloc(&d, bytes ? bytes : 16) != cudaSuccess || cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+            if (ok) set_err("device allocation/copy failed for weight " + id);
+            ok = false;
+            return nullptr;
+        }
+        e.wcache[id] = d;
+        return d;
+    }
+    bool cached(const std::string& id, void** out) {
+        auto it = e.wcache.find(id);
+        if (it == e.wcache.end()) return false;
+        *out = it->second;
+        return true;
+    }
+    float* f32(const std::string& id, const std::vector<float>& v) { return (float*)upload(id, v.data(), v.size() * 4); }
+    void* act(const std::string& id, const std::vector<float>& v) {
+        void* c;
+        if (cached(id, &c)) return c;
+        if (e.act_dt == WS_F32) return upload(id, v.data(), v.size() * 4);
+        std::vector<unsigned short> h(v.size());
+        for (size_t i = 0; i < v.size(); ++i)
+            h[i] = e.act_dt == WS_BF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v[i]))
+                                       : __half_as_ushort(__float2half_rn(v[i]));
+        return upload(id, h.data(), h.size() * 2);
+    }
+    const float* vec(const std::string& key) {
+        void* c;
+        if (cached("v:" + key, &c)) return (const float*)c;
+        const HostT* t = get(key);
+        return t ? f32("v:" + key, t->v) : nullptr;
+    }
+    // eval-mode BatchNorm as per-channel affine: scale = w / sqrt(var + eps), shift = b - mean * scale
+    bool bn(const std::string& p, bool affine, std::vector<float>& scale, std::vector<float>& shift) {
+        const HostT* m = get(p + ".running_mean");
+        const HostT* v = get(p + ".running_var");
+        const HostT* w = affine ? get(p + ".weight") : nullptr;
+        const HostT* b = affine ? get(p + ".bias") : nullptr;
+        if (!m || !v || (affine && (!w || !b))) return false;
+        const size_t n = m->v.size();
+        scale.resize(n); shift.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            const double s = (affine ? (double)w->v[i] : 1.0) / std::sqrt((double)v->v[i] + 1e-5);
+            scale[i] = (float)s;
+            shift[i] = (float)((affine ? (double)b->v[i] : 0.0) - (double)m->v[i] * s);
+        }
+        return true;
+    }
+    // conv weight (Cout, Cin, k) or (Cout, Cin, kf, kt) -> [Cout][tap][Cin] (tap-major), optional per-row scale
+    bool pack_conv(const std::string& key, const std::vector<float>* rowscale, std::vector<float>& out, int* Cout,
+                   int* Cin, int* ntap) {
+        const HostT* t = get(key);
+        if (!t) return false;
+        const int co = (int)t->shape[0], ci = (int)t->shape[1];
+        int taps = 1;
+        for (size_t i = 2; i < t->shape.size(); ++i) taps *= (int)t->shape[i];
+        out.resize((size_t)co * ci * taps);
+        for (int o = 0; o < co; ++o) {
+            const float sc = rowscale ? (*rowscale)[o] : 1.f;
+            for (int c = 0; c < ci; ++c)
+                for (int j = 0; j < taps; ++j)
+                    out[((size_t)o * taps + j) * ci + c] = t->v[((size_t)o * ci + c) * taps + j] * sc;
+        }
+        *Cout = co; *Cin = ci; *ntap = taps;
+        return true;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ plan builder
+struct Builder {
+    ws_engine& e;
+    Plan& p;
+    Weights w;
+    bool ok = true;
+    Builder(ws_engine& eng, Plan& pl) : e(eng), p(pl), w(eng) {}
+    bool good() const { return ok && w.ok; }
+
+    void* raw(size_t bytes) {
+        void* d = nullptr;
+        if (cudaMalloc(&d, bytes ? bytes : 16) != cudaSuccess) {
+            if (ok) set_err("cudaMalloc failed for an activation buffer");
+            ok = false;
+            return nullptr;
+        }
+        p.bufs.push_back(d);
+        return d;
+    }
+    View act(int B, int F, int T, int C) {
+        View v;
+        v.B = B; v.F = F; v.T = T; v.C = C; v.ld = C; v.dt = e.act_dt;
+        v.p = raw((size_t)B * F * T * C * ws_esize(e.act_dt));
+        return v;
+    }
+    float* f32(size_t n) { return (float*)raw(n * 4); }
+    void push(Op op) { p.ops.push_back(std::move(op)); }
+    void conv(const ConvSpec& s) {
+        if (!good()) return;
+        Op op;
+        if (!make_conv_op(s, e.use_tc, &op)) { ok = false; return; }
+        push(std::move(op));
+    }
+    static WsSrc src_of(const View& v) {
+        WsSrc s;
+        s.ptr = v.p; s.B = v.B; s.F = v.F; s.T = v.T; s.C = v.C;
+        s.sT = v.ld; s.sF = (long long)v.T * v.ld; s.sB = (long long)v.F * v.T * v.ld;
+        return s;
+    }
+    // plain conv over one input view; returns output dims via out view (must be pre-sized by caller)
+    void conv_simple(const View& x, const View& out, const void* W, int kf, int kt, int dil_f, int dil_t, int pad_f,
+                     int pad_t, int sf, int st_, const WsEpi& epi_in) {
+        if (!good()) return;
+        ConvSpec s;
+        s.dt = e.act_dt;
+        int Fo, To;
+        const int K = add_conv_taps(s, x, kf, kt, dil_f, dil_t, pad_f, pad_t, sf, st_, 0, &Fo, &To);
+        if (K < 0 || Fo != out.F || To != out.T) { set_err("internal: conv shape mismatch"); ok = false; return; }
+        s.W = W; s.Ktot = K; s.Cout = out.C; s.B = out.B; s.F = Fo; s.T = To;
+        s.dense_pointwise = (kf == 1 && kt == 1 && sf == 1 && st_ == 1);
+        s.epi = epi_in;
+        fill_epi_out(s.epi, out);
+        conv(s);
+    }
+    void tstats(const View& x, const float* pre_scale, const float* pre_shift, float* out, long long out_ld, int std_off) {
+        View xv = x;
+        push([=](cudaStream_t s) {
+            return ws_launch_tstats(xv.p, xv.dt, xv.B, xv.F, xv.T, xv.C, xv.ld, pre_scale, pre_shift, out, WS_F32, out_ld,
+                                    std_off, 1e-7f, s);
+        });
+    }
+    void linear(const float* in, long long in_ld, const float* in2, long long in2_ld, int rows_per_b, const float* W,
+                const float* bias, float* out, long long out_ld, int R, int I, int O, int act) {
+        push([=](cudaStream_t s) {
+            return ws_launch_linear_rows(in, in_ld, in2, in2_ld, rows_per_b, W, bias, out, out_ld, R, I, O, act, s);
+        });
+    }
+};
+
+// ----------------------------------------------------------------------------------------------- ECAPA-TDNN
+// ecapa_tdnn.py:160-234.  Channels-last buffers; torch.cat is free (layer outputs are written into slices of one
+// (B,T,3C) buffer), Res2 "sp + spx[i]" is produced by the previous conv's epilogue (out2 = out + add2).
+bool build_ecapa(Builder& b) {
+    ws_engine& e = b.e;
+    const int B = b.p.B, T = b.p.T, C = e.channels, w8 = C / 8, Fd = e.feat_dim, E = e.embed_dim;
+    View x0 = b.act(B, 1, T, Fd);
+    View out1 = b.act(B, 1, T, C), cat = b.act(B, 1, T, 3 * C);
+    View tA = b.act(B, 1, T, C), tB = b.act(B, 1, T, C), tC = b.act(B, 1, T, C);
+    View sc[2] = {b.act(B, 1, T, w8), b.act(B, 1, T, w8)};
+    View frame = b.act(B, 1, T, 1536), hid = b.act(B, 1, T, 128), logits = b.act(B, 1, T, 1536);
+    float* semean = b.f32((size_t)B * C);
+    float* sehid = b.f32((size_t)B * 128);
+    float* segate = b.f32((size_t)B * C);
+    float* stats = b.f32((size_t)B * 3072);
+    if (!b.good()) return false;
+    {
+        const float* fin = b.p.feats_in;
+        void* xo = x0.p;
+        const int dt = e.act_dt;
+        const long long n = (long long)B * T * Fd;
+        b.push([=](cudaStream_t s) { return ws_launch_convert(fin, xo, dt, n, s); });
+    }
+    // Conv1dReluBn (ecapa_tdnn.py:85-106): bn(relu(conv(x)+bias))
+    auto conv_relu_bn = [&](const std::string& pfx, const View& x, const View& out, int k, int dil, int pad) {
+        std::vector<float> wp, s, h;
+        int co, ci, nt;
+        if (!b.w.pack_conv(pfx + ".conv.weight", nullptr, wp, &co, &ci, &nt) || !b.w.bn(pfx + ".bn", true, s, h)) return;
+        WsEpi ep{};
+        ep.bias = b.w.vec(pfx + ".conv.bias");
+        ep.act1 = WS_ACT_RELU;
+        ep.scale = b.w.f32("bns:" + pfx, s);
+        ep.shift = b.w.f32("bnh:" + pfx, h);
+        b.conv_simple(x, out, b.w.act("w:" + pfx, wp), 1, k, 1, dil, 0, pad, 1, 1, ep);
+    };
+    conv_relu_bn("layer1", x0, out1, 5, 1, 2);
+    View xin = out1;
+    for (int L = 2; L <= 4 && b.good(); ++L) {
+        const int d = L;
+        const std::string pf = "layer" + std::to_string(L) + ".se_res2block";
+        conv_relu_bn(pf + ".0", xin, tA, 1, 1, 0);
+        // Res2Conv1dReluBn (ecapa_tdnn.py:29-78): 7 dependent dilated k=3 convs on w8-channel groups
+        for (int i = 0; i < 7 && b.good(); ++i) {
+            const std::string cp = pf + ".1.convs." + std::to_string(i), bp = pf + ".1.bns." + std::to_string(i);
+            std::vector<float> wp, s, h;
+            int co, ci, nt;
+            if (!b.w.pack_conv(cp + ".weight", nullptr, wp, &co, &ci, &nt) || !b.w.bn(bp, true, s, h)) break;
+            WsEpi ep{};
+            ep.bias = b.w.vec(cp + ".bias");
+            ep.act1 = WS_ACT_RELU;
+            ep.scale = b.w.f32("bns:" + bp, s);
+            ep.shift = b.w.f32("bnh:" + bp, h);
+            if (i < 6) {
+                View nx = tA.ch((i + 1) * w8, w8);
+                ep.out2 = sc[i & 1].p; ep.out2_ld = sc[i & 1].ld;
+                ep.add2 = nx.p; ep.add2_ld = nx.ld;
+            }
+            const View src = (i == 0) ? tA.ch(0, w8) : sc[(i - 1) & 1];
+            b.conv_simple(src, tB.ch(i * w8, w8), b.w.act("w:" + cp, wp), 1, 3, 1, d, 0, d, 1, 1, ep);
+        }
+        if (!b.good()) break;
+        {   // third block: 1x1 conv over cat[sp_0..sp_6, spx_7]: two K ranges from two buffers
+            const std::string cp = pf + ".2";
+            std::vector<float> wp, s, h;
+            int co, ci, nt;
+            if (!b.w.pack_conv(cp + ".conv.weight", nullptr, wp, &co, &ci, &nt) || !b.w.bn(cp + ".bn", true, s, h)) break;
+            ConvSpec cs;
+            cs.dt = e.act_dt;
+            cs.src[0] = Builder::src_of(tB.ch(0, 7 * w8));
+            cs.src[1] = Builder::src_of(tA.ch(7 * w8, w8));
+            cs.nsrc = 2;
+            cs.taps.push_back(WsTap{0, 0, 0, 0, 0, 7 * w8});
+            cs.taps.push_back(WsTap{1, 0, 0, 0, 7 * w8, w8});
+            cs.W = b.w.act("w:" + cp, wp); cs.Ktot = C; cs.Cout = C; cs.B = B; cs.F = 1; cs.T = T;
+            cs.dense_pointwise = true;
+            cs.epi.bias = b.w.vec(cp + ".conv.bias");
+            cs.epi.act1 = WS_ACT_RELU;
+            cs.epi.scale = b.w.f32("bns:" + cp, s);
+            cs.epi.shift = b.w.f32("bnh:" + cp, h);
+            fill_epi_out(cs.epi, tC);
+            b.conv(cs);
+        }
+        // SE_Connect (ecapa_tdnn.py:113-126) + residual (:157)
+        b.tstats(tC, nullptr, nullptr, semean, C, -1);
+        b.linear(semean, C, nullptr, 0, 1, b.w.vec(pf + ".3.linear1.weight"), b.w.vec(pf + ".3.linear1.bias"), sehid, 128, B,
+                 C, 128, WS_ACT_RELU);
+        b.linear(sehid, 128, nullptr, 0, 1, b.w.vec(pf + ".3.linear2.weight"), b.w.vec(pf + ".3.linear2.bias"), segate, C,
+                 B, 128, C, WS_ACT_SIGMOID);
+        {
+            View o = cat.ch((L - 2) * C, C), xi = xin, tc = tC;
+            const int dt = e.act_dt;
+            b.push([=](cudaStream_t s) {
+                return ws_launch_scale_residual(tc.p, tc.ld, segate, xi.p, xi.ld, o.p, o.ld, dt, B, T, C, s);
+            });
+            xin = o;
+        }
+    }
+    if (!b.good()) return false;
+    {   // self.conv (1x1, 3C -> 1536) then F.relu (ecapa_tdnn.py:217-218,229)
+        std::vector<float> wp;
+        int co, ci, nt;
+        if (!b.w.pack_conv("conv.weight", nullptr, wp, &co, &ci, &nt)) return false;
+        WsEpi ep{};
+        ep.bias = b.w.vec("conv.bias");
+        ep.act1 = WS_ACT_RELU;
+        b.conv_simple(cat, frame, b.w.act("w:conv", wp), 1, 1, 1, 1, 0, 0, 1, 1, ep);
+    }
+    // ASTP (pooling_layers.py:119-144).  Global context: W1 [x; mean; std] = W1x x + (W1m mean + W1s std): the
+    // broadcast part becomes a per-utterance bias row added in the GEMM epilogue.
+    const float* rowbias = nullptr;
+    {
+        const HostT* w1 = b.w.get("pool.linear1.weight");
+        if (!w1) return false;
+        const int in_dim = (int)w1->shape[1];
+        std::vector<float> wx((size_t)128 * 1536);
+        for (int o = 0; o < 128; ++o)
+            for (int c = 0; c < 1536; ++c) wx[(size_t)o * 1536 + c] = w1->v[(size_t)o * in_dim + c];
+        if (e.glob) {
+            if (in_dim != 3 * 1536) { set_err("pool.linear1.weight: expected 4608 inputs for global_context_att"); return false; }
+            std::vector<float> wc((size_t)128 * 3072);
+            for (int o = 0; o < 128; ++o)
+                for (int c = 0; c < 3072; ++c) wc[(size_t)o * 3072 + c] = w1->v[(size_t)o * in_dim + 1536 + c];
+            float* ctx = b.f32((size_t)B * 3072);
+            float* rb = b.f32((size_t)B * 128);
+            b.tstats(frame, nullptr, nullptr, ctx, 3072, 1536);
+            b.linear(ctx, 3072, nullptr, 0, 1, b.w.f32("w:pool.linear1.ctx", wc), nullptr, rb, 128, B, 3072, 128, WS_ACT_NONE);
+            rowbias = rb;
+        } else if (in_dim != 1536) {
+            set_err("pool.linear1.weight: expected 1536 inputs"); return false;
+        }
+        WsEpi ep{};
+        ep.bias = b.w.vec("pool.linear1.bias");
+        ep.rowbias = rowbias; ep.rowbias_ld = 128;
+        ep.act1 = WS_ACT_TANH;
+        b.conv_simple(frame, hid, b.w.act("w:pool.linear1.x", wx), 1, 1, 1, 1, 0, 0, 1, 1, ep);
+        std::vector<float> w2;
+        int co, ci, nt;
+        if (!b.w.pack_conv("pool.linear2.weight", nullptr, w2, &co, &ci, &nt)) return false;
+        WsEpi ep2{};
+        ep2.bias = b.w.vec("pool.linear2.bias");
+        b.conv_simple(hid, logits, b.w.act("w:pool.linear2", w2), 1, 1, 1, 1, 0, 0, 1, 1, ep2);
+        View fr = frame, lg = logits;
+        b.push([=](cudaStream_t s) { return ws_launch_astp_stats(fr.p, lg.p, fr.dt, B, T, 1536, fr.ld, stats, s); });
+    }
+    {   // bn(3072) then linear (ecapa_tdnn.py:230-231): fold the affine into the linear; optional bn2 (emb_bn)
+        std::vector<float> s, h;
+        const HostT* lw = b.w.get("linear.weight");
+        const HostT* lb = b.w.get("linear.bias");
+        if (!lw || !lb || !b.w.bn("bn", true, s, h)) return false;
+        if ((int)lw->shape[0] != E) { set_err("linear.weight: embed_dim mismatch"); return false; }
+        std::vector<float> wf((size_t)E * 3072), bf(E);
+        std::vector<float> s2(E, 1.f), h2(E, 0.f);
+        if (e.opt("emb_bn", 0) && !b.w.bn("bn2", true, s2, h2)) return false;
+        for (int o = 0; o < E; ++o) {
+            double acc = lb->v[o];
+            for (int i = 0; i < 3072; ++i) {
+                wf[(size_t)o * 3072 + i] = (float)((double)lw->v[(size_t)o * 3072 + i] * s[i] * s2[o]);
+                acc += (double)lw->v[(size_t)o * 3072 + i] * h[i];
+            }
+            bf[o] = (float)(acc * s2[o] + h2[o]);
+        }
+        b.linear(stats, 3072, nullptr, 0, 1, b.w.f32("w:linear.folded", wf), b.w.f32("b:linear.folded", bf), b.p.emb, E, B,
+                 3072, E, WS_ACT_NONE);
+    }
+    return b.good();
+}
+
+// ----------------------------------------------------------------------------------------------- 2-D residual blocks
+// BasicBlock (resnet.py:35-69) / BasicResBlock (campplus.py:245-279): eval BN folded into the conv weights, the
+// 1x1 strided shortcut conv is merged into conv2's GEMM as one extra K range, residual/ReLU in the epilogue.
+View basic_block(Builder& b, const std::string& p, const View& x, int cout, int sf, int st_, View hbuf, View obuf) {
+    std::vector<float> s1, h1, s2, h2, w1, w2;
+    int co, ci, nt;
+    View none;
+    if (!b.w.bn(p + ".bn1", true, s1, h1) || !b.w.bn(p + ".bn2", true, s2, h2) ||
+        !b.w.pack_conv(p + ".conv1.weight", &s1, w1, &co, &ci, &nt) || !b.w.pack_conv(p + ".conv2.weight", &s2, w2, &co, &ci, &nt))
+        return none;
+    const int Fo = (x.F + 2 - 3) / sf + 1, To = (x.T + 2 - 3) / st_ + 1;
+    View h = hbuf; h.B = x.B; h.F = Fo; h.T = To; h.C = cout; h.ld = cout;
+    View o = obuf; o.B = x.B; o.F = Fo; o.T = To; o.C = cout; o.ld = cout;
+    WsEpi e1{};
+    e1.bias = b.w.f32("bnh:" + p + ".bn1", h1);
+    e1.act1 = WS_ACT_RELU;
+    b.conv_simple(x, h, b.w.act("w:" + p + ".conv1", w1), 3, 3, 1, 1, 1, 1, sf, st_, e1);
+    if (!b.good()) return none;
+    ConvSpec cs;
+    cs.dt = b.e.act_dt;
+    int F2, T2;
+    int K = add_conv_taps(cs, h, 3, 3, 1, 1, 1, 1, 1, 1, 0, &F2, &T2);
+    std::vector<float> bias2 = h2;
+    const bool has_sc = b.e.sd.count(p + ".shortcut.0.weight") != 0;
+    if (has_sc) {
+        std::vector<float> ss, hs, wsv;
+        if (!b.w.bn(p + ".shortcut.1", true, ss, hs) || !b.w.pack_conv(p + ".shortcut.0.weight", &ss, wsv, &co, &ci, &nt)) return none;
+        int F3, T3;
+        const int K2 = add_conv_taps(cs, x, 1, 1, 1, 1, 0, 0, sf, st_, K, &F3, &T3);
+        if (K2 < 0 || F3 != Fo || T3 != To) { set_err("internal: shortcut shape mismatch"); b.ok = false; return none; }
+        std::vector<float> wm((size_t)cout * (K + K2));
+        for (int r = 0; r < cout; ++r) {
+            memcpy(&wm[(size_t)r * (K + K2)], &w2[(size_t)r * K], (size_t)K * 4);
+            memcpy(&wm[(size_t)r * (K + K2) + K], &wsv[(size_t)r * K2], (size_t)K2 * 4);
+        }
+        w2.swap(wm);
+        K += K2;
+        for (int i = 0; i < cout; ++i) bias2[i] += hs[i];
+    } else {
+        cs.epi.res = x.p;
+        cs.epi.res_ld = x.ld;
+    }
+    cs.W = b.w.act("w:" + p + ".conv2m", w2); cs.Ktot = K; cs.Cout = cout; cs.B = x.B; cs.F = Fo; cs.T = To;
+    cs.epi.bias = b.w.f32("bnh:" + p + ".bn2m", bias2);
+    cs.epi.act2 = WS_ACT_RELU;
+    fill_epi_out(cs.epi, o);
+    b.conv(cs);
+    return o;
+}
+
+View stem(Builder& b, const std::string& convkey, const std::string& bnkey, View outbuf) {
+    std::vector<float> s, h, w9;
+    int co, ci, nt;
+    View none;
+    if (!b.w.bn(bnkey, true, s, h) || !b.w.pack_conv(convkey, &s, w9, &co, &ci, &nt)) return none;
+    if (ci != 1 || nt != 9) { set_err(convkey + ": expected (Cout,1,3,3)"); b.ok = false; return none; }
+    const int B = b.p.B, T = b.p.T, Fd = b.e.feat_dim;
+    View o = outbuf; o.B = B; o.F = Fd; o.T = T; o.C = co; o.ld = co;
+    const float* wd = b.w.f32("w:" + convkey + ".stem", w9);   // [Cout][9] (tap = df*3 + dt)
+    const float* hd = b.w.f32("bnh:" + bnkey, h);
+    const float* fin = b.p.feats_in;
+    const int dt = b.e.act_dt;
+    void* op = o.p;
+    b.push([=](cudaStream_t st) { return ws_launch_stem(fin, wd, hd, op, dt, B, T, Fd, co, st); });
+    return o;
+}
+
+// resnet.py:110-204
+bool build_resnet(Builder& b) {
+    ws_engine& e = b.e;
+    const int B = b.p.B, T = b.p.T, Fd = e.feat_dim, E = e.embed_dim, m = 32;
+    const size_t big = (size_t)B * Fd * T * m;
+    View bufs[3];
+    for (int i = 0; i < 3; ++i) { bufs[i].dt = e.act_dt; bufs[i].p = b.raw(big * ws_esize(e.act_dt)); }
+    if (!b.good()) return false;
+    View cur = stem(b, "conv1.weight", "bn1", bufs[0]);
+    int ci = 0;
+    for (int li = 1; li <= 4 && b.good(); ++li) {
+        const int cout = m << (li - 1);
+        for (int bi = 0; bi < e.num_blocks[li - 1] && b.good(); ++bi) {
+            const int s = (bi == 0 && li > 1) ? 2 : 1;
+            const std::string p = "layer" + std::to_string(li) + "." + std::to_string(bi);
+            View o = basic_block(b, p, cur, cout, s, s, bufs[(ci + 1) % 3], bufs[(ci + 2) % 3]);
+            ci = (ci + 2) % 3;
+            cur = o;
+        }
+    }
+    if (!b.good()) return false;
+    const int sd = cur.C * cur.F;  // stats_dim
+    float* stats = b.f32((size_t)B * 2 * sd);
+    b.tstats(cur, nullptr, nullptr, stats, 2 * sd, sd);  // TSTP, index c*F' + f (pooling_layers.py:78-85)
+    const HostT* w1 = b.w.get("seg_1.weight");
+    if (!w1) return false;
+    if ((int)w1->shape[1] != 2 * sd || (int)w1->shape[0] != E) { set_err("seg_1.weight shape mismatch"); return false; }
+    if (e.opt("two_emb_layer", 0)) {
+        // embed_b = seg_2(seg_bn_1(relu(embed_a))) (resnet.py:196-200): BN (affine=False) folded into seg_2
+        float* ea = b.f32((size_t)B * E);
+        std::vector<float> s, h;
+        const HostT* w2 = b.w.get("seg_2.weight");
+        const HostT* b2 = b.w.get("seg_2.bias");
+        if (!w2 || !b2 || !b.w.bn("seg_bn_1", false, s, h)) return false;
+        std::vector<float> wf((size_t)E * E), bf(E);
+        for (int o = 0; o < E; ++o) {
+            double acc = b2->v[o];
+            for (int i = 0; i < E; ++i) {
+                wf[(size_t)o * E + i] = w2->v[(size_t)o * E + i] * s[i];
+                acc += (double)w2->v[(size_t)o * E + i] * h[i];
+            }
+            bf[o] = (float)acc;
+        }
+        b.linear(stats, 2 * sd, nullptr, 0, 1, b.w.vec("seg_1.weight"), b.w.vec("seg_1.bias"), ea, E, B, 2 * sd, E, WS_ACT_RELU);
+        b.linear(ea, E, nullptr, 0, 1, b.w.f32("w:seg_2.folded", wf), b.w.f32("b:seg_2.folded", bf), b.p.emb, E, B, E, E, WS_ACT_NONE);
+    } else {
+        b.linear(stats, 2 * sd, nullptr, 0, 1, b.w.vec("seg_1.weight"), b.w.vec("seg_1.bias"), b.p.emb, E, B, 2 * sd, E, WS_ACT_NONE);
+    }
+    return b.good();
+}
+
+// ----------------------------------------------------------------------------------------------- CAM++
+// campplus.py:282-413
+bool build_campplus(Builder& b) {
+    ws_engine& e = b.e;
+    const int B = b.p.B, T = b.p.T, Fd = e.feat_dim, E = e.embed_dim, m = 32;
+    const size_t big = (size_t)B * Fd * T * m;
+    View bufs[3];
+    for (int i = 0; i < 3; ++i) { bufs[i].dt = e.act_dt; bufs[i].p = b.raw(big * ws_esize(e.act_dt)); }
+    if (!b.good()) return false;
+    // FCM head (campplus.py:282-330): frequency-only striding
+    View cur = stem(b, "head.conv1.weight", "head.bn1", bufs[0]);
+    int ci = 0;
+    for (int li = 1; li <= 2 && b.good(); ++li)
+        for (int bi = 0; bi < 2 && b.good(); ++bi) {
+            const std::string p = "head.layer" + std::to_string(li) + "." + std::to_string(bi);
+            View o = basic_block(b, p, cur, m, bi == 0 ? 2 : 1, 1, bufs[(ci + 1) % 3], bufs[(ci + 2) % 3]);
+            ci = (ci + 2) % 3;
+            cur = o;
+        }
+    if (!b.good()) return false;
+    View y;
+    {
+        std::vector<float> s, h, wp;
+        int co, cin, nt;
+        if (!b.w.bn("head.bn2", true, s, h) || !b.w.pack_conv("head.conv2.weight", &s, wp, &co, &cin, &nt)) return false;
+        y = bufs[(ci + 1) % 3];
+        y.B = B; y.F = (cur.F + 2 - 3) / 2 + 1; y.T = cur.T; y.C = m; y.ld = m;
+        WsEpi ep{};
+        ep.bias = b.w.f32("bnh:head.bn2", h);
+        ep.act1 = WS_ACT_RELU;
+        b.conv_simple(cur, y, b.w.act("w:head.conv2", wp), 3, 3, 1, 1, 1, 1, 2, 1, ep);
+    }
+    if (!b.good()) return false;
+    // xvector.tdnn: Conv1d(C*F -> 128, k5, stride 2, pad 2) on the (B, C*F, T) reshape (channel = c*F + f),
+    // + BN + ReLU (campplus.py:345-355).  The frequency index becomes a tap dimension (df = f), stride 2 uses
+    // the two time-parity planes.
+    const int Fh = y.F, Tp = (T + 4 - 5) / 2 + 1;
+    const int growth = 32, bnc = 128;
+    const int nl[3] = {12, 24, 16}, dil[3] = {1, 2, 2};
+    int c0[3], cmax[3];
+    c0[0] = 128;
+    for (int i = 0; i < 3; ++i) { cmax[i] = c0[i] + nl[i] * growth; if (i < 2) c0[i + 1] = cmax[i] / 2; }
+    View X[3];
+    for (int i = 0; i < 3; ++i) X[i] = b.act(B, 1, Tp, cmax[i]);
+    View Xf = b.act(B, 1, Tp, cmax[2] / 2);
+    View scratch = b.act(B, 1, Tp, cmax[2]);
+    View hid = b.act(B, 1, Tp, bnc);
+    const int nseg = (Tp + 99) / 100;
+    float* cmean = b.f32((size_t)B * bnc);
+    float* csegm = b.f32((size_t)B * nseg * bnc);
+    float* chid = b.f32((size_t)B * nseg * (bnc / 2));
+    float* cgate = b.f32((size_t)B * nseg * growth);
+    if (!b.good()) return false;
+    {
+        const HostT* tw = b.w.get("xvector.tdnn.linear.weight");
+        std::vector<float> s, h;
+        if (!tw || !b.w.bn("xvector.tdnn.nonlinear.batchnorm", true, s, h)) return false;
+        const int co = (int)tw->shape[0], cin = (int)tw->shape[1];
+        if (cin != m * Fh || tw->shape[2] != 5) { set_err("xvector.tdnn.linear.weight shape mismatch"); return false; }
+        ConvSpec cs;
+        cs.dt = e.act_dt;
+        std::vector<float> wp((size_t)co * 5 * Fh * m);
+        int tapi = 0;
+        for (int kt = 0; kt < 5; ++kt) {
+            const int off = kt - 2;
+            const int pt = ((off % 2) + 2) % 2;
+            WsSrc v = Builder::src_of(y);
+            v.ptr = (const char*)y.p + (size_t)pt * y.ld * ws_esize(e.act_dt);
+            v.T = (y.T - pt + 1) / 2;
+            v.sT = y.ld * 2;
+            int si = -1;
+            for (int i = 0; i < cs.nsrc; ++i) if (cs.src[i].ptr == v.ptr) si = i;
+            if (si < 0) { si = cs.nsrc; cs.src[cs.nsrc++] = v; }
+            const int dtp = (off - pt) / 2;
+            for (int f = 0; f < Fh; ++f, ++tapi) {
+                cs.taps.push_back(WsTap{si, 0, dtp, f, tapi * m, m});
+                for (int o = 0; o < co; ++o)
+                    for (int c = 0; c < m; ++c)
+                        wp[((size_t)o * 5 * Fh + tapi) * m + c] = tw->v[((size_t)o * cin + (c * Fh + f)) * 5 + kt] * s[o];
+            }
+        }
+        cs.W = b.w.act("w:xvector.tdnn", wp); cs.Ktot = 5 * Fh * m; cs.Cout = co; cs.B = B; cs.F = 1; cs.T = Tp;
+        cs.epi.bias = b.w.f32("bnh:xvector.tdnn", h);
+        cs.epi.act1 = WS_ACT_RELU;
+        fill_epi_out(cs.epi, X[0].ch(0, co));
+        b.conv(cs);
+    }
+    const int dt = e.act_dt;
+    const long long npos = (long long)B * Tp;
+    for (int bl = 0; bl < 3 && b.good(); ++bl) {
+        for (int j = 1; j <= nl[bl] && b.good(); ++j) {
+            const std::string p = "xvector.block" + std::to_string(bl + 1) + ".tdnnd" + std::to_string(j);
+            const int cin = c0[bl] + (j - 1) * growth;
+            std::vector<float> s1, h1, s2, h2, w1, wl;
+            int co, ci2, nt;
+            if (!b.w.bn(p + ".nonlinear1.batchnorm", true, s1, h1) || !b.w.bn(p + ".nonlinear2.batchnorm", true, s2, h2) ||
+                !b.w.pack_conv(p + ".linear1.weight", &s2, w1, &co, &ci2, &nt) ||
+                !b.w.pack_conv(p + ".cam_layer.linear_local.weight", nullptr, wl, &co, &ci2, &nt))
+                break;
+            // nonlinear1 (BN-ReLU on the growing concat) -> scratch
+            View xs = X[bl].ch(0, cin);
+            View sv = scratch; sv.C = cin; sv.ld = cin;
+            const float* s1d = b.w.f32("bns:" + p + ".n1", s1);
+            const float* h1d = b.w.f32("bnh:" + p + ".n1", h1);
+            b.push([=](cudaStream_t st) { return ws_launch_bnrelu(xs.p, xs.ld, s1d, h1d, sv.p, sv.ld, dt, npos, cin, st); });
+            // linear1 (1x1, no bias) + nonlinear2 (BN folded) + ReLU -> hid
+            WsEpi e1{};
+            e1.bias = b.w.f32("bnh:" + p + ".n2", h2);
+            e1.act1 = WS_ACT_RELU;
+            b.conv_simple(sv, hid, b.w.act("w:" + p + ".linear1", w1), 1, 1, 1, 1, 0, 0, 1, 1, e1);
+            // CAM context mask (campplus.py:108-115): sigmoid(W2 relu(W1 (mean_T + segmean_100)))
+            View hv = hid;
+            b.push([=](cudaStream_t st) { return ws_launch_seg_means(hv.p, dt, B, Tp, bnc, hv.ld, 100, cmean, csegm, st); });
+            b.linear(csegm, bnc, cmean, bnc, nseg, b.w.vec(p + ".cam_layer.linear1.weight"), b.w.vec(p + ".cam_layer.linear1.bias"),
+                     chid, bnc / 2, B * nseg, bnc, bnc / 2, WS_ACT_RELU);
+            b.linear(chid, bnc / 2, nullptr, 0, 1, b.w.vec(p + ".cam_layer.linear2.weight"), b.w.vec(p + ".cam_layer.linear2.bias"),
+                     cgate, growth, B * nseg, bnc / 2, growth, WS_ACT_SIGMOID);
+            // linear_local (k3, dilated, no bias) * mask -> appended to the concat buffer
+            WsEpi e2{};
+            e2.gate = cgate; e2.gate_ld = growth; e2.gate_seg = 100; e2.gate_nseg = nseg;
+            b.conv_simple(hid, X[bl].ch(cin, growth), b.w.act("w:" + p + ".local", wl), 1, 3, 1, dil[bl], 0, dil[bl], 1, 1, e2);
+        }
+        if (!b.good()) break;
+        // TransitLayer (campplus.py:204-218): BN-ReLU-Conv1x1 (no bias)
+        const std::string tp = "xvector.transit" + std::to_string(bl + 1);
+        std::vector<float> s, h, wt;
+        int co, ci2, nt;
+        if (!b.w.bn(tp + ".nonlinear.batchnorm", true, s, h) || !b.w.pack_conv(tp + ".linear.weight", nullptr, wt, &co, &ci2, &nt)) break;
+        View xs = X[bl];
+        View sv = scratch; sv.C = cmax[bl]; sv.ld = cmax[bl];
+        const float* sd_ = b.w.f32("bns:" + tp, s);
+        const float* hd_ = b.w.f32("bnh:" + tp, h);
+        const int cc = cmax[bl];
+        b.push([=](cudaStream_t st) { return ws_launch_bnrelu(xs.p, xs.ld, sd_, hd_, sv.p, sv.ld, dt, npos, cc, st); });
+        WsEpi et{};
+        View dst = (bl < 2) ? X[bl + 1].ch(0, cmax[bl] / 2) : Xf;
+        b.conv_simple(sv, dst, b.w.act("w:" + tp, wt), 1, 1, 1, 1, 0, 0, 1, 1, et);
+    }
+    if (!b.good()) return false;
+    {   // out_nonlinear (BN-ReLU) fused into TSTP; dense (1024 -> E, no bias) + BN(affine=False) folded
+        std::vector<float> s, h, sdn, hdn;
+        const int cf = Xf.C;
+        if (!b.w.bn("xvector.out_nonlinear.batchnorm", true, s, h) || !b.w.bn("xvector.dense.nonlinear.batchnorm", false, sdn, hdn)) return false;
+        float* stats = b.f32((size_t)B * 2 * cf);
+        b.tstats(Xf, b.w.f32("bns:out_nl", s), b.w.f32("bnh:out_nl", h), stats, 2 * cf, cf);
+        const HostT* dw = b.w.get("xvector.dense.linear.weight");
+        if (!dw) return false;
+        if ((int)dw->shape[0] != E || (int)dw->shape[1] != 2 * cf) { set_err("xvector.dense.linear.weight shape mismatch"); return false; }
+        std::vector<float> wf((size_t)E * 2 * cf);
+        for (int o = 0; o < E; ++o)
+            for (int i = 0; i < 2 * cf; ++i) wf[(size_t)o * 2 * cf + i] = dw->v[(size_t)o * 2 * cf + i] * sdn[o];
+        b.linear(stats, 2 * cf, nullptr, 0, 1, b.w.f32("w:dense.folded", wf), b.w.f32("b:dense.folded", hdn), b.p.emb, E, B, 2 * cf, E, WS_ACT_NONE);
+    }
+    return b.good();
+}
+
+Plan* get_plan(ws_engine* e, int B, int T) {
+    auto key = std::make_pair(B, T);
+    auto it = e->plans.find(key);
+    if (it != e->plans.end()) return it->second.get();
+    if (B <= 0 || T <= 0) { set_err("forward: B and T must be positive"); return nullptr; }
+    std::unique_ptr<Plan> p(new Plan());
+    p->B = B; p->T = T;
+    Builder b(*e, *p);
+    p->feats_in = b.f32((size_t)B * T * e->feat_dim);
+    p->emb = b.f32((size_t)B * e->embed_dim);
+    bool ok = b.good();
+    if (ok) {
+        if (e->model.rfind("ECAPA", 0) == 0) ok = build_ecapa(b);
+        else if (e->model.rfind("ResNet", 0) == 0) ok = build_resnet(b);
+        else ok = build_campplus(b);
+    }
+    if (!ok) return nullptr;
+    if (e->plans.size() >= 64) e->plans.clear();  // bound memory for many distinct (B,T) shapes
+    Plan* raw = p.get();
+    e->plans[key] = std::move(p);
+    return raw;
+}
+
+int run_plan(ws_engine* e, Plan* p, cudaStream_t s) {
+    const bool want_graph = e->opt("cuda_graph", 1) != 0 && !p->graph_failed;
+    if (want_graph && p->gexec == nullptr) {
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const char* m = nullptr;
+            for (auto& op : p->ops) { m = op(s); if (m) break; }
+            cudaError_t ce = cudaStreamEndCapture(s, &g);
+            if (m == nullptr && ce == cudaSuccess && g != nullptr &&
+                cudaGraphInstantiate(&p->gexec, g, 0) == cudaSuccess) {
+            } else {
+                p->gexec = nullptr;
+                p->graph_failed = true;
+                if (m) { set_err(std::string("kernel launch failed during capture: ") + m); if (g) cudaGraphDestroy(g); return 1; }
+            }
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+        } else {
+            p->graph_failed = true;
+            cudaGetLastError();
+        }
+    }
+    if (p->gexec != nullptr) {
+        WS_CK(cudaGraphLaunch(p->gexec, s));
+    } else {
+        for (auto& op : p->ops) WS_CKS(op(s));
+    }
+    e->last_launches = (long long)p->ops.size();
+    return 0;
+}
+
+const FbankTables* fbank_tables(ws_engine* e, const char* window_type) {
+    const std::string wt = window_type ? window_type : "hamming";
+    auto it = e->fb.find(wt);
+    if (it != e->fb.end()) return &it->second;
+    std::vector<float> win(400);
+    for (int j = 0; j < 400; ++j) {
+        const double c = std::cos(2.0 * M_PI * j / 399.0);
+        if (wt == "hamming") win[j] = (float)(0.54 - 0.46 * c);
+        else if (wt == "povey") win[j] = (float)std::pow(0.5 - 0.5 * c, 0.85);
+        else if (wt == "hanning") win[j] = (float)(0.5 - 0.5 * c);
+        else if (wt == "rectangular") win[j] = 1.f;
+        else { set_err("unknown window_type " + wt); return nullptr; }
+    }
+    // torchaudio kaldi.py get_mel_banks (80 bins, 20 Hz .. Nyquist, padded 512) in float32 like the reference
+    const int nb = 80, nfft = 256;
+    const double mel_low = 1127.0 * std::log(1.0 + 20.0 / 700.0), mel_high = 1127.0 * std::log(1.0 + 8000.0 / 700.0);
+    const float delta = (float)((mel_high - mel_low) / (nb + 1)), lowf = (float)mel_low;
+    std::vector<std::vector<float>> rows(nb, std::vector<float>(nfft, 0.f));
+    std::vector<int> start(nb, 0), len(nb, 0);
+    int maxlen = 1;
+    for (int m = 0; m < nb; ++m) {
+        const float left = lowf + (float)m * delta, center = lowf + ((float)m + 1.0f) * delta, right = lowf + ((float)m + 2.0f) * delta;
+        int first = -1, last = -1;
+        for (int k = 0; k < nfft; ++k) {
+            const float mel = 1127.0f * std::log(1.0f + (31.25f * (float)k) / 700.0f);
+            const float up = (mel - left) / (center - left), down = (right - mel) / (right - center);
+            const float wv = std::max(0.f, std::min(up, down));
+            rows[m][k] = wv;
+            if (wv > 0.f) { if (first < 0) first = k; last = k; }
+        }
+        if (first >= 0) { start[m] = first; len[m] = last - first + 1; maxlen = std::max(maxlen, len[m]); }
+    }
+    std::vector<float> melw((size_t)nb * maxlen, 0.f);
+    for (int m = 0; m < nb; ++m)
+        for (int i = 0; i < len[m]; ++i) melw[(size_t)m * maxlen + i] = rows[m][start[m] + i];
+    FbankTables t;
+    t.maxlen = maxlen;
+    if (cudaMalloc(&t.window, 400 * 4) != cudaSuccess || cudaMalloc(&t.melw, melw.size() * 4) != cudaSuccess ||
+        cudaMalloc(&t.melstart, nb * 4) != cudaSuccess || cudaMalloc(&t.mellen, nb * 4) != cudaSuccess) {
+        set_err("fbank tables: cudaMalloc failed");
+        return nullptr;
+    }
+    cudaMemcpy(t.window, win.data(), 400 * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(t.melw, melw.data(), melw.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(t.melstart, start.data(), nb * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(t.mellen, len.data(), nb * 4, cudaMemcpyHostToDevice);
+    e->fb[wt] = t;
+    return &e->fb[wt];
+}
+
+// engine-less fbank tables for ws_fbank()
+ws_engine* fbank_holder(int device) {
+    static std::map<int, ws_engine*> holders;
+    auto it = holders.find(device);
+    if (it != holders.end()) return it->second;
+    ws_engine* h = new ws_engine();
+    h->device = device;
+    holders[device] = h;
+    return h;
+}
+
+int enter_stream(ws_engine* e, cudaStream_t user) {
+    WS_CK(cudaEventRecord(e->ev_in, user));
+    WS_CK(cudaStreamWaitEvent(e->st, e->ev_in, 0));
+    return 0;
+}
+int leave_stream(ws_engine* e, cudaStream_t user) {
+    WS_CK(cudaEventRecord(e->ev_out, e->st));
+    WS_CK(cudaStreamWaitEvent(user, e->ev_out, 0));
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================= C ABI
+extern "C" {
+
+int ws_engine_create(const char* model_name, const char* precision, int feat_dim, int embed_dim, int device,
+                     ws_engine** out) {
+    if (!model_name || !precision || !out) { set_err("ws_engine_create: null argument"); return 1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_err("ws_engine_create: no CUDA device (this engine has no CPU fallback)");
+        return 1;
+    }
+    WS_CK(cudaSetDevice(device));
+    std::unique_ptr<ws_engine> e(new ws_engine());
+    e->model = model_name; e->prec = precision; e->feat_dim = feat_dim; e->embed_dim = embed_dim; e->device = device;
+    const std::string m = e->model;
+    if (m == "ECAPA_TDNN_c512") { e->channels = 512; e->glob = false; }
+    else if (m == "ECAPA_TDNN_GLOB_c512") { e->channels = 512; e->glob = true; }
+    else if (m == "ECAPA_TDNN_c1024") { e->channels = 1024; e->glob = false; }
+    else if (m == "ECAPA_TDNN_GLOB_c1024") { e->channels = 1024; e->glob = true; }
+    else if (m == "ResNet18") e->num_blocks = {2, 2, 2, 2};
+    else if (m == "ResNet34") e->num_blocks = {3, 4, 6, 3};
+    else if (m == "CAMPPlus") {}
+    else { set_err("unknown / out-of-scope model name: " + m); return 1; }
+    const std::string p = e->prec;
+    if (p == "fp32") { e->act_dt = WS_F32; e->use_tc = false; }
+    else if (p == "tf32") { e->act_dt = WS_F32; e->use_tc = true; }
+    else if (p == "bf16") { e->act_dt = WS_BF16; e->use_tc = true; }
+    else if (p == "fp16") { e->act_dt = WS_F16; e->use_tc = true; }
+    else { set_err("unknown precision (fp32|tf32|bf16|fp16): " + p); return 1; }
+    if (feat_dim % 8 != 0) { set_err("feat_dim must be a multiple of 8"); return 1; }
+    WS_CKS(ws_tc_init());
+    WS_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    WS_CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+    WS_CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+    *out = e.release();
+    return 0;
+}
+
+int ws_engine_set_option(ws_engine* e, const char* key, long long value) {
+    if (!e || !key) { set_err("ws_engine_set_option: null argument"); return 1; }
+    const std::string k = key;
+    if (k == "force_simt") { if (value) e->use_tc = false; }
+    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph") { set_err("unknown option " + k); return 1; }
+    e->opts[k] = value;
+    e->plans.clear();
+    return 0;
+}
+
+int ws_engine_set_tensor(ws_engine* e, const char* key, const float* host_data, const long long* shape, int ndim) {
+    if (!e || !key || (!host_data && ndim > 0) || ndim < 0 || ndim > 8) { set_err("ws_engine_set_tensor: bad argument"); return 1; }
+    if (e->finalized) { set_err("ws_engine_set_tensor after finalize"); return 1; }
+    HostT t;
+    t.shape.assign(shape, shape + ndim);
+    const long long n = t.numel();
+    t.v.assign(host_data, host_data + n);
+    e->sd[key] = std::move(t);
+    return 0;
+}
+
+int ws_engine_finalize(ws_engine* e) {
+    if (!e) { set_err("ws_engine_finalize: null engine"); return 1; }
+    WS_CK(cudaSetDevice(e->device));
+    // Build (and drop) a nominal plan: this packs/folds/uploads every weight and reports missing keys.
+    Plan* p = get_plan(e, 1, 200);
+    if (p == nullptr) return 1;
+    e->plans.clear();
+    e->finalized = true;
+    return 0;
+}
+
+int ws_engine_embed_dim(const ws_engine* e) { return e ? e->embed_dim : -1; }
+long long ws_engine_last_launches(const ws_engine* e) { return e ? e->last_launches : -1; }
+
+int ws_engine_forward(ws_engine* e, const float* feats_dev, int B, int T, float* embs_dev, void* stream) {
+    if (!e || !feats_dev || !embs_dev) { set_err("ws_engine_forward: null argument"); return 1; }
+    if (!e->finalized) { set_err("ws_engine_forward before ws_engine_finalize"); return 1; }
+    WS_CK(cudaSetDevice(e->device));
+    Plan* p = get_plan(e, B, T);
+    if (!p) return 1;
+    cudaStream_t us = (cudaStream_t)stream;
+    if (enter_stream(e, us)) return 1;
+    WS_CK(cudaMemcpyAsync(p->feats_in, feats_dev, (size_t)B * T * e->feat_dim * 4, cudaMemcpyDeviceToDevice, e->st));
+    if (run_plan(e, p, e->st)) return 1;
+    WS_CK(cudaMemcpyAsync(embs_dev, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToDevice, e->st));
+    return leave_stream(e, us);
+}
+
+int ws_engine_forward_host(ws_engine* e, const float* feats_host, int B, int T, float* embs_host) {
+    if (!e || !feats_host || !embs_host) { set_err("ws_engine_forward_host: null argument"); return 1; }
+    if (!e->finalized) { set_err("ws_engine_forward_host before ws_engine_finalize"); return 1; }
+    WS_CK(cudaSetDevice(e->device));
+    Plan* p = get_plan(e, B, T);
+    if (!p) return 1;
+    WS_CK(cudaMemcpyAsync(p->feats_in, feats_host, (size_t)B * T * e->feat_dim * 4, cudaMemcpyHostToDevice, e->st));
+    if (run_plan(e, p, e->st)) return 1;
+    WS_CK(cudaMemcpyAsync(embs_host, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToHost, e->st));
+    WS_CK(cudaStreamSynchronize(e->st));
+    return 0;
+}
+
+int ws_fbank_num_frames(int nsamples) { return nsamples < 400 ? 0 : 1 + (nsamples - 400) / 160; }
+
+static int fbank_into(ws_engine* e, const void* wav_dev, int is_i16, long long wav_ld, int nsamples, int B,
+                      const char* window_type, int apply_cmn, float* feats, cudaStream_t s) {
+    const FbankTables* t = fbank_tables(e, window_type);
+    if (!t) return 1;
+    const int T = ws_fbank_num_frames(nsamples);
+    WS_CKS(ws_launch_fbank(wav_dev, is_i16, wav_ld, nsamples, B, T, t->window, t->melw, t->melstart, t->mellen, t->maxlen, feats, s));
+    if (apply_cmn) WS_CKS(ws_launch_cmn(feats, B, T, 80, s));
+    return 0;
+}
+
+int ws_fbank(const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples, int B, const char* window_type,
+             int apply_cmn, float* feats_dev, void* stream) {
+    if (!wav_dev || !feats_dev) { set_err("ws_fbank: null argument"); return 1; }
+    int dev = 0;
+    WS_CK(cudaGetDevice(&dev));
+    return fbank_into(fbank_holder(dev), wav_dev, wav_is_i16, wav_ld, nsamples, B, window_type, apply_cmn, feats_dev,
+                      (cudaStream_t)stream);
+}
+
+int ws_engine_extract_wav(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples, int B,
+                          const char* window_type, float* embs_dev, float* feats_out_dev, void* stream) {
+    if (!e || !wav_dev || !embs_dev) { set_err("ws_engine_extract_wav: null argument"); return 1; }
+    if (!e->finalized) { set_err("ws_engine_extract_wav before ws_engine_finalize"); return 1; }
+    if (e->feat_dim != 80) { set_err("ws_engine_extract_wav: the fbank frontend produces 80 bins"); return 1; }
+    WS_CK(cudaSetDevice(e->device));
+    const int T = ws_fbank_num_frames(nsamples);
+    if (T <= 0) { set_err("ws_engine_extract_wav: waveform shorter than one 25 ms frame"); return 1; }
+    Plan* p = get_plan(e, B, T);
+    if (!p) return 1;
+    cudaStream_t us = (cudaStream_t)stream;
+    if (enter_stream(e, us)) return 1;
+    if (fbank_into(e, wav_dev, wav_is_i16, wav_ld, nsamples, B, window_type, 1, p->feats_in, e->st)) return 1;
+    if (feats_out_dev)
+        WS_CK(cudaMemcpyAsync(feats_out_dev, p->feats_in, (size_t)B * T * 80 * 4, cudaMemcpyDeviceToDevice, e->st));
+    if (run_plan(e, p, e->st)) return 1;
+    e->last_launches += 2;
+    WS_CK(cudaMemcpyAsync(embs_dev, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToDevice, e->st));
+    return leave_stream(e, us);
+}
+
+int ws_engine_extract_wav_host(ws_engine* e, const void* wav_host, int wav_is_i16, int nsamples, int B,
+                               const char* window_type, float* embs_host) {
+    if (!e || !wav_host || !embs_host) { set_err("ws_engine_extract_wav_host: null argument"); return 1; }
+    if (!e->finalized) { set_err("ws_engine_extract_wav_host before ws_engine_finalize"); return 1; }
+    WS_CK(cudaSetDevice(e->device));
+    const int T = ws_fbank_num_frames(nsamples);
+    if (T <= 0) { set_err("ws_engine_extract_wav_host: waveform shorter than one 25 ms frame"); return 1; }
+    const size_t bytes = (size_t)B * nsamples * (wav_is_i16 ? 2 : 4);
+    if (bytes > e->wav_bytes) {
+        if (e->wav_dev) cudaFree(e->wav_dev);
+        e->wav_dev = nullptr; e->wav_bytes = 0;
+        WS_CK(cudaMalloc(&e->wav_dev, bytes));
+        e->wav_bytes = bytes;
+    }
+    Plan* p = get_plan(e, B, T);
+    if (!p) return 1;
+    WS_CK(cudaMemcpyAsync(e->wav_dev, wav_host, bytes, cudaMemcpyHostToDevice, e->st));
+    if (fbank_into(e, e->wav_dev, wav_is_i16, nsamples, nsamples, B, window_type, 1, p->feats_in, e->st)) return 1;
+    if (run_plan(e, p, e->st)) return 1;
+    e->last_launches += 2;
+    WS_CK(cudaMemcpyAsync(embs_host, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToHost, e->st));
+    WS_CK(cudaStreamSynchronize(e->st));
+    return 0;
+}
+
+void ws_engine_destroy(ws_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    delete e;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// Kaldi-compatible 80-bin log-mel fbank + per-utterance CMN on the GPU (HBM-bound: 128 KB in, 63 KB out per
+// 2 s utterance).  Restates what the reference gets from torchaudio.compliance.kaldi.fbank with the arguments
+// of wespeaker/dataset/processor.py:518-525 / cli/speaker.py:92-97; native twin of
+// runtime/core/frontend/fbank.h:138-198.
+//
+// One warp per 25 ms frame (8 frames per block): coalesced sample loads, DC removal via warp-shuffle sum,
+// pre-emphasis, window, then a 512-point real FFT computed as a 256-point complex radix-2 FFT in shared memory
+// (twiddles from sincospif, exact argument reduction) + the real-input split step, power spectrum, triangular mel
+// filters as short per-bin dot products (each lane owns bins lane, lane+32, lane+64), log with the float-eps floor.
+#include "ws_kernels.cuh"
+
+namespace {
+
+constexpr int kFrameLen = 400, kFrameShift = 160, kNfft = 512, kBins = 80;
+constexpr float kEps = 1.1920928955078125e-07f;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float ld_sample(const void* wav, int is_i16, long long i) {
+    return is_i16 ? (float)((const short*)wav)[i] : ((const float*)wav)[i];
+}
+
+__global__ void __launch_bounds__(256) fbank_kernel(const void* __restrict__ wav, int is_i16, long long wav_ld, int T,
+                                                    const float* __restrict__ window, const float* __restrict__ melw,
+                                                    const int* __restrict__ melstart, const int* __restrict__ mellen,
+                                                    int mel_maxlen, float* __restrict__ feats) {
+    __shared__ float2 s_tw[256];        // W_512^k = exp(-2*pi*i*k/512)
+    __shared__ float2 s_z[8][256];      // per-warp FFT buffer
+    __shared__ float s_p[8][256];       // per-warp power spectrum (bins 0..255; Nyquist has zero mel weight)
+    __shared__ float s_win[kFrameLen];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        float sn, cs;
+        sincospif((float)threadIdx.x / 256.0f, &sn, &cs);
+        s_tw[threadIdx.x] = make_float2(cs, -sn);
+        for (int i = threadIdx.x; i < kFrameLen; i += 256) s_win[i] = window[i];
+    }
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int frame = blockIdx.x * 8 + warp;
+    if (frame >= T) return;
+    const long long base = (long long)b * wav_ld + (long long)frame * kFrameShift;
+
+    // per-frame mean (remove_dc_offset)
+    float s = 0.f;
+    for (int j = lane; j < kFrameLen; j += 32) s += ld_sample(wav, is_i16, base + j);
+    const float mu = warp_sum(s) / (float)kFrameLen;
+
+    // z[n] = y[2n] + i*y[2n+1], y = window * ((x - mu) - 0.97 * (x_prev - mu)), stored bit-reversed for DIT
+    float2* z = s_z[warp];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int n = lane + 32 * k;
+        float2 v = make_float2(0.f, 0.f);
+        if (n < kFrameLen / 2) {
+            const int j = 2 * n;
+            const float xm1 = ld_sample(wav, is_i16, base + (j > 0 ? j - 1 : 0)) - mu;
+            const float x0 = ld_sample(wav, is_i16, base + j) - mu;
+            const float x1 = ld_sample(wav, is_i16, base + j + 1) - mu;
+            v.x = (x0 - 0.97f * xm1) * s_win[j];
+            v.y = (x1 - 0.97f * x0) * s_win[j + 1];
+        }
+        z[__brev((unsigned)n) >> 24] = v;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int st = 1; st <= 8; ++st) {
+        const int half = 1 << (st - 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = lane + 32 * k;
+            const int j = idx & (half - 1);
+            const int i0 = ((idx >> (st - 1)) << st) + j;
+            const int i1 = i0 + half;
+            const float2 w = s_tw[j << (9 - st)];
+            const float2 u = z[i0], a = z[i1];
+            const float2 v = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+            z[i0] = make_float2(u.x + v.x, u.y + v.y);
+            z[i1] = make_float2(u.x - v.x, u.y - v.y);
+        }
+        __syncwarp();
+    }
+    // split step: X[k] = E[k] + W_512^k * O[k],  E = (Z[k] + conj(Z[256-k]))/2,  O = -i (Z[k] - conj(Z[256-k]))/2
+    float* pw = s_p[warp];
+#pragma unroll
+    for (int k8 = 0; k8 < 8; ++k8) {
+        const int k = lane + 32 * k8;
+        const float2 a = z[k];
+        const float2 c = z[(256 - k) & 255];
+        const float er = 0.5f * (a.x + c.x), ei = 0.5f * (a.y - c.y);
+        const float orr = 0.5f * (a.y + c.y), oi = -0.5f * (a.x - c.x);
+        const float2 w = s_tw[k];
+        const float xr = er + (orr * w.x - oi * w.y);
+        const float xi = ei + (orr * w.y + oi * w.x);
+        pw[k] = xr * xr + xi * xi;
+    }
+    __syncwarp();
+    float* out = feats + ((long long)b * T + frame) * kBins;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int m = lane + 32 * k;
+        if (m < kBins) {
+            const int st = melstart[m], len = mellen[m];
+            const float* w = melw + (long long)m * mel_maxlen;
+            float e = 0.f;
+            for (int i = 0; i < len; ++i) e = fmaf(pw[st + i], w[i], e);
+            out[m] = logf(fmaxf(e, kEps));
+        }
+    }
+}
+
+// block (32, 8): subtract the per-utterance mean over T from every bin (dataset_utils.py:19-26)
+__global__ void __launch_bounds__(256) cmn_kernel(float* __restrict__ feats, int T, int Fdim) {
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int b = blockIdx.y;
+    const bool cv = c < Fdim;
+    float* p = feats + (long long)b * T * Fdim + c;
+    float s = 0.f;
+    if (cv)
+        for (int t = threadIdx.y; t < T; t += 8) s += p[(long long)t * Fdim];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    float mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mean += red[i][threadIdx.x];
+    mean /= (float)T;
+    if (cv)
+        for (int t = threadIdx.y; t < T; t += 8) p[(long long)t * Fdim] -= mean;
+}
+
+}  // namespace
+
+const char* ws_launch_fbank(const void* wav, int wav_is_i16, long long wav_ld, int nsamples, int B, int T,
+                            const float* window400, const float* melw, const int* melstart, const int* mellen,
+                            int mel_maxlen, float* feats, cudaStream_t s) {
+    if (T <= 0 || B <= 0) return nullptr;
+    if ((long long)(T - 1) * kFrameShift + kFrameLen > nsamples) return "fbank: T frames do not fit in nsamples";
+    dim3 grid((T + 7) / 8, B);
+    fbank_kernel<<<grid, 256, 0, s>>>(wav, wav_is_i16, wav_ld, T, window400, melw, melstart, mellen, mel_maxlen, feats);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* ws_launch_cmn(float* feats, int B, int T, int Fdim, cudaStream_t s) {
+    if (T <= 0 || B <= 0) return nullptr;
+    dim3 grid((Fdim + 31) / 32, B), block(32, 8);
+    cmn_kernel<<<grid, block, 0, s>>>(feats, T, Fdim);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}

@@ -1,0 +1,74 @@
+// Host-side plumbing shared by the engine translation units: error reporting, activation views, the conv
+// operator builder (tcgen05/TMA or FFMA), device allocation tracking.
+#pragma once
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ws_kernels.cuh"
+
+namespace ws {
+
+void set_err(const std::string& msg);
+const std::string& get_err();
+
+#define WS_CK(call)                                                                               \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            ws::set_err(std::string(#call) + ": " + cudaGetErrorString(e__));                     \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+#define WS_CKS(expr)                                                                              \
+    do {                                                                                          \
+        const char* m__ = (expr);                                                                 \
+        if (m__ != nullptr) {                                                                     \
+            ws::set_err(std::string(#expr) + ": " + m__);                                         \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+// channels-last activation view: element (b,f,t,c) at p[((b*F+f)*T+t)*ld + c]
+struct View {
+    void* p = nullptr;
+    int B = 0, F = 1, T = 0, C = 0;
+    long long ld = 0;
+    int dt = WS_F32;
+    long long npos() const { return (long long)B * F * T; }
+    View ch(int c0, int c) const {
+        View v = *this;
+        v.p = (char*)p + (size_t)c0 * ws_esize(dt);
+        v.C = c;
+        return v;
+    }
+};
+
+// one fused conv/GEMM launch
+struct ConvSpec {
+    WsSrc src[WS_MAX_SRC];
+    int nsrc = 0;
+    std::vector<WsTap> taps;
+    const void* W = nullptr;  // [Cout][Ktot] in activation dtype
+    int Ktot = 0, Cout = 0;
+    int B = 0, F = 1, T = 0;  // output extents
+    int dt = WS_F32;
+    WsEpi epi{};
+    bool dense_pointwise = false;  // every tap has dt=df=0 on a dense src with the output's extents -> flatten positions
+};
+
+// Append the taps of a (kf x kt) conv over `x` to `spec` (weights columns start at wk0, tap-major then channel).
+// Strided convs are expressed with parity-plane source views so every tap is unit-stride (TMA-friendly).
+// Returns the number of K columns consumed (kf*kt*x.C) and sets Fo/To.
+int add_conv_taps(ConvSpec& spec, const View& x, int kf, int kt, int dil_f, int dil_t, int pad_f, int pad_t,
+                  int stride_f, int stride_t, int wk0, int* Fo, int* To);
+
+using Op = std::function<const char*(cudaStream_t)>;
+// Build a launch closure for `spec`; use_tc selects the tcgen05 kernel (needs dt-aligned shapes) else FFMA.
+// Returns false and sets the error string if the spec cannot be mapped.
+bool make_conv_op(const ConvSpec& spec, bool use_tc, Op* out);
+
+void fill_epi_out(WsEpi& e, const View& out);
+
+}  // namespace ws

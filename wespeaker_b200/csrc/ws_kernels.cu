@@ -1,0 +1,324 @@
+// Bandwidth-bound kernels of the embedding path: statistics pooling (TSTP / ASTP), SE gating, small
+// fully-connected layers, BN-ReLU pre-activation, the 1-channel stem conv.  All operate on channels-last
+// activations so that a warp always touches 32 consecutive channels (coalesced 128-B / 64-B rows); the
+// reductions over T are split over 8 warps per block and merged through shared memory, reductions over
+// input features in the FC kernel use warp shuffles.
+#include "ws_kernels.cuh"
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void convert_kernel(const float* __restrict__ in, void* __restrict__ out, int dt, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) ws_st(out, dt, i, in[i]);
+}
+
+// block (32, 8): x = channel lane, y = T slice.
+__global__ void __launch_bounds__(256) tstats_kernel(const void* __restrict__ x, int dt, int F, int T, int C,
+                                                     long long ld, const float* __restrict__ pre_scale,
+                                                     const float* __restrict__ pre_shift, void* __restrict__ out,
+                                                     int odt, long long out_ld, int std_off, float eps) {
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int f = blockIdx.y, b = blockIdx.z;
+    const bool cv = c < C;
+    const long long base = ((long long)b * F + f) * T * ld + c;
+    float ps = 1.f, ph = 0.f;
+    const bool pre = pre_scale != nullptr;
+    if (pre && cv) { ps = pre_scale[c]; ph = pre_shift[c]; }
+    float s = 0.f;
+    if (cv)
+        for (int t = threadIdx.y; t < T; t += 8) {
+            float v = ws_ld(x, dt, base + (long long)t * ld);
+            if (pre) v = fmaxf(fmaf(v, ps, ph), 0.f);
+            s += v;
+        }
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    float mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mean += red[i][threadIdx.x];
+    mean /= (float)T;
+    __syncthreads();
+    float ss = 0.f;
+    if (cv && std_off >= 0)
+        for (int t = threadIdx.y; t < T; t += 8) {
+            float v = ws_ld(x, dt, base + (long long)t * ld);
+            if (pre) v = fmaxf(fmaf(v, ps, ph), 0.f);
+            const float d = v - mean;
+            ss = fmaf(d, d, ss);
+        }
+    red[threadIdx.y][threadIdx.x] = ss;
+    __syncthreads();
+    if (threadIdx.y == 0 && cv) {
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x];
+        const long long o = (long long)b * out_ld + (long long)c * F + f;
+        ws_st(out, odt, o, mean);
+        if (std_off >= 0) ws_st(out, odt, o + std_off, sqrtf(tot / (float)(T - 1) + eps));  // torch.var: unbiased
+    }
+}
+
+// 8 warps: warp w -> output feature o; 8 input rows per block share each weight row.
+__global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restrict__ in, long long in_ld,
+                                                          const float* __restrict__ in2, long long in2_ld,
+                                                          int rows_per_b, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, float* __restrict__ out,
+                                                          long long out_ld, int R, int I, int O, int act) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 8 + warp;
+    const int r0 = blockIdx.y * 8;
+    if (o >= O) return;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const float* w = W + (long long)o * I;
+    for (int i = lane; i < I; i += 32) {
+        const float wv = __ldg(w + i);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = r0 + j;
+            if (r < R) {
+                float v = in[(long long)r * in_ld + i];
+                if (in2 != nullptr) v += in2[(long long)(r / rows_per_b) * in2_ld + i];
+                acc[j] = fmaf(wv, v, acc[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float v = warp_sum(acc[j]);
+        const int r = r0 + j;
+        if (lane == 0 && r < R) out[(long long)r * out_ld + o] = ws_act(v + (bias != nullptr ? bias[o] : 0.f), act);
+    }
+}
+
+__global__ void scale_residual_kernel(const void* __restrict__ x, long long x_ld, const float* __restrict__ gate,
+                                      const void* __restrict__ res, long long res_ld, void* __restrict__ out,
+                                      long long out_ld, int dt, int T, int C, long long nvec) {
+    const int cv = C >> 2;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < nvec; i += stride) {
+        const long long pos = i / cv;
+        const int c = (int)(i % cv) * 4;
+        const int b = (int)(pos / T);
+        float v[4], r[4];
+        ws_ldv<4>(x, dt, pos * x_ld + c, v);
+        ws_ldv<4>(res, dt, pos * res_ld + c, r);
+        const float4 g = *reinterpret_cast<const float4*>(gate + (long long)b * C + c);
+        v[0] = fmaf(v[0], g.x, r[0]); v[1] = fmaf(v[1], g.y, r[1]);
+        v[2] = fmaf(v[2], g.z, r[2]); v[3] = fmaf(v[3], g.w, r[3]);
+        ws_stv<4>(out, dt, pos * out_ld + c, v);
+    }
+}
+
+// block (32, 8); softmax over T per (b, c), then attention-weighted mean / std.
+__global__ void __launch_bounds__(256) astp_stats_kernel(const void* __restrict__ x, const void* __restrict__ lg,
+                                                         int dt, int T, int C, long long ld, float* __restrict__ out) {
+    __shared__ float red[3][8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int b = blockIdx.y;
+    const bool cv = c < C;
+    const long long base = (long long)b * T * ld + c;
+    float m = -INFINITY;
+    if (cv)
+        for (int t = threadIdx.y; t < T; t += 8) m = fmaxf(m, ws_ld(lg, dt, base + (long long)t * ld));
+    red[0][threadIdx.y][threadIdx.x] = m;
+    __syncthreads();
+    m = red[0][0][threadIdx.x];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[0][i][threadIdx.x]);
+    __syncthreads();
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (cv)
+        for (int t = threadIdx.y; t < T; t += 8) {
+            const float e = expf(ws_ld(lg, dt, base + (long long)t * ld) - m);
+            const float v = ws_ld(x, dt, base + (long long)t * ld);
+            s0 += e;
+            s1 = fmaf(e, v, s1);
+            s2 = fmaf(e * v, v, s2);
+        }
+    red[0][threadIdx.y][threadIdx.x] = s0;
+    red[1][threadIdx.y][threadIdx.x] = s1;
+    red[2][threadIdx.y][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.y == 0 && cv) {
+        s0 = s1 = s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s0 += red[0][i][threadIdx.x]; s1 += red[1][i][threadIdx.x]; s2 += red[2][i][threadIdx.x];
+        }
+        const float mean = s1 / s0;
+        const float var = s2 / s0 - mean * mean;
+        out[(long long)b * 2 * C + c] = mean;
+        out[(long long)b * 2 * C + C + c] = sqrtf(fmaxf(var, 1e-7f));
+    }
+}
+
+__global__ void bnrelu_kernel(const void* __restrict__ x, long long x_ld, const float* __restrict__ scale,
+                              const float* __restrict__ shift, void* __restrict__ out, long long out_ld, int dt,
+                              int C, long long nvec) {
+    const int cv = C >> 2;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < nvec; i += stride) {
+        const long long pos = i / cv;
+        const int c = (int)(i % cv) * 4;
+        float v[4];
+        ws_ldv<4>(x, dt, pos * x_ld + c, v);
+        const float4 sc = *reinterpret_cast<const float4*>(scale + c);
+        const float4 sh = *reinterpret_cast<const float4*>(shift + c);
+        v[0] = fmaxf(fmaf(v[0], sc.x, sh.x), 0.f); v[1] = fmaxf(fmaf(v[1], sc.y, sh.y), 0.f);
+        v[2] = fmaxf(fmaf(v[2], sc.z, sh.z), 0.f); v[3] = fmaxf(fmaf(v[3], sc.w, sh.w), 0.f);
+        ws_stv<4>(out, dt, pos * out_ld + c, v);
+    }
+}
+
+// one thread per output position (b, f, t): 9 taps x Cout channels, weights in shared memory.
+template <int COUT>
+__global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ feats, const float* __restrict__ w9,
+                                                   const float* __restrict__ shift, void* __restrict__ out, int dt,
+                                                   int B, int T, int Fdim) {
+    __shared__ float sw[COUT * 9];
+    __shared__ float sh[COUT];
+    for (int i = threadIdx.x; i < COUT * 9; i += blockDim.x) sw[i] = w9[i];
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) sh[i] = shift[i];
+    __syncthreads();
+    const long long n = (long long)B * Fdim * T;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int t = (int)(idx % T);
+    const int f = (int)((idx / T) % Fdim);
+    const int b = (int)(idx / ((long long)T * Fdim));
+    float in[9];
+#pragma unroll
+    for (int df = 0; df < 3; ++df)
+#pragma unroll
+        for (int dtp = 0; dtp < 3; ++dtp) {
+            const int ff = f + df - 1, tt = t + dtp - 1;
+            in[df * 3 + dtp] = (ff >= 0 && ff < Fdim && tt >= 0 && tt < T) ? feats[((long long)b * T + tt) * Fdim + ff] : 0.f;
+        }
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a = sh[c0 + j];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) a = fmaf(in[k], sw[(c0 + j) * 9 + k], a);
+            v[j] = fmaxf(a, 0.f);
+        }
+        ws_stv<8>(out, dt, idx * COUT + c0, v);
+    }
+}
+
+// block (32, 8)
+__global__ void __launch_bounds__(256) seg_means_kernel(const void* __restrict__ x, int dt, int T, int C, long long ld,
+                                                        int seg_len, float* __restrict__ mean,
+                                                        float* __restrict__ segmean) {
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int b = blockIdx.y;
+    const bool cv = c < C;
+    const int nseg = (T + seg_len - 1) / seg_len;
+    const long long base = (long long)b * T * ld + c;
+    float total = 0.f;
+    for (int sgi = 0; sgi < nseg; ++sgi) {
+        const int ta = sgi * seg_len, tb = min(T, ta + seg_len);
+        float s = 0.f;
+        if (cv)
+            for (int t = ta + threadIdx.y; t < tb; t += 8) s += ws_ld(x, dt, base + (long long)t * ld);
+        red[threadIdx.y][threadIdx.x] = s;
+        __syncthreads();
+        if (threadIdx.y == 0) {
+            float tot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x];
+            total += tot;
+            if (cv) segmean[((long long)b * nseg + sgi) * C + c] = tot / (float)(tb - ta);  // ceil_mode partial window
+        }
+        __syncthreads();
+    }
+    if (threadIdx.y == 0 && cv) mean[(long long)b * C + c] = total / (float)T;
+}
+
+inline const char* last_err() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+inline int grid_for(long long n, int block, int cap = 148 * 16) {
+    long long g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    return (int)(g > cap ? cap : g);
+}
+
+}  // namespace
+
+const char* ws_launch_convert(const float* in, void* out, int dt, long long n, cudaStream_t s) {
+    convert_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, dt, n);
+    return last_err();
+}
+
+const char* ws_launch_tstats(const void* x, int dt, int B, int F, int T, int C, long long ld, const float* pre_scale,
+                             const float* pre_shift, void* out, int odt, long long out_ld, int std_off, float eps,
+                             cudaStream_t s) {
+    dim3 grid((C + 31) / 32, F, B), block(32, 8);
+    tstats_kernel<<<grid, block, 0, s>>>(x, dt, F, T, C, ld, pre_scale, pre_shift, out, odt, out_ld, std_off, eps);
+    return last_err();
+}
+
+const char* ws_launch_linear_rows(const float* in, long long in_ld, const float* in2, long long in2_ld,
+                                  int rows_per_b, const float* W, const float* bias, float* out, long long out_ld,
+                                  int R, int I, int O, int act, cudaStream_t s) {
+    dim3 grid((O + 7) / 8, (R + 7) / 8);
+    linear_rows_kernel<<<grid, 256, 0, s>>>(in, in_ld, in2, in2_ld, rows_per_b < 1 ? 1 : rows_per_b, W, bias, out,
+                                            out_ld, R, I, O, act);
+    return last_err();
+}
+
+const char* ws_launch_scale_residual(const void* x, long long x_ld, const float* gate, const void* res,
+                                     long long res_ld, void* out, long long out_ld, int dt, int B, int T, int C,
+                                     cudaStream_t s) {
+    const long long nvec = (long long)B * T * (C / 4);
+    scale_residual_kernel<<<grid_for(nvec, 256), 256, 0, s>>>(x, x_ld, gate, res, res_ld, out, out_ld, dt, T, C, nvec);
+    return last_err();
+}
+
+const char* ws_launch_astp_stats(const void* x, const void* logits, int dt, int B, int T, int C, long long ld,
+                                 float* out, cudaStream_t s) {
+    dim3 grid((C + 31) / 32, B), block(32, 8);
+    astp_stats_kernel<<<grid, block, 0, s>>>(x, logits, dt, T, C, ld, out);
+    return last_err();
+}
+
+const char* ws_launch_bnrelu(const void* x, long long x_ld, const float* scale, const float* shift, void* out,
+                             long long out_ld, int dt, long long npos, int C, cudaStream_t s) {
+    const long long nvec = npos * (C / 4);
+    bnrelu_kernel<<<grid_for(nvec, 256), 256, 0, s>>>(x, x_ld, scale, shift, out, out_ld, dt, C, nvec);
+    return last_err();
+}
+
+const char* ws_launch_stem(const float* feats, const float* w9, const float* shift, void* out, int dt, int B, int T,
+                           int Fdim, int Cout, cudaStream_t s) {
+    const long long n = (long long)B * Fdim * T;
+    const int grid = (int)((n + 127) / 128);
+    if (Cout == 32) stem_kernel<32><<<grid, 128, 0, s>>>(feats, w9, shift, out, dt, B, T, Fdim);
+    else if (Cout == 64) stem_kernel<64><<<grid, 128, 0, s>>>(feats, w9, shift, out, dt, B, T, Fdim);
+    else return "stem conv supports 32 or 64 output channels";
+    return last_err();
+}
+
+const char* ws_launch_seg_means(const void* x, int dt, int B, int T, int C, long long ld, int seg_len, float* mean,
+                                float* segmean, cudaStream_t s) {
+    dim3 grid((C + 31) / 32, B), block(32, 8);
+    seg_means_kernel<<<grid, block, 0, s>>>(x, dt, T, C, ld, seg_len, mean, segmean);
+    return last_err();
+}

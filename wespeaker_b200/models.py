@@ -1,0 +1,254 @@
+"""Drop-in model objects for the reference operator seam B1:
+
+    model = get_speaker_model(name)(**model_args)      # wespeaker/models/speaker_model.py:31-62
+    load_checkpoint(model, path)                       # wespeaker/utils/checkpoint.py:20-85
+    model.to(device).eval()
+    outputs = model(features)                          # features: float32 (B,T,feat_dim)
+    embeds = outputs[-1] if isinstance(outputs, tuple) else outputs   # bin/extract.py:133-134
+
+``B200SpeakerModel`` is an ``nn.Module``-shaped object holding the *reference* ``state_dict`` (same
+key names / shapes) whose ``forward`` runs the hand-written sm_100a engine through the C ABI
+(include/wespeaker_b200.h).  PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections import OrderedDict, namedtuple
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .synthetic import CAMPP_NAMES, DEFAULT_MODEL_ARGS, ECAPA_NAMES, RESNET_NAMES, state_dict_spec
+
+_IncompatibleKeys = namedtuple("IncompatibleKeys", ["missing_keys", "unexpected_keys"])
+SUPPORTED_MODELS = tuple(ECAPA_NAMES) + tuple(RESNET_NAMES) + tuple(CAMPP_NAMES)
+
+
+class B200SpeakerModel(torch.nn.Module):
+    """One reference speaker model executed by the B200 engine.
+
+    precision: "fp32" (exact fp32 FFMA path, embeddings <=1e-4 rel of the reference), "tf32", "bf16",
+    "fp16" (tcgen05 tensor-core paths).  Default from $WESPEAKER_B200_PRECISION or "fp32".
+    """
+
+    def __init__(self, model_name: str, precision: str | None = None, **model_args):
+        super().__init__()
+        if model_name not in SUPPORTED_MODELS:
+            raise ValueError(f"{model_name} is not on the B200 hot path (supported: {SUPPORTED_MODELS})")
+        args = dict(DEFAULT_MODEL_ARGS[model_name])
+        args.update(model_args)
+        self.model_name = model_name
+        self.model_args = args
+        self.precision = precision or os.environ.get("WESPEAKER_B200_PRECISION", "fp32")
+        self.feat_dim = int(args["feat_dim"])
+        self.embed_dim = int(args["embed_dim"])
+        self._spec = state_dict_spec(model_name, **args)
+        self._sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        self._device = torch.device("cpu")
+        self._engine = None
+        self._engine_device = None
+        self.frontend_type = "fbank"
+        self.options = {}
+
+    # ------------------------------------------------------------------ nn.Module-compatible surface
+    def state_dict(self, *a, **k):
+        sd = OrderedDict()
+        for key, shape in self._spec.items():
+            if key in self._sd:
+                sd[key] = self._sd[key]
+            elif key.endswith("num_batches_tracked"):
+                sd[key] = torch.zeros((), dtype=torch.long)
+            else:
+                sd[key] = torch.zeros(shape, dtype=torch.float32)
+        return sd
+
+    def load_state_dict(self, state_dict, strict: bool = True, **_):
+        missing = [k for k in self._spec if k not in state_dict and not k.endswith("num_batches_tracked")]
+        unexpected = [k for k in state_dict if k not in self._spec]
+        errors = []
+        for k, shape in self._spec.items():
+            if k in state_dict:
+                v = state_dict[k]
+                v = torch.as_tensor(np.asarray(v)) if not torch.is_tensor(v) else v
+                if tuple(v.shape) != tuple(shape):
+                    errors.append(f"size mismatch for {k}: checkpoint {tuple(v.shape)} vs model {tuple(shape)}")
+                    continue
+                self._sd[k] = v.detach().to("cpu")
+        if errors or (strict and (missing or unexpected)):
+            raise RuntimeError("Error(s) in loading state_dict for {}:\n\t{}".format(
+                self.model_name, "\n\t".join(errors + [f"missing: {missing}"] * bool(strict and missing)
+                                             + [f"unexpected: {unexpected}"] * bool(strict and unexpected))))
+        self._drop_engine()
+        return _IncompatibleKeys(missing, unexpected)
+
+    def to(self, device=None, *a, **k):
+        if device is not None and not isinstance(device, torch.dtype):
+            self._device = torch.device(device)
+            if self._device.type == "cuda" and self._device.index is None:
+                self._device = torch.device("cuda", torch.cuda.current_device())
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", device if device is not None else torch.cuda.current_device()))
+
+    def eval(self):
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("wespeaker_b200 is an inference engine (training is out of scope)")
+        return self
+
+    def set_option(self, key: str, value: int):
+        self.options[key] = int(value)
+        self._drop_engine()
+
+    # ------------------------------------------------------------------ engine
+    def _drop_engine(self):
+        if self._engine is not None:
+            _lib.load().ws_engine_destroy(self._engine)
+            self._engine = None
+
+    def __del__(self):
+        try:
+            self._drop_engine()
+        except Exception:
+            pass
+
+    def _ensure_engine(self, dev_index: int):
+        if self._engine is not None and self._engine_device == dev_index:
+            return self._engine
+        self._drop_engine()
+        L = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.B200Error("wespeaker_b200 needs a CUDA device (no CPU fallback)")
+        h = _lib.c_engine_p()
+        _lib.check(L.ws_engine_create(self.model_name.encode(), self.precision.encode(), self.feat_dim,
+                                      self.embed_dim, dev_index, C.byref(h)), "ws_engine_create")
+        try:
+            for opt in ("two_emb_layer", "emb_bn"):
+                if self.model_args.get(opt):
+                    _lib.check(L.ws_engine_set_option(h, opt.encode(), 1), "ws_engine_set_option")
+            for k, v in self.options.items():
+                _lib.check(L.ws_engine_set_option(h, k.encode(), v), "ws_engine_set_option")
+            for k, v in self._sd.items():
+                if k.endswith("num_batches_tracked"):
+                    continue
+                a = np.ascontiguousarray(v.detach().cpu().numpy(), dtype=np.float32)
+                shape = (C.c_longlong * a.ndim)(*a.shape)
+                _lib.check(L.ws_engine_set_tensor(h, k.encode(), a.ctypes.data, shape, a.ndim),
+                           "ws_engine_set_tensor")
+            _lib.check(L.ws_engine_finalize(h), "ws_engine_finalize")
+        except Exception:
+            L.ws_engine_destroy(h)
+            raise
+        self._engine, self._engine_device = h, dev_index
+        return h
+
+    def _dev_index(self, t: torch.Tensor | None = None) -> int:
+        if t is not None and t.is_cuda:
+            return t.device.index
+        if self._device.type == "cuda":
+            return self._device.index
+        return torch.cuda.current_device() if torch.cuda.is_available() else 0
+
+    # ------------------------------------------------------------------ forward paths
+    def embed(self, features: torch.Tensor) -> torch.Tensor:
+        """(B,T,feat_dim) float32 -> (B,embed_dim) float32 on the same device class as the input."""
+        if features.dim() != 3 or features.shape[2] != self.feat_dim:
+            raise ValueError(f"expected features (B,T,{self.feat_dim}), got {tuple(features.shape)}")
+        L = _lib.load()
+        B, T, _ = features.shape
+        if features.is_cuda:
+            idx = features.device.index
+            h = self._ensure_engine(idx)
+            x = features.detach().contiguous().float()
+            out = torch.empty((B, self.embed_dim), dtype=torch.float32, device=features.device)
+            with torch.cuda.device(idx):
+                _lib.check(L.ws_engine_forward(h, x.data_ptr(), B, T, out.data_ptr(), _lib.cur_stream_ptr(idx)),
+                           "ws_engine_forward")
+            return out
+        # host tensor (cli/speaker.py:160-166 hands CPU feats to the model): H2D + forward + D2H inside the ABI
+        idx = self._dev_index()
+        h = self._ensure_engine(idx)
+        x = features.detach().contiguous().float()
+        out = torch.empty((B, self.embed_dim), dtype=torch.float32)
+        _lib.check(L.ws_engine_forward_host(h, x.data_ptr(), B, T, out.data_ptr()), "ws_engine_forward_host")
+        return out
+
+    def forward(self, features: torch.Tensor):
+        emb = self.embed(features)
+        if self.model_name in CAMPP_NAMES:
+            return emb  # campplus.py:409-413 returns a bare tensor
+        # ecapa_tdnn.py:234 returns (out4, emb); resnet.py:204 returns (tensor(0.), embed_a).  Callers use [-1].
+        return torch.tensor(0.0), emb
+
+    def extract_from_wav(self, wav: torch.Tensor, window_type: str = "hamming", return_feats: bool = False):
+        """wav: (B,N) float32 (int16 range, i.e. ``wav * (1 << 15)``) or int16 PCM, CUDA or host.
+        fbank (dither 0) + CMN + forward entirely on the GPU."""
+        if wav.dim() != 2:
+            raise ValueError("wav must be (B, N)")
+        L = _lib.load()
+        is_i16 = 1 if wav.dtype == torch.int16 else 0
+        if not is_i16:
+            wav = wav.float()
+        wav = wav.contiguous()
+        B, N = wav.shape
+        if wav.is_cuda:
+            idx = wav.device.index
+            h = self._ensure_engine(idx)
+            out = torch.empty((B, self.embed_dim), dtype=torch.float32, device=wav.device)
+            T = L.ws_fbank_num_frames(N)
+            feats = torch.empty((B, T, 80), dtype=torch.float32, device=wav.device) if return_feats else None
+            with torch.cuda.device(idx):
+                _lib.check(L.ws_engine_extract_wav(h, wav.data_ptr(), is_i16, N, N, B, window_type.encode(),
+                                                   out.data_ptr(), feats.data_ptr() if return_feats else None,
+                                                   _lib.cur_stream_ptr(idx)), "ws_engine_extract_wav")
+            return (out, feats) if return_feats else out
+        h = self._ensure_engine(self._dev_index())
+        out = torch.empty((B, self.embed_dim), dtype=torch.float32)
+        _lib.check(L.ws_engine_extract_wav_host(h, wav.data_ptr(), is_i16, N, B, window_type.encode(),
+                                                out.data_ptr()), "ws_engine_extract_wav_host")
+        return out
+
+    def last_launches(self) -> int:
+        return int(_lib.load().ws_engine_last_launches(self._engine)) if self._engine is not None else 0
+
+
+def get_speaker_model(model_name: str):
+    """Mirror of `wespeaker/models/speaker_model.py:31-62`: name -> constructor taking **model_args."""
+    if model_name not in SUPPORTED_MODELS:
+        # the reference prints and exit(1)s (speaker_model.py:60-62); raising is the library-friendly equivalent
+        raise ValueError(f"{model_name} not found / not on the B200 hot path; supported: {SUPPORTED_MODELS}")
+
+    def ctor(**model_args):
+        return B200SpeakerModel(model_name, **model_args)
+
+    ctor.__name__ = model_name
+    return ctor
+
+
+def load_checkpoint(model, path: str):
+    """Mirror of `wespeaker/utils/checkpoint.py:20-85`: torch.load, unwrap ``state_dict``, ignore
+    ``projection.*`` (training head), ``load_state_dict(strict=False)`` with warnings."""
+    import logging
+    checkpoint = torch.load(path, map_location="cpu", weights_only=False)
+    if isinstance(checkpoint, dict) and "state_dict" in checkpoint:
+        checkpoint = checkpoint["state_dict"]
+    missing, unexpected = model.load_state_dict(checkpoint, strict=False)
+    for key in missing:
+        if "projection" not in key:
+            logging.warning("missing tensor: %s", key)
+    for key in unexpected:
+        if "projection" not in key:
+            logging.warning("unexpected tensor: %s", key)
+
+
+def from_synthetic(model_name: str, seed: int = 0, precision: str | None = None, **model_args):
+    """Random-init model of the reference architecture (no pretrained checkpoints offline)."""
+    from .synthetic import make_state_dict
+    m = B200SpeakerModel(model_name, precision=precision, **model_args)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in make_state_dict(model_name, seed, **model_args).items()})
+    return m
