@@ -167,6 +167,7 @@ static bool build_tc(const ConvSpec& s, WsTcParams* p) {
     p->B = B; p->F = F; p->T = T;
     p->bn = s.Cout % 128 == 0 ? 128 : (s.Cout % 64 == 0 ? 64 : (s.Cout % 32 == 0 ? 32 : 16));
     p->tiles_n = s.Cout / p->bn;
+    if ((p->bn * p->bk_bytes) % 1024 != 0) { set_err("tc conv: weight tile not a multiple of the 1024-B swizzle atom"); return false; }
     const int stage_bytes = (128 + p->bn) * p->bk_bytes;
     int ns = (96 * 1024) / stage_bytes;
     p->nstages = ns < 2 ? 2 : (ns > WS_TC_MAX_STAGES ? WS_TC_MAX_STAGES : ns);

@@ -114,6 +114,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+constexpr int kMaxDynSmem = 200 * 1024;  // dynamic + static (barriers) must stay under the 227 KB opt-in limit
 constexpr int kThreads = 192;  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue
 
 template <int KIND>
@@ -253,10 +254,10 @@ __global__ void __launch_bounds__(kThreads) ws_conv_gemm_tc_kernel(const __grid_
 extern "C" const char* ws_tc_init(void) {
     static bool done = false;
     if (done) return nullptr;
-    cudaError_t e = cudaFuncSetAttribute(ws_conv_gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ws_conv_gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(ws_conv_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return cudaGetErrorString(e);
+        e = cudaFuncSetAttribute(ws_conv_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    if (e != cudaSuccess) { cudaGetLastError(); return cudaGetErrorString(e); }
     done = true;
     return nullptr;
 }

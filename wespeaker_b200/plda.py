@@ -130,6 +130,8 @@ class TwoCovPLDA:
         N, M = e.shape[0], t.shape[0]
         if out is None:
             out = torch.empty((N, M), dtype=out_dtype, device=e.device)
+        if N == 0 or M == 0:
+            return out
         cnt, const_n = None, 1
         if np.isscalar(counts) or (torch.is_tensor(counts) and counts.dim() == 0):
             const_n = int(counts)
