@@ -145,7 +145,7 @@ def run_reference(args, wl):
     }))
 
 
-def time_dominant_kernel(model, prec, B, T, iters=10):
+def time_dominant_kernel(model, prec, B, T, iters=10, tc_version=2):
     """Roofline leg: the dominant launch of the step — ECAPA's 1x1 conv 3C->1536 over B*T positions
     (ecapa_tdnn.py:200,218; 47-49% of the model's MACs) — timed live with CUDA events on the launching stream
     through ws_conv.  Algorithmic FLOPs per launch = 2 * B*T * 3C * 1536."""
@@ -172,7 +172,7 @@ def time_dominant_kernel(model, prec, B, T, iters=10):
         d.x, d.B, d.F, d.T, d.Cin, d.x_ld = x.data_ptr(), B, 1, T, cin, cin
         d.w, d.Cout, d.kf, d.kt = w.data_ptr(), cout, 1, 1
         d.dil_f = d.dil_t = d.stride_f = d.stride_t = 1
-        d.bias, d.act1, d.out, d.out_ld, d.dtype, d.use_tc = bias.data_ptr(), 1, o.data_ptr(), cout, code, int(prec != "fp32")
+        d.bias, d.act1, d.out, d.out_ld, d.dtype, d.use_tc = bias.data_ptr(), 1, o.data_ptr(), cout, code, (0 if prec == "fp32" else tc_version)
         descs.append(d)
     st = lib.cur_stream_ptr()
     for i in range(3):

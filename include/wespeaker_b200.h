@@ -29,7 +29,8 @@ const char* ws_last_error(void);
  * precision:  "fp32" (exact IEEE fp32 FFMA path, parity <= 1e-4), "tf32", "bf16", "fp16" (tcgen05 tensor cores). */
 int ws_engine_create(const char* model_name, const char* precision, int feat_dim, int embed_dim, int device,
                      ws_engine** out);
-/* options: "two_emb_layer", "emb_bn" (model_args), "cuda_graph" (default 1), "force_simt" (debug cross-check) */
+/* options: "two_emb_layer", "emb_bn" (model_args), "cuda_graph" (default 1), "force_simt" (debug cross-check),
+ * "tc_version" (1: one-tile-per-CTA tcgen05 kernel, 2 (default): persistent / TMA-store kernel) */
 int ws_engine_set_option(ws_engine* e, const char* key, long long value);
 /* one reference state_dict entry (fp32 host data, reference key names). */
 int ws_engine_set_tensor(ws_engine* e, const char* key, const float* host_data, const long long* shape, int ndim);
@@ -78,7 +79,7 @@ typedef struct {
     void* out;                /* [B][Fo][To][out_ld] */
     long long out_ld;
     int dtype;                /* 0 fp32 (tf32 MMA when use_tc), 1 bf16, 2 fp16 */
-    int use_tc;               /* 1: tcgen05 kernel, 0: fp32 FFMA kernel */
+    int use_tc;               /* 0: fp32 FFMA kernel, 1: tcgen05 v1 kernel, 2: persistent tcgen05 v2 kernel */
 } ws_conv_desc;
 int ws_conv(const ws_conv_desc* d, void* stream);
 

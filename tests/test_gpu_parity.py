@@ -60,7 +60,7 @@ def run_conv(x_cl, w, bias, scale, shift, res, prec, use_tc, kf, kt, dil, pad, s
         r = res.to(DEV, tdt).contiguous()
         keep.append(r)
         d.res, d.res_ld = r.data_ptr(), Cout
-    d.act1, d.act2, d.out, d.out_ld, d.dtype, d.use_tc = act1, act2, out.data_ptr(), Cout, code, int(use_tc)
+    d.act1, d.act2, d.out, d.out_ld, d.dtype, d.use_tc = act1, act2, out.data_ptr(), Cout, code, int(use_tc)  # 0 FFMA, 1 tc v1, 2 tc v2
     lib.check(lib.load().ws_conv(C.byref(d), None), "ws_conv")
     torch.cuda.synchronize()
     return out.float().cpu()
@@ -95,11 +95,13 @@ CONV_CASES = [
     ("c3x3_s21", 2, 10, 45, 32, 32, 3, 3, (1, 1), (1, 1), (2, 1)),
     ("pw_s2", 2, 20, 37, 64, 128, 1, 1, (1, 1), (0, 0), (2, 2)),
     ("k3_d2_128_32", 2, 1, 100, 128, 32, 1, 3, (1, 2), (0, 2), (1, 1)),
+    ("pw_1536_nores", 2, 1, 200, 256, 1536, 1, 1, (1, 1), (0, 0), (1, 1)),
+    ("pw_many_tiles", 64, 1, 200, 128, 512, 1, 1, (1, 1), (0, 0), (1, 1)),
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-@pytest.mark.parametrize("mode", ["fp32-simt", "tf32-tc", "bf16-tc", "fp16-tc", "bf16-simt"])
+@pytest.mark.parametrize("mode", ["fp32-simt", "tf32-tc", "bf16-tc", "fp16-tc", "bf16-simt", "tf32-tc2", "bf16-tc2", "fp16-tc2"])
 def test_conv_operator(case, mode):
     name, B, F, T, Cin, Cout, kf, kt, dil, pad, stride = case
     prec, path = mode.split("-")
@@ -111,8 +113,8 @@ def test_conv_operator(case, mode):
     shift = 0.1 * torch.randn(Cout, generator=g)
     Fo = (F + 2 * pad[0] - dil[0] * (kf - 1) - 1) // stride[0] + 1
     To = (T + 2 * pad[1] - dil[1] * (kt - 1) - 1) // stride[1] + 1
-    res = torch.randn(B, Fo, To, Cout, generator=g)
-    out = run_conv(x, w, bias, scale, shift, res, prec, path == "tc", kf, kt, dil, pad, stride, 1, 1)
+    res = None if name.endswith("nores") else torch.randn(B, Fo, To, Cout, generator=g)
+    out = run_conv(x, w, bias, scale, shift, res, prec, {"simt": 0, "tc": 1, "tc2": 2}[path], kf, kt, dil, pad, stride, 1, 1)
     tdt = DT[prec][1]
     ref = ref_conv(x, w, bias, scale, shift, res, tdt, kf, kt, dil, pad, stride, 1, 1)
     err = (out.double() - ref).abs().max().item()
@@ -181,6 +183,19 @@ def test_model_fp32_matches_reference_golden(key):
 
 
 TC_TOL = {"tf32": 1e-2, "bf16": 3e-2, "fp16": 1e-2}
+
+
+def test_tc_v1_kernel_still_matches():
+    """The one-tile-per-CTA tcgen05 kernel (tc_version=1) stays available as a cross-check of the persistent one."""
+    key = "ECAPA_TDNN_c512__s0_B4_T198"
+    name, seed, B, T = parse_case(key)
+    feats = torch.from_numpy(syn.make_feats(B, T, 80, seed=seed + 17 * T)).to(DEV)
+    m1 = from_synthetic(name, seed, precision="bf16")
+    m1.set_option("tc_version", 1)
+    m2 = from_synthetic(name, seed, precision="bf16")
+    e1, e2 = m1.embed(feats).cpu().numpy(), m2.embed(feats).cpu().numpy()
+    assert rel_l2(e1, G_MODELS[key]).max() <= 3e-2 and rel_l2(e2, G_MODELS[key]).max() <= 3e-2
+    assert rel_l2(e1, e2).max() <= 2e-2
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16", "fp16"])

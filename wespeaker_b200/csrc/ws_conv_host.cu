@@ -2,6 +2,7 @@
 // construction, tile-shape selection and the launch closures for the tcgen05 and FFMA kernels.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -150,6 +151,8 @@ static bool build_tc(const ConvSpec& s, WsTcParams* p) {
     int B = s.B, F = s.F, T = s.T;
     bool flat = s.dense_pointwise;
     int bt = 128, bf = 1, bb = 1;
+    const char* env_bt = getenv("WS_TILE_BT");  // tuning knob: minimum time-extent of a non-flat tile
+    const int min_bt = env_bt ? atoi(env_bt) : 1;
     if (flat) {
         T = s.B * s.F * s.T; F = 1; B = 1;
     } else {
@@ -158,6 +161,7 @@ static bool build_tc(const ConvSpec& s, WsTcParams* p) {
             for (int f = 1; t * f <= 128; f <<= 1) {
                 const int b = 128 / (t * f);
                 if (F == 1 && f != 1) continue;
+                if (t < min_bt && t < 128 && F == 1) continue;
                 const long long cost = (long long)((T + t - 1) / t) * t * ((F + f - 1) / f) * f * ((B + b - 1) / b) * b;
                 if (best < 0 || cost < best || (cost == best && t > bt)) { best = cost; bt = t; bf = f; bb = b; }
             }
@@ -200,6 +204,95 @@ static bool build_tc(const ConvSpec& s, WsTcParams* p) {
     return true;
 }
 
+
+// ---- v2 (persistent, TMA-store epilogue).  Returns false *without* error if the spec needs the v1 kernel.
+static int g_num_sms = 0;
+static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported) {
+    *unsupported = false;
+    const WsEpi& e = s.epi;
+    if ((e.res != nullptr && e.out2 != nullptr) || s.Cout % 32 != 0) { *unsupported = true; return false; }
+    WsTcParams v1;
+    if (!build_tc(s, &v1)) return false;
+    memset(q, 0, sizeof(*q));
+    const int es = ws_esize(s.dt);
+    for (int i = 0; i < WS_MAX_SRC; ++i) q->amap[i] = v1.amap[i];
+    memcpy(q->taps, v1.taps, sizeof(v1.taps));
+    q->ntaps = v1.ntaps; q->nk_total = v1.nk_total; q->bk_bytes = v1.bk_bytes;
+    q->bt_log2 = v1.bt_log2; q->bf_log2 = v1.bf_log2; q->bb_log2 = v1.bb_log2;
+    q->tiles_t = v1.tiles_t; q->tiles_f = v1.tiles_f; q->tiles_b = v1.tiles_b;
+    q->B = v1.B; q->F = v1.F; q->T = v1.T; q->kind = v1.kind;
+    q->has_out2 = e.out2 != nullptr;
+    q->has_epin = (e.res != nullptr) || (e.out2 != nullptr);
+    const int nstage_bufs = 1 + (q->has_out2 ? 1 : 0) + (q->has_epin ? 1 : 0);
+    const int budget = ws_tc2_max_smem() - 1024;
+    // widest N tile whose staging + >=3 ring stages fit (>=2 accepted as a last resort)
+    int bn = 0, nst = 0;
+    const int cands[4] = {256, 128, 64, 32};
+    const char* env_bn = getenv("WS_TC2_MAX_BN");
+    const int max_bn = env_bn ? atoi(env_bn) : 256;
+    const char* env_st = getenv("WS_TC2_MAX_STAGES");
+    const int max_st = env_st ? atoi(env_st) : WS_TC_MAX_STAGES;
+    for (int pass = 0; pass < 2 && bn == 0; ++pass)
+        for (int ci = 0; ci < 4; ++ci) {
+            const int c = cands[ci];
+            if (s.Cout % c != 0 || c > max_bn) continue;
+            if (c == 256 && es == 4) continue;  // fp32 staging of a 128x256 tile would not leave room for the ring
+            if ((c * q->bk_bytes) % 1024 != 0) continue;
+            const int staging = nstage_bufs * 128 * c * es + 3 * c * 4;
+            const int stage_bytes = (128 + c) * q->bk_bytes;
+            const int n = (budget - staging) / stage_bytes;
+            if (n >= (pass == 0 ? 3 : 2)) { bn = c; nst = n > max_st ? max_st : n; break; }
+        }
+    if (bn == 0) { *unsupported = true; return false; }
+    q->bn = bn; q->nstages = nst;
+    q->tiles_n = s.Cout / bn;
+    q->num_tiles = q->tiles_n * q->tiles_t * q->tiles_f * q->tiles_b;
+    const uint32_t fmt = s.dt == WS_F32 ? 2u : (s.dt == WS_BF16 ? 1u : 0u);
+    q->idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    q->panel_bytes = bn * es >= 128 ? 128 : bn * es;
+    const int panel_cols = q->panel_bytes / es;
+    const int bk_elems = q->bk_bytes / es;
+    {   // weights map with the v2 N tile
+        cuuint64_t dims[2] = {(cuuint64_t)s.Ktot, (cuuint64_t)s.Cout};
+        cuuint64_t str[1] = {(cuuint64_t)s.Ktot * es};
+        cuuint32_t box[2] = {(cuuint32_t)bk_elems, (cuuint32_t)bn};
+        if (!encode_map(&q->wmap, s.dt, s.W, 2, dims, str, box, q->bk_bytes)) return false;
+    }
+    // output / epilogue-input maps: same tile geometry as the A maps over the output positions
+    const bool flat = s.dense_pointwise;
+    auto out_map = [&](CUtensorMap* m, const void* ptr, long long ld) -> bool {
+        cuuint64_t dims[4], str[3];
+        cuuint32_t box[4] = {(cuuint32_t)panel_cols, (cuuint32_t)(1 << q->bt_log2), (cuuint32_t)(1 << q->bf_log2),
+                             (cuuint32_t)(1 << q->bb_log2)};
+        if (flat) {
+            dims[0] = (cuuint64_t)s.Cout; dims[1] = (cuuint64_t)q->T; dims[2] = 1; dims[3] = 1;
+            str[0] = (cuuint64_t)ld * es; str[1] = (cuuint64_t)q->T * ld * es; str[2] = str[1];
+        } else {
+            dims[0] = (cuuint64_t)s.Cout; dims[1] = (cuuint64_t)s.T; dims[2] = (cuuint64_t)s.F; dims[3] = (cuuint64_t)s.B;
+            str[0] = (cuuint64_t)ld * es; str[1] = (cuuint64_t)s.T * ld * es; str[2] = (cuuint64_t)s.F * s.T * ld * es;
+        }
+        return encode_map(m, s.dt, ptr, 4, dims, str, box, q->panel_bytes);
+    };
+    if (!out_map(&q->omap, e.out, e.out_ld)) return false;
+    if (q->has_out2) {
+        if (!out_map(&q->o2map, e.out2, e.out2_ld) || !out_map(&q->imap, e.add2, e.add2_ld)) return false;
+    } else if (q->has_epin) {
+        if (!out_map(&q->imap, e.res, e.res_ld)) return false;
+    }
+    if (!q->has_out2) q->o2map = q->omap;
+    if (!q->has_epin) q->imap = q->omap;
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    q->grid = q->num_tiles < g_num_sms ? q->num_tiles : g_num_sms;
+    q->smem_bytes = nst * (128 + bn) * q->bk_bytes + nstage_bufs * 128 * bn * es + 3 * bn * 4 + 1024;
+    q->epi = e;
+    return true;
+}
+
 static bool build_simt(const ConvSpec& s, WsSimtParams* p) {
     memset(p, 0, sizeof(*p));
     if ((int)s.taps.size() > WS_MAX_TAPS) { set_err("conv: too many taps"); return false; }
@@ -214,7 +307,16 @@ static bool build_simt(const ConvSpec& s, WsSimtParams* p) {
     return true;
 }
 
-bool make_conv_op(const ConvSpec& spec, bool use_tc, Op* out) {
+bool make_conv_op(const ConvSpec& spec, int use_tc, Op* out) {
+    if (use_tc >= 2) {
+        auto q = std::make_shared<WsTc2Params>();
+        bool unsupported = false;
+        if (build_tc2(spec, q.get(), &unsupported)) {
+            *out = [q](cudaStream_t s) { return ws_tc2_launch(q.get(), s); };
+            return true;
+        }
+        if (!unsupported) return false;
+    }
     if (use_tc) {
         auto p = std::make_shared<WsTcParams>();
         if (!build_tc(spec, p.get())) return false;
@@ -251,8 +353,8 @@ extern "C" int ws_conv(const ws_conv_desc* d, void* stream) {
     s.epi.bias = d->bias; s.epi.act1 = d->act1; s.epi.scale = d->scale; s.epi.shift = d->shift;
     s.epi.res = d->res; s.epi.res_ld = d->res_ld; s.epi.act2 = d->act2;
     Op op;
-    if (d->use_tc) WS_CKS(ws_tc_init());
-    if (!make_conv_op(s, d->use_tc != 0, &op)) return 1;
+    if (d->use_tc) { WS_CKS(ws_tc_init()); WS_CKS(ws_tc2_init()); }
+    if (!make_conv_op(s, d->use_tc, &op)) return 1;
     const char* m = op((cudaStream_t)stream);
     if (m != nullptr) { set_err(std::string("ws_conv launch: ") + m); return 1; }
     return 0;

@@ -57,7 +57,7 @@ struct ws_engine {
     std::string model, prec;
     int feat_dim = 80, embed_dim = 0, device = 0;
     int act_dt = WS_F32;
-    bool use_tc = false;
+    int use_tc = 0;  // 0 FFMA, 1 tcgen05 v1, 2 tcgen05 v2
     std::map<std::string, long long> opts;
     std::map<std::string, HostT> sd;
     bool finalized = false;
@@ -841,13 +841,14 @@ int ws_engine_create(const char* model_name, const char* precision, int feat_dim
     else if (m == "CAMPPlus") {}
     else { set_err("unknown / out-of-scope model name: " + m); return 1; }
     const std::string p = e->prec;
-    if (p == "fp32") { e->act_dt = WS_F32; e->use_tc = false; }
-    else if (p == "tf32") { e->act_dt = WS_F32; e->use_tc = true; }
-    else if (p == "bf16") { e->act_dt = WS_BF16; e->use_tc = true; }
-    else if (p == "fp16") { e->act_dt = WS_F16; e->use_tc = true; }
+    if (p == "fp32") { e->act_dt = WS_F32; e->use_tc = 0; }
+    else if (p == "tf32") { e->act_dt = WS_F32; e->use_tc = 2; }
+    else if (p == "bf16") { e->act_dt = WS_BF16; e->use_tc = 2; }
+    else if (p == "fp16") { e->act_dt = WS_F16; e->use_tc = 2; }
     else { set_err("unknown precision (fp32|tf32|bf16|fp16): " + p); return 1; }
     if (feat_dim % 8 != 0) { set_err("feat_dim must be a multiple of 8"); return 1; }
     WS_CKS(ws_tc_init());
+    WS_CKS(ws_tc2_init());
     WS_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     WS_CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
     WS_CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
@@ -858,7 +859,8 @@ int ws_engine_create(const char* model_name, const char* precision, int feat_dim
 int ws_engine_set_option(ws_engine* e, const char* key, long long value) {
     if (!e || !key) { set_err("ws_engine_set_option: null argument"); return 1; }
     const std::string k = key;
-    if (k == "force_simt") { if (value) e->use_tc = false; }
+    if (k == "force_simt") { if (value) e->use_tc = 0; }
+    else if (k == "tc_version") { if (e->use_tc) e->use_tc = value >= 2 ? 2 : 1; }
     else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph") { set_err("unknown option " + k); return 1; }
     e->opts[k] = value;
     e->plans.clear();

@@ -67,7 +67,7 @@ int add_conv_taps(ConvSpec& spec, const View& x, int kf, int kt, int dil_f, int 
 using Op = std::function<const char*(cudaStream_t)>;
 // Build a launch closure for `spec`; use_tc selects the tcgen05 kernel (needs dt-aligned shapes) else FFMA.
 // Returns false and sets the error string if the spec cannot be mapped.
-bool make_conv_op(const ConvSpec& spec, bool use_tc, Op* out);
+bool make_conv_op(const ConvSpec& spec, int use_tc, Op* out);  // 0 FFMA, 1 tcgen05 v1, 2 tcgen05 v2 (falls back to v1)
 
 void fill_epi_out(WsEpi& e, const View& out);
 
