@@ -88,25 +88,44 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_run(model_name, nsamples, batch, budget_s, max_batches):
-    """Oracle port of the reference CPU path (numpy fbank+CMN, torch-CPU fp32 forward, all host threads)."""
+def _cpu_path(model_name, nsamples, batch):
+    """Oracle port of the reference CPU path: numpy fbank+CMN, torch-CPU fp32 forward."""
     from oracle import fbank_np, models_torch
     from wespeaker_b200 import synthetic as syn
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     sd = {k: torch.from_numpy(np.asarray(v)) for k, v in syn.make_state_dict(model_name, 0).items()}
     wavs = syn.make_wavs(batch, nsamples, seed=0)
 
     def one():
         feats = np.stack([fbank_np.cmn(fbank_np.fbank(w)) for w in wavs])
         return models_torch.forward(model_name, sd, torch.from_numpy(feats))
+    return one
 
-    one()  # warm-up
+
+def _best_threads(one):
+    """torch's CPU convs collapse when oversubscribed (128 threads: ~1 utt/s on the 128-core bench host), so give the
+    reference arm the thread count at which it is fastest."""
+    cores = os.cpu_count() or 1
+    best, best_t = None, None
+    for nt in sorted({t for t in (8, 16, 32, 64, cores) if t <= cores}):
+        torch.set_num_threads(nt)
+        one()
+        t0 = time.perf_counter(); one(); dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = nt, dt
+        if dt > 4 * best_t:
+            break
+    torch.set_num_threads(best)
+    return best, cores
+
+
+def cpu_reference_run(model_name, nsamples, batch, budget_s, max_batches):
+    one = _cpu_path(model_name, nsamples, batch)
+    threads, cores = _best_threads(one)
     t0, nb = time.perf_counter(), 0
     while nb < max_batches and (time.perf_counter() - t0 < budget_s or nb == 0):
         one(); nb += 1
     dt = time.perf_counter() - t0
-    return nb * batch / dt, cores, nb, dt
+    return nb * batch / dt, threads, cores, nb, dt
 
 
 def run_reference(args, wl):
@@ -114,19 +133,9 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    batch = 16
-    # each "step" = one bounded sample (16 utterances) of the same workload
-    from oracle import fbank_np, models_torch
-    from wespeaker_b200 import synthetic as syn
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in syn.make_state_dict(model, 0).items()}
-    wavs = syn.make_wavs(batch, nsamples, seed=0)
-
-    def one():
-        feats = np.stack([fbank_np.cmn(fbank_np.fbank(w)) for w in wavs])
-        return models_torch.forward(model, sd, torch.from_numpy(feats))
-
+    batch = 16  # each "step" = one bounded sample (16 utterances) of the same workload
+    one = _cpu_path(model, nsamples, batch)
+    threads, cores = _best_threads(one)
     for _ in range(max(1, min(args.warmup, 3))):
         one()
     t0 = time.perf_counter()
@@ -134,15 +143,53 @@ def run_reference(args, wl):
         one()
     dt = time.perf_counter() - t0
     v = args.steps * batch / dt
-    sample = f"{args.steps} steps x {batch} utts of {nsamples} samples, oracle port (numpy fbank + torch-CPU fp32), {cores} threads"
+    sample = (f"{args.steps} steps x {batch} utts of {nsamples} samples, oracle port of the reference CPU path (numpy fbank+CMN, "
+              f"torch-CPU fp32 forward), {threads} torch threads (fastest of 8..{cores} on this {cores}-core host)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl, "model": model, "batch_per_step": batch, "samples_per_utt": nsamples},
-        "cpu_baseline": {"value": v, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "utt/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def plda_bench(dev, n_enroll=32768, n_test=100000, dim=256, iters=3):
+    """Secondary metric of BASELINE.json: PLDA scores/s (configs[4]: 1M x 100k, D=256).  The all-pairs job is tiled over
+    enroll rows into a reused fp32 score buffer (10^11 scores do not fit in HBM); one tile = n_enroll x n_test."""
+    from wespeaker_b200 import synthetic as syn
+    from wespeaker_b200.plda import TwoCovPLDA
+    from oracle import plda_np
+    pm = syn.make_plda(dim, seed=3, normalize_length=True)
+    p = TwoCovPLDA.from_arrays(**pm, device=dev.index)
+    e = torch.from_numpy(syn.make_embeddings(n_enroll, dim, seed=3)).to(dev)
+    t = torch.from_numpy(syn.make_embeddings(n_test, dim, seed=4)).to(dev)
+    e_t, t_t = p.transform_batch(e), p.transform_batch(t)
+    out = torch.empty((n_enroll, n_test), dtype=torch.float32, device=dev)
+    p.score_matrix(e_t, t_t, 1, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        p.score_matrix(e_t, t_t, 1, out=out)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    scores = float(n_enroll) * n_test
+    # CPU: the reference's per-trial Python loop (two_cov_plda.py:248-256), single thread, on a 20k-trial sample
+    et, tt = e_t[:200].cpu().numpy(), t_t[:100].cpu().numpy()
+    t0 = time.perf_counter()
+    for i in range(200):
+        for j in range(100):
+            plda_np.log_likelihood_ratio(pm, et[i], tt[j], 1)
+    cpu_loop = 20000 / (time.perf_counter() - t0)
+    ref = plda_np.llr_matrix(pm, et, tt, 1)
+    err = float(np.abs(out[:200, :100].double().cpu().numpy() - ref).max())
+    return {"value": scores / (ms * 1e-3), "unit": "scores/s", "dtype": "f64", "enroll_tile": n_enroll, "test": n_test, "dim": dim,
+            "ms_per_tile": ms, "tflops_f64": scores * 2 * dim / (ms * 1e-3) / 1e12, "out_gbs": scores * 4 / (ms * 1e-3) / 1e9,
+            "max_abs_err_vs_fp64_oracle": err,
+            "cpu_baseline": {"value": cpu_loop, "unit": "scores/s", "cores": 1, "kind": "port",
+                             "sample": "20000 trials, per-trial log_likelihood_ratio loop as in eval_sv"}}
 
 
 def time_dominant_kernel(model, prec, B, T, iters=10, tc_version=2):
@@ -198,6 +245,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-plda", action="store_true")
     args = ap.parse_args()
     wl = args.workload
     if args.impl == "reference":
@@ -276,9 +324,13 @@ def main():
                 "peak_source": peaks["src"] + " (sustained, whole step)"}
     cpu = None
     if not args.no_cpu_baseline:
-        v, cores, nb, cdt = cpu_reference_run(model_name, nsamples, 16, budget_s=12.0, max_batches=40)
-        cpu = {"value": v, "unit": "utt/s", "cores": cores, "kind": "port",
-               "sample": f"{nb} batches x 16 utts of {nsamples} samples in {cdt:.1f}s: numpy fbank+CMN + torch-CPU fp32 forward (oracle port of the reference path)"}
+        v, threads, cores, nb, cdt = cpu_reference_run(model_name, nsamples, 16, budget_s=10.0, max_batches=200)
+        cpu = {"value": v, "unit": "utt/s", "cores": threads, "kind": "port",
+               "sample": f"{nb} batches x 16 utts of {nsamples} samples in {cdt:.1f}s: numpy fbank+CMN + torch-CPU fp32 forward "
+                         f"(oracle port of the reference path), {threads} torch threads = fastest of 8..{cores} on this {cores}-core host"}
+    plda = None
+    if not args.no_plda:
+        plda = plda_bench(dev)
     act_mb = B * L_frames * (1536 * 2 + 128 + (1024 if '1024' in model_name else 512) * 7) * (4 if prec in ("fp32", "tf32") else 2) / 1e6
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -291,7 +343,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": B * nsamples * 2, "d2h_bytes_per_step": B * model.embed_dim * 4,
                 "api": "B200SpeakerModel.extract_from_wav(pinned int16 PCM host tensor)"},
         "gpu_launches": int(launches_per_step * args.steps),
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "plda": plda,
     }))
 
 

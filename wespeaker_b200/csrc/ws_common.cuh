@@ -144,6 +144,41 @@ __device__ __forceinline__ void ws_stv(void* p, int dt, long long off, const flo
     }
 }
 
+// 8 consecutive elements (off % 8 == 0): one 16-byte access for 16-bit types, two for fp32
+__device__ __forceinline__ void ws_ldv8(const void* p, int dt, long long off, float* v) {
+    if (dt == WS_F32) {
+        ws_ldv<8>(p, dt, off, v);
+    } else {
+        const uint4 x = *reinterpret_cast<const uint4*>((const unsigned short*)p + off);
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = ws_16_to_f(w[i] & 0xffffu, dt);
+            v[2 * i + 1] = ws_16_to_f(w[i] >> 16, dt);
+        }
+    }
+}
+__device__ __forceinline__ void ws_stv8(void* p, int dt, long long off, const float* v) {
+    if (dt == WS_F32) {
+        ws_stv<8>(p, dt, off, v);
+    } else {
+        uint4 x;
+        x.x = ws_pack2(v[0], v[1], dt); x.y = ws_pack2(v[2], v[3], dt);
+        x.z = ws_pack2(v[4], v[5], dt); x.w = ws_pack2(v[6], v[7], dt);
+        *reinterpret_cast<uint4*>((unsigned short*)p + off) = x;
+    }
+}
+// 2 consecutive elements (off % 2 == 0)
+__device__ __forceinline__ void ws_ld2(const void* p, int dt, long long off, float* v) {
+    if (dt == WS_F32) {
+        const float2 x = *reinterpret_cast<const float2*>((const float*)p + off);
+        v[0] = x.x; v[1] = x.y;
+    } else {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>((const unsigned short*)p + off);
+        v[0] = ws_16_to_f(w & 0xffffu, dt); v[1] = ws_16_to_f(w >> 16, dt);
+    }
+}
+
 // Apply the fused epilogue to NV consecutive output channels [col0, col0+NV) of output position `pos`.
 template <int NV>
 __device__ __forceinline__ void ws_epilogue(const WsEpi& e, long long pos, int col0, float* v) {

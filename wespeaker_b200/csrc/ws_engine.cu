@@ -41,6 +41,7 @@ struct Plan {
     int B = 0, T = 0;
     std::vector<Op> ops;
     std::vector<void*> bufs;
+    int extra_launches = 0;     // ops that launch more than one kernel (split-K FC = 2)
     float* feats_in = nullptr;  // fp32 [B][T][feat_dim]
     float* emb = nullptr;       // fp32 [B][embed_dim]
     cudaGraphExec_t gexec = nullptr;
@@ -241,8 +242,15 @@ struct Builder {
     }
     void linear(const float* in, long long in_ld, const float* in2, long long in2_ld, int rows_per_b, const float* W,
                 const float* bias, float* out, long long out_ld, int R, int I, int O, int act) {
+        // split K so that the launch fills the machine (these layers are latency-bound otherwise)
+        const int blocks = ((O + 31) / 32) * ((R + 15) / 16);
+        int nsplit = 1;
+        while (blocks * nsplit < 296 && I / (nsplit * 2) >= 128 && nsplit < 16) nsplit *= 2;
+        float* wsp = nsplit > 1 ? f32((size_t)nsplit * R * O) : nullptr;
+        if (nsplit > 1) p.extra_launches += 1;
         push([=](cudaStream_t s) {
-            return ws_launch_linear_rows(in, in_ld, in2, in2_ld, rows_per_b, W, bias, out, out_ld, R, I, O, act, s);
+            return ws_launch_linear_rows(in, in_ld, in2, in2_ld, rows_per_b, W, bias, out, out_ld, R, I, O, act, wsp,
+                                         nsplit, s);
         });
     }
 };
@@ -738,7 +746,7 @@ int run_plan(ws_engine* e, Plan* p, cudaStream_t s) {
     } else {
         for (auto& op : p->ops) WS_CKS(op(s));
     }
-    e->last_launches = (long long)p->ops.size();
+    e->last_launches = (long long)p->ops.size() + p->extra_launches;
     return 0;
 }
 

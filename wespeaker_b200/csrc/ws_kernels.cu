@@ -66,100 +66,142 @@ __global__ void __launch_bounds__(256) tstats_kernel(const void* __restrict__ x,
     }
 }
 
-// 8 warps: warp w -> output feature o; 8 input rows per block share each weight row.
+// Small fully-connected layers (SE, CAM context, global-context row bias, embedding head) as a shared-memory tiled
+// fp32 GEMM: block = 16 rows x 32 outputs (thread: 1 row x 2 outputs), K streamed in chunks of 64 with coalesced loads.
 __global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restrict__ in, long long in_ld,
                                                           const float* __restrict__ in2, long long in2_ld,
                                                           int rows_per_b, const float* __restrict__ W,
                                                           const float* __restrict__ bias, float* __restrict__ out,
                                                           long long out_ld, int R, int I, int O, int act) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int o = blockIdx.x * 8 + warp;
-    const int r0 = blockIdx.y * 8;
-    if (o >= O) return;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const float* w = W + (long long)o * I;
-    for (int i = lane; i < I; i += 32) {
-        const float wv = __ldg(w + i);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int r = r0 + j;
-            if (r < R) {
-                float v = in[(long long)r * in_ld + i];
-                if (in2 != nullptr) v += in2[(long long)(r / rows_per_b) * in2_ld + i];
-                acc[j] = fmaf(wv, v, acc[j]);
+    constexpr int TR = 16, TO = 32, TK = 64;
+    __shared__ float Xs[TR][TK + 1];
+    __shared__ float Ws[TO][TK + 1];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int r0 = blockIdx.y * TR, o0 = blockIdx.x * TO;
+    // split-K: blockIdx.z owns the k range [kbeg, kend); partial sums go to out + z*R*out_ld (no bias/act), a second
+    // kernel reduces them in a fixed order (deterministic, unlike atomics)
+    const int nsplit = gridDim.z;
+    const int kper = ((I + nsplit - 1) / nsplit + TK - 1) / TK * TK;
+    const int kbeg = blockIdx.z * kper, kend = min(I, kbeg + kper);
+    if (nsplit > 1) { out += (long long)blockIdx.z * R * out_ld; bias = nullptr; act = WS_ACT_NONE; }
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int k0 = kbeg; k0 < kend; k0 += TK) {
+        __syncthreads();
+        for (int idx = tid; idx < TR * TK; idx += 256) {
+            const int rr = idx / TK, kk = idx % TK, r = r0 + rr, k = k0 + kk;
+            float v = 0.f;
+            if (r < R && k < kend) {
+                v = in[(long long)r * in_ld + k];
+                if (in2 != nullptr) v += in2[(long long)(r / rows_per_b) * in2_ld + k];
             }
+            Xs[rr][kk] = v;
+        }
+        for (int idx = tid; idx < TO * TK; idx += 256) {
+            const int oo = idx / TK, kk = idx % TK, o = o0 + oo, k = k0 + kk;
+            Ws[oo][kk] = (o < O && k < kend) ? __ldg(W + (long long)o * I + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 16
+        for (int kk = 0; kk < TK; ++kk) {
+            const float x = Xs[ty][kk];
+            acc0 = fmaf(x, Ws[tx][kk], acc0);
+            acc1 = fmaf(x, Ws[tx + 16][kk], acc1);
         }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float v = warp_sum(acc[j]);
-        const int r = r0 + j;
-        if (lane == 0 && r < R) out[(long long)r * out_ld + o] = ws_act(v + (bias != nullptr ? bias[o] : 0.f), act);
+    const int r = r0 + ty;
+    if (r < R) {
+        const int oa = o0 + tx, ob = o0 + tx + 16;
+        if (oa < O) out[(long long)r * out_ld + oa] = ws_act(acc0 + (bias != nullptr ? bias[oa] : 0.f), act);
+        if (ob < O) out[(long long)r * out_ld + ob] = ws_act(acc1 + (bias != nullptr ? bias[ob] : 0.f), act);
     }
+}
+
+__global__ void linear_reduce_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ bias,
+                                     float* __restrict__ out, long long out_ld, int R, int O, int act) {
+    const long long n = (long long)R * O;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = (int)(i / O), o = (int)(i % O);
+    float a = 0.f;
+    for (int s = 0; s < nsplit; ++s) a += part[((long long)s * R + r) * O + o];
+    out[(long long)r * out_ld + o] = ws_act(a + (bias != nullptr ? bias[o] : 0.f), act);
 }
 
 __global__ void scale_residual_kernel(const void* __restrict__ x, long long x_ld, const float* __restrict__ gate,
                                       const void* __restrict__ res, long long res_ld, void* __restrict__ out,
                                       long long out_ld, int dt, int T, int C, long long nvec) {
-    const int cv = C >> 2;
+    const int cv = C >> 3;  // 8 channels per thread: 16-byte accesses for 16-bit activations
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < nvec; i += stride) {
         const long long pos = i / cv;
-        const int c = (int)(i % cv) * 4;
+        const int c = (int)(i % cv) * 8;
         const int b = (int)(pos / T);
-        float v[4], r[4];
-        ws_ldv<4>(x, dt, pos * x_ld + c, v);
-        ws_ldv<4>(res, dt, pos * res_ld + c, r);
-        const float4 g = *reinterpret_cast<const float4*>(gate + (long long)b * C + c);
-        v[0] = fmaf(v[0], g.x, r[0]); v[1] = fmaf(v[1], g.y, r[1]);
-        v[2] = fmaf(v[2], g.z, r[2]); v[3] = fmaf(v[3], g.w, r[3]);
-        ws_stv<4>(out, dt, pos * out_ld + c, v);
+        float v[8], r[8];
+        ws_ldv8(x, dt, pos * x_ld + c, v);
+        ws_ldv8(res, dt, pos * res_ld + c, r);
+        const float4 g0 = *reinterpret_cast<const float4*>(gate + (long long)b * C + c);
+        const float4 g1 = *reinterpret_cast<const float4*>(gate + (long long)b * C + c + 4);
+        v[0] = fmaf(v[0], g0.x, r[0]); v[1] = fmaf(v[1], g0.y, r[1]); v[2] = fmaf(v[2], g0.z, r[2]); v[3] = fmaf(v[3], g0.w, r[3]);
+        v[4] = fmaf(v[4], g1.x, r[4]); v[5] = fmaf(v[5], g1.y, r[5]); v[6] = fmaf(v[6], g1.z, r[6]); v[7] = fmaf(v[7], g1.w, r[7]);
+        ws_stv8(out, dt, pos * out_ld + c, v);
     }
 }
 
-// block (32, 8); softmax over T per (b, c), then attention-weighted mean / std.
+// block (32, 8), 2 channels per thread; ONE pass over (x, logits) with an online softmax per (b, c): running max m and
+// sums rescaled by exp(m_old - m_new); the 8 T-slices are merged through shared memory.
 __global__ void __launch_bounds__(256) astp_stats_kernel(const void* __restrict__ x, const void* __restrict__ lg,
                                                          int dt, int T, int C, long long ld, float* __restrict__ out) {
-    __shared__ float red[3][8][33];
-    const int c = blockIdx.x * 32 + threadIdx.x;
+    __shared__ float red[4][8][65];
+    const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
     const int b = blockIdx.y;
     const bool cv = c < C;
     const long long base = (long long)b * T * ld + c;
-    float m = -INFINITY;
-    if (cv)
-        for (int t = threadIdx.y; t < T; t += 8) m = fmaxf(m, ws_ld(lg, dt, base + (long long)t * ld));
-    red[0][threadIdx.y][threadIdx.x] = m;
-    __syncthreads();
-    m = red[0][0][threadIdx.x];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[0][i][threadIdx.x]);
-    __syncthreads();
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    if (cv)
-        for (int t = threadIdx.y; t < T; t += 8) {
-            const float e = expf(ws_ld(lg, dt, base + (long long)t * ld) - m);
-            const float v = ws_ld(x, dt, base + (long long)t * ld);
-            s0 += e;
-            s1 = fmaf(e, v, s1);
-            s2 = fmaf(e * v, v, s2);
+    float m[2] = {-INFINITY, -INFINITY}, s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+    if (cv) {
+        for (int t = threadIdx.y; t < T; t += 8) {   // this thread's slice maximum (logits only)
+            float l[2];
+            ws_ld2(lg, dt, base + (long long)t * ld, l);
+            m[0] = fmaxf(m[0], l[0]); m[1] = fmaxf(m[1], l[1]);
         }
-    red[0][threadIdx.y][threadIdx.x] = s0;
-    red[1][threadIdx.y][threadIdx.x] = s1;
-    red[2][threadIdx.y][threadIdx.x] = s2;
-    __syncthreads();
-    if (threadIdx.y == 0 && cv) {
-        s0 = s1 = s2 = 0.f;
+        for (int t = threadIdx.y; t < T; t += 8) {   // one expf per element (logits re-read hits L1/L2)
+            float l[2], v[2];
+            ws_ld2(lg, dt, base + (long long)t * ld, l);
+            ws_ld2(x, dt, base + (long long)t * ld, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            s0 += red[0][i][threadIdx.x]; s1 += red[1][i][threadIdx.x]; s2 += red[2][i][threadIdx.x];
+            for (int k = 0; k < 2; ++k) {
+                const float e = expf(l[k] - m[k]);
+                s0[k] += e;
+                s1[k] = fmaf(e, v[k], s1[k]);
+                s2[k] = fmaf(e * v[k], v[k], s2[k]);
+            }
         }
-        const float mean = s1 / s0;
-        const float var = s2 / s0 - mean * mean;
-        out[(long long)b * 2 * C + c] = mean;
-        out[(long long)b * 2 * C + C + c] = sqrtf(fmaxf(var, 1e-7f));
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        red[0][threadIdx.y][2 * threadIdx.x + k] = m[k];
+        red[1][threadIdx.y][2 * threadIdx.x + k] = s0[k];
+        red[2][threadIdx.y][2 * threadIdx.x + k] = s1[k];
+        red[3][threadIdx.y][2 * threadIdx.x + k] = s2[k];
+    }
+    __syncthreads();
+    if (threadIdx.y < 2) {
+        const int col = 2 * threadIdx.x + threadIdx.y, cc = c + threadIdx.y;
+        if (cv && cc < C) {
+            float M = red[0][0][col];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) M = fmaxf(M, red[0][i][col]);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float w = red[0][i][col] == -INFINITY ? 0.f : expf(red[0][i][col] - M);
+                a0 = fmaf(red[1][i][col], w, a0); a1 = fmaf(red[2][i][col], w, a1); a2 = fmaf(red[3][i][col], w, a2);
+            }
+            const float mean = a1 / a0;
+            const float var = a2 / a0 - mean * mean;
+            out[(long long)b * 2 * C + cc] = mean;
+            out[(long long)b * 2 * C + C + cc] = sqrtf(fmaxf(var, 1e-7f));
+        }
     }
 }
 
@@ -277,24 +319,34 @@ const char* ws_launch_tstats(const void* x, int dt, int B, int F, int T, int C, 
 
 const char* ws_launch_linear_rows(const float* in, long long in_ld, const float* in2, long long in2_ld,
                                   int rows_per_b, const float* W, const float* bias, float* out, long long out_ld,
-                                  int R, int I, int O, int act, cudaStream_t s) {
-    dim3 grid((O + 7) / 8, (R + 7) / 8);
-    linear_rows_kernel<<<grid, 256, 0, s>>>(in, in_ld, in2, in2_ld, rows_per_b < 1 ? 1 : rows_per_b, W, bias, out,
-                                            out_ld, R, I, O, act);
+                                  int R, int I, int O, int act, float* workspace, int nsplit, cudaStream_t s) {
+    dim3 grid((O + 31) / 32, (R + 15) / 16, nsplit < 1 ? 1 : nsplit);
+    if (grid.z == 1) {
+        linear_rows_kernel<<<grid, 256, 0, s>>>(in, in_ld, in2, in2_ld, rows_per_b < 1 ? 1 : rows_per_b, W, bias, out,
+                                                out_ld, R, I, O, act);
+        return last_err();
+    }
+    if (workspace == nullptr) return "linear_rows: split-K needs a workspace";
+    linear_rows_kernel<<<grid, 256, 0, s>>>(in, in_ld, in2, in2_ld, rows_per_b < 1 ? 1 : rows_per_b, W, nullptr,
+                                            workspace, O, R, I, O, WS_ACT_NONE);
+    const long long n = (long long)R * O;
+    linear_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(workspace, nsplit, bias, out, out_ld, R, O, act);
     return last_err();
 }
 
 const char* ws_launch_scale_residual(const void* x, long long x_ld, const float* gate, const void* res,
                                      long long res_ld, void* out, long long out_ld, int dt, int B, int T, int C,
                                      cudaStream_t s) {
-    const long long nvec = (long long)B * T * (C / 4);
+    if (C % 8 != 0) return "scale_residual: C must be a multiple of 8";
+    const long long nvec = (long long)B * T * (C / 8);
     scale_residual_kernel<<<grid_for(nvec, 256), 256, 0, s>>>(x, x_ld, gate, res, res_ld, out, out_ld, dt, T, C, nvec);
     return last_err();
 }
 
 const char* ws_launch_astp_stats(const void* x, const void* logits, int dt, int B, int T, int C, long long ld,
                                  float* out, cudaStream_t s) {
-    dim3 grid((C + 31) / 32, B), block(32, 8);
+    if (C % 2 != 0) return "astp_stats: C must be even";
+    dim3 grid((C + 63) / 64, B), block(32, 8);
     astp_stats_kernel<<<grid, block, 0, s>>>(x, logits, dt, T, C, ld, out);
     return last_err();
 }

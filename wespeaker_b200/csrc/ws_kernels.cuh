@@ -14,7 +14,7 @@ const char* ws_launch_tstats(const void* x, int dt, int B, int F, int T, int C, 
 // out[r][o] = act( sum_i W[o][i] * (in[r][i] + in2[r / rows_per_b][i]) + bias[o] ),  fp32 in/out, W fp32 [O][I]
 const char* ws_launch_linear_rows(const float* in, long long in_ld, const float* in2, long long in2_ld,
                                   int rows_per_b, const float* W, const float* bias, float* out, long long out_ld,
-                                  int R, int I, int O, int act, cudaStream_t s);
+                                  int R, int I, int O, int act, float* workspace, int nsplit, cudaStream_t s);
 // SE apply + residual (ecapa_tdnn.py:124,157): out[pos][c] = x[pos][c]*gate[b][c] + res[pos][c]
 const char* ws_launch_scale_residual(const void* x, long long x_ld, const float* gate, const void* res,
                                      long long res_ld, void* out, long long out_ld, int dt, int B, int T, int C,
