@@ -273,6 +273,8 @@ def main():
     emb = None
     for i in range(max(3, args.warmup)):
         emb = model.extract_from_wav(wav_dev[i % nrot])
+    if world > 1:  # warm the communicator: the first NCCL collective pays lazy init
+        parallel.gather_embeddings(torch.cat([emb, emb], 0), 2 * B * world)
     torch.cuda.synchronize()
     launches_per_step = model.last_launches()
 
@@ -349,3 +351,5 @@ def main():
 
 if __name__ == "__main__":
     main()
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()

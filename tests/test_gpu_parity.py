@@ -296,3 +296,71 @@ def test_plda_4096_block_vs_oracle_and_symmetry():
     ref2 = plda_np.llr_matrix(pm, a_t[:130].cpu().numpy(), b_t[:67].cpu().numpy(), 3)
     assert _tol_ok(s2, ref2).all()
     assert p.score_matrix(a_t[:0], b_t[:5], 1).shape == (0, 5)
+
+
+# ------------------------------------------------------------------------------------------ config 4 + drop-in seams
+def test_config4_campplus_variable_length_bucketed():
+    """BASELINE.json configs[3]: CAM++, durations U{1..10} s, bucketed by exact length; parity per utterance against the
+    oracle run at batch 1 with that utterance's own T (the reference has no padding/masking)."""
+    name = "CAMPPlus"
+    rng = np.random.default_rng(2)
+    durs = rng.integers(1, 11, size=12)
+    Ts = [1 + (int(d) * 16000 - 400) // 160 for d in durs]
+    feats = [torch.from_numpy(syn.make_feats(1, T, 80, seed=100 + i)[0]) for i, T in enumerate(Ts)]
+    sd = syn.make_state_dict(name, 0)
+    ref = np.stack([models_torch.forward(name, sd, f[None]).numpy()[0] for f in feats])
+    m32 = from_synthetic(name, 0, precision="fp32")
+    e32 = m32.embed_list(feats, device=DEV).cpu().numpy()
+    assert rel_l2(e32, ref).max() <= 1e-4, rel_l2(e32, ref)
+    mb = from_synthetic(name, 0, precision="bf16")
+    eb = mb.embed_list(feats, device=DEV).cpu().numpy()
+    print(f"config4 CAM++ variable length: fp32 {rel_l2(e32, ref).max():.2e}, bf16 {rel_l2(eb, ref).max():.2e}, T={sorted(set(Ts))}")
+    assert rel_l2(eb, ref).max() <= 3e-2
+
+
+def _write_wav(path, pcm_i16):
+    import wave
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(np.asarray(pcm_i16, dtype="<i2").tobytes())
+
+
+def test_extract_dropin_and_speaker_api(tmp_path):
+    """Seams B2/B3: extract(config, **kwargs) writes Kaldi ark/scp from a raw data list; Speaker.extract_embedding*
+    returns the same vectors; both equal the oracle pipeline (fbank -> CMN -> forward) to fp32 accuracy."""
+    import json
+    import yaml
+    from wespeaker_b200 import kaldi_io
+    from wespeaker_b200.extract import extract
+    from wespeaker_b200.speaker import Speaker
+    name = "ECAPA_TDNN_GLOB_c512"
+    sd_np = syn.make_state_dict(name, 0)
+    mdir = tmp_path / "model"
+    mdir.mkdir()
+    torch.save({k: torch.from_numpy(np.asarray(v)) for k, v in sd_np.items()}, mdir / "avg_model.pt")
+    cfg = {"model": name, "model_args": dict(syn.DEFAULT_MODEL_ARGS[name]),
+           "dataset_args": {"resample_rate": 16000, "fbank_args": {"num_mel_bins": 80, "dither": 1.0}}}
+    (mdir / "config.yaml").write_text(yaml.safe_dump(cfg))
+    wavs = np.concatenate([syn.make_wavs(3, 32000, seed=3), syn.make_wavs(3, 32000, seed=4)])
+    lens = [32000, 32000, 24000, 32000, 24000, 17000]
+    lines = []
+    for i, n in enumerate(lens):
+        _write_wav(tmp_path / f"u{i}.wav", wavs[i, :n].astype(np.int16))
+        lines.append(json.dumps({"key": f"utt{i}", "wav": str(tmp_path / f"u{i}.wav"), "spk": "s"}))
+    (tmp_path / "raw.list").write_text("\n".join(lines) + "\n")
+    ark = tmp_path / "emb" / "xvector.ark"
+    n = extract(str(mdir / "config.yaml"), model_path=str(mdir / "avg_model.pt"), data_type="raw",
+                data_list=str(tmp_path / "raw.list"), embed_ark=str(ark), batch_size=2, precision="fp32")
+    assert n == 6
+    got = kaldi_io.read_vec_scp_file(str(ark)[:-3] + "scp")
+    assert sorted(got) == [f"utt{i}" for i in range(6)]
+    spk = Speaker(str(mdir), precision="fp32")
+    for i, nsamp in enumerate(lens):
+        w = wavs[i, :nsamp]
+        ref = models_torch.forward(name, sd_np, torch.from_numpy(fbank_np.cmn(fbank_np.fbank(w)))[None]).numpy()[0]
+        assert rel_l2(got[f"utt{i}"], ref) <= 1e-3, (i, rel_l2(got[f"utt{i}"], ref))
+        e = spk.extract_embedding(str(tmp_path / f"u{i}.wav")).numpy()
+        assert rel_l2(e, got[f"utt{i}"]) <= 1e-6
+    fb = spk.compute_features(torch.from_numpy(wavs[:1]), cmn=True)[0].cpu().numpy()
+    e_feats = spk.extract_embedding_from_feats([fb], batch_size=4, subseg_cmn=True)
+    assert rel_l2(e_feats[0], got["utt0"]) <= 1e-5

@@ -652,11 +652,22 @@ bool build_campplus(Builder& b) {
             b.conv_simple(sv, hid, b.w.act("w:" + p + ".linear1", w1), 1, 1, 1, 1, 0, 0, 1, 1, e1);
             // CAM context mask (campplus.py:108-115): sigmoid(W2 relu(W1 (mean_T + segmean_100)))
             View hv = hid;
-            b.push([=](cudaStream_t st) { return ws_launch_seg_means(hv.p, dt, B, Tp, bnc, hv.ld, 100, cmean, csegm, st); });
-            b.linear(csegm, bnc, cmean, bnc, nseg, b.w.vec(p + ".cam_layer.linear1.weight"), b.w.vec(p + ".cam_layer.linear1.bias"),
-                     chid, bnc / 2, B * nseg, bnc, bnc / 2, WS_ACT_RELU);
-            b.linear(chid, bnc / 2, nullptr, 0, 1, b.w.vec(p + ".cam_layer.linear2.weight"), b.w.vec(p + ".cam_layer.linear2.bias"),
-                     cgate, growth, B * nseg, bnc / 2, growth, WS_ACT_SIGMOID);
+            {
+                const float* w1c = b.w.vec(p + ".cam_layer.linear1.weight");
+                const float* b1c = b.w.vec(p + ".cam_layer.linear1.bias");
+                const float* w2c = b.w.vec(p + ".cam_layer.linear2.weight");
+                const float* b2c = b.w.vec(p + ".cam_layer.linear2.bias");
+                const size_t cam_smem = (size_t)((bnc / 2) * bnc + nseg * bnc + 16 * bnc + nseg * (bnc / 2) + bnc) * 4;
+                if (cam_smem <= 48 * 1024) {
+                    b.push([=](cudaStream_t st) {
+                        return ws_launch_cam_gate(hv.p, dt, B, Tp, bnc, hv.ld, 100, w1c, b1c, w2c, b2c, bnc / 2, growth, cgate, st);
+                    });
+                } else {  // very long utterances: unfused path
+                    b.push([=](cudaStream_t st) { return ws_launch_seg_means(hv.p, dt, B, Tp, bnc, hv.ld, 100, cmean, csegm, st); });
+                    b.linear(csegm, bnc, cmean, bnc, nseg, w1c, b1c, chid, bnc / 2, B * nseg, bnc, bnc / 2, WS_ACT_RELU);
+                    b.linear(chid, bnc / 2, nullptr, 0, 1, w2c, b2c, cgate, growth, B * nseg, bnc / 2, growth, WS_ACT_SIGMOID);
+                }
+            }
             // linear_local (k3, dilated, no bias) * mask -> appended to the concat buffer
             WsEpi e2{};
             e2.gate = cgate; e2.gate_ld = growth; e2.gate_seg = 100; e2.gate_nseg = nseg;
@@ -713,7 +724,7 @@ Plan* get_plan(ws_engine* e, int B, int T) {
         else ok = build_campplus(b);
     }
     if (!ok) return nullptr;
-    if (e->plans.size() >= 64) e->plans.clear();  // bound memory for many distinct (B,T) shapes
+    if (e->plans.size() >= 96) e->plans.erase(e->plans.begin());  // bound memory for many distinct (B,T) shapes
     Plan* raw = p.get();
     e->plans[key] = std::move(p);
     return raw;

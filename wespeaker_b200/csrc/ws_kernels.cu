@@ -292,6 +292,85 @@ __global__ void __launch_bounds__(256) seg_means_kernel(const void* __restrict__
     if (threadIdx.y == 0 && cv) mean[(long long)b * C + c] = total / (float)T;
 }
 
+// CAM++ context gate in one launch (campplus.py:108-135): per utterance, mean over T + per-100-frame segment means of
+// h (C=128), then for every segment  gate = sigmoid(W2 relu(W1 (mean + segmean) + b1) + b2).  One block per utterance;
+// replaces seg_means + 2 tiny FC launches (3 latency-bound launches per dense layer, 52 layers).
+template <int C, int H, int G>
+__global__ void __launch_bounds__(256) cam_gate_kernel(const void* __restrict__ x, int dt, int T, long long ld, int seg_len,
+                                                       const float* __restrict__ W1, const float* __restrict__ b1,
+                                                       const float* __restrict__ W2, const float* __restrict__ b2,
+                                                       float* __restrict__ gate /*[B][nseg][G]*/) {
+    extern __shared__ float sm[];
+    const int nseg = (T + seg_len - 1) / seg_len;
+    float* w1s = sm;                  // [H][C] staged once (all loads in flight) instead of latency-bound __ldg chains
+    float* ssum = w1s + H * C;        // [nseg][C] segment sums -> context vectors
+    float* part = ssum + nseg * C;    // [16][C] partial sums of the 16 T-slices
+    float* hid = part + 16 * C;       // [nseg][H]
+    float* tot = hid + nseg * H;      // [C]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    {
+        const float4* src = reinterpret_cast<const float4*>(W1);
+        float4* dst = reinterpret_cast<float4*>(w1s);
+        for (int i = tid; i < H * C / 4; i += 256) dst[i] = __ldg(src + i);
+    }
+    const int c8 = (tid & 15) * 8, ts = tid >> 4;  // 16 groups of 8 channels x 16 T-slices
+    const long long base = (long long)b * T * ld;
+    for (int sg = 0; sg < nseg; ++sg) {
+        const int ta = sg * seg_len, tb = min(T, ta + seg_len);
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int t = ta + ts; t < tb; t += 16) {
+            float v[8];
+            ws_ldv8(x, dt, base + (long long)t * ld + c8, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) part[ts * C + c8 + k] = a[k];
+        __syncthreads();
+        if (tid < C) {
+            float t_ = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t_ += part[i * C + tid];
+            ssum[sg * C + tid] = t_;
+        }
+        __syncthreads();
+    }
+    if (tid < C) {
+        float t_ = 0.f;
+        for (int sg = 0; sg < nseg; ++sg) t_ += ssum[sg * C + tid];
+        tot[tid] = t_ / (float)T;
+    }
+    __syncthreads();
+    for (int i = tid; i < nseg * C; i += 256) {
+        const int sg = i / C, c = i % C;
+        const int cnt = min(T, (sg + 1) * seg_len) - sg * seg_len;   // ceil_mode partial window divides by its own count
+        ssum[i] = ssum[i] / (float)cnt + tot[c];
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int o = warp; o < nseg * H; o += 8) {       // hidden = relu(W1 ctx + b1): one warp per output, lanes over C
+        const int sg = o / H, h = o % H;
+        float a = 0.f;
+#pragma unroll
+        for (int c = lane; c < C; c += 32) a = fmaf(w1s[h * C + c], ssum[sg * C + c], a);
+        a = warp_sum(a);
+        if (lane == 0) hid[o] = fmaxf(a + b1[h], 0.f);
+    }
+    __syncthreads();
+    for (int o = tid; o < nseg * G; o += 256) {      // gate: one thread per output, W2 row (H floats) read as float4
+        const int sg = o / G, g = o % G;
+        const float4* w = reinterpret_cast<const float4*>(W2 + g * H);
+        float a = b2[g];
+#pragma unroll
+        for (int h4 = 0; h4 < H / 4; ++h4) {
+            const float4 q = __ldg(w + h4);
+            a = fmaf(q.x, hid[sg * H + 4 * h4], a); a = fmaf(q.y, hid[sg * H + 4 * h4 + 1], a);
+            a = fmaf(q.z, hid[sg * H + 4 * h4 + 2], a); a = fmaf(q.w, hid[sg * H + 4 * h4 + 3], a);
+        }
+        gate[((long long)b * nseg + sg) * G + g] = 1.f / (1.f + expf(-a));
+    }
+}
+
 inline const char* last_err() {
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
@@ -372,5 +451,16 @@ const char* ws_launch_seg_means(const void* x, int dt, int B, int T, int C, long
                                 float* segmean, cudaStream_t s) {
     dim3 grid((C + 31) / 32, B), block(32, 8);
     seg_means_kernel<<<grid, block, 0, s>>>(x, dt, T, C, ld, seg_len, mean, segmean);
+    return last_err();
+}
+
+const char* ws_launch_cam_gate(const void* x, int dt, int B, int T, int C, long long ld, int seg_len, const float* W1,
+                               const float* b1, const float* W2, const float* b2, int H, int G, float* gate,
+                               cudaStream_t s) {
+    if (C != 128 || H != 64 || G != 32) return "cam_gate: expected C=128, H=64, G=32 (CAM++ bn_channels / reduction / growth)";
+    const int nseg = (T + seg_len - 1) / seg_len;
+    const size_t smem = (size_t)(H * C + nseg * C + 16 * C + nseg * H + C) * sizeof(float);
+    if (smem > 48 * 1024) return "cam_gate: utterance too long for the shared-memory context buffer";
+    cam_gate_kernel<128, 64, 32><<<B, 256, smem, s>>>(x, dt, T, ld, seg_len, W1, b1, W2, b2, gate);
     return last_err();
 }

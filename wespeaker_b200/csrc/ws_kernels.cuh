@@ -32,6 +32,11 @@ const char* ws_launch_stem(const float* feats, const float* w9 /*[Cout][9]*/, co
 const char* ws_launch_seg_means(const void* x, int dt, int B, int T, int C, long long ld, int seg_len, float* mean,
                                 float* segmean /*[B][nseg][C]*/, cudaStream_t s);
 
+// fused CAM context gate: gate[b][seg][g] = sigmoid(W2 relu(W1 (mean_T(x) + segmean(x)) + b1) + b2)
+const char* ws_launch_cam_gate(const void* x, int dt, int B, int T, int C, long long ld, int seg_len, const float* W1,
+                               const float* b1, const float* W2, const float* b2, int H, int G, float* gate,
+                               cudaStream_t s);
+
 // ---- fbank + CMN (ws_fbank.cu)
 // wav: [B][wav_ld] samples in int16 range (float32 if wav_is_i16 == 0 else int16).  feats fp32 [B][T][80].
 const char* ws_launch_fbank(const void* wav, int wav_is_i16, long long wav_ld, int nsamples, int B, int T,

@@ -213,6 +213,42 @@ class B200SpeakerModel(torch.nn.Module):
                                                 out.data_ptr()), "ws_engine_extract_wav_host")
         return out
 
+    # ------------------------------------------------------------------ variable-length batches (BASELINE config 4)
+    def embed_list(self, feats_list, max_batch: int = 64, device=None):
+        """Embeddings for utterances of DIFFERENT lengths.  The reference has no length masking (test sets
+        run at batch 1), so padding would change results; instead utterances are bucketed by exact frame count and each
+        bucket runs as one batch (one cached plan / CUDA graph per (B,T)).  feats_list: list of (T_i, feat_dim) tensors.
+        Returns (N, embed_dim) in input order, on the device of the inputs (CUDA if `device` is given)."""
+        if len(feats_list) == 0:
+            return torch.empty((0, self.embed_dim))
+        buckets = {}
+        for i, f in enumerate(feats_list):
+            buckets.setdefault(int(f.shape[0]), []).append(i)
+        dev = torch.device(device) if device is not None else feats_list[0].device
+        out = torch.empty((len(feats_list), self.embed_dim), dtype=torch.float32, device=dev)
+        for T, idx in sorted(buckets.items()):
+            for s0 in range(0, len(idx), max_batch):
+                sel = idx[s0:s0 + max_batch]
+                x = torch.stack([feats_list[i] for i in sel]).to(dev)
+                out[torch.as_tensor(sel, device=dev)] = self.embed(x).to(dev)
+        return out
+
+    def extract_from_wav_list(self, wavs, window_type: str = "hamming", max_batch: int = 64, device=None):
+        """Same bucketing for raw waveforms (1-D tensors of different lengths, int16 or int16-range float32)."""
+        if len(wavs) == 0:
+            return torch.empty((0, self.embed_dim))
+        buckets = {}
+        for i, w in enumerate(wavs):
+            buckets.setdefault(int(w.shape[-1]), []).append(i)
+        dev = torch.device(device) if device is not None else wavs[0].device
+        out = torch.empty((len(wavs), self.embed_dim), dtype=torch.float32, device=dev)
+        for n, idx in sorted(buckets.items()):
+            for s0 in range(0, len(idx), max_batch):
+                sel = idx[s0:s0 + max_batch]
+                x = torch.stack([wavs[i].reshape(-1) for i in sel]).to(dev)
+                out[torch.as_tensor(sel, device=dev)] = self.extract_from_wav(x, window_type=window_type).to(dev)
+        return out
+
     def last_launches(self) -> int:
         return int(_lib.load().ws_engine_last_launches(self._engine)) if self._engine is not None else 0
 
