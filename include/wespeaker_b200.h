@@ -26,7 +26,8 @@ const char* ws_last_error(void);
  *      and is the B200 back-end for `SpeakerModel::ExtractEmbedding` (runtime/core/speaker/speaker_model.h:25-32).
  * model_name: ECAPA_TDNN_c512 | ECAPA_TDNN_GLOB_c512 | ECAPA_TDNN_c1024 | ECAPA_TDNN_GLOB_c1024 | ResNet18 |
  *             ResNet34 | CAMPPlus.
- * precision:  "fp32" (exact IEEE fp32 FFMA path, parity <= 1e-4), "tf32", "bf16", "fp16" (tcgen05 tensor cores). */
+ * precision:  "fp32" (exact IEEE fp32 FFMA path, parity <= 1e-4), "tf32x3" (tcgen05 with 3xTF32 error compensation,
+ *             fp32-grade accuracy), "tf32", "bf16", "fp16" (tcgen05 tensor cores). */
 int ws_engine_create(const char* model_name, const char* precision, int feat_dim, int embed_dim, int device,
                      ws_engine** out);
 /* options: "two_emb_layer", "emb_bn" (model_args), "cuda_graph" (default 1), "force_simt" (debug cross-check),
@@ -80,6 +81,10 @@ typedef struct {
     long long out_ld;
     int dtype;                /* 0 fp32 (tf32 MMA when use_tc), 1 bf16, 2 fp16 */
     int use_tc;               /* 0: fp32 FFMA kernel, 1: tcgen05 v1 kernel, 2: persistent tcgen05 v2 kernel */
+    /* 3xTF32 (dtype 0, use_tc 2): low parts v - tf32_trunc(v) of x and w (inputs) and of out (written); all NULL = off */
+    const void* x_lo;
+    const void* w_lo;
+    void* out_lo;
 } ws_conv_desc;
 int ws_conv(const ws_conv_desc* d, void* stream);
 

@@ -39,6 +39,8 @@ struct WsEpi {
     long long out2_ld;
     const void* add2;
     long long add2_ld;
+    void* out_lo;   // 3xTF32 mode: out_lo = out - tf32_trunc(out) (same ld); null otherwise
+    void* out2_lo;
     int dtype;  // dtype of res/out/out2/add2 (activation dtype)
     int FT;     // F*T of the output tensor (pos / FT = b)
     int T;      // T of the output tensor   (pos % T = t)
@@ -91,6 +93,9 @@ __device__ __forceinline__ uint32_t ws_f_to_16(float v, int dt) {
 __device__ __forceinline__ float ws_16_to_f(uint32_t u, int dt) {
     return dt == WS_BF16 ? ws_bf16_bits_to_f(u) : ws_f16_bits_to_f(u);
 }
+
+// low part of the 3xTF32 split: v - tf32_trunc(v) (exact in fp32; the tensor core truncates fp32 operands to tf32)
+__device__ __forceinline__ float ws_tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
 // scalar typed load/store (any alignment)
 __device__ __forceinline__ float ws_ld(const void* p, int dt, long long i) {
@@ -227,10 +232,11 @@ __device__ __forceinline__ void ws_epilogue(const WsEpi& e, long long pos, int c
 // Activations are channels-last [B][F][T][C]; one "tap" contributes  sum_c X_src[b, f+df, t+dt, c0+c] * W[co][wk+c]
 // for c in [0, nch).  Strided convs use parity-plane source views so taps stay unit-stride.
 #define WS_MAX_SRC 4
-#define WS_MAX_TAPS 64
+#define WS_MAX_TAPS 52
 
 struct WsSrc {
     const void* ptr;
+    const void* ptr_lo;      // 3xTF32 mode: x - tf32_trunc(x) twin of the same geometry (or null)
     int B, F, T, C;          // extents of the (possibly strided) view; reads outside are zero (conv padding)
     long long sB, sF, sT;    // element strides
 };
@@ -272,10 +278,11 @@ struct WsTcParams {
 // persistent / TMEM-double-buffered / TMA-store variant (ws_gemm_tc2.cu)
 struct WsTc2Params {
     CUtensorMap amap[WS_MAX_SRC];
+    CUtensorMap amap_lo[WS_MAX_SRC];  // 3xTF32: low parts of the activations
     CUtensorMap wmap;
-    CUtensorMap omap;    // output tile store
-    CUtensorMap o2map;   // second output (Res2 "out + next group"), if has_out2
-    CUtensorMap imap;    // epilogue input tile (residual, or add2 when has_out2), if has_epin
+    CUtensorMap wmap_lo;              // 3xTF32: low parts of the weights
+    CUtensorMap omap[4];  // output tile stores: [0] out, then (if split) out_lo, (if has_out2) out2, (both) out2_lo
+    CUtensorMap imap;     // epilogue input tile (residual, or add2 when has_out2), if has_epin
     WsTcTap taps[WS_MAX_TAPS];
     int ntaps, nk_total;
     int bk_bytes;
@@ -287,6 +294,8 @@ struct WsTc2Params {
     int kind;
     int panel_bytes;     // 128 or 64: row bytes of one swizzled staging panel
     int has_out2, has_epin;
+    int nsplit;          // 1, or 3 = 3xTF32 error-compensated passes (x_lo*W, x*W_lo, x*W)
+    int nout;            // number of output tiles staged per tile (1..4)
     int grid, smem_bytes;
     WsEpi epi;
 };

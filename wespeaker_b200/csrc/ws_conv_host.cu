@@ -18,6 +18,7 @@ const std::string& get_err() { return g_err; }
 
 void fill_epi_out(WsEpi& e, const View& out) {
     e.out = out.p;
+    e.out_lo = out.plo;
     e.out_ld = out.ld;
     e.dtype = out.dt;
     e.FT = out.F * out.T;
@@ -48,6 +49,7 @@ int add_conv_taps(ConvSpec& spec, const View& x, int kf, int kt, int dil_f, int 
             const int pf = ((offf % stride_f) + stride_f) % stride_f, pt = ((offt % stride_t) + stride_t) % stride_t;
             WsSrc v;
             v.ptr = (const char*)x.p + ((size_t)pf * sF + (size_t)pt * sT) * es;
+            v.ptr_lo = x.plo ? (const char*)x.plo + ((size_t)pf * sF + (size_t)pt * sT) * es : nullptr;
             v.B = x.B;
             v.F = (x.F - pf + stride_f - 1) / stride_f;
             v.T = (x.T - pt + stride_t - 1) / stride_t;
@@ -223,7 +225,16 @@ static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported) {
     q->B = v1.B; q->F = v1.F; q->T = v1.T; q->kind = v1.kind;
     q->has_out2 = e.out2 != nullptr;
     q->has_epin = (e.res != nullptr) || (e.out2 != nullptr);
-    const int nstage_bufs = 1 + (q->has_out2 ? 1 : 0) + (q->has_epin ? 1 : 0);
+    q->nsplit = s.split ? 3 : 1;
+    if (s.split) {
+        if (s.dt != WS_F32 || s.W_lo == nullptr || e.out_lo == nullptr || (q->has_out2 && e.out2_lo == nullptr)) {
+            set_err("tc conv: 3xTF32 needs fp32 activations with lo twins for W / out / out2"); return false;
+        }
+        for (int i = 0; i < s.nsrc; ++i)
+            if (s.src[i].ptr_lo == nullptr) { set_err("tc conv: 3xTF32 source without a lo twin"); return false; }
+    }
+    q->nout = (s.split ? 2 : 1) * (q->has_out2 ? 2 : 1);
+    const int nstage_bufs = q->nout + (q->has_epin ? 1 : 0);
     const int budget = ws_tc2_max_smem() - 1024;
     // widest N tile whose staging + >=3 ring stages fit (>=2 accepted as a last resort)
     int bn = 0, nst = 0;
@@ -257,6 +268,16 @@ static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported) {
         cuuint64_t str[1] = {(cuuint64_t)s.Ktot * es};
         cuuint32_t box[2] = {(cuuint32_t)bk_elems, (cuuint32_t)bn};
         if (!encode_map(&q->wmap, s.dt, s.W, 2, dims, str, box, q->bk_bytes)) return false;
+        q->wmap_lo = q->wmap;
+        if (s.split && !encode_map(&q->wmap_lo, s.dt, s.W_lo, 2, dims, str, box, q->bk_bytes)) return false;
+    }
+    for (int i = 0; i < WS_MAX_SRC; ++i) q->amap_lo[i] = q->amap[i];
+    if (s.split) {   // lo twins of the activation maps: same geometry, different base pointer
+        ConvSpec lo = s;
+        for (int i = 0; i < lo.nsrc; ++i) lo.src[i].ptr = lo.src[i].ptr_lo;
+        WsTcParams v1lo;
+        if (!build_tc(lo, &v1lo)) return false;
+        for (int i = 0; i < WS_MAX_SRC; ++i) q->amap_lo[i] = v1lo.amap[i];
     }
     // output / epilogue-input maps: same tile geometry as the A maps over the output positions
     const bool flat = s.dense_pointwise;
@@ -273,14 +294,18 @@ static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported) {
         }
         return encode_map(m, s.dt, ptr, 4, dims, str, box, q->panel_bytes);
     };
-    if (!out_map(&q->omap, e.out, e.out_ld)) return false;
+    int oi = 0;
+    if (!out_map(&q->omap[oi++], e.out, e.out_ld)) return false;
+    if (s.split && !out_map(&q->omap[oi++], e.out_lo, e.out_ld)) return false;
     if (q->has_out2) {
-        if (!out_map(&q->o2map, e.out2, e.out2_ld) || !out_map(&q->imap, e.add2, e.add2_ld)) return false;
+        if (!out_map(&q->omap[oi++], e.out2, e.out2_ld)) return false;
+        if (s.split && !out_map(&q->omap[oi++], e.out2_lo, e.out2_ld)) return false;
+        if (!out_map(&q->imap, e.add2, e.add2_ld)) return false;
     } else if (q->has_epin) {
         if (!out_map(&q->imap, e.res, e.res_ld)) return false;
     }
-    if (!q->has_out2) q->o2map = q->omap;
-    if (!q->has_epin) q->imap = q->omap;
+    for (; oi < 4; ++oi) q->omap[oi] = q->omap[0];
+    if (!q->has_epin) q->imap = q->omap[0];
     if (g_num_sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -336,7 +361,7 @@ extern "C" int ws_conv(const ws_conv_desc* d, void* stream) {
     using namespace ws;
     if (d == nullptr) { set_err("ws_conv: null descriptor"); return 1; }
     View x;
-    x.p = const_cast<void*>(d->x); x.B = d->B; x.F = d->F; x.T = d->T; x.C = d->Cin; x.ld = d->x_ld; x.dt = d->dtype;
+    x.p = const_cast<void*>(d->x); x.plo = const_cast<void*>(d->x_lo); x.B = d->B; x.F = d->F; x.T = d->T; x.C = d->Cin; x.ld = d->x_ld; x.dt = d->dtype;
     ConvSpec s;
     s.dt = d->dtype;
     int Fo = 0, To = 0;
@@ -344,11 +369,12 @@ extern "C" int ws_conv(const ws_conv_desc* d, void* stream) {
                                 &Fo, &To);
     if (K < 0) { set_err("ws_conv: too many source planes"); return 1; }
     s.W = d->w; s.Ktot = K; s.Cout = d->Cout;
+    s.W_lo = d->w_lo; s.split = (d->x_lo != nullptr);
     s.B = d->B; s.F = Fo; s.T = To;
     s.dense_pointwise = (d->kf == 1 && d->kt == 1 && d->stride_f == 1 && d->stride_t == 1 && d->pad_f == 0 &&
                          d->pad_t == 0);
     View o;
-    o.p = d->out; o.B = d->B; o.F = Fo; o.T = To; o.C = d->Cout; o.ld = d->out_ld; o.dt = d->dtype;
+    o.p = d->out; o.plo = d->out_lo; o.B = d->B; o.F = Fo; o.T = To; o.C = d->Cout; o.ld = d->out_ld; o.dt = d->dtype;
     fill_epi_out(s.epi, o);
     s.epi.bias = d->bias; s.epi.act1 = d->act1; s.epi.scale = d->scale; s.epi.shift = d->shift;
     s.epi.res = d->res; s.epi.res_ld = d->res_ld; s.epi.act2 = d->act2;

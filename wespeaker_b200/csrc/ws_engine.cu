@@ -59,6 +59,8 @@ struct ws_engine {
     int feat_dim = 80, embed_dim = 0, device = 0;
     int act_dt = WS_F32;
     int use_tc = 0;  // 0 FFMA, 1 tcgen05 v1, 2 tcgen05 v2
+    bool split = false;  // 3xTF32: fp32 activations/weights carry lo twins, GEMMs run 3 error-compensated passes
+    std::map<const void*, const void*> wlo;  // packed weight -> its lo twin
     std::map<std::string, long long> opts;
     std::map<std::string, HostT> sd;
     bool finalized = false;
@@ -130,7 +132,22 @@ struct Weights {
     void* act(const std::string& id, const std::vector<float>& v) {
         void* c;
         if (cached(id, &c)) return c;
-        if (e.act_dt == WS_F32) return upload(id, v.data(), v.size() * 4);
+        if (e.act_dt == WS_F32) {
+            void* hi = upload(id, v.data(), v.size() * 4);
+            if (e.split && hi != nullptr) {
+                std::vector<float> lo(v.size());
+                for (size_t i = 0; i < v.size(); ++i) {
+                    uint32_t u;
+                    memcpy(&u, &v[i], 4);
+                    u &= 0xffffe000u;
+                    float t;
+                    memcpy(&t, &u, 4);
+                    lo[i] = v[i] - t;
+                }
+                e.wlo[hi] = upload(id + ":lo", lo.data(), lo.size() * 4);
+            }
+            return hi;
+        }
         std::vector<unsigned short> h(v.size());
         for (size_t i = 0; i < v.size(); ++i)
             h[i] = e.act_dt == WS_BF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v[i]))
@@ -202,19 +219,27 @@ struct Builder {
         View v;
         v.B = B; v.F = F; v.T = T; v.C = C; v.ld = C; v.dt = e.act_dt;
         v.p = raw((size_t)B * F * T * C * ws_esize(e.act_dt));
+        if (e.split) v.plo = raw((size_t)B * F * T * C * 4);
         return v;
     }
     float* f32(size_t n) { return (float*)raw(n * 4); }
     void push(Op op) { p.ops.push_back(std::move(op)); }
-    void conv(const ConvSpec& s) {
+    void conv(const ConvSpec& s_in) {
         if (!good()) return;
+        ConvSpec s = s_in;
+        if (e.split) {
+            auto it = e.wlo.find(s.W);
+            if (it == e.wlo.end()) { set_err("internal: 3xTF32 weight without a lo twin"); ok = false; return; }
+            s.W_lo = it->second;
+            s.split = true;
+        }
         Op op;
         if (!make_conv_op(s, e.use_tc, &op)) { ok = false; return; }
         push(std::move(op));
     }
     static WsSrc src_of(const View& v) {
         WsSrc s;
-        s.ptr = v.p; s.B = v.B; s.F = v.F; s.T = v.T; s.C = v.C;
+        s.ptr = v.p; s.ptr_lo = v.plo; s.B = v.B; s.F = v.F; s.T = v.T; s.C = v.C;
         s.sT = v.ld; s.sF = (long long)v.T * v.ld; s.sB = (long long)v.F * v.T * v.ld;
         return s;
     }
@@ -274,9 +299,10 @@ bool build_ecapa(Builder& b) {
     {
         const float* fin = b.p.feats_in;
         void* xo = x0.p;
+        float* xlo = (float*)x0.plo;
         const int dt = e.act_dt;
         const long long n = (long long)B * T * Fd;
-        b.push([=](cudaStream_t s) { return ws_launch_convert(fin, xo, dt, n, s); });
+        b.push([=](cudaStream_t s) { return ws_launch_convert(fin, xo, xlo, dt, n, s); });
     }
     // Conv1dReluBn (ecapa_tdnn.py:85-106): bn(relu(conv(x)+bias))
     auto conv_relu_bn = [&](const std::string& pfx, const View& x, const View& out, int k, int dil, int pad) {
@@ -309,7 +335,7 @@ bool build_ecapa(Builder& b) {
             ep.shift = b.w.f32("bnh:" + bp, h);
             if (i < 6) {
                 View nx = tA.ch((i + 1) * w8, w8);
-                ep.out2 = sc[i & 1].p; ep.out2_ld = sc[i & 1].ld;
+                ep.out2 = sc[i & 1].p; ep.out2_lo = sc[i & 1].plo; ep.out2_ld = sc[i & 1].ld;
                 ep.add2 = nx.p; ep.add2_ld = nx.ld;
             }
             const View src = (i == 0) ? tA.ch(0, w8) : sc[(i - 1) & 1];
@@ -347,7 +373,7 @@ bool build_ecapa(Builder& b) {
             View o = cat.ch((L - 2) * C, C), xi = xin, tc = tC;
             const int dt = e.act_dt;
             b.push([=](cudaStream_t s) {
-                return ws_launch_scale_residual(tc.p, tc.ld, segate, xi.p, xi.ld, o.p, o.ld, dt, B, T, C, s);
+                return ws_launch_scale_residual(tc.p, tc.ld, segate, xi.p, xi.ld, o.p, (float*)o.plo, o.ld, dt, B, T, C, s);
             });
             xin = o;
         }
@@ -485,7 +511,8 @@ View stem(Builder& b, const std::string& convkey, const std::string& bnkey, View
     const float* fin = b.p.feats_in;
     const int dt = b.e.act_dt;
     void* op = o.p;
-    b.push([=](cudaStream_t st) { return ws_launch_stem(fin, wd, hd, op, dt, B, T, Fd, co, st); });
+    float* olo = (float*)o.plo;
+    b.push([=](cudaStream_t st) { return ws_launch_stem(fin, wd, hd, op, olo, dt, B, T, Fd, co, st); });
     return o;
 }
 
@@ -495,7 +522,10 @@ bool build_resnet(Builder& b) {
     const int B = b.p.B, T = b.p.T, Fd = e.feat_dim, E = e.embed_dim, m = 32;
     const size_t big = (size_t)B * Fd * T * m;
     View bufs[3];
-    for (int i = 0; i < 3; ++i) { bufs[i].dt = e.act_dt; bufs[i].p = b.raw(big * ws_esize(e.act_dt)); }
+    for (int i = 0; i < 3; ++i) {
+        bufs[i].dt = e.act_dt; bufs[i].p = b.raw(big * ws_esize(e.act_dt));
+        if (e.split) bufs[i].plo = b.raw(big * 4);
+    }
     if (!b.good()) return false;
     View cur = stem(b, "conv1.weight", "bn1", bufs[0]);
     int ci = 0;
@@ -547,7 +577,10 @@ bool build_campplus(Builder& b) {
     const int B = b.p.B, T = b.p.T, Fd = e.feat_dim, E = e.embed_dim, m = 32;
     const size_t big = (size_t)B * Fd * T * m;
     View bufs[3];
-    for (int i = 0; i < 3; ++i) { bufs[i].dt = e.act_dt; bufs[i].p = b.raw(big * ws_esize(e.act_dt)); }
+    for (int i = 0; i < 3; ++i) {
+        bufs[i].dt = e.act_dt; bufs[i].p = b.raw(big * ws_esize(e.act_dt));
+        if (e.split) bufs[i].plo = b.raw(big * 4);
+    }
     if (!b.good()) return false;
     // FCM head (campplus.py:282-330): frequency-only striding
     View cur = stem(b, "head.conv1.weight", "head.bn1", bufs[0]);
@@ -608,6 +641,7 @@ bool build_campplus(Builder& b) {
             const int pt = ((off % 2) + 2) % 2;
             WsSrc v = Builder::src_of(y);
             v.ptr = (const char*)y.p + (size_t)pt * y.ld * ws_esize(e.act_dt);
+            if (y.plo) v.ptr_lo = (const char*)y.plo + (size_t)pt * y.ld * ws_esize(e.act_dt);
             v.T = (y.T - pt + 1) / 2;
             v.sT = y.ld * 2;
             int si = -1;
@@ -644,7 +678,7 @@ bool build_campplus(Builder& b) {
             View sv = scratch; sv.C = cin; sv.ld = cin;
             const float* s1d = b.w.f32("bns:" + p + ".n1", s1);
             const float* h1d = b.w.f32("bnh:" + p + ".n1", h1);
-            b.push([=](cudaStream_t st) { return ws_launch_bnrelu(xs.p, xs.ld, s1d, h1d, sv.p, sv.ld, dt, npos, cin, st); });
+            b.push([=](cudaStream_t st) { return ws_launch_bnrelu(xs.p, xs.ld, s1d, h1d, sv.p, (float*)sv.plo, sv.ld, dt, npos, cin, st); });
             // linear1 (1x1, no bias) + nonlinear2 (BN folded) + ReLU -> hid
             WsEpi e1{};
             e1.bias = b.w.f32("bnh:" + p + ".n2", h2);
@@ -684,7 +718,7 @@ bool build_campplus(Builder& b) {
         const float* sd_ = b.w.f32("bns:" + tp, s);
         const float* hd_ = b.w.f32("bnh:" + tp, h);
         const int cc = cmax[bl];
-        b.push([=](cudaStream_t st) { return ws_launch_bnrelu(xs.p, xs.ld, sd_, hd_, sv.p, sv.ld, dt, npos, cc, st); });
+        b.push([=](cudaStream_t st) { return ws_launch_bnrelu(xs.p, xs.ld, sd_, hd_, sv.p, (float*)sv.plo, sv.ld, dt, npos, cc, st); });
         WsEpi et{};
         View dst = (bl < 2) ? X[bl + 1].ch(0, cmax[bl] / 2) : Xf;
         b.conv_simple(sv, dst, b.w.act("w:" + tp, wt), 1, 1, 1, 1, 0, 0, 1, 1, et);
@@ -862,9 +896,10 @@ int ws_engine_create(const char* model_name, const char* precision, int feat_dim
     const std::string p = e->prec;
     if (p == "fp32") { e->act_dt = WS_F32; e->use_tc = 0; }
     else if (p == "tf32") { e->act_dt = WS_F32; e->use_tc = 2; }
+    else if (p == "tf32x3") { e->act_dt = WS_F32; e->use_tc = 2; e->split = true; }
     else if (p == "bf16") { e->act_dt = WS_BF16; e->use_tc = 2; }
     else if (p == "fp16") { e->act_dt = WS_F16; e->use_tc = 2; }
-    else { set_err("unknown precision (fp32|tf32|bf16|fp16): " + p); return 1; }
+    else { set_err("unknown precision (fp32|tf32x3|tf32|bf16|fp16): " + p); return 1; }
     if (feat_dim % 8 != 0) { set_err("feat_dim must be a multiple of 8"); return 1; }
     WS_CKS(ws_tc_init());
     WS_CKS(ws_tc2_init());
@@ -879,7 +914,7 @@ int ws_engine_set_option(ws_engine* e, const char* key, long long value) {
     if (!e || !key) { set_err("ws_engine_set_option: null argument"); return 1; }
     const std::string k = key;
     if (k == "force_simt") { if (value) e->use_tc = 0; }
-    else if (k == "tc_version") { if (e->use_tc) e->use_tc = value >= 2 ? 2 : 1; }
+    else if (k == "tc_version") { if (e->use_tc && !e->split) e->use_tc = value >= 2 ? 2 : 1; }
     else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph") { set_err("unknown option " + k); return 1; }
     e->opts[k] = value;
     e->plans.clear();

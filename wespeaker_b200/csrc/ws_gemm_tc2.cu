@@ -187,9 +187,8 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
     const int npanels = p.bn / panel_cols;
     const int tile_out_bytes = 128 * p.bn * es;          // one full output tile in staging
     const uint32_t ring = base;
-    const uint32_t stg_out = ring + (uint32_t)(p.nstages * stage_bytes);
-    const uint32_t stg_out2 = stg_out + (uint32_t)tile_out_bytes;                        // only if p.has_out2
-    const uint32_t stg_in = stg_out + (uint32_t)((p.has_out2 ? 2 : 1) * tile_out_bytes);  // only if p.has_epin
+    const uint32_t stg_out = ring + (uint32_t)(p.nstages * stage_bytes);                  // p.nout output tiles
+    const uint32_t stg_in = stg_out + (uint32_t)(p.nout * tile_out_bytes);                // only if p.has_epin
     const uint32_t s_par = stg_in + (uint32_t)(p.has_epin ? tile_out_bytes : 0);          // 3 * bn floats
     const uint32_t bar_full = smem_u32(&s_bar[0]);
     const uint32_t bar_empty = smem_u32(&s_bar[WS_TC_MAX_STAGES]);
@@ -202,8 +201,7 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < WS_MAX_SRC; ++i) prefetch_tmap(&p.amap[i]);
         prefetch_tmap(&p.wmap);
-        prefetch_tmap(&p.omap);
-        if (p.has_out2) prefetch_tmap(&p.o2map);
+        for (int i = 0; i < p.nout; ++i) prefetch_tmap(&p.omap[i]);
         if (p.has_epin) prefetch_tmap(&p.imap);
     }
     if (warp == 1 && lane == 0) {
@@ -243,15 +241,20 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
                 const int b0 = tt << p.bb_log2;
                 for (int tp = 0; tp < p.ntaps; ++tp) {
                     const WsTcTap tap = p.taps[tp];
-                    for (int kb = 0; kb < tap.nkb; ++kb, ++it) {
-                        const int s = it % p.nstages;
-                        const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
-                        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                        mbar_expect_tx(bar_full + 8 * s, (uint32_t)stage_bytes);
-                        const uint32_t sa = ring + (uint32_t)(s * stage_bytes);
-                        tma_load_4d(sa, &p.amap[tap.map], bar_full + 8 * s, tap.c0 + kb * bk_elems, t0 + tap.dt,
-                                    f0 + tap.df, b0);
-                        tma_load_2d(sa + (uint32_t)a_bytes, &p.wmap, bar_full + 8 * s, tap.wk + kb * bk_elems, n0);
+                    for (int kb = 0; kb < tap.nkb; ++kb) {
+                        // 3xTF32: three passes per k-block, small terms first: x_lo*W, x*W_lo, x*W (fp32 operands are
+                        // truncated to tf32 by the tensor core, so x and W themselves serve as the high parts)
+                        for (int ps = 3 - p.nsplit; ps < 3; ++ps, ++it) {
+                            const int s = it % p.nstages;
+                            const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+                            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                            mbar_expect_tx(bar_full + 8 * s, (uint32_t)stage_bytes);
+                            const uint32_t sa = ring + (uint32_t)(s * stage_bytes);
+                            tma_load_4d(sa, ps == 0 ? &p.amap_lo[tap.map] : &p.amap[tap.map], bar_full + 8 * s,
+                                        tap.c0 + kb * bk_elems, t0 + tap.dt, f0 + tap.df, b0);
+                            tma_load_2d(sa + (uint32_t)a_bytes, ps == 1 ? &p.wmap_lo : &p.wmap, bar_full + 8 * s,
+                                        tap.wk + kb * bk_elems, n0);
+                        }
                     }
                 }
                 // epilogue-input tile (residual / add2): issued after this tile's operand loads so that waiting for
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
                 mbar_wait(bar_tempty + 8 * buf, (((uint32_t)j >> 1) & 1u) ^ 1u);  // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * p.bn);
-                for (int kit = 0; kit < p.nk_total; ++kit, ++it) {
+                for (int kit = 0; kit < p.nk_total * p.nsplit; ++kit, ++it) {
                     const int s = it % p.nstages;
                     const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
                     mbar_wait(bar_full + 8 * s, ph);
@@ -382,11 +385,25 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
                     for (int i = 0; i < 32; ++i) v[i] += rin[i];
                 }
                 ws_act_vec<32>(v, e.act2);
-                stage_store32(stg_out + (uint32_t)(pn * 128 * panel_bytes), r, panel_bytes, cin, e.dtype, v);
+                const uint32_t poff = (uint32_t)(pn * 128 * panel_bytes);
+                int ob = 0;
+                stage_store32(stg_out + poff, r, panel_bytes, cin, e.dtype, v);
                 if (p.has_out2) {  // Res2: next conv's input = this output + the next channel group
 #pragma unroll
                     for (int i = 0; i < 32; ++i) rin[i] += v[i];
-                    stage_store32(stg_out2 + (uint32_t)(pn * 128 * panel_bytes), r, panel_bytes, cin, e.dtype, rin);
+                }
+                if (p.nsplit == 3) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = ws_tf32_lo(v[i]);
+                    stage_store32(stg_out + (uint32_t)(++ob * tile_out_bytes) + poff, r, panel_bytes, cin, e.dtype, v);
+                }
+                if (p.has_out2) {
+                    stage_store32(stg_out + (uint32_t)(++ob * tile_out_bytes) + poff, r, panel_bytes, cin, e.dtype, rin);
+                    if (p.nsplit == 3) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) rin[i] = ws_tf32_lo(rin[i]);
+                        stage_store32(stg_out + (uint32_t)(++ob * tile_out_bytes) + poff, r, panel_bytes, cin, e.dtype, rin);
+                    }
                 }
             }
             // accumulator buffer (and the epilogue-input tile) are drained: hand them back
@@ -399,11 +416,10 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             epi_bar_sync();
             if (et == 0) {
-                for (int pn = 0; pn < npanels; ++pn) {
-                    tma_store_4d(&p.omap, stg_out + (uint32_t)(pn * 128 * panel_bytes), n0 + pn * panel_cols, t0, f0, b0);
-                    if (p.has_out2)
-                        tma_store_4d(&p.o2map, stg_out2 + (uint32_t)(pn * 128 * panel_bytes), n0 + pn * panel_cols, t0, f0, b0);
-                }
+                for (int o = 0; o < p.nout; ++o)
+                    for (int pn = 0; pn < npanels; ++pn)
+                        tma_store_4d(&p.omap[o], stg_out + (uint32_t)(o * tile_out_bytes + pn * 128 * panel_bytes),
+                                     n0 + pn * panel_cols, t0, f0, b0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }

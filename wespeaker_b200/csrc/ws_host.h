@@ -33,6 +33,7 @@ const std::string& get_err();
 // channels-last activation view: element (b,f,t,c) at p[((b*F+f)*T+t)*ld + c]
 struct View {
     void* p = nullptr;
+    void* plo = nullptr;  // 3xTF32 mode: twin buffer holding x - tf32_trunc(x)
     int B = 0, F = 1, T = 0, C = 0;
     long long ld = 0;
     int dt = WS_F32;
@@ -40,6 +41,7 @@ struct View {
     View ch(int c0, int c) const {
         View v = *this;
         v.p = (char*)p + (size_t)c0 * ws_esize(dt);
+        if (plo) v.plo = (char*)plo + (size_t)c0 * ws_esize(dt);
         v.C = c;
         return v;
     }
@@ -51,6 +53,8 @@ struct ConvSpec {
     int nsrc = 0;
     std::vector<WsTap> taps;
     const void* W = nullptr;  // [Cout][Ktot] in activation dtype
+    const void* W_lo = nullptr;  // 3xTF32: W - tf32_trunc(W)
+    bool split = false;          // 3xTF32 error-compensated GEMM (fp32 activations with lo twins)
     int Ktot = 0, Cout = 0;
     int B = 0, F = 1, T = 0;  // output extents
     int dt = WS_F32;

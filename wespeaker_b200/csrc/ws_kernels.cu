@@ -13,10 +13,14 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-__global__ void convert_kernel(const float* __restrict__ in, void* __restrict__ out, int dt, long long n) {
+__global__ void convert_kernel(const float* __restrict__ in, void* __restrict__ out, float* __restrict__ lo, int dt,
+                               long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) ws_st(out, dt, i, in[i]);
+    for (; i < n; i += stride) {
+        ws_st(out, dt, i, in[i]);
+        if (lo != nullptr) lo[i] = ws_tf32_lo(in[i]);
+    }
 }
 
 // block (32, 8): x = channel lane, y = T slice.
@@ -129,7 +133,7 @@ __global__ void linear_reduce_kernel(const float* __restrict__ part, int nsplit,
 
 __global__ void scale_residual_kernel(const void* __restrict__ x, long long x_ld, const float* __restrict__ gate,
                                       const void* __restrict__ res, long long res_ld, void* __restrict__ out,
-                                      long long out_ld, int dt, int T, int C, long long nvec) {
+                                      float* __restrict__ lo, long long out_ld, int dt, int T, int C, long long nvec) {
     const int cv = C >> 3;  // 8 channels per thread: 16-byte accesses for 16-bit activations
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -145,6 +149,11 @@ __global__ void scale_residual_kernel(const void* __restrict__ x, long long x_ld
         v[0] = fmaf(v[0], g0.x, r[0]); v[1] = fmaf(v[1], g0.y, r[1]); v[2] = fmaf(v[2], g0.z, r[2]); v[3] = fmaf(v[3], g0.w, r[3]);
         v[4] = fmaf(v[4], g1.x, r[4]); v[5] = fmaf(v[5], g1.y, r[5]); v[6] = fmaf(v[6], g1.z, r[6]); v[7] = fmaf(v[7], g1.w, r[7]);
         ws_stv8(out, dt, pos * out_ld + c, v);
+        if (lo != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = ws_tf32_lo(v[k]);
+            ws_stv8(lo, WS_F32, pos * out_ld + c, v);
+        }
     }
 }
 
@@ -206,8 +215,8 @@ __global__ void __launch_bounds__(256) astp_stats_kernel(const void* __restrict_
 }
 
 __global__ void bnrelu_kernel(const void* __restrict__ x, long long x_ld, const float* __restrict__ scale,
-                              const float* __restrict__ shift, void* __restrict__ out, long long out_ld, int dt,
-                              int C, long long nvec) {
+                              const float* __restrict__ shift, void* __restrict__ out, float* __restrict__ lo,
+                              long long out_ld, int dt, int C, long long nvec) {
     const int cv = C >> 2;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -221,14 +230,18 @@ __global__ void bnrelu_kernel(const void* __restrict__ x, long long x_ld, const 
         v[0] = fmaxf(fmaf(v[0], sc.x, sh.x), 0.f); v[1] = fmaxf(fmaf(v[1], sc.y, sh.y), 0.f);
         v[2] = fmaxf(fmaf(v[2], sc.z, sh.z), 0.f); v[3] = fmaxf(fmaf(v[3], sc.w, sh.w), 0.f);
         ws_stv<4>(out, dt, pos * out_ld + c, v);
+        if (lo != nullptr) {
+            v[0] = ws_tf32_lo(v[0]); v[1] = ws_tf32_lo(v[1]); v[2] = ws_tf32_lo(v[2]); v[3] = ws_tf32_lo(v[3]);
+            ws_stv<4>(lo, WS_F32, pos * out_ld + c, v);
+        }
     }
 }
 
 // one thread per output position (b, f, t): 9 taps x Cout channels, weights in shared memory.
 template <int COUT>
 __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ feats, const float* __restrict__ w9,
-                                                   const float* __restrict__ shift, void* __restrict__ out, int dt,
-                                                   int B, int T, int Fdim) {
+                                                   const float* __restrict__ shift, void* __restrict__ out,
+                                                   float* __restrict__ lo, int dt, int B, int T, int Fdim) {
     __shared__ float sw[COUT * 9];
     __shared__ float sh[COUT];
     for (int i = threadIdx.x; i < COUT * 9; i += blockDim.x) sw[i] = w9[i];
@@ -259,6 +272,11 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ fea
             v[j] = fmaxf(a, 0.f);
         }
         ws_stv<8>(out, dt, idx * COUT + c0, v);
+        if (lo != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = ws_tf32_lo(v[j]);
+            ws_stv<8>(lo, WS_F32, idx * COUT + c0, v);
+        }
     }
 }
 
@@ -383,8 +401,8 @@ inline int grid_for(long long n, int block, int cap = 148 * 16) {
 
 }  // namespace
 
-const char* ws_launch_convert(const float* in, void* out, int dt, long long n, cudaStream_t s) {
-    convert_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, dt, n);
+const char* ws_launch_convert(const float* in, void* out, float* lo, int dt, long long n, cudaStream_t s) {
+    convert_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, lo, dt, n);
     return last_err();
 }
 
@@ -414,11 +432,11 @@ const char* ws_launch_linear_rows(const float* in, long long in_ld, const float*
 }
 
 const char* ws_launch_scale_residual(const void* x, long long x_ld, const float* gate, const void* res,
-                                     long long res_ld, void* out, long long out_ld, int dt, int B, int T, int C,
-                                     cudaStream_t s) {
+                                     long long res_ld, void* out, float* lo, long long out_ld, int dt, int B, int T,
+                                     int C, cudaStream_t s) {
     if (C % 8 != 0) return "scale_residual: C must be a multiple of 8";
     const long long nvec = (long long)B * T * (C / 8);
-    scale_residual_kernel<<<grid_for(nvec, 256), 256, 0, s>>>(x, x_ld, gate, res, res_ld, out, out_ld, dt, T, C, nvec);
+    scale_residual_kernel<<<grid_for(nvec, 256), 256, 0, s>>>(x, x_ld, gate, res, res_ld, out, lo, out_ld, dt, T, C, nvec);
     return last_err();
 }
 
@@ -431,18 +449,18 @@ const char* ws_launch_astp_stats(const void* x, const void* logits, int dt, int 
 }
 
 const char* ws_launch_bnrelu(const void* x, long long x_ld, const float* scale, const float* shift, void* out,
-                             long long out_ld, int dt, long long npos, int C, cudaStream_t s) {
+                             float* lo, long long out_ld, int dt, long long npos, int C, cudaStream_t s) {
     const long long nvec = npos * (C / 4);
-    bnrelu_kernel<<<grid_for(nvec, 256), 256, 0, s>>>(x, x_ld, scale, shift, out, out_ld, dt, C, nvec);
+    bnrelu_kernel<<<grid_for(nvec, 256), 256, 0, s>>>(x, x_ld, scale, shift, out, lo, out_ld, dt, C, nvec);
     return last_err();
 }
 
-const char* ws_launch_stem(const float* feats, const float* w9, const float* shift, void* out, int dt, int B, int T,
-                           int Fdim, int Cout, cudaStream_t s) {
+const char* ws_launch_stem(const float* feats, const float* w9, const float* shift, void* out, float* lo, int dt, int B,
+                           int T, int Fdim, int Cout, cudaStream_t s) {
     const long long n = (long long)B * Fdim * T;
     const int grid = (int)((n + 127) / 128);
-    if (Cout == 32) stem_kernel<32><<<grid, 128, 0, s>>>(feats, w9, shift, out, dt, B, T, Fdim);
-    else if (Cout == 64) stem_kernel<64><<<grid, 128, 0, s>>>(feats, w9, shift, out, dt, B, T, Fdim);
+    if (Cout == 32) stem_kernel<32><<<grid, 128, 0, s>>>(feats, w9, shift, out, lo, dt, B, T, Fdim);
+    else if (Cout == 64) stem_kernel<64><<<grid, 128, 0, s>>>(feats, w9, shift, out, lo, dt, B, T, Fdim);
     else return "stem conv supports 32 or 64 output channels";
     return last_err();
 }

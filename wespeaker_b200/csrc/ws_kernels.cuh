@@ -4,7 +4,8 @@
 #include "ws_common.cuh"
 
 // ---- elementwise / reductions over channels-last activations [rows][ld]
-const char* ws_launch_convert(const float* in, void* out, int dt, long long n, cudaStream_t s);
+// (`lo`: optional fp32 twin receiving v - tf32_trunc(v) for the 3xTF32 GEMM path; pass nullptr otherwise)
+const char* ws_launch_convert(const float* in, void* out, float* lo, int dt, long long n, cudaStream_t s);
 // mean (and optional unbiased std, sqrt(var + eps)) over T for every (b, f, c).  x: [B][F][T][ld], channels [0,C).
 // Optional per-channel pre-affine + relu (CAM++ out_nonlinear, campplus.py:378-379).  Output (fp32 or `odt`):
 //   mean -> out[b*out_ld + c*F + f],  std -> out[b*out_ld + std_off + c*F + f]   (std skipped if std_off < 0)
@@ -17,17 +18,17 @@ const char* ws_launch_linear_rows(const float* in, long long in_ld, const float*
                                   int R, int I, int O, int act, float* workspace, int nsplit, cudaStream_t s);
 // SE apply + residual (ecapa_tdnn.py:124,157): out[pos][c] = x[pos][c]*gate[b][c] + res[pos][c]
 const char* ws_launch_scale_residual(const void* x, long long x_ld, const float* gate, const void* res,
-                                     long long res_ld, void* out, long long out_ld, int dt, int B, int T, int C,
-                                     cudaStream_t s);
+                                     long long res_ld, void* out, float* lo, long long out_ld, int dt, int B, int T,
+                                     int C, cudaStream_t s);
 // ASTP statistics (pooling_layers.py:138-144): softmax over T of logits, weighted mean / std of x
 const char* ws_launch_astp_stats(const void* x, const void* logits, int dt, int B, int T, int C, long long ld,
                                  float* out /*[B][2C]*/, cudaStream_t s);
 // out[pos][c] = relu(x[pos][c]*scale[c] + shift[c])  (CAM++ pre-activation BN-ReLU, campplus.py:164-166,214)
 const char* ws_launch_bnrelu(const void* x, long long x_ld, const float* scale, const float* shift, void* out,
-                             long long out_ld, int dt, long long npos, int C, cudaStream_t s);
+                             float* lo, long long out_ld, int dt, long long npos, int C, cudaStream_t s);
 // ResNet / FCM stem: Conv2d(1->Cout,3x3,pad 1) + folded BN + ReLU.  feats fp32 [B][T][Fdim] -> out [B][Fdim][T][Cout]
-const char* ws_launch_stem(const float* feats, const float* w9 /*[Cout][9]*/, const float* shift, void* out, int dt,
-                           int B, int T, int Fdim, int Cout, cudaStream_t s);
+const char* ws_launch_stem(const float* feats, const float* w9 /*[Cout][9]*/, const float* shift, void* out, float* lo,
+                           int dt, int B, int T, int Fdim, int Cout, cudaStream_t s);
 // CAM context (campplus.py:108-135): mean over T and per-segment (seg_len) means with ceil-mode partial segment
 const char* ws_launch_seg_means(const void* x, int dt, int B, int T, int C, long long ld, int seg_len, float* mean,
                                 float* segmean /*[B][nseg][C]*/, cudaStream_t s);
