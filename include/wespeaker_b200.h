@@ -51,6 +51,13 @@ int ws_engine_extract_wav(ws_engine* e, const void* wav_dev, int wav_is_i16, lon
                           const char* window_type, float* embs_dev, float* feats_out_dev, void* stream);
 int ws_engine_extract_wav_host(ws_engine* e, const void* wav_host, int wav_is_i16, int nsamples, int B,
                                const char* window_type, float* embs_host);
+/* Pipelined variant of ws_engine_extract_wav_host: submit() enqueues H2D (copy stream) + fbank + CMN + forward + D2H
+ * for `slot` (0 or 1) and returns; collect() blocks until that slot's embs_host is filled.  Alternating the two slots
+ * overlaps the H2D copy of batch i+1 with the kernels of batch i — the role DataLoader workers / prefetch_factor play
+ * in extract.py:99-103.  Host buffers should be pinned and must stay valid until collect(). */
+int ws_engine_submit_wav_host(ws_engine* e, int slot, const void* wav_host, int wav_is_i16, int nsamples, int B,
+                              const char* window_type, float* embs_host);
+int ws_engine_collect(ws_engine* e, int slot);
 /* number of this library's kernels launched by the most recent forward/extract call */
 long long ws_engine_last_launches(const ws_engine* e);
 void ws_engine_destroy(ws_engine* e);

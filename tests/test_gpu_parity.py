@@ -264,6 +264,12 @@ def test_config1_ecapa512_16utts_wav_to_embedding():
     assert np.array_equal(emb_h, emb)
     emb_i16 = m.extract_from_wav(torch.from_numpy(wavs).to(torch.int16)).numpy()
     assert np.array_equal(emb_i16, emb)
+    # pipelined host API (double-buffered H2D): same bits, batch order preserved, ragged last batch
+    w16 = torch.from_numpy(wavs).to(torch.int16)
+    chunks = [w16[0:6].pin_memory(), w16[6:12].pin_memory(), w16[12:16].pin_memory(), w16[0:6].pin_memory(), w16[3:5]]
+    outs = [o.numpy().copy() for o in m.extract_stream(chunks)]
+    assert [o.shape[0] for o in outs] == [6, 6, 4, 6, 2]
+    assert np.array_equal(np.concatenate(outs[:3]), emb) and np.array_equal(outs[3], emb[:6]) and np.array_equal(outs[4], emb[3:5])
 
 
 @pytest.mark.parametrize("name,prec", [("ECAPA_TDNN_c1024", "bf16"), ("ResNet34", "fp16"), ("CAMPPlus", "bf16")])

@@ -315,6 +315,8 @@ static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported) {
     q->grid = q->num_tiles < g_num_sms ? q->num_tiles : g_num_sms;
     q->smem_bytes = nst * (128 + bn) * q->bk_bytes + nstage_bufs * 128 * bn * es + 3 * bn * 4 + 1024;
     q->epi = e;
+    const char* env_sh = getenv("WS_TC2_SHIFT_TEST");
+    q->dbg_shift = env_sh ? atoi(env_sh) : -1;
     return true;
 }
 

@@ -72,6 +72,11 @@ struct ws_engine {
     std::map<std::string, FbankTables> fb;
     void* wav_dev = nullptr;
     size_t wav_bytes = 0;
+    // double-buffered host->device pipeline (ws_engine_submit_wav_host / ws_engine_collect)
+    cudaStream_t copy_st = nullptr;
+    void* slot_wav[2] = {nullptr, nullptr};
+    size_t slot_bytes[2] = {0, 0};
+    cudaEvent_t slot_copied[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
     // model hyper-parameters
     int channels = 512;
     bool glob = false;
@@ -83,6 +88,12 @@ struct ws_engine {
             cudaFree(kv.second.window); cudaFree(kv.second.melw); cudaFree(kv.second.melstart); cudaFree(kv.second.mellen);
         }
         if (wav_dev) cudaFree(wav_dev);
+        for (int i = 0; i < 2; ++i) {
+            if (slot_wav[i]) cudaFree(slot_wav[i]);
+            if (slot_copied[i]) cudaEventDestroy(slot_copied[i]);
+            if (slot_done[i]) cudaEventDestroy(slot_done[i]);
+        }
+        if (copy_st) cudaStreamDestroy(copy_st);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
         if (st) cudaStreamDestroy(st);
@@ -1037,6 +1048,53 @@ int ws_engine_extract_wav_host(ws_engine* e, const void* wav_host, int wav_is_i1
     e->last_launches += 2;
     WS_CK(cudaMemcpyAsync(embs_host, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToHost, e->st));
     WS_CK(cudaStreamSynchronize(e->st));
+    return 0;
+}
+
+// Pipelined host path: submit() enqueues H2D of batch i on a copy stream and the fbank+CMN+forward+D2H on the compute
+// stream behind it, then returns immediately; collect() blocks until that slot's embeddings are in embs_host.  With two
+// slots the H2D copy of batch i+1 overlaps the kernels of batch i (the reference overlaps with DataLoader workers and
+// prefetch_factor=4, extract.py:99-103).
+int ws_engine_submit_wav_host(ws_engine* e, int slot, const void* wav_host, int wav_is_i16, int nsamples, int B,
+                              const char* window_type, float* embs_host) {
+    if (!e || !wav_host || !embs_host || slot < 0 || slot > 1) { set_err("ws_engine_submit_wav_host: bad argument"); return 1; }
+    if (!e->finalized) { set_err("ws_engine_submit_wav_host before ws_engine_finalize"); return 1; }
+    WS_CK(cudaSetDevice(e->device));
+    const int T = ws_fbank_num_frames(nsamples);
+    if (T <= 0) { set_err("ws_engine_submit_wav_host: waveform shorter than one 25 ms frame"); return 1; }
+    if (e->copy_st == nullptr) {
+        WS_CK(cudaStreamCreateWithFlags(&e->copy_st, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            WS_CK(cudaEventCreateWithFlags(&e->slot_copied[i], cudaEventDisableTiming));
+            WS_CK(cudaEventCreateWithFlags(&e->slot_done[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t bytes = (size_t)B * nsamples * (wav_is_i16 ? 2 : 4);
+    if (bytes > e->slot_bytes[slot]) {
+        WS_CK(cudaStreamSynchronize(e->st));
+        if (e->slot_wav[slot]) cudaFree(e->slot_wav[slot]);
+        e->slot_wav[slot] = nullptr; e->slot_bytes[slot] = 0;
+        WS_CK(cudaMalloc(&e->slot_wav[slot], bytes));
+        e->slot_bytes[slot] = bytes;
+    }
+    Plan* p = get_plan(e, B, T);
+    if (!p) return 1;
+    // the slot's staging buffer is free once the previous job that used it finished its fbank (slot_done covers it)
+    WS_CK(cudaStreamWaitEvent(e->copy_st, e->slot_done[slot], 0));
+    WS_CK(cudaMemcpyAsync(e->slot_wav[slot], wav_host, bytes, cudaMemcpyHostToDevice, e->copy_st));
+    WS_CK(cudaEventRecord(e->slot_copied[slot], e->copy_st));
+    WS_CK(cudaStreamWaitEvent(e->st, e->slot_copied[slot], 0));
+    if (fbank_into(e, e->slot_wav[slot], wav_is_i16, nsamples, nsamples, B, window_type, 1, p->feats_in, e->st)) return 1;
+    if (run_plan(e, p, e->st)) return 1;
+    e->last_launches += 2;
+    WS_CK(cudaMemcpyAsync(embs_host, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToHost, e->st));
+    WS_CK(cudaEventRecord(e->slot_done[slot], e->st));
+    return 0;
+}
+
+int ws_engine_collect(ws_engine* e, int slot) {
+    if (!e || slot < 0 || slot > 1 || e->slot_done[slot] == nullptr) { set_err("ws_engine_collect: bad argument"); return 1; }
+    WS_CK(cudaEventSynchronize(e->slot_done[slot]));
     return 0;
 }
 

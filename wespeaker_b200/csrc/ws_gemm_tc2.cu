@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
                             mbar_expect_tx(bar_full + 8 * s, (uint32_t)stage_bytes);
                             const uint32_t sa = ring + (uint32_t)(s * stage_bytes);
                             tma_load_4d(sa, ps == 0 ? &p.amap_lo[tap.map] : &p.amap[tap.map], bar_full + 8 * s,
-                                        tap.c0 + kb * bk_elems, t0 + tap.dt, f0 + tap.df, b0);
+                                        tap.c0 + kb * bk_elems, t0 + tap.dt - (p.dbg_shift >= 0 ? 1 : 0), f0 + tap.df, b0);
                             tma_load_2d(sa + (uint32_t)a_bytes, ps == 1 ? &p.wmap_lo : &p.wmap, bar_full + 8 * s,
                                         tap.wk + kb * bk_elems, n0);
                         }
@@ -284,7 +284,9 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
                     mbar_wait(bar_full + 8 * s, ph);
                     tc_fence_after();
                     const uint32_t sa = ring + (uint32_t)(s * stage_bytes);
-                    const uint64_t adesc = umma_desc(sa, p.bk_bytes);
+                    uint64_t adesc = umma_desc(sa, p.bk_bytes);
+                    if (p.dbg_shift >= 0)  // row-shifted operand read: start one row in, base_offset field [49,52)
+                        adesc = umma_desc(sa + (uint32_t)p.bk_bytes, p.bk_bytes) | ((uint64_t)(p.dbg_shift & 7) << 49);
                     const uint64_t bdesc = umma_desc(sa + (uint32_t)a_bytes, p.bk_bytes);
                     for (int k = 0; k < kper; ++k)
                         umma<KIND>(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
