@@ -31,7 +31,8 @@ const char* ws_last_error(void);
 int ws_engine_create(const char* model_name, const char* precision, int feat_dim, int embed_dim, int device,
                      ws_engine** out);
 /* options: "two_emb_layer", "emb_bn" (model_args), "cuda_graph" (default 1), "force_simt" (debug cross-check),
- * "tc_version" (1: one-tile-per-CTA tcgen05 kernel, 2 (default): persistent / TMA-store kernel) */
+ * "tc_version" (1: one-tile-per-CTA tcgen05 kernel, 2 (default): persistent / TMA-store kernel),
+ * "res2_fused" (default 1: ECAPA Res2 chains run as one fused persistent kernel per stage for 16-bit precisions) */
 int ws_engine_set_option(ws_engine* e, const char* key, long long value);
 /* one reference state_dict entry (fp32 host data, reference key names). */
 int ws_engine_set_tensor(ws_engine* e, const char* key, const float* host_data, const long long* shape, int ndim);
@@ -52,8 +53,8 @@ int ws_engine_extract_wav(ws_engine* e, const void* wav_dev, int wav_is_i16, lon
 int ws_engine_extract_wav_host(ws_engine* e, const void* wav_host, int wav_is_i16, int nsamples, int B,
                                const char* window_type, float* embs_host);
 /* Pipelined variant of ws_engine_extract_wav_host: submit() enqueues H2D (copy stream) + fbank + CMN + forward + D2H
- * for `slot` (0 or 1) and returns; collect() blocks until that slot's embs_host is filled.  Alternating the two slots
- * overlaps the H2D copy of batch i+1 with the kernels of batch i — the role DataLoader workers / prefetch_factor play
+ * for `slot` (0..3) and returns; collect() blocks until that slot's embs_host is filled.  Cycling through the slots
+ * overlaps the H2D copies of the next batches with the kernels of batch i and rides out host scheduling jitter — the role DataLoader workers / prefetch_factor play
  * in extract.py:99-103.  Host buffers should be pinned and must stay valid until collect(). */
 int ws_engine_submit_wav_host(ws_engine* e, int slot, const void* wav_host, int wav_is_i16, int nsamples, int B,
                               const char* window_type, float* embs_host);

@@ -200,6 +200,21 @@ def test_model_fp32_matches_reference_golden(key):
 TC_TOL = {"tf32": 1e-2, "bf16": 3e-2, "fp16": 1e-2}
 
 
+@pytest.mark.parametrize("name,B,T,prec", [("ECAPA_TDNN_c1024", 5, 200, "bf16"), ("ECAPA_TDNN_c512", 3, 198, "fp16"),
+                                           ("ECAPA_TDNN_GLOB_c512", 2, 61, "bf16"), ("ECAPA_TDNN_c512", 150, 256, "bf16")])
+def test_res2_fused_chain_matches_unfused(name, B, T, prec):
+    """The fused Res2 chain kernel (7 dilated convs on-chip per utterance) must reproduce the 7-launch path: same
+    roundings (sp_i and s_{i+1} are rounded to the activation dtype at the same points), same tap order."""
+    feats = torch.from_numpy(syn.make_feats(B, T, 80, seed=5)).to(DEV)
+    mf = from_synthetic(name, 0, precision=prec)
+    mu = from_synthetic(name, 0, precision=prec)
+    mu.set_option("res2_fused", 0)
+    ef, eu = mf.embed(feats).cpu().numpy(), mu.embed(feats).cpu().numpy()
+    print(f"res2 fused vs unfused {name} {prec} B{B} T{T}: rel {rel_l2(ef, eu).max():.2e}, launches {mf.last_launches()} vs {mu.last_launches()}")
+    assert mf.last_launches() == mu.last_launches() - 18
+    assert rel_l2(ef, eu).max() <= 2e-3
+
+
 @pytest.mark.parametrize("key", list(G_MODELS.files))
 def test_model_tf32x3_tensor_cores_meet_fp32_bar(key):
     """3xTF32 on tcgen05 (x_lo*W + x*W_lo + x*W, fp32 accumulation in TMEM): the tensor-core path itself meets the

@@ -31,3 +31,8 @@ t0 = time.perf_counter()
 n = 0
 for o in m.extract_stream(pins[i % 4] for i in range(10)): n += 1
 print("generator ms/step", (time.perf_counter() - t0) * 100)
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+for o in m.extract_stream(pins[i % 4] for i in range(10)): n += 1
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(12)

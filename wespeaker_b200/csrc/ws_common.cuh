@@ -301,9 +301,26 @@ struct WsTc2Params {
     WsEpi epi;
 };
 
+// fused Res2 chain (ws_res2_fused.cu)
+struct WsRes2Params {
+    CUtensorMap xmap;   // block input  [B][T][C] (channels-last, 16-bit): dims (C, T, B), box (64, 128, 1), SWIZZLE_128B
+    CUtensorMap wmap;   // 7 packed conv weights [7*w8][3*w8] K-major: box (64, w8)
+    CUtensorMap omap;   // block output [B][T][C]: same geometry as xmap
+    const void* x;      // raw pointer of the block input (x_{i+1} groups are read directly in the epilogue)
+    long long ld;       // row stride (elements) of the block input
+    const float* bias;  // [7][w8]
+    const float* scale; // [7][w8] BN affine after ReLU
+    const float* shift;
+    int B, T, w8, dil, dtype;
+    uint32_t idesc;
+    int grid, smem_bytes;
+};
+
 #ifdef __cplusplus
 extern "C" {
 #endif
+const char* ws_res2_init(void);
+const char* ws_res2_launch(const WsRes2Params* p, cudaStream_t s);
 const char* ws_tc2_init(void);
 int ws_tc2_max_smem(void);
 const char* ws_tc2_launch(const WsTc2Params* p, cudaStream_t s);

@@ -356,6 +356,45 @@ bool make_conv_op(const ConvSpec& spec, int use_tc, Op* out) {
     return true;
 }
 
+bool make_res2_op(const View& x, const View& out, const void* W7, const float* bias, const float* scale,
+                  const float* shift, int w8, int dil, Op* op, bool* unsupported) {
+    *unsupported = false;
+    if (x.dt == WS_F32 || (w8 != 64 && w8 != 128) || x.T > 256 || x.F != 1 || dil < 1 || dil > 7 || getenv("WS_NO_RES2_FUSED")) {
+        *unsupported = true;
+        return false;
+    }
+    auto q = std::make_shared<WsRes2Params>();
+    memset(q.get(), 0, sizeof(WsRes2Params));
+    auto act_map = [&](CUtensorMap* m, const View& v) {
+        cuuint64_t dims[3] = {(cuuint64_t)v.C, (cuuint64_t)v.T, (cuuint64_t)v.B};
+        cuuint64_t str[2] = {(cuuint64_t)v.ld * 2, (cuuint64_t)v.T * v.ld * 2};
+        cuuint32_t box[3] = {64, 128, 1};
+        return encode_map(m, v.dt, v.p, 3, dims, str, box, 128);
+    };
+    if (!act_map(&q->xmap, x) || !act_map(&q->omap, out)) return false;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)(3 * w8), (cuuint64_t)(7 * w8)};
+        cuuint64_t str[1] = {(cuuint64_t)(3 * w8) * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)w8};
+        if (!encode_map(&q->wmap, x.dt, W7, 2, dims, str, box, 128)) return false;
+    }
+    q->x = x.p; q->ld = x.ld; q->bias = bias; q->scale = scale; q->shift = shift;
+    q->B = x.B; q->T = x.T; q->w8 = w8; q->dil = dil; q->dtype = x.dt;
+    const uint32_t fmt = x.dt == WS_BF16 ? 1u : 0u;
+    q->idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(w8 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    q->grid = x.B < g_num_sms ? x.B : g_num_sms;
+    const int npan = w8 / 64;
+    q->smem_bytes = npan * 272 * 128 + 4 * w8 * 128 + npan * 256 * 128 + 1024;
+    *op = [q](cudaStream_t s) { return ws_res2_launch(q.get(), s); };
+    return true;
+}
+
 }  // namespace ws
 
 // ------------------------------------------------------------------------------------------------ C ABI: ws_conv

@@ -74,9 +74,10 @@ struct ws_engine {
     size_t wav_bytes = 0;
     // double-buffered host->device pipeline (ws_engine_submit_wav_host / ws_engine_collect)
     cudaStream_t copy_st = nullptr;
-    void* slot_wav[2] = {nullptr, nullptr};
-    size_t slot_bytes[2] = {0, 0};
-    cudaEvent_t slot_copied[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
+    static constexpr int kSlots = 4;
+    void* slot_wav[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    size_t slot_bytes[kSlots] = {0, 0, 0, 0};
+    cudaEvent_t slot_copied[kSlots] = {nullptr, nullptr, nullptr, nullptr}, slot_done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
     // model hyper-parameters
     int channels = 512;
     bool glob = false;
@@ -88,7 +89,7 @@ struct ws_engine {
             cudaFree(kv.second.window); cudaFree(kv.second.melw); cudaFree(kv.second.melstart); cudaFree(kv.second.mellen);
         }
         if (wav_dev) cudaFree(wav_dev);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kSlots; ++i) {
             if (slot_wav[i]) cudaFree(slot_wav[i]);
             if (slot_copied[i]) cudaEventDestroy(slot_copied[i]);
             if (slot_done[i]) cudaEventDestroy(slot_done[i]);
@@ -334,7 +335,36 @@ bool build_ecapa(Builder& b) {
         const std::string pf = "layer" + std::to_string(L) + ".se_res2block";
         conv_relu_bn(pf + ".0", xin, tA, 1, 1, 0);
         // Res2Conv1dReluBn (ecapa_tdnn.py:29-78): 7 dependent dilated k=3 convs on w8-channel groups
-        for (int i = 0; i < 7 && b.good(); ++i) {
+        bool fused = false;
+        if (e.use_tc == 2 && e.act_dt != WS_F32 && e.opt("res2_fused", 1)) {
+            // one persistent launch per stage: the chain stays in shared memory / TMEM (ws_res2_fused.cu)
+            std::vector<float> w7((size_t)7 * w8 * 3 * w8), b7((size_t)7 * w8), s7((size_t)7 * w8), h7((size_t)7 * w8);
+            bool okw = true;
+            for (int i = 0; i < 7 && okw; ++i) {
+                const std::string cp = pf + ".1.convs." + std::to_string(i), bp = pf + ".1.bns." + std::to_string(i);
+                std::vector<float> wp, s, h;
+                int co, ci, nt;
+                const HostT* bt = b.w.get(cp + ".bias");
+                okw = bt && b.w.pack_conv(cp + ".weight", nullptr, wp, &co, &ci, &nt) && b.w.bn(bp, true, s, h);
+                if (!okw) break;
+                memcpy(&w7[(size_t)i * w8 * 3 * w8], wp.data(), wp.size() * 4);
+                memcpy(&b7[(size_t)i * w8], bt->v.data(), (size_t)w8 * 4);
+                memcpy(&s7[(size_t)i * w8], s.data(), (size_t)w8 * 4);
+                memcpy(&h7[(size_t)i * w8], h.data(), (size_t)w8 * 4);
+            }
+            if (!okw) break;
+            Op op;
+            bool unsupported = false;
+            if (make_res2_op(tA, tB, b.w.act("w7:" + pf, w7), b.w.f32("b7:" + pf, b7), b.w.f32("s7:" + pf, s7),
+                             b.w.f32("h7:" + pf, h7), w8, d, &op, &unsupported)) {
+                b.push(std::move(op));
+                fused = true;
+            } else if (!unsupported) {
+                b.ok = false;
+                break;
+            }
+        }
+        for (int i = 0; i < 7 && b.good() && !fused; ++i) {
             const std::string cp = pf + ".1.convs." + std::to_string(i), bp = pf + ".1.bns." + std::to_string(i);
             std::vector<float> wp, s, h;
             int co, ci, nt;
@@ -914,6 +944,7 @@ int ws_engine_create(const char* model_name, const char* precision, int feat_dim
     if (feat_dim % 8 != 0) { set_err("feat_dim must be a multiple of 8"); return 1; }
     WS_CKS(ws_tc_init());
     WS_CKS(ws_tc2_init());
+    WS_CKS(ws_res2_init());
     WS_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     WS_CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
     WS_CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
@@ -926,7 +957,7 @@ int ws_engine_set_option(ws_engine* e, const char* key, long long value) {
     const std::string k = key;
     if (k == "force_simt") { if (value) e->use_tc = 0; }
     else if (k == "tc_version") { if (e->use_tc && !e->split) e->use_tc = value >= 2 ? 2 : 1; }
-    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph") { set_err("unknown option " + k); return 1; }
+    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused") { set_err("unknown option " + k); return 1; }
     e->opts[k] = value;
     e->plans.clear();
     return 0;
@@ -1057,14 +1088,14 @@ int ws_engine_extract_wav_host(ws_engine* e, const void* wav_host, int wav_is_i1
 // prefetch_factor=4, extract.py:99-103).
 int ws_engine_submit_wav_host(ws_engine* e, int slot, const void* wav_host, int wav_is_i16, int nsamples, int B,
                               const char* window_type, float* embs_host) {
-    if (!e || !wav_host || !embs_host || slot < 0 || slot > 1) { set_err("ws_engine_submit_wav_host: bad argument"); return 1; }
+    if (!e || !wav_host || !embs_host || slot < 0 || slot >= ws_engine::kSlots) { set_err("ws_engine_submit_wav_host: bad argument"); return 1; }
     if (!e->finalized) { set_err("ws_engine_submit_wav_host before ws_engine_finalize"); return 1; }
     WS_CK(cudaSetDevice(e->device));
     const int T = ws_fbank_num_frames(nsamples);
     if (T <= 0) { set_err("ws_engine_submit_wav_host: waveform shorter than one 25 ms frame"); return 1; }
     if (e->copy_st == nullptr) {
         WS_CK(cudaStreamCreateWithFlags(&e->copy_st, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < ws_engine::kSlots; ++i) {
             WS_CK(cudaEventCreateWithFlags(&e->slot_copied[i], cudaEventDisableTiming));
             WS_CK(cudaEventCreateWithFlags(&e->slot_done[i], cudaEventDisableTiming));
         }
@@ -1093,7 +1124,7 @@ int ws_engine_submit_wav_host(ws_engine* e, int slot, const void* wav_host, int 
 }
 
 int ws_engine_collect(ws_engine* e, int slot) {
-    if (!e || slot < 0 || slot > 1 || e->slot_done[slot] == nullptr) { set_err("ws_engine_collect: bad argument"); return 1; }
+    if (!e || slot < 0 || slot >= ws_engine::kSlots || e->slot_done[slot] == nullptr) { set_err("ws_engine_collect: bad argument"); return 1; }
     WS_CK(cudaEventSynchronize(e->slot_done[slot]));
     return 0;
 }

@@ -75,4 +75,11 @@ bool make_conv_op(const ConvSpec& spec, int use_tc, Op* out);  // 0 FFMA, 1 tcge
 
 void fill_epi_out(WsEpi& e, const View& out);
 
+// Fused Res2 chain over a whole SE_Res2Block stage (7 dilated k=3 convs on w8-channel groups, ecapa_tdnn.py:29-78).
+// x: block input (B,1,T,8*w8), out: block output buffer (groups 0..6 are written).  W7: [7*w8][3*w8] packed weights in
+// the activation dtype; bias/scale/shift: [7][w8] fp32.  Returns false with *unsupported=true when the shape/dtype is
+// outside the fused kernel's envelope (16-bit activations, w8 in {64,128}, T <= 256).
+bool make_res2_op(const View& x, const View& out, const void* W7, const float* bias, const float* scale,
+                  const float* shift, int w8, int dil, Op* op, bool* unsupported);
+
 }  // namespace ws

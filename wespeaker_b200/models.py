@@ -213,10 +213,10 @@ class B200SpeakerModel(torch.nn.Module):
                                                 out.data_ptr()), "ws_engine_extract_wav_host")
         return out
 
-    def extract_stream(self, host_batches, window_type: str = "hamming"):
+    def extract_stream(self, host_batches, window_type: str = "hamming", depth: int = 4):
         """Pipelined extraction over an iterable of HOST waveform batches ((B,N) int16 or int16-range float32, ideally
         pinned).  Yields one pinned CPU (B, embed_dim) tensor per batch, in order.  The H2D copy of batch i+1 overlaps
-        the kernels of batch i (two staging slots inside the C ABI) — the analogue of the reference's DataLoader
+        the kernels of batch i (`depth` <= 4 staging slots inside the C ABI) — the analogue of the reference's DataLoader
         prefetching (extract.py:99-103)."""
         L = _lib.load()
         h = self._ensure_engine(self._dev_index())
@@ -231,10 +231,10 @@ class B200SpeakerModel(torch.nn.Module):
             is_i16 = 1 if wav.dtype == torch.int16 else 0
             w = wav.contiguous() if is_i16 else wav.float().contiguous()
             B, N = w.shape
-            if len(pending) == 2:  # the slot we are about to reuse must have been collected
+            if len(pending) == depth:  # the slot we are about to reuse must have been collected
                 s0, _, o0 = pending.pop(0)
                 _lib.check(L.ws_engine_collect(h, s0), "ws_engine_collect")
-                yield o0.clone()
+                yield self._unpinned_copy(o0)
             key = (slot, B)
             if key not in pool:  # pinned result buffers are allocated once per (slot, batch size): cudaHostAlloc is slow
                 pool[key] = torch.empty((B, self.embed_dim), dtype=torch.float32).pin_memory()
@@ -242,10 +242,18 @@ class B200SpeakerModel(torch.nn.Module):
             _lib.check(L.ws_engine_submit_wav_host(h, slot, w.data_ptr(), is_i16, N, B, window_type.encode(),
                                                    out.data_ptr()), "ws_engine_submit_wav_host")
             pending.append((slot, w, out))
-            slot ^= 1
+            slot = (slot + 1) % depth
         for s0, _, o0 in pending:
             _lib.check(L.ws_engine_collect(h, s0), "ws_engine_collect")
-            yield o0.clone()
+            yield self._unpinned_copy(o0)
+
+    @staticmethod
+    def _unpinned_copy(t: torch.Tensor) -> torch.Tensor:
+        # Tensor.clone() of a pinned tensor allocates pinned memory again (a cudaHostAlloc per batch, ~6 ms); copy into
+        # ordinary pageable memory instead
+        out = torch.empty(t.shape, dtype=t.dtype)
+        out.copy_(t)
+        return out
 
     # ------------------------------------------------------------------ variable-length batches (BASELINE config 4)
     def embed_list(self, feats_list, max_batch: int = 64, device=None):
