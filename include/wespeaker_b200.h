@@ -31,7 +31,8 @@ const char* ws_last_error(void);
 int ws_engine_create(const char* model_name, const char* precision, int feat_dim, int embed_dim, int device,
                      ws_engine** out);
 /* options: "two_emb_layer", "emb_bn" (model_args), "cuda_graph" (default 1), "force_simt" (debug cross-check),
- * "tc_version" (1: one-tile-per-CTA tcgen05 kernel, 2 (default): persistent / TMA-store kernel),
+ * "tc_version" (1: one-tile-per-CTA tcgen05 kernel, 2: persistent / TMA-store kernel, 3: + cta_group::2 CTA pairs on
+ * the large layers),
  * "res2_fused" (default 1: ECAPA Res2 chains run as one fused persistent kernel per stage for 16-bit precisions) */
 int ws_engine_set_option(ws_engine* e, const char* key, long long value);
 /* one reference state_dict entry (fp32 host data, reference key names). */
@@ -88,7 +89,7 @@ typedef struct {
     void* out;                /* [B][Fo][To][out_ld] */
     long long out_ld;
     int dtype;                /* 0 fp32 (tf32 MMA when use_tc), 1 bf16, 2 fp16 */
-    int use_tc;               /* 0: fp32 FFMA kernel, 1: tcgen05 v1 kernel, 2: persistent tcgen05 v2 kernel */
+    int use_tc;               /* 0: fp32 FFMA kernel, 1: tcgen05 v1, 2: persistent tcgen05 v2, 3: v2 with cta_group::2 pairs */
     /* 3xTF32 (dtype 0, use_tc 2): low parts v - tf32_trunc(v) of x and w (inputs) and of out (written); all NULL = off */
     const void* x_lo;
     const void* w_lo;

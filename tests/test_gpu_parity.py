@@ -116,7 +116,7 @@ CONV_CASES = [
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 @pytest.mark.parametrize("mode", ["fp32-simt", "tf32-tc", "bf16-tc", "fp16-tc", "bf16-simt", "tf32-tc2", "bf16-tc2", "fp16-tc2",
-                                  "tf32x3-tc2"])
+                                  "tf32x3-tc2", "bf16-tc3", "tf32-tc3", "fp16-tc3"])
 def test_conv_operator(case, mode):
     name, B, F, T, Cin, Cout, kf, kt, dil, pad, stride = case
     prec, path = mode.split("-")
@@ -129,7 +129,15 @@ def test_conv_operator(case, mode):
     Fo = (F + 2 * pad[0] - dil[0] * (kf - 1) - 1) // stride[0] + 1
     To = (T + 2 * pad[1] - dil[1] * (kt - 1) - 1) // stride[1] + 1
     res = None if name.endswith("nores") else torch.randn(B, Fo, To, Cout, generator=g)
-    out = run_conv(x, w, bias, scale, shift, res, prec, {"simt": 0, "tc": 1, "tc2": 2}[path], kf, kt, dil, pad, stride, 1, 1)
+    if path == "tc3":
+        if Cout % 128 != 0:
+            pytest.skip("cta_group::2 pairs need Cout % 128 == 0 (smaller layers use the 1-CTA kernel)")
+        os.environ["WS_TC3_MIN_POS"] = "1"   # force the pair kernel on these small shapes (odd tile tails included)
+    try:
+        out = run_conv(x, w, bias, scale, shift, res, prec, {"simt": 0, "tc": 1, "tc2": 2, "tc3": 3}[path], kf, kt, dil, pad,
+                       stride, 1, 1)
+    finally:
+        os.environ.pop("WS_TC3_MIN_POS", None)
     tdt = DT[prec][1]
     ref = ref_conv(x, w, bias, scale, shift, res, tdt, kf, kt, dil, pad, stride, 1, 1)
     err = (out.double() - ref).abs().max().item()

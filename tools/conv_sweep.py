@@ -40,8 +40,8 @@ if __name__ == "__main__":
     which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(shapes)
     for name in which:
         B, T, ci, co, k, d = shapes[name]
-        for tcv in (1, 2):
-            for knobs in ({}, {"WS_TILE_BT": "32"}, {"WS_TILE_BT": "128"}, {"WS_TC2_MAX_STAGES": "2"}, {"WS_TC2_MAX_BN": "128"}):
+        for tcv in (2, 3):
+            for knobs in ({}, {"WS_TC2_MAX_BN": "128"}):
                 if tcv == 1 and any(kk.startswith("WS_TC2") for kk in knobs): continue
                 if k == 1 and "WS_TILE_BT" in knobs: continue
                 for kk in ("WS_TILE_BT", "WS_TC2_MAX_STAGES", "WS_TC2_MAX_BN"): os.environ.pop(kk, None)

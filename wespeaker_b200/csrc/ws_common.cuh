@@ -321,6 +321,9 @@ extern "C" {
 #endif
 const char* ws_res2_init(void);
 const char* ws_res2_launch(const WsRes2Params* p, cudaStream_t s);
+const char* ws_tc3_init(void);
+int ws_tc3_max_smem(void);
+const char* ws_tc3_launch(const WsTc2Params* p, cudaStream_t s);
 const char* ws_tc2_init(void);
 int ws_tc2_max_smem(void);
 const char* ws_tc2_launch(const WsTc2Params* p, cudaStream_t s);

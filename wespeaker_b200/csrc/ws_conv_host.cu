@@ -209,7 +209,7 @@ static bool build_tc(const ConvSpec& s, WsTcParams* p) {
 
 // ---- v2 (persistent, TMA-store epilogue).  Returns false *without* error if the spec needs the v1 kernel.
 static int g_num_sms = 0;
-static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported) {
+static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported, bool pair = false) {
     *unsupported = false;
     const WsEpi& e = s.epi;
     if ((e.res != nullptr && e.out2 != nullptr) || s.Cout % 32 != 0) { *unsupported = true; return false; }
@@ -248,25 +248,28 @@ static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported) {
             const int c = cands[ci];
             if (s.Cout % c != 0 || c > max_bn) continue;
             if (c == 256 && es == 4) continue;  // fp32 staging of a 128x256 tile would not leave room for the ring
-            if ((c * q->bk_bytes) % 1024 != 0) continue;
+            if (pair && c < 128) continue;      // cta_group::2: each CTA stages bn/2 weight rows
+            const int wrows = pair ? c / 2 : c;
+            if ((wrows * q->bk_bytes) % 1024 != 0) continue;
             const int staging = nstage_bufs * 128 * c * es + 3 * c * 4;
-            const int stage_bytes = (128 + c) * q->bk_bytes;
+            const int stage_bytes = (128 + wrows) * q->bk_bytes;
             const int n = (budget - staging) / stage_bytes;
             if (n >= (pass == 0 ? 3 : 2)) { bn = c; nst = n > max_st ? max_st : n; break; }
         }
     if (bn == 0) { *unsupported = true; return false; }
     q->bn = bn; q->nstages = nst;
     q->tiles_n = s.Cout / bn;
-    q->num_tiles = q->tiles_n * q->tiles_t * q->tiles_f * q->tiles_b;
+    const int mtiles = q->tiles_t * q->tiles_f * q->tiles_b;
+    q->num_tiles = q->tiles_n * (pair ? (mtiles + 1) / 2 : mtiles);
     const uint32_t fmt = s.dt == WS_F32 ? 2u : (s.dt == WS_BF16 ? 1u : 0u);
-    q->idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    q->idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((pair ? 256 : 128) >> 4) << 24);
     q->panel_bytes = bn * es >= 128 ? 128 : bn * es;
     const int panel_cols = q->panel_bytes / es;
     const int bk_elems = q->bk_bytes / es;
     {   // weights map with the v2 N tile
         cuuint64_t dims[2] = {(cuuint64_t)s.Ktot, (cuuint64_t)s.Cout};
         cuuint64_t str[1] = {(cuuint64_t)s.Ktot * es};
-        cuuint32_t box[2] = {(cuuint32_t)bk_elems, (cuuint32_t)bn};
+        cuuint32_t box[2] = {(cuuint32_t)bk_elems, (cuuint32_t)(pair ? bn / 2 : bn)};
         if (!encode_map(&q->wmap, s.dt, s.W, 2, dims, str, box, q->bk_bytes)) return false;
         q->wmap_lo = q->wmap;
         if (s.split && !encode_map(&q->wmap_lo, s.dt, s.W_lo, 2, dims, str, box, q->bk_bytes)) return false;
@@ -312,8 +315,13 @@ static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported) {
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (g_num_sms <= 0) g_num_sms = 148;
     }
-    q->grid = q->num_tiles < g_num_sms ? q->num_tiles : g_num_sms;
-    q->smem_bytes = nst * (128 + bn) * q->bk_bytes + nstage_bufs * 128 * bn * es + 3 * bn * 4 + 1024;
+    if (pair) {
+        const int pairs = g_num_sms / 2;
+        q->grid = 2 * (q->num_tiles < pairs ? q->num_tiles : pairs);
+    } else {
+        q->grid = q->num_tiles < g_num_sms ? q->num_tiles : g_num_sms;
+    }
+    q->smem_bytes = nst * (128 + (pair ? bn / 2 : bn)) * q->bk_bytes + nstage_bufs * 128 * bn * es + 3 * bn * 4 + 1024;
     q->epi = e;
     const char* env_sh = getenv("WS_TC2_SHIFT_TEST");
     q->dbg_shift = env_sh ? atoi(env_sh) : -1;
@@ -335,6 +343,18 @@ static bool build_simt(const ConvSpec& s, WsSimtParams* p) {
 }
 
 bool make_conv_op(const ConvSpec& spec, int use_tc, Op* out) {
+    const char* env_mp = getenv("WS_TC3_MIN_POS");
+    const long long min_pos = env_mp ? atoll(env_mp) : 148LL * 128;
+    if (use_tc >= 3 && spec.Cout % 128 == 0 && (long long)spec.B * spec.F * spec.T >= min_pos) {
+        // big layers: CTA pairs (cta_group::2) halve the weight-operand traffic per CTA
+        auto q = std::make_shared<WsTc2Params>();
+        bool unsupported = false;
+        if (build_tc2(spec, q.get(), &unsupported, true)) {
+            *out = [q](cudaStream_t s) { return ws_tc3_launch(q.get(), s); };
+            return true;
+        }
+        if (!unsupported) return false;
+    }
     if (use_tc >= 2) {
         auto q = std::make_shared<WsTc2Params>();
         bool unsupported = false;
@@ -420,7 +440,7 @@ extern "C" int ws_conv(const ws_conv_desc* d, void* stream) {
     s.epi.bias = d->bias; s.epi.act1 = d->act1; s.epi.scale = d->scale; s.epi.shift = d->shift;
     s.epi.res = d->res; s.epi.res_ld = d->res_ld; s.epi.act2 = d->act2;
     Op op;
-    if (d->use_tc) { WS_CKS(ws_tc_init()); WS_CKS(ws_tc2_init()); }
+    if (d->use_tc) { WS_CKS(ws_tc_init()); WS_CKS(ws_tc2_init()); WS_CKS(ws_tc3_init()); }
     if (!make_conv_op(s, d->use_tc, &op)) return 1;
     const char* m = op((cudaStream_t)stream);
     if (m != nullptr) { set_err(std::string("ws_conv launch: ") + m); return 1; }

@@ -336,7 +336,7 @@ bool build_ecapa(Builder& b) {
         conv_relu_bn(pf + ".0", xin, tA, 1, 1, 0);
         // Res2Conv1dReluBn (ecapa_tdnn.py:29-78): 7 dependent dilated k=3 convs on w8-channel groups
         bool fused = false;
-        if (e.use_tc == 2 && e.act_dt != WS_F32 && e.opt("res2_fused", 1)) {
+        if (e.use_tc >= 2 && e.act_dt != WS_F32 && e.opt("res2_fused", 1)) {
             // one persistent launch per stage: the chain stays in shared memory / TMEM (ws_res2_fused.cu)
             std::vector<float> w7((size_t)7 * w8 * 3 * w8), b7((size_t)7 * w8), s7((size_t)7 * w8), h7((size_t)7 * w8);
             bool okw = true;
@@ -945,6 +945,7 @@ int ws_engine_create(const char* model_name, const char* precision, int feat_dim
     WS_CKS(ws_tc_init());
     WS_CKS(ws_tc2_init());
     WS_CKS(ws_res2_init());
+    WS_CKS(ws_tc3_init());
     WS_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     WS_CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
     WS_CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
@@ -956,7 +957,7 @@ int ws_engine_set_option(ws_engine* e, const char* key, long long value) {
     if (!e || !key) { set_err("ws_engine_set_option: null argument"); return 1; }
     const std::string k = key;
     if (k == "force_simt") { if (value) e->use_tc = 0; }
-    else if (k == "tc_version") { if (e->use_tc && !e->split) e->use_tc = value >= 2 ? 2 : 1; }
+    else if (k == "tc_version") { if (e->use_tc) e->use_tc = value >= 3 ? 3 : (value >= 2 || e->split ? 2 : 1); }
     else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused") { set_err("unknown option " + k); return 1; }
     e->opts[k] = value;
     e->plans.clear();

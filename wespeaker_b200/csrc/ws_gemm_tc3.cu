@@ -1,0 +1,503 @@
+// 2-CTA (cta_group::2) variant of the persistent conv/GEMM (ws_gemm_tc2.cu): a cluster of two CTAs on one TPC computes a
+// 256-position x bn-channel tile with UMMA M=256.  Each CTA loads its own 128-row activation tile and HALF of the bn-row
+// weight tile; the leader CTA issues tcgen05.mma.cta_group::2, which reads both halves across the pair, so L2 operand
+// traffic per FLOP drops by a third versus two independent 128 x bn tiles (the round-1 profile showed the 1-CTA kernel is
+// L2-operand-bandwidth bound).  Completion is multicast to both CTAs' mbarriers; each CTA runs its own epilogue from its
+// own TMEM; accumulator buffers are handed back through the leader's barrier with remote (mapa) arrives.
+//
+// ---- original v2 header:
+// Persistent warp-specialised conv/GEMM on tcgen05 + TMEM + TMA (sm_100a), version 2.
+//
+// Same operator as ws_gemm_tc.cu (taps over rank-4 TMA maps, 128 positions x bn channels per tile, K-major swizzled
+// operands) with the three things the round-1 profile asked for:
+//   * persistent CTAs (one per SM) walking a static tile schedule, TMEM accumulator double-buffered (2 x bn columns)
+//     so the epilogue of tile i overlaps the MMAs of tile i+1, no per-tile prologue (TMEM alloc, barrier init);
+//   * bn up to 256: A tile (16 KB) is reused against a 256-row W tile -> 25 % less L2 operand traffic per FLOP;
+//   * coalesced, asynchronous epilogue: per-channel parameters staged in smem, residual / Res2 "add2" tiles fetched by
+//     TMA into swizzled smem while the mainloop runs, outputs packed into 128-B-swizzled smem panels and written with
+//     TMA stores (cp.async.bulk.tensor ... bulk_group), which also clips out-of-range rows/positions for free.
+//
+// Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4..w7 epilogue.
+#include "ws_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+        "%6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank)
+        : "memory");
+}
+// 2-SM TMA loads: executed by both CTAs, data lands in the issuing CTA's smem, transaction bytes are credited to the
+// LEADER CTA's mbarrier (peer bit of the barrier address cleared, cute::Sm100MmaPeerBitMask)
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                             int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+        "%5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(dst),
+        "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int bk_bytes) {
+    const uint64_t layout = bk_bytes == 128 ? 2ull : (bk_bytes == 64 ? 4ull : 6ull);
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * bk_bytes) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= layout << 61;
+    return d;
+}
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    if (KIND == 0) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    }
+}
+// completion of all prior MMAs -> arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 16-byte chunk index after the TMA/UMMA swizzle for a row of `row_bytes` (128/64/32) inside a 1024-B aligned panel
+__device__ __forceinline__ int swz_chunk(int chunk, int row, int row_bytes) {
+    return row_bytes == 128 ? (chunk ^ (row & 7)) : (row_bytes == 64 ? (chunk ^ ((row >> 1) & 3)) : (chunk ^ ((row >> 2) & 1)));
+}
+
+constexpr int kThreads3 = 256;
+constexpr int kMaxDynSmem3 = 220 * 1024;
+
+// 32 consecutive fp32 values -> packed activation dtype -> swizzled staging panel row
+__device__ __forceinline__ void stage_store32(uint32_t panel_base, int row, int row_bytes, int col_in_panel, int dt,
+                                              const float* v) {
+    const uint32_t rbase = panel_base + (uint32_t)(row * row_bytes);
+    if (dt == WS_F32) {
+        const int c0 = (col_in_panel * 4) >> 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t a = rbase + (uint32_t)(swz_chunk(c0 + i, row, row_bytes) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * i]), "f"(v[4 * i + 1]),
+                         "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                         : "memory");
+        }
+    } else {
+        const int c0 = (col_in_panel * 2) >> 4;
+        const bool bf = dt == WS_BF16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                w[j] = bf ? ws_pack2(v[8 * i + 2 * j], v[8 * i + 2 * j + 1], WS_BF16)
+                          : ws_pack2(v[8 * i + 2 * j], v[8 * i + 2 * j + 1], WS_F16);
+            const uint32_t a = rbase + (uint32_t)(swz_chunk(c0 + i, row, row_bytes) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                         : "memory");
+        }
+    }
+}
+// inverse: read 32 consecutive values of a TMA-loaded swizzled panel row
+__device__ __forceinline__ void stage_load32(uint32_t panel_base, int row, int row_bytes, int col_in_panel, int dt,
+                                             float* v) {
+    const uint32_t rbase = panel_base + (uint32_t)(row * row_bytes);
+    if (dt == WS_F32) {
+        const int c0 = (col_in_panel * 4) >> 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t a = rbase + (uint32_t)(swz_chunk(c0 + i, row, row_bytes) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v[4 * i]), "=f"(v[4 * i + 1]), "=f"(v[4 * i + 2]), "=f"(v[4 * i + 3])
+                         : "r"(a));
+        }
+    } else {
+        const int c0 = (col_in_panel * 2) >> 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t w[4];
+            const uint32_t a = rbase + (uint32_t)(swz_chunk(c0 + i, row, row_bytes) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(a));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[8 * i + 2 * j] = ws_16_to_f(w[j] & 0xffffu, dt);
+                v[8 * i + 2 * j + 1] = ws_16_to_f(w[j] >> 16, dt);
+            }
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads3, 1) ws_conv_gemm_tc3_kernel(const __grid_constant__ WsTc2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar[2 * WS_TC_MAX_STAGES + 6];
+    __shared__ uint32_t s_tmem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int a_bytes = 128 * p.bk_bytes, b_bytes = (p.bn / 2) * p.bk_bytes;   // own A tile + own HALF of the W tile
+    const int stage_bytes = a_bytes + b_bytes;
+    const int es = KIND == 0 ? 4 : 2;
+    const int panel_bytes = p.panel_bytes;               // row bytes of one staging panel (128 / 64)
+    const int panel_cols = panel_bytes / es;
+    const int npanels = p.bn / panel_cols;
+    const int tile_out_bytes = 128 * p.bn * es;          // one full output tile in staging
+    const uint32_t ring = base;
+    const uint32_t stg_out = ring + (uint32_t)(p.nstages * stage_bytes);                  // p.nout output tiles
+    const uint32_t stg_in = stg_out + (uint32_t)(p.nout * tile_out_bytes);                // only if p.has_epin
+    const uint32_t s_par = stg_in + (uint32_t)(p.has_epin ? tile_out_bytes : 0);          // 3 * bn floats
+    const uint32_t bar_full = smem_u32(&s_bar[0]);
+    const uint32_t bar_empty = smem_u32(&s_bar[WS_TC_MAX_STAGES]);
+    const uint32_t bar_tfull = smem_u32(&s_bar[2 * WS_TC_MAX_STAGES]);       // [2]
+    const uint32_t bar_tempty = smem_u32(&s_bar[2 * WS_TC_MAX_STAGES + 2]);  // [2]
+    const uint32_t bar_ifull = smem_u32(&s_bar[2 * WS_TC_MAX_STAGES + 4]);
+    const uint32_t bar_iempty = smem_u32(&s_bar[2 * WS_TC_MAX_STAGES + 5]);
+    const uint32_t tmem_cols = (uint32_t)(2 * p.bn < 32 ? 32 : 2 * p.bn);
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < WS_MAX_SRC; ++i) prefetch_tmap(&p.amap[i]);
+        prefetch_tmap(&p.wmap);
+        for (int i = 0; i < p.nout; ++i) prefetch_tmap(&p.omap[i]);
+        if (p.has_epin) prefetch_tmap(&p.imap);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.nstages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 8);  // one arrive per epilogue warp of BOTH CTAs (leader's copy is the live one)
+        }
+        mbar_init(bar_ifull, 1);
+        mbar_init(bar_iempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();   // both CTAs' barriers initialised and TMEM allocated before any cross-CTA traffic
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            const int bk_elems = p.bk_bytes / es;
+            int it = 0, j = 0;
+            for (int tile = blockIdx.x >> 1; tile < p.num_tiles; tile += gridDim.x >> 1, ++j) {
+                int tt = (tile / p.tiles_n) * 2 + (int)rank;           // this CTA's position tile inside the pair
+                const int n0 = (tile % p.tiles_n) * p.bn;
+                const int t0 = (tt % p.tiles_t) << p.bt_log2; tt /= p.tiles_t;
+                const int f0 = (tt % p.tiles_f) << p.bf_log2; tt /= p.tiles_f;
+                const int b0 = tt << p.bb_log2;                            // >= B for the odd tail tile: all OOB
+                for (int tp = 0; tp < p.ntaps; ++tp) {
+                    const WsTcTap tap = p.taps[tp];
+                    for (int kb = 0; kb < tap.nkb; ++kb) {
+                        // 3xTF32: three passes per k-block, small terms first: x_lo*W, x*W_lo, x*W (fp32 operands are
+                        // truncated to tf32 by the tensor core, so x and W themselves serve as the high parts)
+                        for (int ps = 3 - p.nsplit; ps < 3; ++ps, ++it) {
+                            const int s = it % p.nstages;
+                            const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+                            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                            if (leader) mbar_expect_tx(bar_full + 8 * s, (uint32_t)(2 * stage_bytes));  // both CTAs' bytes
+                            const uint32_t sa = ring + (uint32_t)(s * stage_bytes);
+                            tma2_load_4d(sa, ps == 0 ? &p.amap_lo[tap.map] : &p.amap[tap.map], bar_full + 8 * s,
+                                         tap.c0 + kb * bk_elems, t0 + tap.dt, f0 + tap.df, b0);
+                            tma2_load_2d(sa + (uint32_t)a_bytes, ps == 1 ? &p.wmap_lo : &p.wmap, bar_full + 8 * s,
+                                         tap.wk + kb * bk_elems, n0 + (int)rank * (p.bn / 2));
+                        }
+                    }
+                }
+                // epilogue-input tile (residual / add2): issued after this tile's operand loads so that waiting for
+                // the previous tile's epilogue to release the buffer never starves the MMA pipe
+                if (p.has_epin) {
+                    mbar_wait(bar_iempty, ((uint32_t)j & 1u) ^ 1u);
+                    mbar_expect_tx(bar_ifull, (uint32_t)tile_out_bytes);
+                    for (int pn = 0; pn < npanels; ++pn)
+                        tma_load_4d(stg_in + (uint32_t)(pn * 128 * panel_bytes), &p.imap, bar_ifull, n0 + pn * panel_cols,
+                                    t0, f0, b0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA only) ================================
+        if (lane == 0 && leader) {
+            const int kper = p.bk_bytes / 32;
+            int it = 0, j = 0;
+            for (int tile = blockIdx.x >> 1; tile < p.num_tiles; tile += gridDim.x >> 1, ++j) {
+                const int buf = j & 1;
+                mbar_wait(bar_tempty + 8 * buf, (((uint32_t)j >> 1) & 1u) ^ 1u);  // epilogue drained this buffer
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * p.bn);
+                for (int kit = 0; kit < p.nk_total * p.nsplit; ++kit, ++it) {
+                    const int s = it % p.nstages;
+                    const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = ring + (uint32_t)(s * stage_bytes);
+                    const uint64_t adesc = umma_desc(sa, p.bk_bytes);
+                    const uint64_t bdesc = umma_desc(sa + (uint32_t)a_bytes, p.bk_bytes);
+                    for (int k = 0; k < kper; ++k)
+                        umma<KIND>(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                                   (uint32_t)((kit | k) != 0));
+                    umma_commit(bar_empty + 8 * s);
+                }
+                umma_commit(bar_tfull + 8 * buf);
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue ================================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int et = threadIdx.x - 128;  // 0..127
+        const WsEpi& e = p.epi;
+        float* spar = reinterpret_cast<float*>(smem_raw + (s_par - smem_u32(smem_raw)));
+        int j = 0, last_n0 = -1;
+        for (int tile = blockIdx.x >> 1; tile < p.num_tiles; tile += gridDim.x >> 1, ++j) {
+            int tt = (tile / p.tiles_n) * 2 + (int)rank;
+            const int n0 = (tile % p.tiles_n) * p.bn;
+            const int t0 = (tt % p.tiles_t) << p.bt_log2; tt /= p.tiles_t;
+            const int f0 = (tt % p.tiles_f) << p.bf_log2; tt /= p.tiles_f;
+            const int b0 = tt << p.bb_log2;
+            const int buf = j & 1;
+            // staging buffers are free once the previous tile's TMA stores have finished reading them
+            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (n0 != last_n0) {
+                for (int c = et; c < p.bn; c += 128) {
+                    spar[c] = e.bias ? e.bias[n0 + c] : 0.f;
+                    spar[p.bn + c] = e.scale ? e.scale[n0 + c] : 1.f;
+                    spar[2 * p.bn + c] = e.scale ? e.shift[n0 + c] : 0.f;
+                }
+                last_n0 = n0;
+            }
+            epi_bar_sync();
+            // row -> output position (for the per-row epilogue inputs that are not tile-shaped)
+            const int t = t0 + (r & ((1 << p.bt_log2) - 1));
+            const int f = f0 + ((r >> p.bt_log2) & ((1 << p.bf_log2) - 1));
+            const int b = b0 + (r >> (p.bt_log2 + p.bf_log2));
+            const bool valid = (t < p.T) && (f < p.F) && (b < p.B);
+            const long long pos = ((long long)b * p.F + f) * p.T + t;
+            int eb = 0, etm = 0;
+            if (valid && (e.rowbias != nullptr || e.gate != nullptr)) {
+                eb = (int)(pos / e.FT);
+                etm = (int)(pos % e.T);
+            }
+            mbar_wait(bar_tfull + 8 * buf, ((uint32_t)j >> 1) & 1u);
+            tc_fence_after();
+            if (p.has_epin) mbar_wait(bar_ifull, (uint32_t)j & 1u);
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.bn);
+            for (int c = 0; c < p.bn; c += 32) {
+                uint32_t raw[32];
+                tmem_ld32(trow + (uint32_t)c, raw);
+                tmem_ld_wait();
+                float v[32];
+                {
+                    const float4* sb = reinterpret_cast<const float4*>(spar + c);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 x = sb[i];
+                        v[4 * i] = __uint_as_float(raw[4 * i]) + x.x; v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + x.y;
+                        v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + x.z; v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + x.w;
+                    }
+                }
+                if (e.rowbias != nullptr && valid) {
+                    const float4* rb = reinterpret_cast<const float4*>(e.rowbias + (long long)eb * e.rowbias_ld + n0 + c);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 x = __ldg(rb + i);
+                        v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+                    }
+                }
+                ws_act_vec<32>(v, e.act1);
+                if (e.scale != nullptr) {
+                    const float4* ss = reinterpret_cast<const float4*>(spar + p.bn + c);
+                    const float4* sh = reinterpret_cast<const float4*>(spar + 2 * p.bn + c);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 a = ss[i], d = sh[i];
+                        v[4 * i] = fmaf(v[4 * i], a.x, d.x); v[4 * i + 1] = fmaf(v[4 * i + 1], a.y, d.y);
+                        v[4 * i + 2] = fmaf(v[4 * i + 2], a.z, d.z); v[4 * i + 3] = fmaf(v[4 * i + 3], a.w, d.w);
+                    }
+                }
+                if (e.gate != nullptr && valid) {
+                    const float4* g = reinterpret_cast<const float4*>(
+                        e.gate + ((long long)eb * e.gate_nseg + etm / e.gate_seg) * e.gate_ld + n0 + c);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 x = __ldg(g + i);
+                        v[4 * i] *= x.x; v[4 * i + 1] *= x.y; v[4 * i + 2] *= x.z; v[4 * i + 3] *= x.w;
+                    }
+                }
+                const int pn = c / panel_cols, cin = c % panel_cols;
+                float rin[32];
+                if (p.has_epin) stage_load32(stg_in + (uint32_t)(pn * 128 * panel_bytes), r, panel_bytes, cin, e.dtype, rin);
+                if (p.has_epin && !p.has_out2) {  // residual
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += rin[i];
+                }
+                ws_act_vec<32>(v, e.act2);
+                const uint32_t poff = (uint32_t)(pn * 128 * panel_bytes);
+                int ob = 0;
+                stage_store32(stg_out + poff, r, panel_bytes, cin, e.dtype, v);
+                if (p.has_out2) {  // Res2: next conv's input = this output + the next channel group
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) rin[i] += v[i];
+                }
+                if (p.nsplit == 3) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = ws_tf32_lo(v[i]);
+                    stage_store32(stg_out + (uint32_t)(++ob * tile_out_bytes) + poff, r, panel_bytes, cin, e.dtype, v);
+                }
+                if (p.has_out2) {
+                    stage_store32(stg_out + (uint32_t)(++ob * tile_out_bytes) + poff, r, panel_bytes, cin, e.dtype, rin);
+                    if (p.nsplit == 3) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) rin[i] = ws_tf32_lo(rin[i]);
+                        stage_store32(stg_out + (uint32_t)(++ob * tile_out_bytes) + poff, r, panel_bytes, cin, e.dtype, rin);
+                    }
+                }
+            }
+            // accumulator buffer (and the epilogue-input tile) are drained: hand them back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_remote(bar_tempty + 8 * buf, 0);   // the MMA issuer lives in the leader CTA
+                if (p.has_epin) mbar_arrive(bar_iempty);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            epi_bar_sync();
+            if (et == 0) {
+                for (int o = 0; o < p.nout; ++o)
+                    for (int pn = 0; pn < npanels; ++pn)
+                        tma_store_4d(&p.omap[o], stg_out + (uint32_t)(o * tile_out_bytes + pn * 128 * panel_bytes),
+                                     n0 + pn * panel_cols, t0, f0, b0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+
+    tc_fence_before();
+    cluster_sync_all();   // neither CTA may exit (or free TMEM) while its peer can still touch its smem / TMEM / barriers
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+}  // namespace
+
+extern "C" const char* ws_tc3_init(void) {
+    static bool done = false;
+    if (done) return nullptr;
+    cudaError_t e = cudaFuncSetAttribute(ws_conv_gemm_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem3);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(ws_conv_gemm_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem3);
+    if (e != cudaSuccess) { cudaGetLastError(); return cudaGetErrorString(e); }
+    done = true;
+    return nullptr;
+}
+
+extern "C" int ws_tc3_max_smem(void) { return kMaxDynSmem3; }
+
+extern "C" const char* ws_tc3_launch(const WsTc2Params* p, cudaStream_t s) {
+    if (p->kind == 0) ws_conv_gemm_tc3_kernel<0><<<p->grid, kThreads3, p->smem_bytes, s>>>(*p);
+    else ws_conv_gemm_tc3_kernel<1><<<p->grid, kThreads3, p->smem_bytes, s>>>(*p);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
