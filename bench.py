@@ -192,7 +192,7 @@ def plda_bench(dev, n_enroll=32768, n_test=100000, dim=256, iters=3):
                              "sample": "20000 trials, per-trial log_likelihood_ratio loop as in eval_sv"}}
 
 
-def time_dominant_kernel(model, prec, B, T, iters=10, tc_version=2):
+def time_dominant_kernel(model, prec, B, T, iters=10, tc_version=3):
     """Roofline leg: the dominant launch of the step — ECAPA's 1x1 conv 3C->1536 over B*T positions
     (ecapa_tdnn.py:200,218; 47-49% of the model's MACs) — timed live with CUDA events on the launching stream
     through ws_conv.  Algorithmic FLOPs per launch = 2 * B*T * 3C * 1536."""
@@ -234,7 +234,7 @@ def time_dominant_kernel(model, prec, B, T, iters=10, tc_version=2):
     ms = e0.elapsed_time(e1) / iters
     flops = 2.0 * B * T * cin * cout
     return dict(ms=ms, tflops=flops / (ms * 1e-3) / 1e12, flops=flops, nbuf=nbuf,
-                kernel=f"ws_conv_gemm_tc2_kernel 1x1 {cin}->{cout} over {B * T} positions")
+                kernel=f"ws_conv_gemm_tc{tc_version}_kernel 1x1 {cin}->{cout} over {B * T} positions")
 
 
 def main():
@@ -253,6 +253,7 @@ def main():
         run_reference(args, wl)
         return
     model_name, prec, B, nsamples, gflop_utt = WORKLOADS[wl]
+    torch.set_num_threads(2)  # the GPU arm needs no host parallelism; idle-spinning worker pools only add scheduler noise
 
     from wespeaker_b200 import parallel
     from wespeaker_b200.models import from_synthetic
@@ -325,11 +326,15 @@ def main():
     if rank != 0:
         return
     # ---------------- roofline for the dominant kernel + whole-step tensor utilisation
-    dom = time_dominant_kernel(model_name, prec, B, L_frames, tc_version=args.tc_version or 2)
+    dom = time_dominant_kernel(model_name, prec, B, L_frames, tc_version=args.tc_version or 3)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tpath) and wl == DEFAULT_WORKLOAD:   # DRAM bytes per launch of this kernel from the committed ncu capture
+        traffic = json.load(open(tpath))["traffic_bytes_per_launch"]
     step_tf = value / world * gflop_utt / 1e3  # TFLOP/s per GPU, algorithmic
     if dom is not None:
         roof = {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                "frac": dom["tflops"] / peaks["tf_burst"], "traffic": None, "kernel": dom["kernel"],
+                "frac": dom["tflops"] / peaks["tf_burst"], "traffic": traffic, "kernel": dom["kernel"],
                 "kernel_ms": dom["ms"], "flops_per_launch": dom["flops"], "peak_source": peaks["src"] + " (burst, kernel timed alone)",
                 "step_tflops_per_gpu": step_tf, "step_frac_of_sustained": step_tf / peaks["tf_sustained"]}
     else:

@@ -31,8 +31,8 @@ const char* ws_last_error(void);
 int ws_engine_create(const char* model_name, const char* precision, int feat_dim, int embed_dim, int device,
                      ws_engine** out);
 /* options: "two_emb_layer", "emb_bn" (model_args), "cuda_graph" (default 1), "force_simt" (debug cross-check),
- * "tc_version" (1: one-tile-per-CTA tcgen05 kernel, 2: persistent / TMA-store kernel, 3: + cta_group::2 CTA pairs on
- * the large layers),
+ * "tc_version" (1: one-tile-per-CTA tcgen05 kernel, 2: persistent / TMA-store kernel, 3 (default): + cta_group::2 CTA pairs
+ * on the large layers),
  * "res2_fused" (default 1: ECAPA Res2 chains run as one fused persistent kernel per stage for 16-bit precisions) */
 int ws_engine_set_option(ws_engine* e, const char* key, long long value);
 /* one reference state_dict entry (fp32 host data, reference key names). */

@@ -58,7 +58,7 @@ struct ws_engine {
     std::string model, prec;
     int feat_dim = 80, embed_dim = 0, device = 0;
     int act_dt = WS_F32;
-    int use_tc = 0;  // 0 FFMA, 1 tcgen05 v1, 2 tcgen05 v2
+    int use_tc = 0;  // 0 FFMA, 1 tcgen05 v1, 2 tcgen05 v2 (persistent), 3 v2 + cta_group::2 pairs on large layers (default)
     bool split = false;  // 3xTF32: fp32 activations/weights carry lo twins, GEMMs run 3 error-compensated passes
     std::map<const void*, const void*> wlo;  // packed weight -> its lo twin
     std::map<std::string, long long> opts;
@@ -936,10 +936,10 @@ int ws_engine_create(const char* model_name, const char* precision, int feat_dim
     else { set_err("unknown / out-of-scope model name: " + m); return 1; }
     const std::string p = e->prec;
     if (p == "fp32") { e->act_dt = WS_F32; e->use_tc = 0; }
-    else if (p == "tf32") { e->act_dt = WS_F32; e->use_tc = 2; }
-    else if (p == "tf32x3") { e->act_dt = WS_F32; e->use_tc = 2; e->split = true; }
-    else if (p == "bf16") { e->act_dt = WS_BF16; e->use_tc = 2; }
-    else if (p == "fp16") { e->act_dt = WS_F16; e->use_tc = 2; }
+    else if (p == "tf32") { e->act_dt = WS_F32; e->use_tc = 3; }
+    else if (p == "tf32x3") { e->act_dt = WS_F32; e->use_tc = 3; e->split = true; }
+    else if (p == "bf16") { e->act_dt = WS_BF16; e->use_tc = 3; }
+    else if (p == "fp16") { e->act_dt = WS_F16; e->use_tc = 3; }
     else { set_err("unknown precision (fp32|tf32x3|tf32|bf16|fp16): " + p); return 1; }
     if (feat_dim % 8 != 0) { set_err("feat_dim must be a multiple of 8"); return 1; }
     WS_CKS(ws_tc_init());

@@ -70,6 +70,36 @@ __global__ void __launch_bounds__(256) tstats_kernel(const void* __restrict__ x,
     }
 }
 
+// mean over T only, 8 channels per thread (16-byte loads): the SE squeeze (ecapa_tdnn.py:120) reads a full activation map
+// per stage.  block (64, 8): x = group of 8 channels, y = T slice.
+__global__ void __launch_bounds__(512) tmean8_kernel(const void* __restrict__ x, int dt, int T, int C, long long ld,
+                                                      float* __restrict__ out, long long out_ld) {
+    __shared__ float red[8][64 * 8 + 8];
+    const int c = (blockIdx.x * 64 + threadIdx.x) * 8;
+    const int b = blockIdx.y;
+    const bool cv = c < C;
+    const long long base = (long long)b * T * ld + c;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (cv)
+        for (int t = threadIdx.y; t < T; t += 8) {
+            float v[8];
+            ws_ldv8(x, dt, base + (long long)t * ld, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += v[k];
+        }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[threadIdx.y][threadIdx.x * 8 + k] = a[k];
+    __syncthreads();
+    const int tid = threadIdx.y * 64 + threadIdx.x;   // 512 threads: one output channel each
+    const int cc = blockIdx.x * 512 + tid;
+    if (cc < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][tid];
+        out[(long long)b * out_ld + cc] = s / (float)T;
+    }
+}
+
 // Small fully-connected layers (SE, CAM context, global-context row bias, embedding head) as a shared-memory tiled
 // fp32 GEMM: block = 16 rows x 32 outputs (thread: 1 row x 2 outputs), K streamed in chunks of 64 with coalesced loads.
 __global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restrict__ in, long long in_ld,
@@ -409,6 +439,11 @@ const char* ws_launch_convert(const float* in, void* out, float* lo, int dt, lon
 const char* ws_launch_tstats(const void* x, int dt, int B, int F, int T, int C, long long ld, const float* pre_scale,
                              const float* pre_shift, void* out, int odt, long long out_ld, int std_off, float eps,
                              cudaStream_t s) {
+    if (std_off < 0 && F == 1 && pre_scale == nullptr && odt == WS_F32 && C % 8 == 0) {
+        dim3 g8((C + 511) / 512, B), b8(64, 8);
+        tmean8_kernel<<<g8, b8, 0, s>>>(x, dt, T, C, ld, (float*)out, out_ld);
+        return last_err();
+    }
     dim3 grid((C + 31) / 32, F, B), block(32, 8);
     tstats_kernel<<<grid, block, 0, s>>>(x, dt, F, T, C, ld, pre_scale, pre_shift, out, odt, out_ld, std_off, eps);
     return last_err();

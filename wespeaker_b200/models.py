@@ -251,9 +251,9 @@ class B200SpeakerModel(torch.nn.Module):
     def _unpinned_copy(t: torch.Tensor) -> torch.Tensor:
         # Tensor.clone() of a pinned tensor allocates pinned memory again (a cudaHostAlloc per batch, ~6 ms); copy into
         # ordinary pageable memory instead
-        out = torch.empty(t.shape, dtype=t.dtype)
-        out.copy_(t)
-        return out
+        # numpy's single-threaded memcpy: a torch copy_ may wake a large intra-op thread pool whose spinning workers get
+        # the process CPU-throttled on shared hosts, which shows up as multi-ms stalls of the next collect()
+        return torch.from_numpy(t.numpy().copy())
 
     # ------------------------------------------------------------------ variable-length batches (BASELINE config 4)
     def embed_list(self, feats_list, max_batch: int = 64, device=None):
