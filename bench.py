@@ -34,6 +34,7 @@ WORKLOADS = {
     "ecapa512_fp32_b16": ("ECAPA_TDNN_c512", "fp32", 16, 32000, 1.898),
     "resnet34_fp16_b64": ("ResNet34", "fp16", 64, 32320, 9.056),
     "campplus_bf16_b64": ("CAMPPlus", "bf16", 64, 32320, 2.252),
+    "ecapa512_tf32x3_b256": ("ECAPA_TDNN_c512", "tf32x3", 256, 32320, 1.917),
 }
 DEFAULT_WORKLOAD = "ecapa1024_bf16_b256"
 METRIC = "utterances/s (2s@16kHz) embedding extraction"
@@ -198,7 +199,7 @@ def time_dominant_kernel(model, prec, B, T, iters=10, tc_version=3):
     through ws_conv.  Algorithmic FLOPs per launch = 2 * B*T * 3C * 1536."""
     import ctypes as C
     from wespeaker_b200 import lib
-    if not model.startswith("ECAPA"):
+    if not model.startswith("ECAPA") or prec not in ("fp32", "tf32", "bf16", "fp16"):
         return None
     Cc = 1024 if "1024" in model else 512
     cin, cout = 3 * Cc, 1536
