@@ -175,6 +175,11 @@ def test_fbank_cmn_short_ragged_and_oracle():
     assert frontend.fbank_batch(torch.zeros(2, 399, device=DEV)).shape == (2, 0, 80)
     one = frontend.fbank_batch(torch.from_numpy(syn.make_wavs(1, 400, seed=1)).to(DEV)).cpu().numpy()
     assert one.shape == (1, 1, 80) and np.abs(one[0] - fbank_np.fbank(syn.make_wavs(1, 400, seed=1)[0])).max() < 2e-3
+    # odd sample counts with B > 1 (rows start at odd offsets: the paired-sample loads must fall back to scalar loads)
+    wo = syn.make_wavs(3, 16077, seed=6)
+    fo = frontend.fbank_batch(torch.from_numpy(wo).to(DEV)).cpu().numpy()
+    for i in range(3):
+        assert np.abs(fo[i] - fbank_np.fbank(wo[i])).max() < 2e-3
     # CMN'd features are invariant to the input gain (log-mel gain is additive): property at full size
     w = torch.from_numpy(syn.make_wavs(8, 32000, seed=7)).to(DEV)
     a = frontend.fbank_batch(w, cmn=True)

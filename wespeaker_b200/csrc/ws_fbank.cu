@@ -23,6 +23,15 @@ __device__ __forceinline__ float ld_sample(const void* wav, int is_i16, long lon
     return is_i16 ? (float)((const short*)wav)[i] : ((const float*)wav)[i];
 }
 
+__device__ __forceinline__ float2 ld_sample2(const void* wav, int is_i16, long long i) {   // samples i, i+1
+    if (i & 1) return make_float2(ld_sample(wav, is_i16, i), ld_sample(wav, is_i16, i + 1));  // odd row stride: scalar loads
+    if (is_i16) {
+        const short2 v = *reinterpret_cast<const short2*>((const short*)wav + i);
+        return make_float2((float)v.x, (float)v.y);
+    }
+    return *reinterpret_cast<const float2*>((const float*)wav + i);
+}
+
 __global__ void __launch_bounds__(256) fbank_kernel(const void* __restrict__ wav, int is_i16, long long wav_ld, int T,
                                                     const float* __restrict__ window, const float* __restrict__ melw,
                                                     const int* __restrict__ melstart, const int* __restrict__ mellen,
@@ -31,37 +40,51 @@ __global__ void __launch_bounds__(256) fbank_kernel(const void* __restrict__ wav
     __shared__ float2 s_z[8][256];      // per-warp FFT buffer
     __shared__ float s_p[8][256];       // per-warp power spectrum (bins 0..255; Nyquist has zero mel weight)
     __shared__ float s_win[kFrameLen];
+    __shared__ float s_melw[kBins * 20];
+    __shared__ short s_mels[kBins], s_mell[kBins];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     {
         float sn, cs;
         sincospif((float)threadIdx.x / 256.0f, &sn, &cs);
         s_tw[threadIdx.x] = make_float2(cs, -sn);
         for (int i = threadIdx.x; i < kFrameLen; i += 256) s_win[i] = window[i];
+        for (int i = threadIdx.x; i < kBins * mel_maxlen; i += 256) s_melw[(i / mel_maxlen) * 20 + (i % mel_maxlen)] = melw[i];
+        if (threadIdx.x < kBins) { s_mels[threadIdx.x] = (short)melstart[threadIdx.x]; s_mell[threadIdx.x] = (short)mellen[threadIdx.x]; }
     }
     __syncthreads();
     const int b = blockIdx.y;
     const int frame = blockIdx.x * 8 + warp;
     if (frame >= T) return;
+    // frame starts are multiples of 160 samples, so pair loads are aligned whenever b * wav_ld is even (else scalar loads)
     const long long base = (long long)b * wav_ld + (long long)frame * kFrameShift;
 
-    // per-frame mean (remove_dc_offset)
+    // each lane owns sample pairs n = lane + 32k (k < 7, n < 200): ONE pass over the samples (coalesced pair loads)
+    float2 x[7];
     float s = 0.f;
-    for (int j = lane; j < kFrameLen; j += 32) s += ld_sample(wav, is_i16, base + j);
-    const float mu = warp_sum(s) / (float)kFrameLen;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const int n = lane + 32 * k;
+        x[k] = n < kFrameLen / 2 ? ld_sample2(wav, is_i16, base + 2 * n) : make_float2(0.f, 0.f);
+        s += x[k].x + x[k].y;
+    }
+    const float mu = warp_sum(s) / (float)kFrameLen;   // remove_dc_offset
 
-    // z[n] = y[2n] + i*y[2n+1], y = window * ((x - mu) - 0.97 * (x_prev - mu)), stored bit-reversed for DIT
+    // z[n] = y[2n] + i*y[2n+1], y = window * ((x - mu) - 0.97 * (x_prev - mu)); x[2n-1] comes from the neighbouring lane
     float2* z = s_z[warp];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int n = lane + 32 * k;
         float2 v = make_float2(0.f, 0.f);
-        if (n < kFrameLen / 2) {
-            const int j = 2 * n;
-            const float xm1 = ld_sample(wav, is_i16, base + (j > 0 ? j - 1 : 0)) - mu;
-            const float x0 = ld_sample(wav, is_i16, base + j) - mu;
-            const float x1 = ld_sample(wav, is_i16, base + j + 1) - mu;
-            v.x = (x0 - 0.97f * xm1) * s_win[j];
-            v.y = (x1 - 0.97f * x0) * s_win[j + 1];
+        if (k < 7) {
+            // previous odd sample: lane-1 of the same k, or lane 31 of k-1 for lane 0 (replicate-pad at n = 0)
+            float prev_same = __shfl_up_sync(0xffffffffu, x[k].y, 1);
+            float prev_wrap = __shfl_sync(0xffffffffu, k > 0 ? x[k > 0 ? k - 1 : 0].y : 0.f, 31);
+            if (n < kFrameLen / 2) {
+                const float xm1 = (lane > 0 ? prev_same : (k > 0 ? prev_wrap : x[0].x)) - mu;
+                const float x0 = x[k].x - mu, x1 = x[k].y - mu;
+                v.x = (x0 - 0.97f * xm1) * s_win[2 * n];
+                v.y = (x1 - 0.97f * x0) * s_win[2 * n + 1];
+            }
         }
         z[__brev((unsigned)n) >> 24] = v;
     }
@@ -103,8 +126,8 @@ __global__ void __launch_bounds__(256) fbank_kernel(const void* __restrict__ wav
     for (int k = 0; k < 3; ++k) {
         const int m = lane + 32 * k;
         if (m < kBins) {
-            const int st = melstart[m], len = mellen[m];
-            const float* w = melw + (long long)m * mel_maxlen;
+            const int st = s_mels[m], len = s_mell[m];
+            const float* w = s_melw + m * 20;
             float e = 0.f;
             for (int i = 0; i < len; ++i) e = fmaf(pw[st + i], w[i], e);
             out[m] = logf(fmaxf(e, kEps));
@@ -139,6 +162,7 @@ const char* ws_launch_fbank(const void* wav, int wav_is_i16, long long wav_ld, i
                             int mel_maxlen, float* feats, cudaStream_t s) {
     if (T <= 0 || B <= 0) return nullptr;
     if ((long long)(T - 1) * kFrameShift + kFrameLen > nsamples) return "fbank: T frames do not fit in nsamples";
+    if (mel_maxlen > 20) return "fbank: mel filter wider than the shared-memory table";
     dim3 grid((T + 7) / 8, B);
     fbank_kernel<<<grid, 256, 0, s>>>(wav, wav_is_i16, wav_ld, T, window400, melw, melstart, mellen, mel_maxlen, feats);
     cudaError_t e = cudaGetLastError();

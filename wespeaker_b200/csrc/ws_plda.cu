@@ -9,15 +9,13 @@
 // counts it is a second K-block (K = 2D): P_i = [m_i/v_i , -1/(2 v_i)], Q_j = [t_j , t_j^2].
 // fp64 keeps |error| ~1e-13, far inside the 1e-5 budget which fp32 accumulators cannot guarantee (sums of
 // magnitude ~256 have ulp 3e-5).  B200 runs DFMA at half the FFMA rate, so this is DFMA-bound, not HBM-bound:
-// 128x128 block tile, 8x8 register tile per thread, K streamed through shared memory.
+// 128x64 block tile, 8x4 register tile per thread, K streamed through shared memory.
 #include "ws_kernels.cuh"
 
 namespace {
 
-constexpr int TM = 128, TN = 128, TK = 8;
+constexpr int TM = 128, TN = 64, TK = 8;
 
-// 128x128 block tile, 256 threads, 8x8 register tile per thread (64 DFMA per 16 shared-memory doubles), register
-// double-buffering of the next K slab while the current one is consumed.
 __global__ void __launch_bounds__(256) dgemm_nt_kernel(const double* __restrict__ A, const double* __restrict__ Bm,
                                                        const double* __restrict__ rowc, const double* __restrict__ colc,
                                                        void* __restrict__ out, int out_is_f64, long long M, long long N,
@@ -25,43 +23,47 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(const double* __restrict_
     __shared__ double As[TK][TM + 2];
     __shared__ double Bs[TK][TN + 2];
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;  // tx -> 8 columns (2 groups of 4), ty -> 8 rows
+    const int tx = tid & 15, ty = tid >> 4;  // tx -> 4 columns, ty -> 8 rows
     const long long m0 = (long long)blockIdx.y * TM, n0 = (long long)blockIdx.x * TN;
-    const int lrow = tid >> 1, lk = (tid & 1) * 4;   // each thread stages 4 consecutive k of one A row and one B row
-    const bool av = (m0 + lrow) < M, bv = (n0 + lrow) < N;
-    const double* ap = A + (m0 + lrow) * (long long)K + lk;
-    const double* bp = Bm + (n0 + lrow) * (long long)K + lk;
-    double acc[8][8];
+    const int arow = tid >> 1, ak = (tid & 1) * 4;
+    const int brow = tid >> 2, bk = (tid & 3) * 2;
+    const bool av = (m0 + arow) < M, bv = (n0 + brow) < N;
+    const double* ap = A + (m0 + arow) * (long long)K + ak;
+    const double* bp = Bm + (n0 + brow) * (long long)K + bk;
+    double acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
-    double a[4], bb[4];
-    auto gload = [&](int k0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            a[j] = (av && k0 + lk + j < K) ? ap[k0 + j] : 0.0;
-            bb[j] = (bv && k0 + lk + j < K) ? bp[k0 + j] : 0.0;
-        }
-    };
-    gload(0);
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
     for (int k0 = 0; k0 < K; k0 += TK) {
+        double a[4] = {0, 0, 0, 0}, bb[2] = {0, 0};
+        if (av) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k0 + ak + j < K) a[j] = ap[k0 + j];
+        }
+        if (bv) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                if (k0 + bk + j < K) bb[j] = bp[k0 + j];
+        }
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { As[lk + j][lrow] = a[j]; Bs[lk + j][lrow] = bb[j]; }
+        for (int j = 0; j < 4; ++j) As[ak + j][arow] = a[j];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) Bs[bk + j][brow] = bb[j];
         __syncthreads();
-        if (k0 + TK < K) gload(k0 + TK);   // next slab's global loads fly during the FMAs below
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
-            double av8[8], bv8[8];
+            double av8[8], bv4[4];
 #pragma unroll
             for (int i = 0; i < 8; ++i) av8[i] = As[k][ty * 8 + i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { bv8[j] = Bs[k][tx * 4 + j]; bv8[4 + j] = Bs[k][64 + tx * 4 + j]; }
+            for (int j = 0; j < 4; ++j) bv4[j] = Bs[k][tx * 4 + j];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fma(av8[i], bv8[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(av8[i], bv4[j], acc[i][j]);
         }
     }
 #pragma unroll
@@ -70,21 +72,12 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(const double* __restrict_
         if (r >= M) continue;
         const double rc = rowc != nullptr ? rowc[r] : 0.0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const long long c0 = n0 + h * 64 + tx * 4;
-            double v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = acc[i][h * 4 + j] + rc + ((colc != nullptr && c0 + j < N) ? colc[c0 + j] : 0.0);
-            if (!out_is_f64 && c0 + 3 < N && ((r * out_ld + c0) & 3) == 0) {
-                *reinterpret_cast<float4*>((float*)out + r * out_ld + c0) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (c0 + j >= N) continue;
-                    if (out_is_f64) ((double*)out)[r * out_ld + c0 + j] = v[j];
-                    else ((float*)out)[r * out_ld + c0 + j] = (float)v[j];
-                }
-            }
+        for (int j = 0; j < 4; ++j) {
+            const long long c = n0 + tx * 4 + j;
+            if (c >= N) continue;
+            const double v = acc[i][j] + rc + (colc != nullptr ? colc[c] : 0.0);
+            if (out_is_f64) ((double*)out)[r * out_ld + c] = v;
+            else ((float*)out)[r * out_ld + c] = (float)v;
         }
     }
 }
