@@ -31,10 +31,15 @@ WORKLOADS = {
     # name: (model, precision, batch per GPU, samples per utterance, GFLOP/utt of conv+linear layers at that T)
     "ecapa1024_bf16_b256": ("ECAPA_TDNN_c1024", "bf16", 256, 32320, 5.141),
     "ecapa512_bf16_b256": ("ECAPA_TDNN_c512", "bf16", 256, 32320, 1.917),
+    "ecapa1024_bf16_b128": ("ECAPA_TDNN_c1024", "bf16", 128, 32320, 5.141),
+    "ecapa1024_bf16_b64": ("ECAPA_TDNN_c1024", "bf16", 64, 32320, 5.141),
+    "ecapa1024_bf16_b512": ("ECAPA_TDNN_c1024", "bf16", 512, 32320, 5.141),
     "ecapa512_fp32_b16": ("ECAPA_TDNN_c512", "fp32", 16, 32000, 1.898),
     "resnet34_fp16_b64": ("ResNet34", "fp16", 64, 32320, 9.056),
     "campplus_bf16_b64": ("CAMPPlus", "bf16", 64, 32320, 2.252),
     "ecapa512_tf32x3_b256": ("ECAPA_TDNN_c512", "tf32x3", 256, 32320, 1.917),
+    "ecapa512_fp32_b256": ("ECAPA_TDNN_c512", "fp32", 256, 32320, 1.917),
+    "ecapa1024_tf32x3_b256": ("ECAPA_TDNN_c1024", "tf32x3", 256, 32320, 5.141),
 }
 DEFAULT_WORKLOAD = "ecapa1024_bf16_b256"
 METRIC = "utterances/s (2s@16kHz) embedding extraction"
@@ -351,11 +356,11 @@ def main():
     plda = None
     if not args.no_plda:
         plda = plda_bench(dev)
-    act_mb = B * L_frames * (1536 * 2 + 128 + (1024 if '1024' in model_name else 512) * 7) * (4 if prec in ("fp32", "tf32") else 2) / 1e6
+    act_mb = B * L_frames * (1536 * 2 + 128 + (1024 if '1024' in model_name else 512) * 7) * (4 if prec in ("fp32", "tf32", "tf32x3") else 2) / 1e6
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16", "fp16": "f16"}[prec], "data": "synthetic",
+        "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3", "bf16": "bf16", "fp16": "f16"}[prec], "data": "synthetic",
         "config": {"workload": wl, "model": model_name, "batch_per_gpu": B, "samples_per_utt": nsamples,
                    "frames": L_frames, "precision": prec, "gflop_per_utt": gflop_utt,
                    "l2": f"inputs rotate over {nrot} batches; per-step activation working set ~{act_mb:.0f} MB > 126 MB L2",

@@ -60,6 +60,8 @@ int ws_engine_extract_wav_host(ws_engine* e, const void* wav_host, int wav_is_i1
 int ws_engine_submit_wav_host(ws_engine* e, int slot, const void* wav_host, int wav_is_i16, int nsamples, int B,
                               const char* window_type, float* embs_host);
 int ws_engine_collect(ws_engine* e, int slot);
+/* tuning aid: per-op device time (ms) of the (B,T) plan, measured with CUDA events in sequence context; returns #ops */
+int ws_engine_profile_ops(ws_engine* e, int B, int T, int iters, float* ms_out, int max_ops);
 /* number of this library's kernels launched by the most recent forward/extract call */
 long long ws_engine_last_launches(const ws_engine* e);
 void ws_engine_destroy(ws_engine* e);

@@ -427,3 +427,18 @@ def test_extract_dropin_and_speaker_api(tmp_path):
     fb = spk.compute_features(torch.from_numpy(wavs[:1]), cmn=True)[0].cpu().numpy()
     e_feats = spk.extract_embedding_from_feats([fb], batch_size=4, subseg_cmn=True)
     assert rel_l2(e_feats[0], got["utt0"]) <= 1e-5
+
+
+def test_plan_cache_eviction_many_shapes():
+    """More distinct (B,T) shapes than the plan cache holds (64): plans are evicted LRU and rebuilt transparently."""
+    name = "ECAPA_TDNN_c512"
+    m = from_synthetic(name, 0, precision="bf16")
+    sd = syn.make_state_dict(name, 0)
+    x0 = torch.from_numpy(syn.make_feats(2, 50, 80, seed=1)).to(DEV)
+    first = m.embed(x0).cpu().numpy()
+    for T in range(51, 51 + 70):
+        m.embed(torch.zeros(1, T, 80, device=DEV))
+    again = m.embed(x0).cpu().numpy()      # (2,50) was evicted: rebuilt plan must give the same bits
+    assert np.array_equal(first, again)
+    ref = models_torch.forward(name, sd, x0.cpu()).numpy()
+    assert rel_l2(again, ref).max() <= 3e-2

@@ -42,6 +42,8 @@ struct Plan {
     std::vector<Op> ops;
     std::vector<void*> bufs;
     int extra_launches = 0;     // ops that launch more than one kernel (split-K FC = 2)
+    size_t bytes = 0;           // device memory held by this plan
+    long long last_use = 0;     // LRU stamp
     float* feats_in = nullptr;  // fp32 [B][T][feat_dim]
     float* emb = nullptr;       // fp32 [B][embed_dim]
     cudaGraphExec_t gexec = nullptr;
@@ -67,6 +69,7 @@ struct ws_engine {
     std::map<std::string, void*> wcache;  // packed device weights by id
     std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
     long long last_launches = 0;
+    long long use_clock = 0;             // LRU clock for the plan cache
     cudaStream_t st = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     std::map<std::string, FbankTables> fb;
@@ -225,6 +228,7 @@ struct Builder {
             return nullptr;
         }
         p.bufs.push_back(d);
+        p.bytes += bytes;
         return d;
     }
     View act(int B, int F, int T, int C) {
@@ -785,7 +789,10 @@ bool build_campplus(Builder& b) {
 Plan* get_plan(ws_engine* e, int B, int T) {
     auto key = std::make_pair(B, T);
     auto it = e->plans.find(key);
-    if (it != e->plans.end()) return it->second.get();
+    if (it != e->plans.end()) {
+        it->second->last_use = ++e->use_clock;
+        return it->second.get();
+    }
     if (B <= 0 || T <= 0) { set_err("forward: B and T must be positive"); return nullptr; }
     std::unique_ptr<Plan> p(new Plan());
     p->B = B; p->T = T;
@@ -799,7 +806,20 @@ Plan* get_plan(ws_engine* e, int B, int T) {
         else ok = build_campplus(b);
     }
     if (!ok) return nullptr;
-    if (e->plans.size() >= 96) e->plans.erase(e->plans.begin());  // bound memory for many distinct (B,T) shapes
+    // Plan cache policy: one plan (buffers + CUDA graph) per distinct (B,T); evict least-recently-used plans beyond 64
+    // entries or 48 GB of activation memory (variable-length workloads touch many shapes; 180 GB HBM is shared with the
+    // caller's tensors).  Eviction waits for in-flight work on the engine stream.
+    size_t total = p->bytes;
+    for (auto& kv : e->plans) total += kv.second->bytes;
+    while (!e->plans.empty() && (e->plans.size() >= 64 || total > (size_t)48 << 30)) {
+        auto victim = e->plans.begin();
+        for (auto i2 = e->plans.begin(); i2 != e->plans.end(); ++i2)
+            if (i2->second->last_use < victim->second->last_use) victim = i2;
+        cudaStreamSynchronize(e->st);
+        total -= victim->second->bytes;
+        e->plans.erase(victim);
+    }
+    p->last_use = ++e->use_clock;
     Plan* raw = p.get();
     e->plans[key] = std::move(p);
     return raw;
@@ -1128,6 +1148,38 @@ int ws_engine_collect(ws_engine* e, int slot) {
     if (!e || slot < 0 || slot >= ws_engine::kSlots || e->slot_done[slot] == nullptr) { set_err("ws_engine_collect: bad argument"); return 1; }
     WS_CK(cudaEventSynchronize(e->slot_done[slot]));
     return 0;
+}
+
+// Tuning aid: run the (B,T) plan op by op (no CUDA graph) with CUDA events between ops, in sequence context (the L2 holds
+// what the previous op left there, unlike ncu's cold-cache replays).  ms_out[i] = duration of op i; returns the op count.
+int ws_engine_profile_ops(ws_engine* e, int B, int T, int iters, float* ms_out, int max_ops) {
+    if (!e || !ms_out || !e->finalized) { set_err("ws_engine_profile_ops: bad argument"); return -1; }
+    if (cudaSetDevice(e->device) != cudaSuccess) return -1;
+    Plan* p = get_plan(e, B, T);
+    if (!p) return -1;
+    const int n = (int)p->ops.size();
+    if (n > max_ops) { set_err("ws_engine_profile_ops: output array too small"); return -1; }
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& x : ev) cudaEventCreate(&x);
+    std::vector<double> acc(n, 0.0);
+    for (int it = 0; it < iters + 1; ++it) {
+        cudaEventRecord(ev[0], e->st);
+        for (int i = 0; i < n; ++i) {
+            const char* m = p->ops[i](e->st);
+            if (m) { set_err(std::string("profile_ops launch: ") + m); return -1; }
+            cudaEventRecord(ev[i + 1], e->st);
+        }
+        if (cudaStreamSynchronize(e->st) != cudaSuccess) { set_err("profile_ops: sync failed"); return -1; }
+        if (it == 0) continue;  // warm-up pass
+        for (int i = 0; i < n; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            acc[i] += ms;
+        }
+    }
+    for (int i = 0; i < n; ++i) ms_out[i] = (float)(acc[i] / iters);
+    for (auto& x : ev) cudaEventDestroy(x);
+    return n;
 }
 
 void ws_engine_destroy(ws_engine* e) {
