@@ -409,11 +409,26 @@ bool build_ecapa(Builder& b) {
             b.conv(cs);
         }
         // SE_Connect (ecapa_tdnn.py:113-126) + residual (:157)
-        b.tstats(tC, nullptr, nullptr, semean, C, -1);
-        b.linear(semean, C, nullptr, 0, 1, b.w.vec(pf + ".3.linear1.weight"), b.w.vec(pf + ".3.linear1.bias"), sehid, 128, B,
-                 C, 128, WS_ACT_RELU);
-        b.linear(sehid, 128, nullptr, 0, 1, b.w.vec(pf + ".3.linear2.weight"), b.w.vec(pf + ".3.linear2.bias"), segate, C,
-                 B, 128, C, WS_ACT_SIGMOID);
+        if (e.opt("se_fused", 1) && (C == 512 || C == 1024)) {
+            const HostT* w2 = b.w.get(pf + ".3.linear2.weight");   // (C, 128) -> transposed (128, C) for coalesced reads
+            if (!w2) break;
+            std::vector<float> w2t((size_t)128 * C);
+            for (int c = 0; c < C; ++c)
+                for (int h = 0; h < 128; ++h) w2t[(size_t)h * C + c] = w2->v[(size_t)c * 128 + h];
+            const float* w1d = b.w.vec(pf + ".3.linear1.weight");
+            const float* b1d = b.w.vec(pf + ".3.linear1.bias");
+            const float* w2d = b.w.f32("w2t:" + pf, w2t);
+            const float* b2d = b.w.vec(pf + ".3.linear2.bias");
+            View tc = tC;
+            const int dt = e.act_dt;
+            b.push([=](cudaStream_t s) { return ws_launch_se_gate(tc.p, dt, B, T, C, tc.ld, w1d, b1d, w2d, b2d, 128, segate, s); });
+        } else {
+            b.tstats(tC, nullptr, nullptr, semean, C, -1);
+            b.linear(semean, C, nullptr, 0, 1, b.w.vec(pf + ".3.linear1.weight"), b.w.vec(pf + ".3.linear1.bias"), sehid, 128, B,
+                     C, 128, WS_ACT_RELU);
+            b.linear(sehid, 128, nullptr, 0, 1, b.w.vec(pf + ".3.linear2.weight"), b.w.vec(pf + ".3.linear2.bias"), segate, C,
+                     B, 128, C, WS_ACT_SIGMOID);
+        }
         {
             View o = cat.ch((L - 2) * C, C), xi = xin, tc = tC;
             const int dt = e.act_dt;
@@ -978,7 +993,7 @@ int ws_engine_set_option(ws_engine* e, const char* key, long long value) {
     const std::string k = key;
     if (k == "force_simt") { if (value) e->use_tc = 0; }
     else if (k == "tc_version") { if (e->use_tc) e->use_tc = value >= 3 ? 3 : (value >= 2 || e->split ? 2 : 1); }
-    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused") { set_err("unknown option " + k); return 1; }
+    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused" && k != "se_fused") { set_err("unknown option " + k); return 1; }
     e->opts[k] = value;
     e->plans.clear();
     return 0;

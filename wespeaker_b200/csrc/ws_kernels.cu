@@ -340,6 +340,70 @@ __global__ void __launch_bounds__(256) seg_means_kernel(const void* __restrict__
     if (threadIdx.y == 0 && cv) mean[(long long)b * C + c] = total / (float)T;
 }
 
+// ECAPA SE_Connect gate in ONE launch (ecapa_tdnn.py:113-126): gate[b] = sigmoid(W2 relu(W1 mean_T(x[b]) + b1) + b2).
+// One block per 2 utterances: (1) mean over T with 16-byte loads (all 512 threads), (2) fc1: one warp per hidden unit, lanes
+// over C (coalesced W1 rows, both utterances share each weight read), (3) fc2 from a TRANSPOSED W2 ([H][C]) so consecutive
+// threads read consecutive weights.  Replaces the mean + split-K fc1 + reduce + fc2 launches (4 latency-bound launches).
+template <int H>
+__global__ void __launch_bounds__(512) se_gate_kernel(const void* __restrict__ x, int dt, int B, int T, int C, long long ld,
+                                                      const float* __restrict__ W1, const float* __restrict__ b1,
+                                                      const float* __restrict__ W2t, const float* __restrict__ b2,
+                                                      float* __restrict__ gate /*[B][C]*/) {
+    extern __shared__ float sm[];
+    float* mean = sm;              // [2][C]
+    float* part = mean + 2 * C;    // [slices][2][C] partial sums of the T slices (slices * C = 4096 floats)
+    float* hid = part + 8192;      // [2][H]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b0 = blockIdx.x * 2;
+    const int nb = min(2, B - b0);
+    const int groups = C >> 3;                 // 8-channel groups (C=1024 -> 128 groups x 4 T slices, C=512 -> 64 x 8)
+    const int slices = 512 / groups;
+    const int sl = tid / groups, gi = tid % groups;
+    for (int u = 0; u < nb; ++u) {
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const long long base = (long long)(b0 + u) * T * ld + gi * 8;
+        for (int t = sl; t < T; t += slices) {
+            float v[8];
+            ws_ldv8(x, dt, base + (long long)t * ld, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) part[(sl * 2 + u) * C + gi * 8 + k] = a[k];
+    }
+    __syncthreads();
+    for (int i = tid; i < nb * C; i += 512) {
+        const int u = i / C, c = i % C;
+        float s = 0.f;
+        for (int k = 0; k < slices; ++k) s += part[(k * 2 + u) * C + c];   // fixed order: deterministic
+        mean[u * C + c] = s / (float)T;
+    }
+    __syncthreads();
+    for (int h = warp; h < H; h += 16) {
+        const float* w = W1 + (long long)h * C;
+        float a0 = 0.f, a1 = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float wv = __ldg(w + c);
+            a0 = fmaf(wv, mean[c], a0);
+            a1 = fmaf(wv, mean[C + c], a1);
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1);
+        if (lane == 0) { hid[h] = fmaxf(a0 + b1[h], 0.f); hid[H + h] = fmaxf(a1 + b1[h], 0.f); }
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += 512) {
+        float a0 = b2[c], a1 = a0;
+#pragma unroll 8
+        for (int h = 0; h < H; ++h) {
+            const float wv = __ldg(W2t + (long long)h * C + c);
+            a0 = fmaf(wv, hid[h], a0);
+            a1 = fmaf(wv, hid[H + h], a1);
+        }
+        gate[(long long)b0 * C + c] = 1.f / (1.f + expf(-a0));
+        if (nb > 1) gate[(long long)(b0 + 1) * C + c] = 1.f / (1.f + expf(-a1));
+    }
+}
+
 // CAM++ context gate in one launch (campplus.py:108-135): per utterance, mean over T + per-100-frame segment means of
 // h (C=128), then for every segment  gate = sigmoid(W2 relu(W1 (mean + segmean) + b1) + b2).  One block per utterance;
 // replaces seg_means + 2 tiny FC launches (3 latency-bound launches per dense layer, 52 layers).
@@ -515,5 +579,19 @@ const char* ws_launch_cam_gate(const void* x, int dt, int B, int T, int C, long 
     const size_t smem = (size_t)(H * C + nseg * C + 16 * C + nseg * H + C) * sizeof(float);
     if (smem > 48 * 1024) return "cam_gate: utterance too long for the shared-memory context buffer";
     cam_gate_kernel<128, 64, 32><<<B, 256, smem, s>>>(x, dt, T, ld, seg_len, W1, b1, W2, b2, gate);
+    return last_err();
+}
+
+const char* ws_launch_se_gate(const void* x, int dt, int B, int T, int C, long long ld, const float* W1, const float* b1,
+                              const float* W2t, const float* b2, int H, float* gate, cudaStream_t s) {
+    if (H != 128 || (C != 512 && C != 1024 && C != 2048 && C != 256)) return "se_gate: expected H=128 and C in {256,512,1024,2048}";
+    const size_t smem = (size_t)(2 * C + 8192 + 2 * H) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(se_gate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr = true;
+    }
+    if (smem > 96 * 1024) return "se_gate: channel count too large for shared memory";
+    se_gate_kernel<128><<<(B + 1) / 2, 512, smem, s>>>(x, dt, B, T, C, ld, W1, b1, W2t, b2, gate);
     return last_err();
 }

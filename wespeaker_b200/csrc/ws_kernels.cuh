@@ -33,6 +33,9 @@ const char* ws_launch_stem(const float* feats, const float* w9 /*[Cout][9]*/, co
 const char* ws_launch_seg_means(const void* x, int dt, int B, int T, int C, long long ld, int seg_len, float* mean,
                                 float* segmean /*[B][nseg][C]*/, cudaStream_t s);
 
+// fused SE gate: gate[b][c] = sigmoid(W2 relu(W1 mean_T(x[b]) + b1) + b2); W2t is W2 transposed to [H][C]
+const char* ws_launch_se_gate(const void* x, int dt, int B, int T, int C, long long ld, const float* W1, const float* b1,
+                              const float* W2t, const float* b2, int H, float* gate, cudaStream_t s);
 // fused CAM context gate: gate[b][seg][g] = sigmoid(W2 relu(W1 (mean_T(x) + segmean(x)) + b1) + b2)
 const char* ws_launch_cam_gate(const void* x, int dt, int B, int T, int C, long long ld, int seg_len, const float* W1,
                                const float* b1, const float* W2, const float* b2, int H, int G, float* gate,
