@@ -54,15 +54,50 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  NVML polled every 5 ms from a
+    thread (the timed region is only tens of ms long); falls back to `nvidia-smi -lms 100` if NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.samples, self.reasons, self.maxclk, self._stop = None, [], set(), None, False
+
+    def _poll(self):
+        n = self.nvml
+        while not self._stop:
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                bus = torch.cuda.get_device_properties(self.index).pci_bus_id
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(f"00000000:{bus:02x}:00.0".encode()) if isinstance(bus, int) \
+                    else pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.maxclk = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -73,6 +108,13 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop = True
+            self.t.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                    "sm_min_mhz": float(min(self.samples)) if self.samples else None,
+                    "sm_max_mhz": float(self.maxclk) if self.maxclk else None, "reasons": sorted(self.reasons),
+                    "samples": len(self.samples), "source": "nvml, 5 ms polling during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -91,7 +133,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def _cpu_path(model_name, nsamples, batch):
