@@ -6,7 +6,7 @@ SRC=wespeaker_b200/csrc
 OUT=wespeaker_b200/lib
 mkdir -p $OUT build
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -DWS_BUILD"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -DWS_BUILD ${EXTRA_NVCC}"
 objs=""
 pids=""
 for f in ws_gemm_tc ws_gemm_tc2 ws_gemm_tc3 ws_res2_fused ws_gemm_simt ws_kernels ws_fbank ws_plda ws_conv_host ws_engine ws_plda_host; do

@@ -116,7 +116,7 @@ CONV_CASES = [
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 @pytest.mark.parametrize("mode", ["fp32-simt", "tf32-tc", "bf16-tc", "fp16-tc", "bf16-simt", "tf32-tc2", "bf16-tc2", "fp16-tc2",
-                                  "tf32x3-tc2", "bf16-tc3", "tf32-tc3", "fp16-tc3"])
+                                  "tf32x3-tc2", "bf16-tc3", "tf32-tc3", "fp16-tc3", "tf32x3-tc3"])
 def test_conv_operator(case, mode):
     name, B, F, T, Cin, Cout, kf, kt, dil, pad, stride = case
     prec, path = mode.split("-")
@@ -147,6 +147,39 @@ def test_conv_operator(case, mode):
     tol = {"fp32": 2e-5, "tf32x3": 2e-5, "tf32": 4e-3, "bf16": 1.2e-2, "fp16": 2e-3}[prec] * max(1.0, scale_ref)
     print(f"{name} {mode}: max|err|={err:.3e} (ref max {scale_ref:.2f}, tol {tol:.1e})")
     assert err <= tol, (name, mode, err, tol)
+
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["bf16-tc2", "fp16-tc2", "tf32-tc2", "tf32x3-tc2", "bf16-tc3", "fp16-tc3", "tf32-tc3", "tf32x3-tc3"])
+@pytest.mark.parametrize("variant", ["bias_relu", "bn", "bn_res_relu"])
+def test_lean_epilogue_is_bit_identical_to_generic(mode, variant):
+    """The tensor-core kernels carry a small 'lean' epilogue instantiation (bias/ReLU/BN/residual/ReLU) next to the generic
+    one; WS_EPI_GENERIC=1 forces the generic one.  Same arithmetic in the same order -> identical bits."""
+    prec, path = mode.split("-")
+    B, F, T, Cin, Cout = 7, 1, 150, 256, 512
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, F, T, Cin, generator=g)
+    w = torch.randn(Cout, Cin, 1, 3, generator=g) / np.sqrt(3 * Cin)
+    bias = 0.1 * torch.randn(Cout, generator=g)
+    scale = shift = res = None
+    act2 = 0
+    if variant != "bias_relu":
+        scale, shift = 0.5 + torch.rand(Cout, generator=g), 0.1 * torch.randn(Cout, generator=g)
+    if variant == "bn_res_relu":
+        res, act2 = torch.randn(B, F, T, Cout, generator=g), 1
+    outs = []
+    for generic in ("0", "1"):
+        os.environ["WS_EPI_GENERIC"] = generic
+        os.environ["WS_TC3_MIN_POS"] = "1"
+        try:
+            outs.append(run_conv(x, w, bias, scale, shift, res, prec, {"tc2": 2, "tc3": 3}[path], 1, 3, (1, 2), (0, 2), (1, 1), 1, act2))
+        finally:
+            os.environ.pop("WS_EPI_GENERIC", None)
+            os.environ.pop("WS_TC3_MIN_POS", None)
+    assert torch.equal(outs[0], outs[1])
+    ref = ref_conv(x, w, bias, scale, shift, res, DT[prec][1], 1, 3, (1, 2), (0, 2), (1, 1), 1, act2)
+    assert (outs[0].double() - ref).abs().max().item() <= {"tf32x3": 2e-5, "tf32": 4e-3, "bf16": 1.2e-2, "fp16": 2e-3}[prec] * max(1.0, ref.abs().max().item())
 
 
 # ------------------------------------------------------------------------------------------ fbank + CMN

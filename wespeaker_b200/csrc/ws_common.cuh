@@ -296,6 +296,7 @@ struct WsTc2Params {
     int has_out2, has_epin;
     int nsplit;          // 1, or 3 = 3xTF32 error-compensated passes (x_lo*W, x*W_lo, x*W)
     int nout;            // number of output tiles staged per tile (1..4)
+    int epi_generic;     // test knob (WS_EPI_GENERIC=1): always run the generic epilogue instantiation
     int dbg_shift;       // -1 off; else experiment: A tile loaded one row early, MMA reads from row 1 with this base_offset
     int grid, smem_bytes;
     WsEpi epi;

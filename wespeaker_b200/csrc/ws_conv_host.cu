@@ -325,6 +325,7 @@ static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported, bool
     q->epi = e;
     const char* env_sh = getenv("WS_TC2_SHIFT_TEST");
     q->dbg_shift = env_sh ? atoi(env_sh) : -1;
+    { const char* eg = getenv("WS_EPI_GENERIC"); q->epi_generic = eg != nullptr && atoi(eg) != 0; }
     return true;
 }
 

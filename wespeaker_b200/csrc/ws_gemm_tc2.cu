@@ -61,7 +61,7 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int bk_bytes) {
     const uint64_t layout = bk_bytes == 128 ? 2ull : (bk_bytes == 64 ? 4ull : 6ull);
@@ -110,7 +110,7 @@ __device__ __forceinline__ int swz_chunk(int chunk, int row, int row_bytes) {
     return row_bytes == 128 ? (chunk ^ (row & 7)) : (row_bytes == 64 ? (chunk ^ ((row >> 1) & 3)) : (chunk ^ ((row >> 2) & 1)));
 }
 
-constexpr int kThreads2 = 256;
+constexpr int kThreads2 = 384;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4..w11 epilogue (2 warps per TMEM lane quadrant)
 constexpr int kMaxDynSmem2 = 220 * 1024;
 
 // 32 consecutive fp32 values -> packed activation dtype -> swizzled staging panel row
@@ -171,7 +171,12 @@ __device__ __forceinline__ void stage_load32(uint32_t panel_base, int row, int r
     }
 }
 
-template <int KIND>
+// LEAN != 0 (= WsDType of the activations + 1) compiles only the common epilogue: bias, ReLU, BN scale/shift, residual
+// tile, ReLU, one output (+ its 3xTF32 low twin for fp32).  The generic epilogue (row bias, gates, Res2 second output,
+// tanh/sigmoid, every dtype) is ~100 KB of SASS of which a given layer executes a few KB scattered between never-taken
+// branches; ncu (2-CTA twin, ws_gemm_tc3.cu) showed its warps stalled on instruction fetch (stall_no_inst) for half of their samples, which made the
+// short-K 1x1 convs epilogue-bound.  The lean chunk body is ~4 KB and stays in the 6 KB L0 instruction cache.
+template <int KIND, int LEAN>
 __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __grid_constant__ WsTc2Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[2 * WS_TC_MAX_STAGES + 6];
@@ -211,10 +216,10 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 4);  // one arrive per epilogue warp
+            mbar_init(bar_tempty + 8 * i, 8);  // one arrive per epilogue warp
         }
         mbar_init(bar_ifull, 1);
-        mbar_init(bar_iempty, 4);
+        mbar_init(bar_iempty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -298,9 +303,14 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
+        // 8 epilogue warps: warps w and w+4 share TMEM lane quadrant (w & 3) and split the tile's columns in halves, so the
+        // epilogue keeps up with short-K mainloops (1x1 convs with K = C were epilogue-bound with 4 warps)
         const int q = warp & 3;
         const int r = q * 32 + lane;
-        const int et = threadIdx.x - 128;  // 0..127
+        const int et = threadIdx.x - 128;  // 0..255
+        const int half_cols = p.bn >= 64 ? p.bn / 2 : p.bn;
+        const int c_beg = ((warp - 4) >> 2) * half_cols;
+        const int c_end = p.bn >= 64 ? c_beg + half_cols : (warp < 8 ? p.bn : 0);
         const WsEpi& e = p.epi;
         float* spar = reinterpret_cast<float*>(smem_raw + (s_par - smem_u32(smem_raw)));
         int j = 0, last_n0 = -1;
@@ -314,10 +324,15 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
             // staging buffers are free once the previous tile's TMA stores have finished reading them
             if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (n0 != last_n0) {
-                for (int c = et; c < p.bn; c += 128) {
-                    spar[c] = e.bias ? e.bias[n0 + c] : 0.f;
-                    spar[p.bn + c] = e.scale ? e.scale[n0 + c] : 1.f;
-                    spar[2 * p.bn + c] = e.scale ? e.shift[n0 + c] : 0.f;
+                for (int c = et; c < p.bn; c += 256) {
+                    // all three loads are issued before the first store: interleaved load/store pairs were serialised by
+                    // the compiler (possible aliasing) and cost three L2 round trips per tile on the epilogue's critical path
+                    const float pb = e.bias ? __ldg(e.bias + n0 + c) : 0.f;
+                    const float ps = e.scale ? __ldg(e.scale + n0 + c) : 1.f;
+                    const float ph = e.scale ? __ldg(e.shift + n0 + c) : 0.f;
+                    spar[c] = pb;
+                    spar[p.bn + c] = ps;
+                    spar[2 * p.bn + c] = ph;
                 }
                 last_n0 = n0;
             }
@@ -337,11 +352,58 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
             tc_fence_after();
             if (p.has_epin) mbar_wait(bar_ifull, (uint32_t)j & 1u);
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.bn);
-            for (int c = 0; c < p.bn; c += 32) {
+            // (the two warps of a lane quadrant interleave on their scheduler: one computes while the other waits on LDTM)
+#pragma unroll 1
+            for (int c = c_beg; c < c_end; c += 32) {
                 uint32_t raw[32];
                 tmem_ld32(trow + (uint32_t)c, raw);
                 tmem_ld_wait();
                 float v[32];
+                if constexpr (LEAN != 0) {
+                    constexpr int DT = LEAN - 1;                          // activation dtype of this instantiation
+                    constexpr int PCOLS = DT == WS_F32 ? 32 : 64;         // columns of one 128-byte staging panel
+                    const float4* sb = reinterpret_cast<const float4*>(spar + c);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 x = sb[i];
+                        v[4 * i] = __uint_as_float(raw[4 * i]) + x.x; v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + x.y;
+                        v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + x.z; v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + x.w;
+                    }
+                    if (e.act1 == WS_ACT_RELU) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    if (e.scale != nullptr) {
+                        const float4* ss = reinterpret_cast<const float4*>(spar + p.bn + c);
+                        const float4* sh = reinterpret_cast<const float4*>(spar + 2 * p.bn + c);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 a = ss[i], d = sh[i];
+                            v[4 * i] = fmaf(v[4 * i], a.x, d.x); v[4 * i + 1] = fmaf(v[4 * i + 1], a.y, d.y);
+                            v[4 * i + 2] = fmaf(v[4 * i + 2], a.z, d.z); v[4 * i + 3] = fmaf(v[4 * i + 3], a.w, d.w);
+                        }
+                    }
+                    const uint32_t poff = (uint32_t)((c / PCOLS) * 128 * 128);
+                    if (p.has_epin) {  // residual
+                        float rin[32];
+                        stage_load32(stg_in + poff, r, 128, c % PCOLS, DT, rin);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] += rin[i];
+                    }
+                    if (e.act2 == WS_ACT_RELU) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    stage_store32(stg_out + poff, r, 128, c % PCOLS, DT, v);
+                    if constexpr (DT == WS_F32) {
+                        if (p.nsplit == 3) {  // 3xTF32: the low twin of the output feeds the next layer's x_lo pass
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = ws_tf32_lo(v[i]);
+                            stage_store32(stg_out + (uint32_t)tile_out_bytes + poff, r, 128, c % PCOLS, DT, v);
+                        }
+                    }
+                    continue;
+                }
                 {
                     const float4* sb = reinterpret_cast<const float4*>(spar + c);
 #pragma unroll
@@ -438,12 +500,35 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
 
 }  // namespace
 
+namespace {
+// 0 = generic epilogue, else activation dtype + 1 (see the LEAN template parameter)
+inline int tc2_lean(const WsTc2Params* p) {
+    const WsEpi& e = p->epi;
+    const bool common = !p->has_out2 && e.rowbias == nullptr && e.gate == nullptr &&
+                        (e.act1 == WS_ACT_NONE || e.act1 == WS_ACT_RELU) &&
+                        (e.act2 == WS_ACT_NONE || e.act2 == WS_ACT_RELU) && p->panel_bytes == 128;
+    if (!common) return 0;
+    if (p->kind == 1 && p->nsplit == 1 && p->nout == 1 && p->bn >= 64 && (e.dtype == WS_BF16 || e.dtype == WS_F16))
+        return e.dtype + 1;
+    if (p->kind == 0 && e.dtype == WS_F32 && p->bn >= 32 &&
+        ((p->nsplit == 1 && p->nout == 1) || (p->nsplit == 3 && p->nout == 2)))
+        return WS_F32 + 1;
+    return 0;
+}
+template <int KIND, int LEAN>
+inline cudaError_t tc2_attr() {
+    return cudaFuncSetAttribute(ws_conv_gemm_tc2_kernel<KIND, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem2);
+}
+}  // namespace
+
 extern "C" const char* ws_tc2_init(void) {
     static bool done = false;
     if (done) return nullptr;
-    cudaError_t e = cudaFuncSetAttribute(ws_conv_gemm_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem2);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(ws_conv_gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem2);
+    cudaError_t e = tc2_attr<0, 0>();
+    if (e == cudaSuccess) e = tc2_attr<1, 0>();
+    if (e == cudaSuccess) e = tc2_attr<0, WS_F32 + 1>();
+    if (e == cudaSuccess) e = tc2_attr<1, WS_BF16 + 1>();
+    if (e == cudaSuccess) e = tc2_attr<1, WS_F16 + 1>();
     if (e != cudaSuccess) { cudaGetLastError(); return cudaGetErrorString(e); }
     done = true;
     return nullptr;
@@ -452,8 +537,12 @@ extern "C" const char* ws_tc2_init(void) {
 extern "C" int ws_tc2_max_smem(void) { return kMaxDynSmem2; }
 
 extern "C" const char* ws_tc2_launch(const WsTc2Params* p, cudaStream_t s) {
-    if (p->kind == 0) ws_conv_gemm_tc2_kernel<0><<<p->grid, kThreads2, p->smem_bytes, s>>>(*p);
-    else ws_conv_gemm_tc2_kernel<1><<<p->grid, kThreads2, p->smem_bytes, s>>>(*p);
+    const int lean = p->epi_generic ? 0 : tc2_lean(p);
+    if (lean == WS_F32 + 1) ws_conv_gemm_tc2_kernel<0, WS_F32 + 1><<<p->grid, kThreads2, p->smem_bytes, s>>>(*p);
+    else if (lean == WS_BF16 + 1) ws_conv_gemm_tc2_kernel<1, WS_BF16 + 1><<<p->grid, kThreads2, p->smem_bytes, s>>>(*p);
+    else if (lean == WS_F16 + 1) ws_conv_gemm_tc2_kernel<1, WS_F16 + 1><<<p->grid, kThreads2, p->smem_bytes, s>>>(*p);
+    else if (p->kind == 0) ws_conv_gemm_tc2_kernel<0, 0><<<p->grid, kThreads2, p->smem_bytes, s>>>(*p);
+    else ws_conv_gemm_tc2_kernel<1, 0><<<p->grid, kThreads2, p->smem_bytes, s>>>(*p);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
