@@ -96,6 +96,10 @@ typedef struct {
     const void* x_lo;
     const void* w_lo;
     void* out_lo;
+    /* fused SE squeeze (dense 1x1 conv, 16-bit dtype, use_tc >= 2, T >= 128; NULL = off): fp32 [2*ceil(B*T/64)][Cout];
+     * row 2u+s = per-channel sum of the stored outputs over the positions of 64-position unit u that belong to
+     * utterance floor(64u/T)+s.  Replaces the mean pass of SE_Connect (ecapa_tdnn.py:120-121). */
+    float* colsum;
 } ws_conv_desc;
 int ws_conv(const ws_conv_desc* d, void* stream);
 

@@ -44,6 +44,11 @@ struct WsEpi {
     int dtype;  // dtype of res/out/out2/add2 (activation dtype)
     int FT;     // F*T of the output tensor (pos / FT = b)
     int T;      // T of the output tensor   (pos % T = t)
+    // SE squeeze fused into a dense 1x1 conv (lean 16-bit tensor-core epilogue only): per 64-position unit u and slot s,
+    // colsum[(2u + s) * Cout + c] = sum of the STORED (rounded) outputs of channel c over the unit's positions that belong
+    // to utterance (64u / colsum_T) + s.  colsum_T >= 128 frames, so a unit touches at most two utterances.
+    float* colsum;
+    int colsum_T;
 };
 
 __device__ __forceinline__ float ws_act(float v, int act) {
@@ -161,6 +166,15 @@ __device__ __forceinline__ void ws_ldv8(const void* p, int dt, long long off, fl
             v[2 * i] = ws_16_to_f(w[i] & 0xffffu, dt);
             v[2 * i + 1] = ws_16_to_f(w[i] >> 16, dt);
         }
+    }
+}
+// 8 packed 16-bit values (one 16-byte load) -> fp32
+__device__ __forceinline__ void ws_unpack8(const uint4& x, int dt, float* v) {
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = ws_16_to_f(w[i] & 0xffffu, dt);
+        v[2 * i + 1] = ws_16_to_f(w[i] >> 16, dt);
     }
 }
 __device__ __forceinline__ void ws_stv8(void* p, int dt, long long off, const float* v) {

@@ -365,6 +365,7 @@ bool make_conv_op(const ConvSpec& spec, int use_tc, Op* out) {
         }
         if (!unsupported) return false;
     }
+    if (spec.epi.colsum != nullptr) { set_err("conv colsum: only the persistent tensor-core kernels (use_tc >= 2) produce column sums"); return false; }
     if (use_tc) {
         auto p = std::make_shared<WsTcParams>();
         if (!build_tc(spec, p.get())) return false;
@@ -440,6 +441,7 @@ extern "C" int ws_conv(const ws_conv_desc* d, void* stream) {
     fill_epi_out(s.epi, o);
     s.epi.bias = d->bias; s.epi.act1 = d->act1; s.epi.scale = d->scale; s.epi.shift = d->shift;
     s.epi.res = d->res; s.epi.res_ld = d->res_ld; s.epi.act2 = d->act2;
+    s.epi.colsum = d->colsum; s.epi.colsum_T = d->colsum ? To : 0;
     Op op;
     if (d->use_tc) { WS_CKS(ws_tc_init()); WS_CKS(ws_tc2_init()); WS_CKS(ws_tc3_init()); }
     if (!make_conv_op(s, d->use_tc, &op)) return 1;

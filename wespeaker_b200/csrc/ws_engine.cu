@@ -284,9 +284,11 @@ struct Builder {
     void linear(const float* in, long long in_ld, const float* in2, long long in2_ld, int rows_per_b, const float* W,
                 const float* bias, float* out, long long out_ld, int R, int I, int O, int act) {
         // split K so that the launch fills the machine (these layers are latency-bound otherwise)
-        const int blocks = ((O + 31) / 32) * ((R + 15) / 16);
+        const bool big = ws_linear_rows_big(in_ld, in2, in2_ld, R, I, O);
+        const int blocks = big ? ((O + 63) / 64) * ((R + 63) / 64) : ((O + 31) / 32) * ((R + 15) / 16);
         int nsplit = 1;
-        while (blocks * nsplit < 296 && I / (nsplit * 2) >= 128 && nsplit < 16) nsplit *= 2;
+        if (big) while (blocks * nsplit < 148 && I / (nsplit * 2) >= 96 && nsplit < 32) nsplit *= 2;
+        else while (blocks * nsplit < 296 && I / (nsplit * 2) >= 128 && nsplit < 16) nsplit *= 2;
         float* wsp = nsplit > 1 ? f32((size_t)nsplit * R * O) : nullptr;
         if (nsplit > 1) p.extra_launches += 1;
         push([=](cudaStream_t s) {
@@ -334,6 +336,10 @@ bool build_ecapa(Builder& b) {
     };
     conv_relu_bn("layer1", x0, out1, 5, 1, 2);
     View xin = out1;
+    float* se_colsum = nullptr;
+    if (e.use_tc >= 2 && e.act_dt != WS_F32 && !e.split && T >= 128 && (C == 512 || C == 1024) && e.opt("se_fused", 1) &&
+        e.opt("se_colsum", 1) && getenv("WS_EPI_GENERIC") == nullptr)
+        se_colsum = b.f32((size_t)2 * (((size_t)B * T + 63) / 64) * C);
     for (int L = 2; L <= 4 && b.good(); ++L) {
         const int d = L;
         const std::string pf = "layer" + std::to_string(L) + ".se_res2block";
@@ -406,6 +412,9 @@ bool build_ecapa(Builder& b) {
             cs.epi.scale = b.w.f32("bns:" + cp, s);
             cs.epi.shift = b.w.f32("bnh:" + cp, h);
             fill_epi_out(cs.epi, tC);
+            // SE squeeze fused into this conv's epilogue (16-bit tensor-core path): per-unit column sums instead of a
+            // second pass over the 100 MB output
+            if (se_colsum != nullptr) { cs.epi.colsum = se_colsum; cs.epi.colsum_T = T; }
             b.conv(cs);
         }
         // SE_Connect (ecapa_tdnn.py:113-126) + residual (:157)
@@ -421,7 +430,8 @@ bool build_ecapa(Builder& b) {
             const float* b2d = b.w.vec(pf + ".3.linear2.bias");
             View tc = tC;
             const int dt = e.act_dt;
-            b.push([=](cudaStream_t s) { return ws_launch_se_gate(tc.p, dt, B, T, C, tc.ld, w1d, b1d, w2d, b2d, 128, segate, s); });
+            const float* cs_in = se_colsum;
+            b.push([=](cudaStream_t s) { return ws_launch_se_gate(tc.p, dt, B, T, C, tc.ld, w1d, b1d, w2d, b2d, 128, segate, cs_in, s); });
         } else {
             b.tstats(tC, nullptr, nullptr, semean, C, -1);
             b.linear(semean, C, nullptr, 0, 1, b.w.vec(pf + ".3.linear1.weight"), b.w.vec(pf + ".3.linear1.bias"), sehid, 128, B,
@@ -993,7 +1003,7 @@ int ws_engine_set_option(ws_engine* e, const char* key, long long value) {
     const std::string k = key;
     if (k == "force_simt") { if (value) e->use_tc = 0; }
     else if (k == "tc_version") { if (e->use_tc) e->use_tc = value >= 3 ? 3 : (value >= 2 || e->split ? 2 : 1); }
-    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused" && k != "se_fused") { set_err("unknown option " + k); return 1; }
+    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused" && k != "se_fused" && k != "se_colsum") { set_err("unknown option " + k); return 1; }
     e->opts[k] = value;
     e->plans.clear();
     return 0;

@@ -555,6 +555,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads3, 1) ws_con
                 PROF_ADD(5, 1);
 #endif
             }
+            if constexpr (LEAN == WS_BF16 + 1 || LEAN == WS_F16 + 1) {
+                // fused SE squeeze (WsEpi::colsum): column sums of the staged (already rounded) tile, read back from the
+                // swizzled staging panels while the TMA store drains them; thread = (column pair, 64-row half)
+                if (e.colsum != nullptr && b0 < p.B && t0 + (et >> 7) * 64 < p.T) {   // units past the last position do not exist
+                    const int cpair = et & 127, rh = et >> 7;
+                    const int pos0 = t0 + rh * 64;
+                    const int nvalid = min(64, p.T - pos0);
+                    const int split = min(nvalid, (pos0 / e.colsum_T + 1) * e.colsum_T - pos0);
+                    const int col = 2 * cpair;
+                    const uint32_t cbase = stg_out + (uint32_t)((col >> 6) * 128 * 128 + (col & 7) * 2);
+                    const int chunk = (col & 63) >> 3;
+                    float a0 = 0.f, a1 = 0.f, b0s = 0.f, b1s = 0.f;
+#pragma unroll 4
+                    for (int rr = 0; rr < split; ++rr) {
+                        const int row = rh * 64 + rr;
+                        uint32_t w;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(cbase + (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4))));
+                        a0 += ws_16_to_f(w & 0xffffu, LEAN - 1); a1 += ws_16_to_f(w >> 16, LEAN - 1);
+                    }
+#pragma unroll 4
+                    for (int rr = max(split, 0); rr < nvalid; ++rr) {
+                        const int row = rh * 64 + rr;
+                        uint32_t w;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(cbase + (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4))));
+                        b0s += ws_16_to_f(w & 0xffffu, LEAN - 1); b1s += ws_16_to_f(w >> 16, LEAN - 1);
+                    }
+                    const long long unit = (long long)(t0 >> 6) + rh;
+                    float* dst = e.colsum + unit * 2 * (long long)(p.tiles_n * p.bn) + n0 + col;
+                    *reinterpret_cast<float2*>(dst) = make_float2(a0, a1);
+                    *reinterpret_cast<float2*>(dst + (long long)(p.tiles_n * p.bn)) = make_float2(b0s, b1s);
+                }
+            }
         }
         if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -614,6 +646,9 @@ extern "C" int ws_tc3_max_smem(void) { return kMaxDynSmem3; }
 
 extern "C" const char* ws_tc3_launch(const WsTc2Params* p, cudaStream_t s) {
     const int lean = p->epi_generic ? 0 : tc3_lean(p);
+    if (p->epi.colsum != nullptr && (lean != WS_BF16 + 1 && lean != WS_F16 + 1 || p->tiles_f != 1 || p->tiles_b != 1 ||
+                                     p->bt_log2 != 7 || p->epi.colsum_T < 128))
+        return "conv colsum: needs the lean 16-bit epilogue on a dense 1x1 conv (flat positions) and >= 128 frames per utterance";
     if (lean == WS_F32 + 1) ws_conv_gemm_tc3_kernel<0, WS_F32 + 1><<<p->grid, kThreads3, p->smem_bytes, s>>>(*p);
     else if (lean == WS_BF16 + 1) ws_conv_gemm_tc3_kernel<1, WS_BF16 + 1><<<p->grid, kThreads3, p->smem_bytes, s>>>(*p);
     else if (lean == WS_F16 + 1) ws_conv_gemm_tc3_kernel<1, WS_F16 + 1><<<p->grid, kThreads3, p->smem_bytes, s>>>(*p);

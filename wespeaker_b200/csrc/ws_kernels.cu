@@ -4,6 +4,7 @@
 // reductions over T are split over 8 warps per block and merged through shared memory, reductions over
 // input features in the FC kernel use warp shuffles.
 #include "ws_kernels.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -150,6 +151,78 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restric
     }
 }
 
+// Larger FC layers (embedding head: 256 rows x 3072 -> 192): 64 x 64 output tile, 4 x 4 register tile per thread, K in
+// chunks of 32 staged TRANSPOSED in smem (so the inner loop is two LDS.128 per 16 FMAs), split-K over blockIdx.z with the
+// same fixed-order reduction kernel.  Needs 16-byte aligned rows (I, in_ld, in2_ld multiples of 4).
+__global__ void __launch_bounds__(256) linear_rows64_kernel(const float* __restrict__ in, long long in_ld,
+                                                            const float* __restrict__ in2, long long in2_ld,
+                                                            int rows_per_b, const float* __restrict__ W,
+                                                            const float* __restrict__ bias, float* __restrict__ out,
+                                                            long long out_ld, int R, int I, int O, int act) {
+    constexpr int TR = 64, TO = 64, TK = 32;
+    __shared__ __align__(16) float Xs[TK][TR + 4];
+    __shared__ __align__(16) float Ws[TK][TO + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int r0 = blockIdx.y * TR, o0 = blockIdx.x * TO;
+    const int nsplit = gridDim.z;
+    const int kper = ((I + nsplit - 1) / nsplit + TK - 1) / TK * TK;
+    const int kbeg = blockIdx.z * kper, kend = min(I, kbeg + kper);
+    if (nsplit > 1) { out += (long long)blockIdx.z * R * out_ld; bias = nullptr; act = WS_ACT_NONE; }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = kbeg; k0 < kend; k0 += TK) {
+        float4 xv[2], wv[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int idx = tid + 256 * j, rr = idx >> 3, k = k0 + (idx & 7) * 4;
+            const int r = r0 + rr, o = o0 + rr;
+            xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            wv[j] = xv[j];
+            if (k < kend) {   // kend - k is a multiple of 4 (I % 4 == 0, kper % 32 == 0)
+                if (r < R) {
+                    xv[j] = *reinterpret_cast<const float4*>(in + (long long)r * in_ld + k);
+                    if (in2 != nullptr) {
+                        const float4 y = *reinterpret_cast<const float4*>(in2 + (long long)(r / rows_per_b) * in2_ld + k);
+                        xv[j].x += y.x; xv[j].y += y.y; xv[j].z += y.z; xv[j].w += y.w;
+                    }
+                }
+                if (o < O) wv[j] = __ldg(reinterpret_cast<const float4*>(W + (long long)o * I + k));
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int idx = tid + 256 * j, rr = idx >> 3, kk = (idx & 7) * 4;
+            Xs[kk][rr] = xv[j].x; Xs[kk + 1][rr] = xv[j].y; Xs[kk + 2][rr] = xv[j].z; Xs[kk + 3][rr] = xv[j].w;
+            Ws[kk][rr] = wv[j].x; Ws[kk + 1][rr] = wv[j].y; Ws[kk + 2][rr] = wv[j].z; Ws[kk + 3][rr] = wv[j].w;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < TK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&Xs[kk][4 * ty]);
+            const float4 w = *reinterpret_cast<const float4*>(&Ws[kk][4 * tx]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, wv4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv4[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 4 * ty + i;
+        if (r >= R) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = o0 + 4 * tx + j;
+            if (o < O) out[(long long)r * out_ld + o] = ws_act(acc[i][j] + (bias != nullptr ? bias[o] : 0.f), act);
+        }
+    }
+}
+
 __global__ void linear_reduce_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ bias,
                                      float* __restrict__ out, long long out_ld, int R, int O, int act) {
     const long long n = (long long)R * O;
@@ -161,16 +234,18 @@ __global__ void linear_reduce_kernel(const float* __restrict__ part, int nsplit,
     out[(long long)r * out_ld + o] = ws_act(a + (bias != nullptr ? bias[o] : 0.f), act);
 }
 
+template <int dt>   // compile-time dtype: one conversion path instead of both + selects (the kernel was issue-limited)
 __global__ void scale_residual_kernel(const void* __restrict__ x, long long x_ld, const float* __restrict__ gate,
                                       const void* __restrict__ res, long long res_ld, void* __restrict__ out,
-                                      float* __restrict__ lo, long long out_ld, int dt, int T, int C, long long nvec) {
-    const int cv = C >> 3;  // 8 channels per thread: 16-byte accesses for 16-bit activations
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < nvec; i += stride) {
-        const long long pos = i / cv;
-        const int c = (int)(i % cv) * 8;
-        const int b = (int)(pos / T);
+                                      float* __restrict__ lo, long long out_ld, int T, int C, long long nvec) {
+    const unsigned cv = (unsigned)C >> 3;  // 8 channels per thread: 16-byte accesses for 16-bit activations
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned stride = gridDim.x * blockDim.x, n = (unsigned)nvec;   // launcher guarantees nvec < 2^31
+    for (; i < n; i += stride) {
+        const unsigned upos = i / cv;          // 32-bit index math (64-bit divisions were most of the instruction stream)
+        const int c = (int)(i - upos * cv) * 8;
+        const int b = (int)(upos / (unsigned)T);
+        const long long pos = upos;
         float v[8], r[8];
         ws_ldv8(x, dt, pos * x_ld + c, v);
         ws_ldv8(res, dt, pos * res_ld + c, r);
@@ -235,6 +310,100 @@ __global__ void __launch_bounds__(256) astp_stats_kernel(const void* __restrict_
             for (int i = 0; i < 8; ++i) {
                 const float w = red[0][i][col] == -INFINITY ? 0.f : expf(red[0][i][col] - M);
                 a0 = fmaf(red[1][i][col], w, a0); a1 = fmaf(red[2][i][col], w, a1); a2 = fmaf(red[3][i][col], w, a2);
+            }
+            const float mean = a1 / a0;
+            const float var = a2 / a0 - mean * mean;
+            out[(long long)b * 2 * C + cc] = mean;
+            out[(long long)b * 2 * C + C + cc] = sqrtf(fmaxf(var, 1e-7f));
+        }
+    }
+}
+
+// 16-bit activations, T <= 256, every load issued up front: block (16, 32) = 16 channel groups of 4 channels (8-byte loads) x 32 T slices,
+// T <= 256: the thread's <= 8 logits rows AND x rows are loaded into registers before any arithmetic (16 independent
+// loads in flight per thread), then max / exp sums run from registers.  The fp32-path kernel above turned out to be
+// instruction-bound (full-precision expf + run-time dtype selects: ~25 instructions per element), so this one is compiled
+// per dtype and uses ex2.approx (__expf, ~1e-6 relative error: far below the 16-bit activation rounding it operates on).
+template <int dt>
+__global__ void __launch_bounds__(512, 2) astp_stats4_kernel(const void* __restrict__ x, const void* __restrict__ lg,
+                                                             int T, int C, long long ld, float* __restrict__ out) {
+    __shared__ float red[16][4][64];
+    const int cg = threadIdx.x, sl = threadIdx.y, warp = sl >> 1;   // a warp = 2 slices x 16 channel groups
+    const int c = (blockIdx.x * 16 + cg) * 4;
+    const int b = blockIdx.y;
+    const bool cv = c < C;
+    const long long base = (long long)b * T * ld + c;
+    float m[4], s0[4], s1[4], s2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m[k] = -INFINITY; s0[k] = 0.f; s1[k] = 0.f; s2[k] = 0.f; }
+    if (cv) {
+        uint2 lr[8], xr[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int t = sl + 32 * i;
+            lr[i] = make_uint2(0u, 0u); xr[i] = lr[i];
+            if (t < T) {
+                lr[i] = *reinterpret_cast<const uint2*>((const unsigned short*)lg + base + (long long)t * ld);
+                xr[i] = *reinterpret_cast<const uint2*>((const unsigned short*)x + base + (long long)t * ld);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (sl + 32 * i < T) {
+                m[0] = fmaxf(m[0], ws_16_to_f(lr[i].x & 0xffffu, dt)); m[1] = fmaxf(m[1], ws_16_to_f(lr[i].x >> 16, dt));
+                m[2] = fmaxf(m[2], ws_16_to_f(lr[i].y & 0xffffu, dt)); m[3] = fmaxf(m[3], ws_16_to_f(lr[i].y >> 16, dt));
+            }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (sl + 32 * i < T) {
+                const float l[4] = {ws_16_to_f(lr[i].x & 0xffffu, dt), ws_16_to_f(lr[i].x >> 16, dt),
+                                    ws_16_to_f(lr[i].y & 0xffffu, dt), ws_16_to_f(lr[i].y >> 16, dt)};
+                const float v[4] = {ws_16_to_f(xr[i].x & 0xffffu, dt), ws_16_to_f(xr[i].x >> 16, dt),
+                                    ws_16_to_f(xr[i].y & 0xffffu, dt), ws_16_to_f(xr[i].y >> 16, dt)};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float e = __expf(l[k] - m[k]);
+                    s0[k] += e;
+                    s1[k] = fmaf(e, v[k], s1[k]);
+                    s2[k] = fmaf(e * v[k], v[k], s2[k]);
+                }
+            }
+    }
+    // lanes l and l^16 hold the same channels for 2 different T slices
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m[k], 16);
+        const float a0 = __shfl_xor_sync(0xffffffffu, s0[k], 16);
+        const float a1 = __shfl_xor_sync(0xffffffffu, s1[k], 16);
+        const float a2 = __shfl_xor_sync(0xffffffffu, s2[k], 16);
+        const float M = fmaxf(m[k], mo);
+        const float wa = m[k] == -INFINITY ? 0.f : expf(m[k] - M);
+        const float wb = mo == -INFINITY ? 0.f : expf(mo - M);
+        s0[k] = s0[k] * wa + a0 * wb;
+        s1[k] = s1[k] * wa + a1 * wb;
+        s2[k] = s2[k] * wa + a2 * wb;
+        m[k] = M;
+    }
+    if ((sl & 1) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            red[warp][0][cg * 4 + k] = m[k]; red[warp][1][cg * 4 + k] = s0[k];
+            red[warp][2][cg * 4 + k] = s1[k]; red[warp][3][cg * 4 + k] = s2[k];
+        }
+    }
+    __syncthreads();
+    const int tid = sl * 16 + cg;
+    if (tid < 64) {
+        const int cc = blockIdx.x * 64 + tid;
+        if (cc < C) {
+            float M = red[0][0][tid];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) M = fmaxf(M, red[i][0][tid]);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float w = red[i][0][tid] == -INFINITY ? 0.f : expf(red[i][0][tid] - M);
+                a0 = fmaf(red[i][1][tid], w, a0); a1 = fmaf(red[i][2][tid], w, a1); a2 = fmaf(red[i][3][tid], w, a2);
             }
             const float mean = a1 / a0;
             const float var = a2 / a0 - mean * mean;
@@ -348,7 +517,8 @@ template <int H>
 __global__ void __launch_bounds__(512) se_gate_kernel(const void* __restrict__ x, int dt, int B, int T, int C, long long ld,
                                                       const float* __restrict__ W1, const float* __restrict__ b1,
                                                       const float* __restrict__ W2t, const float* __restrict__ b2,
-                                                      float* __restrict__ gate /*[B][C]*/) {
+                                                      float* __restrict__ gate /*[B][C]*/,
+                                                      const float* __restrict__ colsum /* WsEpi::colsum or null */) {
     extern __shared__ float sm[];
     float* mean = sm;              // [2][C]
     float* part = mean + 2 * C;    // [slices][2][C] partial sums of the T slices (slices * C = 4096 floats)
@@ -359,7 +529,20 @@ __global__ void __launch_bounds__(512) se_gate_kernel(const void* __restrict__ x
     const int groups = C >> 3;                 // 8-channel groups (C=1024 -> 128 groups x 4 T slices, C=512 -> 64 x 8)
     const int slices = 512 / groups;
     const int sl = tid / groups, gi = tid % groups;
-    for (int u = 0; u < nb; ++u) {
+    if (colsum != nullptr) {
+        // the producing conv already summed its output per 64-position unit (two utterance slots per unit)
+        for (int i = tid; i < nb * C; i += 512) {
+            const int u = i / C, c = i % C, b = b0 + u;
+            const int first = (b * T) >> 6, last = ((b + 1) * T - 1) >> 6;
+            float sacc = 0.f;
+            for (int un = first; un <= last; ++un) {
+                const int slot = ((un << 6) / T == b) ? 0 : 1;
+                sacc += colsum[(long long)(2 * un + slot) * C + c];
+            }
+            mean[u * C + c] = sacc / (float)T;
+        }
+    }
+    for (int u = 0; u < nb && colsum == nullptr; ++u) {
         float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const long long base = (long long)(b0 + u) * T * ld + gi * 8;
         for (int t = sl; t < T; t += slices) {
@@ -372,7 +555,7 @@ __global__ void __launch_bounds__(512) se_gate_kernel(const void* __restrict__ x
         for (int k = 0; k < 8; ++k) part[(sl * 2 + u) * C + gi * 8 + k] = a[k];
     }
     __syncthreads();
-    for (int i = tid; i < nb * C; i += 512) {
+    for (int i = tid; i < nb * C && colsum == nullptr; i += 512) {
         const int u = i / C, c = i % C;
         float s = 0.f;
         for (int k = 0; k < slices; ++k) s += part[(k * 2 + u) * C + c];   // fixed order: deterministic
@@ -513,18 +696,24 @@ const char* ws_launch_tstats(const void* x, int dt, int B, int F, int T, int C, 
     return last_err();
 }
 
+// the 64x64-tile kernel serves FC layers with enough rows and outputs to fill its tile and 16-byte aligned rows
+bool ws_linear_rows_big(long long in_ld, const float* in2, long long in2_ld, int R, int I, int O) {
+    return R >= 48 && O >= 48 && I % 4 == 0 && in_ld % 4 == 0 && (in2 == nullptr || in2_ld % 4 == 0);
+}
+
 const char* ws_launch_linear_rows(const float* in, long long in_ld, const float* in2, long long in2_ld,
                                   int rows_per_b, const float* W, const float* bias, float* out, long long out_ld,
                                   int R, int I, int O, int act, float* workspace, int nsplit, cudaStream_t s) {
-    dim3 grid((O + 31) / 32, (R + 15) / 16, nsplit < 1 ? 1 : nsplit);
+    const bool big = ws_linear_rows_big(in_ld, in2, in2_ld, R, I, O);
+    dim3 grid(big ? (O + 63) / 64 : (O + 31) / 32, big ? (R + 63) / 64 : (R + 15) / 16, nsplit < 1 ? 1 : nsplit);
+    auto kern = big ? linear_rows64_kernel : linear_rows_kernel;
     if (grid.z == 1) {
-        linear_rows_kernel<<<grid, 256, 0, s>>>(in, in_ld, in2, in2_ld, rows_per_b < 1 ? 1 : rows_per_b, W, bias, out,
-                                                out_ld, R, I, O, act);
+        kern<<<grid, 256, 0, s>>>(in, in_ld, in2, in2_ld, rows_per_b < 1 ? 1 : rows_per_b, W, bias, out, out_ld, R, I, O, act);
         return last_err();
     }
     if (workspace == nullptr) return "linear_rows: split-K needs a workspace";
-    linear_rows_kernel<<<grid, 256, 0, s>>>(in, in_ld, in2, in2_ld, rows_per_b < 1 ? 1 : rows_per_b, W, nullptr,
-                                            workspace, O, R, I, O, WS_ACT_NONE);
+    kern<<<grid, 256, 0, s>>>(in, in_ld, in2, in2_ld, rows_per_b < 1 ? 1 : rows_per_b, W, nullptr, workspace, O, R, I, O,
+                              WS_ACT_NONE);
     const long long n = (long long)R * O;
     linear_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(workspace, nsplit, bias, out, out_ld, R, O, act);
     return last_err();
@@ -535,13 +724,24 @@ const char* ws_launch_scale_residual(const void* x, long long x_ld, const float*
                                      int C, cudaStream_t s) {
     if (C % 8 != 0) return "scale_residual: C must be a multiple of 8";
     const long long nvec = (long long)B * T * (C / 8);
-    scale_residual_kernel<<<grid_for(nvec, 256), 256, 0, s>>>(x, x_ld, gate, res, res_ld, out, lo, out_ld, dt, T, C, nvec);
+    if (nvec >= (1LL << 31)) return "scale_residual: tensor too large for 32-bit vector indices";
+    const int g = grid_for(nvec, 256);
+    if (dt == WS_BF16) scale_residual_kernel<WS_BF16><<<g, 256, 0, s>>>(x, x_ld, gate, res, res_ld, out, lo, out_ld, T, C, nvec);
+    else if (dt == WS_F16) scale_residual_kernel<WS_F16><<<g, 256, 0, s>>>(x, x_ld, gate, res, res_ld, out, lo, out_ld, T, C, nvec);
+    else scale_residual_kernel<WS_F32><<<g, 256, 0, s>>>(x, x_ld, gate, res, res_ld, out, lo, out_ld, T, C, nvec);
     return last_err();
 }
 
 const char* ws_launch_astp_stats(const void* x, const void* logits, int dt, int B, int T, int C, long long ld,
                                  float* out, cudaStream_t s) {
     if (C % 2 != 0) return "astp_stats: C must be even";
+    static const int variant = getenv("WS_ASTP_VARIANT") ? atoi(getenv("WS_ASTP_VARIANT")) : 2;
+    if (variant == 2 && C % 4 == 0 && ld % 4 == 0 && dt != WS_F32 && T <= 256) {
+        dim3 grid((C + 63) / 64, B), block(16, 32);
+        if (dt == WS_BF16) astp_stats4_kernel<WS_BF16><<<grid, block, 0, s>>>(x, logits, T, C, ld, out);
+        else astp_stats4_kernel<WS_F16><<<grid, block, 0, s>>>(x, logits, T, C, ld, out);
+        return last_err();
+    }
     dim3 grid((C + 63) / 64, B), block(32, 8);
     astp_stats_kernel<<<grid, block, 0, s>>>(x, logits, dt, T, C, ld, out);
     return last_err();
@@ -583,7 +783,7 @@ const char* ws_launch_cam_gate(const void* x, int dt, int B, int T, int C, long 
 }
 
 const char* ws_launch_se_gate(const void* x, int dt, int B, int T, int C, long long ld, const float* W1, const float* b1,
-                              const float* W2t, const float* b2, int H, float* gate, cudaStream_t s) {
+                              const float* W2t, const float* b2, int H, float* gate, const float* colsum, cudaStream_t s) {
     if (H != 128 || (C != 512 && C != 1024 && C != 2048 && C != 256)) return "se_gate: expected H=128 and C in {256,512,1024,2048}";
     const size_t smem = (size_t)(2 * C + 8192 + 2 * H) * sizeof(float);
     static bool attr = false;
@@ -592,6 +792,7 @@ const char* ws_launch_se_gate(const void* x, int dt, int B, int T, int C, long l
         attr = true;
     }
     if (smem > 96 * 1024) return "se_gate: channel count too large for shared memory";
-    se_gate_kernel<128><<<(B + 1) / 2, 512, smem, s>>>(x, dt, B, T, C, ld, W1, b1, W2t, b2, gate);
+    if (colsum != nullptr && T < 128) return "se_gate: fused column sums need >= 128 frames per utterance";
+    se_gate_kernel<128><<<(B + 1) / 2, 512, smem, s>>>(x, dt, B, T, C, ld, W1, b1, W2t, b2, gate, colsum);
     return last_err();
 }

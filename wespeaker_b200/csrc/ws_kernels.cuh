@@ -13,6 +13,7 @@ const char* ws_launch_tstats(const void* x, int dt, int B, int F, int T, int C, 
                              const float* pre_shift, void* out, int odt, long long out_ld, int std_off, float eps,
                              cudaStream_t s);
 // out[r][o] = act( sum_i W[o][i] * (in[r][i] + in2[r / rows_per_b][i]) + bias[o] ),  fp32 in/out, W fp32 [O][I]
+bool ws_linear_rows_big(long long in_ld, const float* in2, long long in2_ld, int R, int I, int O);
 const char* ws_launch_linear_rows(const float* in, long long in_ld, const float* in2, long long in2_ld,
                                   int rows_per_b, const float* W, const float* bias, float* out, long long out_ld,
                                   int R, int I, int O, int act, float* workspace, int nsplit, cudaStream_t s);
@@ -35,7 +36,7 @@ const char* ws_launch_seg_means(const void* x, int dt, int B, int T, int C, long
 
 // fused SE gate: gate[b][c] = sigmoid(W2 relu(W1 mean_T(x[b]) + b1) + b2); W2t is W2 transposed to [H][C]
 const char* ws_launch_se_gate(const void* x, int dt, int B, int T, int C, long long ld, const float* W1, const float* b1,
-                              const float* W2t, const float* b2, int H, float* gate, cudaStream_t s);
+                              const float* W2t, const float* b2, int H, float* gate, const float* colsum, cudaStream_t s);
 // fused CAM context gate: gate[b][seg][g] = sigmoid(W2 relu(W1 (mean_T(x) + segmean(x)) + b1) + b2)
 const char* ws_launch_cam_gate(const void* x, int dt, int B, int T, int C, long long ld, int seg_len, const float* W1,
                                const float* b1, const float* W2, const float* b2, int H, int G, float* gate,

@@ -62,7 +62,7 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // K-major SWIZZLE_128B operand descriptor (rows 128 B apart, 8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc128(uint32_t saddr) {
@@ -102,10 +102,14 @@ constexpr int kSRows = 256 + 16; // operand buffer rows per K panel
 constexpr int kWStages = 4;
 constexpr int kNumConv = 7;
 
-__global__ void __launch_bounds__(256, 1) ws_res2_fused_kernel(const __grid_constant__ WsRes2Params p) {
+// DT = activation dtype (compile-time so the epilogue carries one conversion path); 384 threads: w0 producer, w1 MMA,
+// w2 TMEM alloc, w4..w11 epilogue (warps w and w+4 share a TMEM lane quadrant and split the w8 columns).  The epilogue
+// sits on the serial conv_i -> conv_{i+1} chain, so its latency (not throughput) is what the kernel time is made of.
+template <int DT>
+__global__ void __launch_bounds__(384, 1) ws_res2_fused_kernel(const __grid_constant__ WsRes2Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[2 * kWStages + 5];
-    __shared__ float s_par[3][128];
+    __shared__ __align__(16) float s_par[3][128];
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(256, 1) ws_res2_fused_kernel(const __grid_cons
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kWStages; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
         mbar_init(bar_x0, 1);
-        mbar_init(bar_sready, 4);
+        mbar_init(bar_sready, 8);
         mbar_init(bar_acc, 1);
         mbar_init(bar_sfree, 1);
         mbar_init(bar_xn, 1);
@@ -210,7 +214,8 @@ __global__ void __launch_bounds__(256, 1) ws_res2_fused_kernel(const __grid_cons
         // The XO buffer holds the next channel group x_{i+1} (TMA-loaded while the MMAs run); each thread reads its chunk,
         // overwrites it with sp_i (stored to HBM by TMA afterwards) and writes s_{i+1} = sp_i + x_{i+1} into the operand
         // buffer.  The elected thread re-arms XO with the following group as soon as the store has read it.
-        const int q = warp & 3, r = q * 32 + lane, et = threadIdx.x - 128;
+        const int q = warp & 3, r = q * 32 + lane, et = threadIdx.x - 128;   // et 0..255
+        const int c_beg = ((warp - 4) >> 2) * (p.w8 >> 1), c_end = c_beg + (p.w8 >> 1);
         const uint32_t xo_bytes = (uint32_t)(npan * nmt * 128 * 128);
         auto load_xn = [&](int bb, int grp) {
             mbar_expect_tx(bar_xn, xo_bytes);
@@ -233,18 +238,28 @@ __global__ void __launch_bounds__(256, 1) ws_res2_fused_kernel(const __grid_cons
                 if (i == kNumConv - 1 && et == 0) mbar_arrive(bar_sfree);  // conv 6 done: S may take the next utterance
                 const bool has_next = i < kNumConv - 1;
                 if (has_next) { mbar_wait(bar_xn, (uint32_t)xc & 1u); ++xc; }
+#pragma unroll 1
                 for (int mt = 0; mt < nmt; ++mt) {
                     const int t = mt * 128 + r;
                     const bool valid = t < p.T;
                     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.w8);
-                    for (int c = 0; c < p.w8; c += 32) {
+#pragma unroll 1
+                    for (int c = c_beg; c < c_end; c += 32) {
                         uint32_t raw[32];
                         tmem_ld32(trow + (uint32_t)c, raw);
                         tmem_ld_wait();
                         float v[32];
+                        const float4* pb = reinterpret_cast<const float4*>(&s_par[0][c]);
+                        const float4* ps = reinterpret_cast<const float4*>(&s_par[1][c]);
+                        const float4* ph = reinterpret_cast<const float4*>(&s_par[2][c]);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            v[j] = fmaf(fmaxf(__uint_as_float(raw[j]) + s_par[0][c + j], 0.f), s_par[1][c + j], s_par[2][c + j]);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = pb[j], s4 = ps[j], h4 = ph[j];
+                            v[4 * j] = fmaf(fmaxf(__uint_as_float(raw[4 * j]) + b4.x, 0.f), s4.x, h4.x);
+                            v[4 * j + 1] = fmaf(fmaxf(__uint_as_float(raw[4 * j + 1]) + b4.y, 0.f), s4.y, h4.y);
+                            v[4 * j + 2] = fmaf(fmaxf(__uint_as_float(raw[4 * j + 2]) + b4.z, 0.f), s4.z, h4.z);
+                            v[4 * j + 3] = fmaf(fmaxf(__uint_as_float(raw[4 * j + 3]) + b4.w, 0.f), s4.w, h4.w);
+                        }
                         const int pn = c >> 6, c16 = (c & 63) >> 3;      // panel, first 16-B chunk inside the 128-B row
                         const uint32_t orow = sO + (uint32_t)((pn * 256 + t) * 128);
                         const uint32_t srow = sS + (uint32_t)((pn * kSRows + kPadRows + t) * 128);
@@ -259,8 +274,8 @@ __global__ void __launch_bounds__(256, 1) ws_res2_fused_kernel(const __grid_cons
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const float a0 = v[8 * j + 2 * k], a1 = v[8 * j + 2 * k + 1];
-                                w[k] = ws_pack2(a0, a1, p.dtype);
-                                o[k] = ws_pack2(a0 + ws_16_to_f(xs[k] & 0xffffu, p.dtype), a1 + ws_16_to_f(xs[k] >> 16, p.dtype), p.dtype);
+                                w[k] = ws_pack2(a0, a1, DT);
+                                o[k] = ws_pack2(a0 + ws_16_to_f(xs[k] & 0xffffu, DT), a1 + ws_16_to_f(xs[k] >> 16, DT), DT);
                             }
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(orow + off), "r"(w[0]), "r"(w[1]),
                                          "r"(w[2]), "r"(w[3]) : "memory");
@@ -301,14 +316,18 @@ __global__ void __launch_bounds__(256, 1) ws_res2_fused_kernel(const __grid_cons
 extern "C" const char* ws_res2_init(void) {
     static bool done = false;
     if (done) return nullptr;
-    cudaError_t e = cudaFuncSetAttribute(ws_res2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ws_res2_fused_kernel<WS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(ws_res2_fused_kernel<WS_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) { cudaGetLastError(); return cudaGetErrorString(e); }
     done = true;
     return nullptr;
 }
 
 extern "C" const char* ws_res2_launch(const WsRes2Params* p, cudaStream_t s) {
-    ws_res2_fused_kernel<<<p->grid, 256, p->smem_bytes, s>>>(*p);
+    if (p->dtype == WS_BF16) ws_res2_fused_kernel<WS_BF16><<<p->grid, 384, p->smem_bytes, s>>>(*p);
+    else if (p->dtype == WS_F16) ws_res2_fused_kernel<WS_F16><<<p->grid, 384, p->smem_bytes, s>>>(*p);
+    else return "res2_fused: 16-bit activations only";
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

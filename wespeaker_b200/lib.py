@@ -30,6 +30,7 @@ class ConvDesc(C.Structure):
         ("scale", C.c_void_p), ("shift", C.c_void_p), ("res", C.c_void_p), ("res_ld", C.c_longlong),
         ("act2", C.c_int), ("out", C.c_void_p), ("out_ld", C.c_longlong), ("dtype", C.c_int),
         ("use_tc", C.c_int), ("x_lo", C.c_void_p), ("w_lo", C.c_void_p), ("out_lo", C.c_void_p),
+        ("colsum", C.c_void_p),
     ]
 
 
