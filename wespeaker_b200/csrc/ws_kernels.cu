@@ -562,28 +562,68 @@ __global__ void __launch_bounds__(512) se_gate_kernel(const void* __restrict__ x
         mean[u * C + c] = s / (float)T;
     }
     __syncthreads();
-    for (int h = warp; h < H; h += 16) {
-        const float* w = W1 + (long long)h * C;
-        float a0 = 0.f, a1 = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float wv = __ldg(w + c);
-            a0 = fmaf(wv, mean[c], a0);
-            a1 = fmaf(wv, mean[C + c], a1);
+    // fc1: two hidden units per warp pass, 16-byte weight loads (C % 128 == 0): 4x fewer dependent-latency steps
+    for (int h = 2 * warp; h < H; h += 32) {
+        const float4* w0 = reinterpret_cast<const float4*>(W1 + (long long)h * C);
+        const float4* w1 = reinterpret_cast<const float4*>(W1 + (long long)(h + 1) * C);
+        float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+#pragma unroll 4
+        for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
+            const float4 x0 = __ldg(w0 + c4), x1 = __ldg(w1 + c4);
+            const float4 m0 = *reinterpret_cast<const float4*>(mean + 4 * c4);
+            const float4 m1 = *reinterpret_cast<const float4*>(mean + C + 4 * c4);
+            a00 = fmaf(x0.x, m0.x, a00); a00 = fmaf(x0.y, m0.y, a00); a00 = fmaf(x0.z, m0.z, a00); a00 = fmaf(x0.w, m0.w, a00);
+            a01 = fmaf(x0.x, m1.x, a01); a01 = fmaf(x0.y, m1.y, a01); a01 = fmaf(x0.z, m1.z, a01); a01 = fmaf(x0.w, m1.w, a01);
+            a10 = fmaf(x1.x, m0.x, a10); a10 = fmaf(x1.y, m0.y, a10); a10 = fmaf(x1.z, m0.z, a10); a10 = fmaf(x1.w, m0.w, a10);
+            a11 = fmaf(x1.x, m1.x, a11); a11 = fmaf(x1.y, m1.y, a11); a11 = fmaf(x1.z, m1.z, a11); a11 = fmaf(x1.w, m1.w, a11);
         }
-        a0 = warp_sum(a0); a1 = warp_sum(a1);
-        if (lane == 0) { hid[h] = fmaxf(a0 + b1[h], 0.f); hid[H + h] = fmaxf(a1 + b1[h], 0.f); }
+        a00 = warp_sum(a00); a01 = warp_sum(a01); a10 = warp_sum(a10); a11 = warp_sum(a11);
+        if (lane == 0) {
+            hid[h] = fmaxf(a00 + b1[h], 0.f); hid[H + h] = fmaxf(a01 + b1[h], 0.f);
+            hid[h + 1] = fmaxf(a10 + b1[h + 1], 0.f); hid[H + h + 1] = fmaxf(a11 + b1[h + 1], 0.f);
+        }
     }
     __syncthreads();
-    for (int c = tid; c < C; c += 512) {
-        float a0 = b2[c], a1 = a0;
+    // fc2: 4 channels per thread (16-byte loads of the transposed weights); threads beyond C/4 split the hidden range
+    {
+        const int nq = C >> 2;                    // channel quads
+        const int parts = 512 / nq;               // 2 (C=1024), 4 (C=512), 8 (C=256); 1 for C=2048 (two rounds)
+        float* acc = part;                        // [parts][2][C] partial sums (part is free after the squeeze)
+        for (int q0 = 0; q0 < nq; q0 += 512) {
+            const int q = q0 + (parts > 0 ? tid % nq : tid), hp = parts > 0 ? tid / nq : 0;
+            const int np = parts > 0 ? parts : 1;
+            if (q < nq) {
+                const int hb = hp * (H / np), he = hb + H / np;
+                float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
-        for (int h = 0; h < H; ++h) {
-            const float wv = __ldg(W2t + (long long)h * C + c);
-            a0 = fmaf(wv, hid[h], a0);
-            a1 = fmaf(wv, hid[H + h], a1);
+                for (int h = hb; h < he; ++h) {
+                    const float4 wv = __ldg(reinterpret_cast<const float4*>(W2t + (long long)h * C) + q);
+                    const float h0 = hid[h], h1 = hid[H + h];
+                    a0[0] = fmaf(wv.x, h0, a0[0]); a0[1] = fmaf(wv.y, h0, a0[1]); a0[2] = fmaf(wv.z, h0, a0[2]); a0[3] = fmaf(wv.w, h0, a0[3]);
+                    a1[0] = fmaf(wv.x, h1, a1[0]); a1[1] = fmaf(wv.y, h1, a1[1]); a1[2] = fmaf(wv.z, h1, a1[2]); a1[3] = fmaf(wv.w, h1, a1[3]);
+                }
+                if (np == 1) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int c = 4 * q + k;
+                        gate[(long long)b0 * C + c] = 1.f / (1.f + expf(-(a0[k] + b2[c])));
+                        if (nb > 1) gate[(long long)(b0 + 1) * C + c] = 1.f / (1.f + expf(-(a1[k] + b2[c])));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { acc[(hp * 2) * C + 4 * q + k] = a0[k]; acc[(hp * 2 + 1) * C + 4 * q + k] = a1[k]; }
+                }
+            }
         }
-        gate[(long long)b0 * C + c] = 1.f / (1.f + expf(-a0));
-        if (nb > 1) gate[(long long)(b0 + 1) * C + c] = 1.f / (1.f + expf(-a1));
+        if (parts > 1) {
+            __syncthreads();
+            for (int i = tid; i < nb * C; i += 512) {
+                const int u = i / C, c = i % C;
+                float a = b2[c];
+                for (int k = 0; k < parts; ++k) a += acc[(k * 2 + u) * C + c];   // fixed order
+                gate[(long long)(b0 + u) * C + c] = 1.f / (1.f + expf(-a));
+            }
+        }
     }
 }
 
