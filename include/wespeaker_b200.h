@@ -122,6 +122,26 @@ int ws_plda_score_trials(ws_plda* p, const double* enroll_t_dev, const int* coun
                          long long ntrials, double* out_dev, void* stream);
 void ws_plda_destroy(ws_plda* p);
 
+/* ---- cosine scoring + S-norm / AS-norm: replaces trials_cosine_score (wespeaker/bin/score.py:38-72),
+ *      get_mean_std (wespeaker/bin/score_norm.py:26-37) and the per-trial normalisation (score_norm.py:102-107).
+ *      All pointers are device pointers; fp32 embeddings in, fp64 arithmetic. */
+/* unit[r] = (x[r] - mean_vec) / |x[r] - mean_vec| (fp64, N x D); norms[r] = |x[r] - mean_vec| (the "mag" columns of
+ * score_norm.py:109-110); mean_vec_dev (D fp64) and norms_dev may be NULL. */
+int ws_score_unit_rows(const float* x_dev, long long N, int D, const double* mean_vec_dev, double* unit_dev,
+                       double* norms_dev, void* stream);
+/* out[k] = <unit[enroll_idx[k]], unit[test_idx[k]]>: cosine_similarity of the listed trials (score.py:62-63) */
+int ws_score_cosine_trials(const double* unit_dev, const long long* enroll_idx_dev, const long long* test_idx_dev,
+                           long long ntrials, int D, double* out_dev, void* stream);
+/* mean / population std of the top_n largest cosine scores of each embedding against the M cohort rows
+ * (get_mean_std; top_n >= M is S-norm).  work_dev: fp32 scratch of work_rows x M score tiles. */
+int ws_score_cohort_stats(const double* unit_emb_dev, long long N, const double* unit_cohort_dev, long long M, int D,
+                          int top_n, float* work_dev, long long work_rows, double* mean_dev, double* std_dev,
+                          void* stream);
+/* out[k] = 0.5 * ((s[k] - emean[ei[k]]) / estd[ei[k]] + (s[k] - tmean[ti[k]]) / tstd[ti[k]]) */
+int ws_score_asnorm(const double* scores_dev, const long long* enroll_idx_dev, const long long* test_idx_dev,
+                    long long ntrials, const double* enroll_mean_dev, const double* enroll_std_dev,
+                    const double* test_mean_dev, const double* test_std_dev, double* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,12 @@ _PROTOS = {
     "ws_plda_score_trials": (C.c_int, [c_plda_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p,
                                        C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "ws_plda_destroy": (None, [c_plda_p]),
+    "ws_score_unit_rows": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ws_score_cosine_trials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
+    "ws_score_cohort_stats": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ws_score_asnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS.keys())
 
