@@ -116,3 +116,24 @@ def test_gather_embeddings_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0 and "OK" in o, o
+
+
+def test_speaker_register_recognize_similarity_host_logic(monkeypatch, capsys):
+    """`cli/speaker.py:180-211` host logic (no GPU involved: extract_embedding is replaced by a lookup table)."""
+    from wespeaker_b200.speaker import Speaker
+    table = {"a.wav": torch.tensor([1.0, 0.0, 0.0]), "b.wav": torch.tensor([0.0, 2.0, 0.0]),
+             "q.wav": torch.tensor([0.6, 0.8, 0.0]), "silence.wav": None}
+    spk = Speaker(model=object())
+    monkeypatch.setattr(spk, "extract_embedding", lambda p: table[p])
+    assert spk.cosine_similarity(table["a.wav"], table["a.wav"]) == pytest.approx(1.0)
+    assert spk.cosine_similarity(table["a.wav"], table["b.wav"]) == pytest.approx(0.5)       # cos 0 -> 0.5
+    assert spk.compute_similarity("a.wav", "q.wav") == pytest.approx((0.6 + 1.0) / 2)
+    assert spk.compute_similarity("a.wav", "silence.wav") == 0.0                              # None embedding
+    spk.register("alice", "a.wav")
+    spk.register("bob", "b.wav")
+    spk.register("alice", "b.wav")                                                            # ignored, with the reference's message
+    assert "already registered" in capsys.readouterr().out
+    assert torch.equal(spk.table["alice"], table["a.wav"])
+    r = spk.recognize("q.wav")
+    assert r["name"] == "bob" and r["confidence"] == pytest.approx((0.8 + 1.0) / 2)
+    assert Speaker(model=object()).recognize.__self__.table == {}

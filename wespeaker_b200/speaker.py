@@ -122,10 +122,37 @@ class Speaker:
         """B200 addition: (B,N) equal-length int16/float waveforms -> (B,E) CUDA tensor in one fused pass."""
         return self.model.extract_from_wav(pcm_batch.to(self._cuda_device()), window_type=self.window_type)
 
-    def compute_similarity_embeddings(self, e1: torch.Tensor, e2: torch.Tensor) -> float:
-        """cosine mapped to [0,1] as `cli/speaker.py:191-194`."""
-        c = torch.dot(e1, e2) / (torch.norm(e1) * torch.norm(e2))
-        return float((c + 1.0) / 2)
+    def compute_similarity(self, audio_path1: str, audio_path2: str) -> float:
+        """`cli/speaker.py:180-186`."""
+        e1 = self.extract_embedding(audio_path1)
+        e2 = self.extract_embedding(audio_path2)
+        if e1 is None or e2 is None:
+            return 0.0
+        return self.cosine_similarity(e1, e2)
+
+    def cosine_similarity(self, e1, e2):
+        """`cli/speaker.py:188-191`: cosine of two (E,) CPU embeddings mapped from [-1, 1] to [0, 1]."""
+        cosine_score = torch.dot(e1, e2) / (torch.norm(e1) * torch.norm(e2))
+        return (cosine_score.item() + 1.0) / 2
+
+    def register(self, name: str, audio_path: str):
+        """`cli/speaker.py:193-197`."""
+        if name in self.table:
+            print("Speaker {} already registered, ignore".format(name))
+        else:
+            self.table[name] = self.extract_embedding(audio_path)
+
+    def recognize(self, audio_path: str):
+        """`cli/speaker.py:199-211`: best-scoring registered speaker, `{'name', 'confidence'}`."""
+        q = self.extract_embedding(audio_path)
+        best_score = 0.0
+        best_name = ""
+        for name, e in self.table.items():
+            score = self.cosine_similarity(q, e)
+            if best_score < score:
+                best_score = score
+                best_name = name
+        return {"name": best_name, "confidence": best_score}
 
 
 def load_model(model_dir: str, precision: str | None = None) -> Speaker:
