@@ -63,6 +63,21 @@ def test_oracle_score_norm_matches_reference_file(method, tag):
     _same_lines([ln.split() for ln in lines], _rows(G[f"{method}_{tag}"]), set(NORM_COLS), NORM_COLS)
 
 
+def test_score_host_helpers(tmp_path):
+    """File-side helpers of score.py (no arithmetic on the device): mean vector of an scp, table reader."""
+    scp = str(tmp_path / "x.scp")
+    with kaldi_io.VectorWriter(str(tmp_path / "x.ark"), scp) as w:
+        for u, v in zip(G["utts"][:7], G["evals"][:7]):
+            w(str(u), v)
+    m = score.calculate_mean_from_kaldi_vec(scp)                      # score.py:25-36
+    assert m.dtype == np.float32 and np.allclose(m, G["evals"][:7].mean(axis=0), atol=1e-6)
+    t = tmp_path / "t.txt"
+    t.write_text("a b 0.5 target\n  c   d -1 nontarget \n")
+    assert score.read_table(str(t)) == [["a", "b", "0.5", "target"], ["c", "d", "-1", "nontarget"]]
+    got = dict(kaldi_io.load_scp_sequential(scp))
+    assert list(got) == [str(u) for u in G["utts"][:7]] and np.array_equal(got[str(G["utts"][3])], G["evals"][3])
+
+
 def test_score_needs_gpu_and_fails_loudly():
     if torch.cuda.is_available():
         pytest.skip("CPU-only check")
