@@ -6,7 +6,6 @@ host<->device staging only; there is no CPU fallback.
 """
 from __future__ import annotations
 
-import ctypes as C
 import logging
 import os
 from pathlib import Path
