@@ -112,6 +112,8 @@ int ws_plda_create(int dim, const double* mu, const double* transform, const dou
  * x_dev fp32 (N,D); mean_vec_host fp64 (D) or NULL; y_dev fp64 (N,D). */
 int ws_plda_transform(ws_plda* p, const float* x_dev, long long N, const double* mean_vec_host, int pre_norm,
                       double* y_dev, void* stream);
+/* same with fp64 rows that are already mean-subtracted (the per-speaker session means of eval_sv :218-233 stay fp64) */
+int ws_plda_transform64(ws_plda* p, const double* x64_dev, long long N, int pre_norm, double* y_dev, void* stream);
 /* all-pairs LLR: out[i*out_ld + j] = log_likelihood_ratio(enroll_t[i], test_t[j], n_i);  n_i = counts_dev[i] or const_n */
 int ws_plda_score_matrix(ws_plda* p, const double* enroll_t_dev, const int* counts_dev, int const_n, long long N,
                          const double* test_t_dev, long long M, void* out_dev, int out_is_f64, long long out_ld,

@@ -331,6 +331,30 @@ struct WsRes2Params {
     int grid, smem_bytes;
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are PER DEVICE: init guards are keyed by the current
+// device so that a second engine on another GPU of the same process gets its opt-in too (one bit per device ordinal).
+inline bool ws_dev_needs_init(unsigned long long* mask, int* dev_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *dev_out = dev;
+    return dev < 0 || dev >= 64 || ((*mask >> dev) & 1ull) == 0;
+}
+inline void ws_dev_mark_init(unsigned long long* mask, int dev) {
+    if (dev >= 0 && dev < 64) *mask |= 1ull << dev;
+}
+inline int ws_num_sms() {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (sms[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
+    }
+    return sms[dev];
+}
+
 #ifdef __cplusplus
 extern "C" {
 #endif

@@ -208,7 +208,6 @@ static bool build_tc(const ConvSpec& s, WsTcParams* p) {
 
 
 // ---- v2 (persistent, TMA-store epilogue).  Returns false *without* error if the spec needs the v1 kernel.
-static int g_num_sms = 0;
 static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported, bool pair = false) {
     *unsupported = false;
     const WsEpi& e = s.epi;
@@ -309,12 +308,7 @@ static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported, bool
     }
     for (; oi < 4; ++oi) q->omap[oi] = q->omap[0];
     if (!q->has_epin) q->imap = q->omap[0];
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
+    const int g_num_sms = ws_num_sms();
     if (pair) {
         const int pairs = g_num_sms / 2;
         q->grid = 2 * (q->num_tiles < pairs ? q->num_tiles : pairs);
@@ -404,12 +398,7 @@ bool make_res2_op(const View& x, const View& out, const void* W7, const float* b
     q->B = x.B; q->T = x.T; q->w8 = w8; q->dil = dil; q->dtype = x.dt;
     const uint32_t fmt = x.dt == WS_BF16 ? 1u : 0u;
     q->idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(w8 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
+    const int g_num_sms = ws_num_sms();
     q->grid = x.B < g_num_sms ? x.B : g_num_sms;
     const int npan = w8 / 64;
     q->smem_bytes = npan * 272 * 128 + 4 * w8 * 128 + npan * 256 * 128 + 1024;

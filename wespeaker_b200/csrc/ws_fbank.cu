@@ -25,7 +25,10 @@ __device__ __forceinline__ float ld_sample(const void* wav, int is_i16, long lon
 }
 
 __device__ __forceinline__ float2 ld_sample2(const void* wav, int is_i16, long long i) {   // samples i, i+1
-    if (i & 1) return make_float2(ld_sample(wav, is_i16, i), ld_sample(wav, is_i16, i + 1));  // odd row stride: scalar loads
+    // the pair load needs an 8-byte (float) / 4-byte (int16) aligned ADDRESS: odd row strides and views whose base pointer
+    // is offset by an odd element count (wavs[1:] of an odd-length batch) take the scalar path
+    const uintptr_t addr = (uintptr_t)wav + (uintptr_t)i * (is_i16 ? 2u : 4u);
+    if (addr & (is_i16 ? 3u : 7u)) return make_float2(ld_sample(wav, is_i16, i), ld_sample(wav, is_i16, i + 1));
     if (is_i16) {
         const short2 v = *reinterpret_cast<const short2*>((const short*)wav + i);
         return make_float2((float)v.x, (float)v.y);

@@ -252,13 +252,14 @@ __global__ void __launch_bounds__(kThreads) ws_conv_gemm_tc_kernel(const __grid_
 }  // namespace
 
 extern "C" const char* ws_tc_init(void) {
-    static bool done = false;
-    if (done) return nullptr;
+    static unsigned long long done = 0;
+    int dev = 0;
+    if (!ws_dev_needs_init(&done, &dev)) return nullptr;
     cudaError_t e = cudaFuncSetAttribute(ws_conv_gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(ws_conv_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     if (e != cudaSuccess) { cudaGetLastError(); return cudaGetErrorString(e); }
-    done = true;
+    ws_dev_mark_init(&done, dev);
     return nullptr;
 }
 

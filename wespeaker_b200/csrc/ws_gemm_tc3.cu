@@ -333,15 +333,16 @@ inline cudaError_t tc3_attr() {
 }  // namespace
 
 extern "C" const char* ws_tc3_init(void) {
-    static bool done = false;
-    if (done) return nullptr;
+    static unsigned long long done = 0;
+    int dev = 0;
+    if (!ws_dev_needs_init(&done, &dev)) return nullptr;
     cudaError_t e = tc3_attr<0, 0>();
     if (e == cudaSuccess) e = tc3_attr<1, 0>();
     if (e == cudaSuccess) e = tc3_attr<0, WS_F32 + 1>();
     if (e == cudaSuccess) e = tc3_attr<1, WS_BF16 + 1>();
     if (e == cudaSuccess) e = tc3_attr<1, WS_F16 + 1>();
     if (e != cudaSuccess) { cudaGetLastError(); return cudaGetErrorString(e); }
-    done = true;
+    ws_dev_mark_init(&done, dev);
     return nullptr;
 }
 

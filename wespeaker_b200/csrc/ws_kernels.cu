@@ -826,10 +826,11 @@ const char* ws_launch_se_gate(const void* x, int dt, int B, int T, int C, long l
                               const float* W2t, const float* b2, int H, float* gate, const float* colsum, cudaStream_t s) {
     if (H != 128 || (C != 512 && C != 1024 && C != 2048 && C != 256)) return "se_gate: expected H=128 and C in {256,512,1024,2048}";
     const size_t smem = (size_t)(2 * C + 8192 + 2 * H) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;   // per-device opt-in (ws_common.cuh)
+    int dev = 0;
+    if (ws_dev_needs_init(&attr, &dev)) {
         cudaFuncSetAttribute(se_gate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr = true;
+        ws_dev_mark_init(&attr, dev);
     }
     if (smem > 96 * 1024) return "se_gate: channel count too large for shared memory";
     if (colsum != nullptr && T < 128) return "se_gate: fused column sums need >= 128 frames per utterance";

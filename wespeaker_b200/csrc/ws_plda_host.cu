@@ -96,6 +96,30 @@ int ws_plda_transform(ws_plda* p, const float* x_dev, long long N, const double*
     return 0;
 }
 
+// fp64-input twin of ws_plda_transform: eval_sv (two_cov_plda.py:218-233) averages a speaker's sessions before the
+// transform and the reference keeps that mean in fp64; x64_dev rows are (already mean-subtracted) fp64 vectors.
+int ws_plda_transform64(ws_plda* p, const double* x64_dev, long long N, int pre_norm, double* y_dev, void* stream) {
+    if (!p || !x64_dev || !y_dev || N < 0) { set_err("ws_plda_transform64: bad argument"); return 1; }
+    if (N == 0) return 0;
+    WS_CK(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int D = p->dim;
+    const double* src = x64_dev;
+    if (pre_norm) {
+        if (ensure(&p->x64, &p->x64_rows, (size_t)N * D)) return 1;
+        WS_CK(cudaMemcpyAsync(p->x64, x64_dev, (size_t)N * D * 8, cudaMemcpyDeviceToDevice, s));
+        WS_CKS(ws_launch_plda_center_norm(p->x64, nullptr, N, D, 1, s));
+        src = p->x64;
+    }
+    const long long chunk = 65535LL * 128;
+    for (long long r = 0; r < N; r += chunk) {
+        const long long n = std::min(chunk, N - r);
+        WS_CKS(ws_launch_dgemm_nt(src + r * D, p->A, nullptr, p->offset, y_dev + r * D, 1, n, D, D, D, s));
+    }
+    if (p->normalize_length) WS_CKS(ws_launch_plda_rownorm(y_dev, N, D, s));
+    return 0;
+}
+
 int ws_plda_score_matrix(ws_plda* p, const double* enroll_t_dev, const int* counts_dev, int const_n, long long N,
                          const double* test_t_dev, long long M, void* out_dev, int out_is_f64, long long out_ld,
                          void* stream) {

@@ -314,13 +314,14 @@ __global__ void __launch_bounds__(384, 1) ws_res2_fused_kernel(const __grid_cons
 }  // namespace
 
 extern "C" const char* ws_res2_init(void) {
-    static bool done = false;
-    if (done) return nullptr;
+    static unsigned long long done = 0;
+    int dev = 0;
+    if (!ws_dev_needs_init(&done, &dev)) return nullptr;
     cudaError_t e = cudaFuncSetAttribute(ws_res2_fused_kernel<WS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(ws_res2_fused_kernel<WS_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) { cudaGetLastError(); return cudaGetErrorString(e); }
-    done = true;
+    ws_dev_mark_init(&done, dev);
     return nullptr;
 }
 

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) unit_rows_kernel(const float* __restrict_
     }
     ss = warp_sum_d(ss);
     const double nrm = sqrt(ss);
-    const double inv = 1.0 / nrm;
+    const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;   // zero vector -> zero row: cosine 0, as sklearn's cosine_similarity
     for (int d = lane; d < D; d += 32)
         unit[r * D + d] = ((double)p[d] - (mean_vec != nullptr ? mean_vec[d] : 0.0)) * inv;
     if (lane == 0 && norms != nullptr) norms[r] = nrm;

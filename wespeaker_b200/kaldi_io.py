@@ -92,3 +92,97 @@ def load_ark(ark_path: str):
                     break
                 key += c
             yield key.decode(), _read_vec(f)
+
+
+# ---------------------------------------------------------------------------------------------- Kaldi <Plda> models
+def _read_plda_vec_binary(f):
+    tok = f.read(3)
+    if tok not in (b"FV ", b"DV "):
+        raise ValueError(f"Kaldi <Plda>: bad vector type {tok!r}")
+    if f.read(1) != b"\4":
+        raise ValueError("Kaldi <Plda>: bad vector header")
+    dim = struct.unpack("<i", f.read(4))[0]
+    if tok == b"FV ":
+        return np.frombuffer(f.read(4 * dim), dtype="<f4")
+    return np.frombuffer(f.read(8 * dim), dtype="<f8")
+
+
+def _read_plda_mat_binary(f):
+    tok = f.read(3)
+    if tok not in (b"FM ", b"DM "):
+        raise ValueError(f"Kaldi <Plda>: unsupported matrix type {tok!r} (FM / DM expected; compressed and sparse "
+                         "matrices never occur in ivector-compute-plda output)")
+    hdr = f.read(10)
+    if hdr[0:1] != b"\4" or hdr[5:6] != b"\4":
+        raise ValueError("Kaldi <Plda>: bad matrix header")
+    rows, cols = struct.unpack("<i", hdr[1:5])[0], struct.unpack("<i", hdr[6:10])[0]
+    if tok == b"FM ":
+        return np.frombuffer(f.read(4 * rows * cols), dtype="<f4").reshape(rows, cols)
+    return np.frombuffer(f.read(8 * rows * cols), dtype="<f8").reshape(rows, cols)
+
+
+def _read_ascii_mat(f):
+    """Rows of a Kaldi text matrix after the opening ' [' was consumed: one row per line, the last ends with ']'."""
+    rows = []
+    while True:
+        line = f.readline()
+        if not line:
+            raise ValueError("Kaldi <Plda>: unterminated text matrix")
+        line = line.strip()
+        if not line:
+            continue
+        last = line.endswith(b"]")
+        vals = line.rstrip(b"]").split()
+        if vals:
+            rows.append(np.array(vals, dtype=np.float32))   # kaldi_io._read_mat_ascii parses into float32
+        if last:
+            return np.vstack(rows)
+
+
+def read_plda(path_or_fd):
+    """Kaldi `<Plda>` model (binary or text) -> (mean, transform, psi), same contract as
+    `wespeaker/utils/plda/kaldi_utils.py:24-55` (whose vector / matrix readers are `:58-108`)."""
+    f = open(path_or_fd, "rb") if isinstance(path_or_fd, (str, os.PathLike)) else path_or_fd
+    try:
+        binary = f.read(2)
+        if binary == b"\0B":
+            if f.read(7) != b"<Plda> ":
+                raise ValueError("Kaldi <Plda>: missing <Plda> token")
+            mean = _read_plda_vec_binary(f)
+            trans = _read_plda_mat_binary(f)
+            psi = _read_plda_vec_binary(f)
+        else:
+            if binary + f.read(5) != b"<Plda> ":
+                raise ValueError("Kaldi <Plda>: missing <Plda> token")
+            mean = np.array(f.readline().decode().strip(" \n[]").split(), dtype=float)
+            if f.read(2) != b" [":
+                raise ValueError("Kaldi <Plda>: expected a text matrix after the mean")
+            trans = _read_ascii_mat(f)
+            psi = np.array(f.readline().decode().strip(" \n[]").split(), dtype=float)
+        if f.read(8) != b"</Plda> ":
+            raise ValueError("Kaldi <Plda>: missing </Plda> token")
+    finally:
+        if f is not path_or_fd:
+            f.close()
+    return mean, trans, psi
+
+
+def write_plda(path, mean, transform, psi, binary=True):
+    """Write a Kaldi `<Plda>` model (double precision, like ivector-compute-plda): the inverse of read_plda."""
+    mean, transform, psi = (np.asarray(a, dtype=np.float64) for a in (mean, transform, psi))
+    with open(path, "wb") as f:
+        if binary:
+            f.write(b"\0B<Plda> ")
+            f.write(b"DV \4" + struct.pack("<i", mean.shape[0]) + mean.astype("<f8").tobytes())
+            f.write(b"DM \4" + struct.pack("<i", transform.shape[0]) + b"\4" + struct.pack("<i", transform.shape[1])
+                    + np.ascontiguousarray(transform, dtype="<f8").tobytes())
+            f.write(b"DV \4" + struct.pack("<i", psi.shape[0]) + psi.astype("<f8").tobytes())
+            f.write(b"</Plda> ")
+        else:
+            fmt = lambda v: " ".join(repr(float(x)) for x in v)  # noqa: E731
+            f.write(("<Plda>  [ " + fmt(mean) + " ]\n").encode())
+            f.write(b" [\n")
+            for i, row in enumerate(transform):
+                f.write(("  " + fmt(row) + (" ]\n" if i == transform.shape[0] - 1 else "\n")).encode())
+            f.write((" [ " + fmt(psi) + " ]\n").encode())
+            f.write(b"</Plda> ")

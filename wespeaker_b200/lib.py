@@ -61,6 +61,7 @@ _PROTOS = {
     "ws_plda_create": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.POINTER(c_plda_p)]),
     "ws_plda_transform": (C.c_int, [c_plda_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ws_plda_transform64": (C.c_int, [c_plda_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "ws_plda_score_matrix": (C.c_int, [c_plda_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p,
                                        C.c_longlong, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "ws_plda_score_trials": (C.c_int, [c_plda_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p,

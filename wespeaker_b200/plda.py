@@ -3,7 +3,7 @@
 ``log_likelihood_ratio``, ``eval_sv``; plus the batched entry points the GPU makes worthwhile
 (``transform_batch`` on (N,D) matrices, ``score_matrix`` all-pairs, ``score_trials``).  All arithmetic is fp64 on
 the device (ws_plda.cu); numpy here is only file parsing and host<->device staging.  Training / adaptation
-(`two_cov_plda.py:106-154,258-309`) is out of scope.
+(`two_cov_plda.py:106-154,258-309`) live in plda_train.py.
 """
 from __future__ import annotations
 
@@ -53,22 +53,47 @@ class TwoCovPLDA:
 
     @staticmethod
     def load_model(model_name: str, from_kaldi: bool = False, device=None):
+        """`two_cov_plda.py:341-363`: HDF5 with the reference's dataset names (needs h5py), a Kaldi `<Plda>` file
+        (``from_kaldi=True``, `kaldi_utils.py:24-55`), or the h5py-free ``.npz`` twin written by save_model."""
         if from_kaldi:
-            raise NotImplementedError("Kaldi <Plda> files are read by the reference's kaldi_utils.read_plda; "
-                                      "convert to .npz/.h5 (IO glue, out of the hot path)")
-        if model_name.endswith(".npz"):
-            z = np.load(model_name)
-            get = lambda k: z[k]  # noqa: E731
-        else:
-            import h5py  # not installed in this image; same dataset names as two_cov_plda.py:311-339
-            f = h5py.File(model_name, "r")
-            get = lambda k: f.get(k)[()]  # noqa: E731
-        return TwoCovPLDA.from_arrays(get("mu"), get("transform"), get("psi"), get("offset"),
-                                      bool(get("normalize_length")), bool(get("subtract_train_set_mean")), device)
+            from .kaldi_io import read_plda
+            mu, transform, psi = read_plda(model_name)
+            return TwoCovPLDA.from_arrays(mu, transform, psi, None, False, False, device)
+        if str(model_name).endswith(".npz"):
+            with np.load(model_name) as z:
+                return TwoCovPLDA.from_arrays(z["mu"], z["transform"], z["psi"], z["offset"],
+                                              bool(z["normalize_length"]), bool(z["subtract_train_set_mean"]), device)
+        try:
+            import h5py
+        except ImportError as e:
+            raise ImportError(f"{model_name}: reading the reference's HDF5 PLDA format needs h5py (not installed); "
+                              "use a .npz written by TwoCovPLDA.save_model or a Kaldi <Plda> file") from e
+        with h5py.File(model_name, "r") as f:
+            return TwoCovPLDA.from_arrays(f.get("mu")[()], f.get("transform")[()], f.get("psi")[()],
+                                          f.get("offset")[()], bool(f.get("normalize_length")[()]),
+                                          bool(f.get("subtract_train_set_mean")[()]), device)
 
-    def save_model(self, path: str):
-        np.savez(path, mu=self.mu, transform=self.transform, psi=self.psi, offset=self.offset,
-                 normalize_length=int(self.normalize_length), subtract_train_set_mean=int(self.subtract_train_set_mean))
+    def save_model(self, output_file_name: str):
+        """`two_cov_plda.py:311-339`.  ``*.npz`` -> numpy archive at exactly that path; anything else -> HDF5 with the
+        reference's dataset names / filters (so the reference's load_model reads it), which needs h5py."""
+        fields = dict(mu=self.mu, transform=self.transform, psi=self.psi, offset=self.offset)
+        flags = dict(normalize_length=int(self.normalize_length),
+                     subtract_train_set_mean=int(self.subtract_train_set_mean))
+        if str(output_file_name).endswith(".npz"):
+            with open(output_file_name, "wb") as f:   # a file object: np.savez never appends ".npz" to it
+                np.savez(f, **fields, **flags)
+            return
+        try:
+            import h5py
+        except ImportError as e:
+            raise ImportError(f"{output_file_name}: writing the reference's HDF5 PLDA format needs h5py (not "
+                              "installed); pass a path ending in .npz") from e
+        with h5py.File(output_file_name, "w") as f:
+            for k, v in fields.items():
+                v = np.asarray(v)
+                f.create_dataset(k, data=v, maxshape=(None,) * v.ndim, compression="gzip", fletcher32=True)
+            for k, v in flags.items():
+                f.create_dataset(k, data=v)
 
     # ------------------------------------------------------------------ device handle
     def _dev(self) -> int:
@@ -164,10 +189,10 @@ class TwoCovPLDA:
 
     # ------------------------------------------------------------------ reference-shaped scalar API
     def transform_embedding(self, embedding):
-        """two_cov_plda.py:156-163 for one (D,) vector: A x + offset (+ length-norm); like the reference, callers
-        pre-normalise with norm_embeddings themselves (eval_sv :225-241).  Input is taken as float32."""
-        x = np.asarray(embedding, dtype=np.float32)
-        return self.transform_batch(x[None], pre_norm=False).cpu().numpy()[0]
+        """two_cov_plda.py:156-163 for one (D,) vector: A x + offset (+ length-norm), fp64 throughout; like the reference,
+        callers pre-normalise with norm_embeddings themselves (eval_sv :225-241)."""
+        x = np.asarray(embedding, dtype=np.float64)
+        return self.transform_batch64(x[None], pre_norm=False).cpu().numpy()[0]
 
     def log_likelihood_ratio(self, transformed_train_embedding, transformed_test_embedding, n):
         """two_cov_plda.py:165-184 for one trial (runs the same device kernel with one trial)."""
@@ -176,40 +201,62 @@ class TwoCovPLDA:
         cnt = np.asarray([int(n)], dtype=np.int32)
         return float(self.score_trials(e, t, np.zeros(1, np.int64), np.zeros(1, np.int64), cnt).cpu()[0])
 
+    def transform_batch64(self, x64, pre_norm: bool | None = None) -> torch.Tensor:
+        """fp64 twin of transform_batch for rows that are already mean-subtracted (speaker means of eval_sv)."""
+        if pre_norm is None:
+            pre_norm = bool(self.normalize_length)
+        x = self._cuda(x64, torch.float64)
+        if x.dim() == 1:
+            x = x[None]
+        y = torch.empty(x.shape, dtype=torch.float64, device=x.device)
+        with torch.cuda.device(self._dev()):
+            _lib.check(_lib.load().ws_plda_transform64(self._handle(), x.data_ptr(), x.shape[0], int(pre_norm),
+                                                       y.data_ptr(), _lib.cur_stream_ptr(self._dev())),
+                       "ws_plda_transform64")
+        return y
+
+    def adapt(self, adapt_scp, ac_scale=0.5, wc_scale=0.5):
+        """`two_cov_plda.py:258-309` (unsupervised adaptation; algebra in plda_train.adapt)."""
+        from .plda_train import adapt_model
+        return adapt_model(self, adapt_scp, ac_scale, wc_scale)
+
     def eval_sv(self, enroll_scp, enroll_utt2spk, test_scp, trials, score_file, multisession_avg=True,
                 indomain_scp=None):
-        """two_cov_plda.py:186-256 with the per-trial Python loop replaced by one device launch."""
+        """`two_cov_plda.py:186-256` with the per-embedding transform loop and the per-trial LLR loop replaced by
+        device launches.  The host part restates the reference's numpy lines on the parsed vectors with the SAME dtype
+        flow (`value - mean_vec`, per-speaker `np.mean(value, 0)`: float32 data stays float32 when an in-domain mean is
+        given, becomes float64 against the default `np.zeros` mean), and everything from the length-norm on is fp64 on
+        the device."""
         enroll = read_vec_scp_file(enroll_scp)
         labels = read_label_file(enroll_utt2spk)
         test = read_vec_scp_file(test_scp)
-        mean_vec = None
         if indomain_scp is not None:
-            mean_vec = np.vstack(list(read_vec_scp_file(indomain_scp).values())).astype(np.float64).mean(0)
+            mean_vec = np.vstack(list(read_vec_scp_file(indomain_scp).values())).mean(0)   # :203-206
+        else:
+            mean_vec = np.zeros(self.dim)
         spk_sessions = {}
-        for key, vec in enroll.items():
+        for key, vec in enroll.items():                                                    # get_data_for_plda
             if key in labels:
                 spk_sessions.setdefault(labels[key], []).append(vec)
             else:
-                print(f"WARNING: {key} not in utt2spk ({enroll_utt2spk}), skipping it.")
+                print("WARNING: {} not in utt2spk ({}), skipping it.".format(key, enroll_utt2spk))
         spks = list(spk_sessions)
-        # per-speaker mean of (sessions - mean_vec): mean commutes with the shift
-        spk_mean = np.stack([np.mean(np.vstack(spk_sessions[s]).astype(np.float64), 0) for s in spks])
-        counts = np.array([1 if multisession_avg else len(spk_sessions[s]) for s in spks], dtype=np.int32)
-        e_t = self.transform_batch(spk_mean.astype(np.float32), mean_vec)
+        counts = np.array([1 if multisession_avg else len(spk_sessions[s]) for s in spks], dtype=np.int32)  # :213-217
+        spk_mean = np.stack([np.mean(np.vstack(spk_sessions[s]) - mean_vec, 0) for s in spks]).astype(np.float64)
         tkeys = list(test)
-        t_t = self.transform_batch(np.stack([test[k] for k in tkeys]).astype(np.float32), mean_vec)
+        test_rows = np.stack([test[k] - mean_vec for k in tkeys]).astype(np.float64)       # :236
+        e_t = self.transform_batch64(spk_mean)
+        t_t = self.transform_batch64(test_rows)
         sidx = {s: i for i, s in enumerate(spks)}
         tidx = {k: i for i, k in enumerate(tkeys)}
         lines, ei, ti = [], [], []
         with open(trials) as f:
             for line in f:
                 seg = line.strip().split()
-                if not seg:
-                    continue
                 lines.append(seg)
                 ei.append(sidx[seg[0]])
                 ti.append(tidx[seg[1]])
         scores = self.score_trials(e_t, t_t, np.asarray(ei, np.int64), np.asarray(ti, np.int64), counts).cpu().numpy()
         with open(score_file, "w") as w:
-            for seg, s in zip(lines, scores):
-                w.write("{} {} {:.5f} {}\n".format(seg[0], seg[1], s, seg[2]))
+            for seg, sc in zip(lines, scores):
+                w.write("{} {} {:.5f} {}\n".format(seg[0], seg[1], sc, seg[2]))

@@ -106,7 +106,11 @@ class TwoCovPLDATrainer:
         ns, inverse, cnt = torch.unique(st.count, return_inverse=True, return_counts=True)
         mix_var = torch.linalg.inv(b_inv[None] + ns[:, None, None] * w_inv[None])         # (U, D, D), one per distinct n
         wm = m @ w_inv.T                                                                   # rows: W^-1 m_k
-        w = st.count[:, None] * torch.bmm(mix_var[inverse], wm[:, :, None])[:, :, 0]      # w_k = mix_var_k (n_k W^-1 m_k)
+        # w_k = mix_var_{n_k} (n_k W^-1 m_k): one GEMM per distinct n (no (K, D, D) gather of the covariances)
+        w = torch.empty_like(wm)
+        for u in range(ns.shape[0]):
+            sel = inverse == u
+            w[sel] = ns[u] * (wm[sel] @ mix_var[u].T)
         m_w = m - w
         cntf = cnt.to(mix_var.dtype)
         b_stats = (cntf[:, None, None] * mix_var).sum(dim=0) + w.T @ w
@@ -133,6 +137,12 @@ class TwoCovPLDATrainer:
         transform = u.T @ t1
         self.mu, self.transform, self.psi = mu.cpu().numpy(), transform.cpu().numpy(), s.cpu().numpy()
         self.offset = -1.0 * (transform @ mu).cpu().numpy()
+
+    def save_model(self, output_file_name):
+        """`two_cov_plda.py:311-339`: same file formats as `plda.TwoCovPLDA.save_model` (HDF5 with the reference's dataset
+        names when h5py is present, `.npz` otherwise)."""
+        print("saving the trained plda to {}".format(output_file_name))
+        self.to_plda().save_model(output_file_name)
 
     def to_plda(self, device=None) -> TwoCovPLDA:
         """The trained model as the GPU scorer (`plda.TwoCovPLDA`)."""
@@ -182,3 +192,12 @@ def adapt(mu, transform, psi, adapt_data, normalize_length=False, ac_scale=0.5, 
     a2 = tt @ a_m @ tt.T
     new_psi = torch.diagonal(a2)
     return (mu_adp.cpu().numpy(), tt.cpu().numpy(), new_psi.cpu().numpy(), (-1.0 * (tt @ mu_adp)).cpu().numpy())
+
+
+def adapt_model(plda: TwoCovPLDA, adapt_scp, ac_scale=0.5, wc_scale=0.5, device=None) -> TwoCovPLDA:
+    """`TwoCovPLDA.adapt(adapt_scp, ac_scale, wc_scale)` (`two_cov_plda.py:258-309`): the adapted model as a scorer object
+    (which has `save_model`), like the reference method returns a new TwoCovPLDA."""
+    mu, tr, psi, off = adapt(plda.mu, plda.transform, plda.psi, adapt_scp, normalize_length=plda.normalize_length,
+                             ac_scale=ac_scale, wc_scale=wc_scale, device=device)
+    # the reference's adapted object is a fresh TwoCovPLDA(): normalize_length / subtract_train_set_mean at their defaults
+    return TwoCovPLDA.from_arrays(mu, tr, psi, off, False, False, device=plda._device)
