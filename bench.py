@@ -1,20 +1,29 @@
 #!/usr/bin/env python
-"""bench.py — headline metric of BASELINE.json: utterances/s (2 s @ 16 kHz) embedding extraction.
+"""bench.py — headline metric of BASELINE.json: utterances/s (2 s @ 16 kHz) embedding extraction; PLDA scores/s.
 
-    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload NAME]
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload NAME] [--no-configs]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path (fbank -> CMN -> model forward) over one batch of synthetic utterances
-per GPU.  Default workload = BASELINE.json configs[1]: ECAPA-TDNN-1024, bf16 tensor-core path, batch 256 of
-2.02 s utterances (32320 samples -> 200 frames, the "256 x 200-frame" case).  `value` is measured with the
-waveforms already resident in HBM; `e2e` is the same metric through the public host-buffer API
-(B200SpeakerModel.extract_from_wav on pinned host int16 PCM: H2D + kernels + D2H inside the timed region).
-Multi-GPU: one rank per GPU, utterances sharded with no data-path collective (weak scaling), ONE NCCL all-gather
-of the embeddings at the end of the job, inside the timed region.  `--impl reference` times the oracle port of
-the reference's CPU PyTorch path (torch fp32 on all host cores) on the same config, rank 0 only.
+A "step" is one pass of the hot path (fbank -> CMN -> model forward) over one batch of synthetic utterances per GPU.
+Default workload = BASELINE.json configs[1]: ECAPA-TDNN-1024, bf16 tensor-core path, batch 256 of 2.02 s utterances
+(32320 samples -> 200 frames, the "256 x 200-frame" case).  `value` is measured with the waveforms already resident in
+HBM; `e2e` is the same metric through the public host-buffer API (B200SpeakerModel.extract_stream on pinned host int16
+PCM: H2D + kernels + D2H inside the timed region).  Multi-GPU: one rank per GPU, utterances sharded with no data-path
+collective (weak scaling), ONE NCCL all-gather of the embeddings at the end of the job, inside the timed region.
+
+The same JSON line carries a `configs` block with one short timed leg per remaining BASELINE.json config (the driver
+only runs the default command): ECAPA-TDNN-512 in tf32x3 (the <= 1e-4 tensor-core path) and bf16, ResNet34 fp16 at 64
+utterances per GPU (= batch 512 sharded when 8 ranks run), CAM++ bf16 on the seed-2 mix of 1-10 s utterances, and the full
+10^6 x 10^5 TwoCov-PLDA scoring job tiled over enroll rows (sharded over ranks).  Every model leg reports
+`parity_rel_l2`: embeddings of utterances OF THE TIMED BATCH against the CPU oracle on identical fbank inputs.
+
+`--impl reference` times the oracle port of the reference's CPU PyTorch path (torch fp32) on the same config, rank 0
+only, using all host cores as a pool of worker processes (the reference's own parallelism is process-level sharding,
+tools/extract_embedding.sh:39-63).
 """
 import argparse
 import json
+import multiprocessing as mp
 import os
 import subprocess
 import sys
@@ -43,6 +52,9 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = "ecapa1024_bf16_b256"
 METRIC = "utterances/s (2s@16kHz) embedding extraction"
+DTYPE_NAME = {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3", "bf16": "bf16", "fp16": "f16"}
+# bars for `parity_rel_l2` (max over the checked utterances of |e - e_ref|_2 / |e_ref|_2), as in tests/test_gpu_parity.py
+PARITY_BAR = {"fp32": 1e-4, "tf32x3": 1e-4, "tf32": 1e-2, "bf16": 1e-2, "fp16": 1e-2}
 
 
 def measured_peaks():
@@ -55,7 +67,9 @@ def measured_peaks():
 
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  NVML polled every 5 ms from a
-    thread (the timed region is only tens of ms long); falls back to `nvidia-smi -lms 100` if NVML is unavailable."""
+    thread (the timed region is only tens of ms long); falls back to `nvidia-smi -lms 100` if NVML is unavailable.
+    start() is called BEFORE the pre-timing barrier (NVML init costs milliseconds: inside the window it skewed rank 0
+    against the other ranks in round 1); mark() / stop() bracket the samples that are kept."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -64,21 +78,23 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
         self.nvml, self.samples, self.reasons, self.maxclk, self._stop = None, [], set(), None, False
+        self._on = False
 
     def _poll(self):
         n = self.nvml
         while not self._stop:
-            try:
-                self.samples.append(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+            if self._on:
                 try:
-                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    self.samples.append(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                    try:
+                        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in self.BITS.items():
+                        if r & bit:
+                            self.reasons.add(name)
                 except Exception:
-                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.BITS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
+                    pass
             time.sleep(0.005)
 
     def start(self):
@@ -107,14 +123,24 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self, on=True):
+        """mark(True) opens a new sampling window (previous samples are dropped); mark(False) closes it."""
+        if on:
+            self.samples, self.reasons = [], set()
+        self._on = on
+
+    def read(self):
+        """Statistics of the last window (NVML mode)."""
+        smp = list(self.samples)
+        return {"sm_mhz": float(np.median(smp)) if smp else None, "sm_min_mhz": float(min(smp)) if smp else None,
+                "sm_max_mhz": float(self.maxclk) if self.maxclk else None, "reasons": sorted(self.reasons),
+                "samples": len(smp), "source": "nvml, 5 ms polling during the timed region"}
+
     def stop(self):
         if self.nvml is not None:
             self._stop = True
             self.t.join(timeout=1)
-            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
-                    "sm_min_mhz": float(min(self.samples)) if self.samples else None,
-                    "sm_max_mhz": float(self.maxclk) if self.maxclk else None, "reasons": sorted(self.reasons),
-                    "samples": len(self.samples), "source": "nvml, 5 ms polling during the timed region"}
+            return self.read()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -136,12 +162,13 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
-def _cpu_path(model_name, nsamples, batch):
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def _cpu_path(model_name, nsamples, batch, seed=0):
     """Oracle port of the reference CPU path: numpy fbank+CMN, torch-CPU fp32 forward."""
     from oracle import fbank_np, models_torch
     from wespeaker_b200 import synthetic as syn
     sd = {k: torch.from_numpy(np.asarray(v)) for k, v in syn.make_state_dict(model_name, 0).items()}
-    wavs = syn.make_wavs(batch, nsamples, seed=0)
+    wavs = syn.make_wavs(batch, nsamples, seed=seed)
 
     def one():
         feats = np.stack([fbank_np.cmn(fbank_np.fbank(w)) for w in wavs])
@@ -149,95 +176,282 @@ def _cpu_path(model_name, nsamples, batch):
     return one
 
 
-def _best_threads(one):
-    """torch's CPU convs collapse when oversubscribed (128 threads: ~1 utt/s on the 128-core bench host), so give the
-    reference arm the thread count at which it is fastest."""
-    cores = os.cpu_count() or 1
-    best, best_t = None, None
-    for nt in sorted({t for t in (8, 16, 32, 64, cores) if t <= cores}):
-        torch.set_num_threads(nt)
-        one()
-        t0 = time.perf_counter(); one(); dt = time.perf_counter() - t0
-        if best_t is None or dt < best_t:
-            best, best_t = nt, dt
-        if dt > 4 * best_t:
+def _cpu_worker(model_name, nsamples, batch, threads, seed, cpus, conn):
+    if cpus:
+        try:
+            os.sched_setaffinity(0, cpus)   # a disjoint core set per worker: no migration, no oversubscription
+        except Exception:
+            pass
+    torch.set_num_threads(threads)
+    one = _cpu_path(model_name, nsamples, batch, seed)
+    one(); one()
+    conn.send("ready")
+    while True:
+        n = conn.recv()
+        if n is None:
             break
-    torch.set_num_threads(best)
-    return best, cores
+        for _ in range(n):
+            one()
+        conn.send("done")
 
 
-def cpu_reference_run(model_name, nsamples, batch, budget_s, max_batches):
-    one = _cpu_path(model_name, nsamples, batch)
-    threads, cores = _best_threads(one)
-    t0, nb = time.perf_counter(), 0
-    while nb < max_batches and (time.perf_counter() - t0 < budget_s or nb == 0):
-        one(); nb += 1
-    dt = time.perf_counter() - t0
-    return nb * batch / dt, threads, cores, nb, dt
+class CpuPool:
+    """All host cores as P worker processes x `threads` torch threads each (torch's intra-op scaling of these small convs
+    collapses beyond ~8 threads, while independent processes over disjoint utterance lists scale — which is also how
+    the reference parallelises extraction, tools/extract_embedding.sh:39-63).  One pool step = every worker runs one
+    batch of `batch` utterances through fbank + CMN + forward."""
+
+    def __init__(self, model_name, nsamples, batch=16, threads=8):
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except Exception:
+            cores = os.cpu_count() or 1
+        self.cores, self.threads, self.batch = cores, min(threads, cores), batch
+        self.nproc = max(1, min(16, cores // self.threads))
+        try:
+            cpu_list = sorted(os.sched_getaffinity(0))
+        except Exception:
+            cpu_list = []
+        ctx = mp.get_context("spawn")
+        self.conns, self.procs = [], []
+        # BLAS / OpenMP pools of the children are sized by the environment they are spawned with (numpy's matmul in the
+        # fbank would otherwise start one thread per host core in EVERY worker)
+        keys = ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS")
+        saved = {k: os.environ.get(k) for k in keys}
+        for k in keys:
+            os.environ[k] = str(self.threads)
+        try:
+            for i in range(self.nproc):
+                a, b = ctx.Pipe()
+                cpus = set(cpu_list[i * self.threads:(i + 1) * self.threads]) if len(cpu_list) >= self.nproc * self.threads else None
+                p = ctx.Process(target=_cpu_worker, args=(model_name, nsamples, batch, self.threads, i, cpus, b), daemon=True)
+                p.start()
+                self.conns.append(a); self.procs.append(p)
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        for c in self.conns:
+            assert c.recv() == "ready"
+
+    def run(self, nsteps):
+        t0 = time.perf_counter()
+        for c in self.conns:
+            c.send(nsteps)
+        for c in self.conns:
+            c.recv()
+        return time.perf_counter() - t0
+
+    @property
+    def utts_per_step(self):
+        return self.nproc * self.batch
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send(None)
+            except Exception:
+                pass
+        for p in self.procs:
+            p.join(timeout=5)
+
+    def describe(self, nsamples):
+        return (f"{self.nproc} worker processes x {self.threads} torch threads = {self.nproc * self.threads} of {self.cores} "
+                f"host cores, each step = {self.nproc} x {self.batch} utterances of {nsamples} samples: numpy fbank+CMN + "
+                f"torch-CPU fp32 forward (oracle port of the reference CPU path)")
 
 
 def run_reference(args, wl):
     model, _, _, nsamples, _ = WORKLOADS[wl]
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
+    if int(os.environ.get("RANK", 0)) != 0:
         return
-    batch = 16  # each "step" = one bounded sample (16 utterances) of the same workload
-    one = _cpu_path(model, nsamples, batch)
-    threads, cores = _best_threads(one)
-    for _ in range(max(1, min(args.warmup, 3))):
-        one()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one()
-    dt = time.perf_counter() - t0
-    v = args.steps * batch / dt
-    sample = (f"{args.steps} steps x {batch} utts of {nsamples} samples, oracle port of the reference CPU path (numpy fbank+CMN, "
-              f"torch-CPU fp32 forward), {threads} torch threads (fastest of 8..{cores} on this {cores}-core host)")
+    pool = CpuPool(model, nsamples)
+    pool.run(max(1, min(args.warmup, 2)))
+    dt = pool.run(args.steps)
+    v = args.steps * pool.utts_per_step / dt
+    sample = f"{args.steps} pool steps; " + pool.describe(nsamples)
+    cores = pool.nproc * pool.threads
+    pool.close()
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl, "model": model, "batch_per_step": batch, "samples_per_utt": nsamples},
-        "cpu_baseline": {"value": v, "unit": "utt/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": wl, "model": model, "utts_per_step": pool.utts_per_step, "samples_per_utt": nsamples},
+        "cpu_baseline": {"value": v, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def plda_bench(dev, n_enroll=32768, n_test=100000, dim=256, iters=3):
-    """Secondary metric of BASELINE.json: PLDA scores/s (configs[4]: 1M x 100k, D=256).  The all-pairs job is tiled over
-    enroll rows into a reused fp32 score buffer (10^11 scores do not fit in HBM); one tile = n_enroll x n_test."""
+# ------------------------------------------------------------------------------------------------ helpers
+def _timed(fn, dev, parallel, world, reps=1):
+    """Device time of fn() (CUDA events on torch's current stream, which every engine call joins), bracketed by barrier +
+    synchronize, streams aligned by an on-device all-reduce right before the start event; max over ranks; best of reps."""
+    import torch.distributed as dist
+    best, ret = None, None
+    tiny = torch.zeros(1, device=dev)
+    for _ in range(reps):
+        parallel.barrier(); torch.cuda.synchronize()
+        if world > 1:
+            dist.all_reduce(tiny)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ret = fn()
+        e1.record()
+        torch.cuda.synchronize(); parallel.barrier()
+        ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+        best = ms if best is None else min(best, ms)
+    return best, ret
+
+
+def _parity(model_name, emb_rows, feats_rows):
+    """max rel-L2 of GPU embedding rows against the CPU oracle on the identical fbank+CMN inputs."""
+    from oracle import models_torch
+    from wespeaker_b200 import synthetic as syn
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in syn.make_state_dict(model_name, 0).items()}
+    worst = 0.0
+    for e, f in zip(emb_rows, feats_rows):
+        ref = models_torch.forward(model_name, sd, f[None].float().cpu())
+        ref = (ref[-1] if isinstance(ref, tuple) else ref)[0].double()
+        worst = max(worst, float(torch.linalg.norm(e.double().cpu() - ref) / torch.linalg.norm(ref)))
+    return worst
+
+
+def model_leg(name, model_name, prec, B, nsamples, gflop_utt, steps, warmup, dev, rank, world, parallel, peaks, sampler,
+              parity_n=4):
+    """One fixed-length config: K timed steps of wav -> fbank -> CMN -> forward on a batch of B per GPU."""
+    from wespeaker_b200.models import from_synthetic
+    from wespeaker_b200 import synthetic as syn
+    model = from_synthetic(model_name, 0, precision=prec).to(dev)
+    base = syn.make_wavs(B, nsamples, seed=300 + rank)
+    wavs = [torch.from_numpy(np.roll(base, i, axis=0)).to(dev) for i in range(2)]
+    for i in range(max(3, warmup)):
+        model.extract_from_wav(wavs[i % 2])
+    launches = model.last_launches()
+
+    def run():
+        out = None
+        for i in range(steps):
+            out = model.extract_from_wav(wavs[i % 2])
+        return out
+    ms, _ = _timed(run, dev, parallel, world)
+    value = world * B * steps / (ms * 1e-3)
+    res = {"workload": name, "model": model_name, "precision": prec, "batch_per_gpu": B, "frames": 1 + (nsamples - 400) // 160,
+           "value": value, "unit": "utt/s", "ms_per_step": ms / steps, "launches_per_step": int(launches),
+           "step_tflops_per_gpu": value / world * gflop_utt / 1e3,
+           "step_frac_of_sustained": value / world * gflop_utt / 1e3 / peaks["tf_sustained"]}
+    if rank == 0:
+        emb, feats = model.extract_from_wav(wavs[0], return_feats=True)   # the timed batch (full B: same kernels / tiles)
+        sel = [int(round(j * (B - 1) / max(1, parity_n - 1))) for j in range(parity_n)]
+        res["parity_rel_l2"] = _parity(model_name, [emb[j] for j in sel], [feats[j] for j in sel])
+        res["parity_bar"] = PARITY_BAR[prec]
+        res["parity_utts"] = sel
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
+def varlen_leg(steps, warmup, dev, rank, world, parallel, peaks, sampler, n_utts=256, parity_n=4):
+    """BASELINE.json configs[3]: CAM++ bf16 on utterances of 1..10 s (durations U{1..10} s, seed 2), bucketed by length."""
+    from wespeaker_b200.models import from_synthetic
+    from wespeaker_b200 import synthetic as syn
+    model_name, prec = "CAMPPlus", "bf16"
+    model = from_synthetic(model_name, 0, precision=prec).to(dev)
+    rng = np.random.default_rng(2 + 1000 * rank)
+    secs = rng.integers(1, 11, n_utts)
+    pool = syn.make_wavs(16, 160000, seed=500 + rank)
+    wavs = [torch.from_numpy(pool[i % 16, : int(s) * 16000].copy()).to(dev) for i, s in enumerate(secs)]
+    frames = [1 + (int(s) * 16000 - 400) // 160 for s in secs]
+    gflop = sum(2.252 * f / 200.0 for f in frames)       # conv+linear FLOPs scale with T (2.252 GFLOP at T=200)
+    for _ in range(max(2, min(warmup, 3))):
+        model.extract_from_wav_list(wavs, max_batch=64, device=dev)
+    nrep = max(1, steps // 10)
+    ms, emb = _timed(lambda: [model.extract_from_wav_list(wavs, max_batch=64, device=dev) for _ in range(nrep)][-1],
+                     dev, parallel, world)
+    value = world * n_utts * nrep / (ms * 1e-3)
+    res = {"workload": "campplus_bf16_varlen_1to10s", "model": model_name, "precision": prec, "utts_per_gpu": n_utts,
+           "durations": "U{1..10} s, seed 2 (+1000*rank), bucketed by exact frame count, <= 64 per launch",
+           "value": value, "unit": "utt/s", "audio_s_per_s": world * float(secs.sum()) * nrep / (ms * 1e-3),
+           "ms_per_pass": ms / nrep, "passes": nrep,
+           "step_tflops_per_gpu": gflop * nrep / (ms * 1e-3) / 1e3,
+           "step_frac_of_sustained": gflop * nrep / (ms * 1e-3) / 1e3 / peaks["tf_sustained"]}
+    if rank == 0:
+        from wespeaker_b200 import frontend
+        order = np.argsort(secs, kind="stable")
+        sel = [int(order[int(round(j * (n_utts - 1) / max(1, parity_n - 1)))]) for j in range(parity_n)]
+        feats = [frontend.fbank_batch(wavs[j][None], cmn=True)[0] for j in sel]
+        res["parity_rel_l2"] = _parity(model_name, [emb[j] for j in sel], feats)
+        res["parity_bar"] = PARITY_BAR[prec]
+        res["parity_utts"] = [f"{int(secs[j])}s" for j in sel]
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
+def fp64_peak(dev, n=4096, iters=5):
+    """Measured fp64 matmul rate of this GPU (torch.matmul = cuBLAS DGEMM, best of `iters`): the denominator of the PLDA
+    roofline fraction, taken the same way MEASURED_PEAKS.json takes the bf16 peak."""
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    best = None
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def plda_leg(dev, rank, world, parallel, peaks, n_enroll=1_000_000, n_test=100_000, dim=256, tile=32768, cpu_loop=True):
+    """BASELINE.json configs[4]: all 10^11 LLR scores of 10^6 enroll x 10^5 test embeddings (D = 256, n = 1), fp64
+    arithmetic, fp32 scores.  The score matrix (400 GB) does not fit in HBM: enroll rows are processed in tiles into ONE
+    reused 32768 x 100000 fp32 buffer; with several ranks the enroll rows are sharded (no output collective)."""
     from wespeaker_b200 import synthetic as syn
     from wespeaker_b200.plda import TwoCovPLDA
     from oracle import plda_np
     pm = syn.make_plda(dim, seed=3, normalize_length=True)
     p = TwoCovPLDA.from_arrays(**pm, device=dev.index)
-    e = torch.from_numpy(syn.make_embeddings(n_enroll, dim, seed=3)).to(dev)
-    t = torch.from_numpy(syn.make_embeddings(n_test, dim, seed=4)).to(dev)
+    lo, hi = parallel.shard_rows(n_enroll, rank, world)
+    g = torch.Generator(device=dev); g.manual_seed(3 + rank)
+    e = torch.randn((hi - lo, dim), generator=g, device=dev, dtype=torch.float32)
+    g.manual_seed(4)
+    t = torch.randn((n_test, dim), generator=g, device=dev, dtype=torch.float32)
     e_t, t_t = p.transform_batch(e), p.transform_batch(t)
-    out = torch.empty((n_enroll, n_test), dtype=torch.float32, device=dev)
-    p.score_matrix(e_t, t_t, 1, out=out)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        p.score_matrix(e_t, t_t, 1, out=out)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    out = torch.empty((min(tile, hi - lo), n_test), dtype=torch.float32, device=dev)
+    p.score_matrix(e_t[:tile], t_t, 1, out=out[: min(tile, hi - lo)])
+    first = out[:200, :100].double().cpu().numpy()
+
+    def run():
+        for r in range(0, hi - lo, tile):
+            n = min(tile, hi - lo - r)
+            p.score_matrix(e_t[r:r + n], t_t, 1, out=out[:n])
+    ms, _ = _timed(run, dev, parallel, world)
     scores = float(n_enroll) * n_test
-    # CPU: the reference's per-trial Python loop (two_cov_plda.py:248-256), single thread, on a 20k-trial sample
-    et, tt = e_t[:200].cpu().numpy(), t_t[:100].cpu().numpy()
-    t0 = time.perf_counter()
-    for i in range(200):
-        for j in range(100):
-            plda_np.log_likelihood_ratio(pm, et[i], tt[j], 1)
-    cpu_loop = 20000 / (time.perf_counter() - t0)
-    ref = plda_np.llr_matrix(pm, et, tt, 1)
-    err = float(np.abs(out[:200, :100].double().cpu().numpy() - ref).max())
-    return {"value": scores / (ms * 1e-3), "unit": "scores/s", "dtype": "f64", "enroll_tile": n_enroll, "test": n_test, "dim": dim,
-            "ms_per_tile": ms, "tflops_f64": scores * 2 * dim / (ms * 1e-3) / 1e12, "out_gbs": scores * 4 / (ms * 1e-3) / 1e9,
-            "max_abs_err_vs_fp64_oracle": err,
-            "cpu_baseline": {"value": cpu_loop, "unit": "scores/s", "cores": 1, "kind": "port",
-                             "sample": "20000 trials, per-trial log_likelihood_ratio loop as in eval_sv"}}
+    res = {"workload": "plda_1Mx100k", "value": scores / (ms * 1e-3), "unit": "scores/s", "dtype": "f64", "enroll": n_enroll,
+           "test": n_test, "dim": dim, "enroll_tile": tile, "ms_total": ms, "sharding": f"enroll rows over {world} rank(s)",
+           "tflops_f64": scores * 2 * dim / (ms * 1e-3) / 1e12 / world, "out_gbs_per_gpu": scores * 4 / (ms * 1e-3) / 1e9 / world}
+    if rank == 0:
+        pk = fp64_peak(dev)
+        res["roofline"] = {"bound": "fp64 matmul", "achieved": res["tflops_f64"], "peak": pk, "unit": "TFLOP/s",
+                           "frac": res["tflops_f64"] / pk, "peak_source": "torch.matmul fp64 4096^3 on this GPU, best of 5",
+                           "hbm_write_frac": res["out_gbs_per_gpu"] / peaks["hbm_gbs"]}
+        ref = plda_np.llr_matrix(pm, e_t[:200].cpu().numpy(), t_t[:100].cpu().numpy(), 1)
+        res["max_abs_err_vs_fp64_oracle"] = float(np.abs(first - ref).max())
+        res["parity_bar"] = "1e-5 * max(1, |s|)"
+        res["parity_ok"] = bool((np.abs(first - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref))).all())
+        if cpu_loop:   # the reference's per-trial Python loop (two_cov_plda.py:248-256), single thread, 20k-trial sample
+            et, tt = e_t[:200].cpu().numpy(), t_t[:100].cpu().numpy()
+            t0 = time.perf_counter()
+            for i in range(200):
+                for j in range(100):
+                    plda_np.log_likelihood_ratio(pm, et[i], tt[j], 1)
+            res["cpu_baseline"] = {"value": 20000 / (time.perf_counter() - t0), "unit": "scores/s", "cores": 1, "kind": "port",
+                                   "sample": "20000 trials, per-trial log_likelihood_ratio loop as in eval_sv"}
+    del out, e_t, t_t, e, t
+    torch.cuda.empty_cache()
+    return res
 
 
 def time_dominant_kernel(model, prec, B, T, iters=10, tc_version=3):
@@ -294,6 +508,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-plda", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config legs (configs block)")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the seconds-long sustained leg (0 = skip)")
     ap.add_argument("--tc-version", type=int, default=0, help="override the engine's tcgen05 kernel generation (1,2,3)")
     args = ap.parse_args()
     wl = args.workload
@@ -312,6 +528,9 @@ def main():
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
     peaks = measured_peaks()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()          # NVML init happens here, far from any timed window
 
     model = from_synthetic(model_name, 0, precision=prec).to(dev)
     if args.tc_version:
@@ -325,39 +544,36 @@ def main():
     emb = None
     for i in range(max(3, args.warmup)):
         emb = model.extract_from_wav(wav_dev[i % nrot])
-    if world > 1:  # warm the communicator: the first NCCL collective pays lazy init
-        parallel.gather_embeddings(torch.cat([emb, emb], 0), 2 * B * world)
+    # warm the communicator with the SHAPE the timed gather uses (first NCCL collective pays lazy init per shape class)
+    parallel.gather_embeddings(torch.cat([emb] * args.steps, 0), args.steps * B * world)
     torch.cuda.synchronize()
     launches_per_step = model.last_launches()
+    embed_dim = model.embed_dim
 
-    # ---------------- device-resident throughput (`value`)
-    sampler = ClockSampler(local)
-    parallel.barrier(); torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    local_embs = []
-    for i in range(args.steps):
-        local_embs.append(model.extract_from_wav(wav_dev[i % nrot]))
-    allemb = torch.cat(local_embs, 0)
-    gathered = parallel.gather_embeddings(allemb, allemb.shape[0] * world)  # the one NCCL all-gather of the job
-    e1.record()
-    torch.cuda.synchronize(); parallel.barrier()
-    ms_total = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
-    clocks = sampler.stop() if rank == 0 else None
+    # ---------------- device-resident throughput (`value`): K steps + the one all-gather, best of 3 windows
+    def value_run():
+        local_embs = [model.extract_from_wav(wav_dev[i % nrot]) for i in range(args.steps)]
+        allemb = torch.cat(local_embs, 0)
+        return parallel.gather_embeddings(allemb, allemb.shape[0] * world)  # the one NCCL all-gather of the job
+    if sampler:
+        sampler.mark(True)
+    ms_total, gathered = _timed(value_run, dev, parallel, world, reps=3)
+    clocks = None
+    if sampler:
+        sampler.mark(False)
+        clocks = sampler.read() if sampler.nvml is not None else None
     assert gathered.shape[0] == args.steps * B * world and torch.isfinite(gathered).all()
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # ---------------- end-to-end through the public host-buffer API (`e2e`)
     # B200SpeakerModel.extract_stream: every step copies that step's pinned int16 PCM batch H2D, runs fbank+CMN+forward
-    # and copies the embeddings back D2H; the copy of batch i+1 overlaps the kernels of batch i (2 staging slots).
+    # and copies the embeddings back D2H; the copy of batch i+1 overlaps the kernels of batch i (4 staging slots).
     # Warm-up stream first (allocations, pinned pools), then time K complete steps: the clock starts before the first
     # timed batch is submitted (its H2D copy is NOT hidden) and stops when the K-th batch's embeddings are in host memory.
     for out_h in model.extract_stream(wav_pin[i % nrot] for i in range(max(4, args.warmup))):
         pass
     best_dt = None
-    for rep in range(3):   # best of 3: the host is a shared 128-core box, a descheduled host thread stalls collect()
+    for rep in range(3):   # best of 3 windows, the same estimator as `value`
         parallel.barrier(); torch.cuda.synchronize()
         t0, nout = time.perf_counter(), 0
         for out_h in model.extract_stream(wav_pin[i % nrot] for i in range(args.steps)):
@@ -370,6 +586,47 @@ def main():
     e2e_value = world * B * args.steps / dt
     assert nout == B * args.steps and torch.isfinite(out_h).all()
     assert torch.equal(out_h.to(dev), model.extract_from_wav(wav_dev[(args.steps - 1) % nrot]))
+
+    # ---------------- seconds-long sustained run (clocks settle under load; MEASURED_PEAKS' sustained figure is its peer)
+    sustained = None
+    if args.sustained_s > 0:
+        n_sus = max(args.steps, int(args.sustained_s * 1e3 / (ms_total / args.steps)))
+        if sampler:
+            sampler.mark(True)
+        ms_sus, _ = _timed(lambda: [model.extract_from_wav(wav_dev[i % nrot]) for i in range(n_sus)][-1], dev, parallel, world)
+        v_sus = world * B * n_sus / (ms_sus * 1e-3)
+        sustained = {"value": v_sus, "unit": "utt/s", "steps": n_sus, "seconds": ms_sus * 1e-3,
+                     "step_frac_of_sustained": v_sus / world * gflop_utt / 1e3 / peaks["tf_sustained"]}
+        if sampler:
+            sampler.mark(False)
+            sustained["clocks"] = sampler.read() if sampler.nvml is not None else None
+
+    # ---------------- parity of the TIMED configuration (full batch: the cta_group::2 kernels at bench size)
+    parity = None
+    if rank == 0:
+        emb_b, feats_b = model.extract_from_wav(wav_dev[0], return_feats=True)
+        sel = [0, B // 3, (2 * B) // 3, B - 1]
+        parity = {"parity_rel_l2": _parity(model_name, [emb_b[j] for j in sel], [feats_b[j] for j in sel]),
+                  "parity_bar": PARITY_BAR[prec], "parity_utts": sel,
+                  "against": "oracle.models_torch (CPU fp32) on the identical GPU fbank+CMN features of the timed batch"}
+    del model
+    torch.cuda.empty_cache()
+
+    # ---------------- the other BASELINE.json configs, one short leg each (all ranks take part; rank 0 reports)
+    configs = None
+    if not args.no_configs:
+        configs = {}
+        for name in ("ecapa512_tf32x3_b256", "ecapa512_bf16_b256", "resnet34_fp16_b64"):
+            m, pr, b, ns, gf = WORKLOADS[name]
+            configs[name] = model_leg(name, m, pr, b, ns, gf, args.steps, args.warmup, dev, rank, world, parallel, peaks, sampler)
+        configs["resnet34_fp16_b64"]["note"] = "BASELINE configs[2] is batch 512 sharded 64/GPU over 8 ranks: this leg IS that job when n_gpus == 8"
+        configs["campplus_bf16_varlen"] = varlen_leg(args.steps, args.warmup, dev, rank, world, parallel, peaks, sampler)
+        if not args.no_plda:
+            configs["plda_1Mx100k"] = plda_leg(dev, rank, world, parallel, peaks)
+    if sampler:
+        last = sampler.stop()
+        if clocks is None:     # nvidia-smi fallback: one window over the whole run
+            clocks = last
 
     if rank != 0:
         return
@@ -390,28 +647,33 @@ def main():
                 "frac": step_tf / peaks["tf_sustained"], "traffic": None, "kernel": "whole step (conv GEMMs)",
                 "peak_source": peaks["src"] + " (sustained, whole step)"}
     cpu = None
-    if not args.no_cpu_baseline:
-        v, threads, cores, nb, cdt = cpu_reference_run(model_name, nsamples, 16, budget_s=10.0, max_batches=200)
-        cpu = {"value": v, "unit": "utt/s", "cores": threads, "kind": "port",
-               "sample": f"{nb} batches x 16 utts of {nsamples} samples in {cdt:.1f}s: numpy fbank+CMN + torch-CPU fp32 forward "
-                         f"(oracle port of the reference path), {threads} torch threads = fastest of 8..{cores} on this {cores}-core host"}
-    plda = None
-    if not args.no_plda:
-        plda = plda_bench(dev)
+    if not args.no_cpu_baseline and world == 1:
+        pool = CpuPool(model_name, nsamples)
+        pool.run(1)
+        nst, cdt = 0, 0.0
+        while cdt < 10.0 and nst < 50:
+            cdt += pool.run(1); nst += 1
+        cpu = {"value": nst * pool.utts_per_step / cdt, "unit": "utt/s", "cores": pool.nproc * pool.threads, "kind": "port",
+               "sample": f"{nst} pool steps in {cdt:.1f} s; " + pool.describe(nsamples)}
+        pool.close()
     act_mb = B * L_frames * (1536 * 2 + 128 + (1024 if '1024' in model_name else 512) * 7) * (4 if prec in ("fp32", "tf32", "tf32x3") else 2) / 1e6
-    print(json.dumps({
+    line = {
         "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3", "bf16": "bf16", "fp16": "f16"}[prec], "data": "synthetic",
+        "dtype": DTYPE_NAME[prec], "data": "synthetic",
         "config": {"workload": wl, "model": model_name, "batch_per_gpu": B, "samples_per_utt": nsamples,
                    "frames": L_frames, "precision": prec, "gflop_per_utt": gflop_utt,
                    "l2": f"inputs rotate over {nrot} batches; per-step activation working set ~{act_mb:.0f} MB > 126 MB L2",
+                   "estimator": "best of 3 windows of K steps for both value and e2e; device events, max over ranks",
                    "collective": "one all_gather_into_tensor of embeddings at job end (inside timed region)" if world > 1 else "none"},
-        "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": B * nsamples * 2, "d2h_bytes_per_step": B * model.embed_dim * 4,
-                "api": "B200SpeakerModel.extract_stream(pinned int16 PCM host batches): H2D + fbank + CMN + forward + D2H per step, copy/compute overlapped over 4 slots; best of 3 runs of K steps"},
+        "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": B * nsamples * 2, "d2h_bytes_per_step": B * embed_dim * 4,
+                "api": "B200SpeakerModel.extract_stream(pinned int16 PCM host batches): H2D + fbank + CMN + forward + D2H per step, copy/compute overlapped over 4 slots; best of 3 windows of K steps"},
         "gpu_launches": int(launches_per_step * args.steps),
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "plda": plda,
-    }))
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity, "sustained": sustained, "configs": configs,
+    }
+    if configs and "plda_1Mx100k" in configs:
+        line["plda"] = configs["plda_1Mx100k"]
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -299,7 +299,7 @@ def test_model_fp32_matches_reference_golden(key):
     assert np.array_equal(emb, emb2)
 
 
-TC_TOL = {"tf32": 1e-2, "bf16": 3e-2, "fp16": 1e-2}
+TC_TOL = {"tf32": 1e-2, "bf16": 1e-2, "fp16": 1e-2}   # measured: <= 7.9e-3 / 4.2e-3 / 5.3e-4; the reference itself drifts 4.1e-3 under bf16 autocast
 
 
 @pytest.mark.parametrize("name,B,T,prec", [("ECAPA_TDNN_c1024", 5, 200, "bf16"), ("ECAPA_TDNN_c512", 3, 198, "fp16"),
@@ -340,7 +340,7 @@ def test_tc_v1_kernel_still_matches():
     m1.set_option("tc_version", 1)
     m2 = from_synthetic(name, seed, precision="bf16")
     e1, e2 = m1.embed(feats).cpu().numpy(), m2.embed(feats).cpu().numpy()
-    assert rel_l2(e1, G_MODELS[key]).max() <= 3e-2 and rel_l2(e2, G_MODELS[key]).max() <= 3e-2
+    assert rel_l2(e1, G_MODELS[key]).max() <= 1e-2 and rel_l2(e2, G_MODELS[key]).max() <= 1e-2
     assert rel_l2(e1, e2).max() <= 2e-2
 
 
@@ -356,6 +356,36 @@ def test_model_tensor_core_precisions(key, prec):
     rel = rel_l2(emb, G_MODELS[key])
     print(f"{key} {prec}: rel-L2 max {rel.max():.3e}")
     assert np.isfinite(emb).all() and rel.max() <= TC_TOL[prec], (key, prec, rel)
+
+
+@pytest.mark.parametrize("name,prec,B", [("ECAPA_TDNN_c1024", "bf16", 256), ("ECAPA_TDNN_c512", "tf32x3", 256),
+                                         ("ECAPA_TDNN_c512", "bf16", 96), ("ResNet34", "fp16", 64)])
+def test_bench_size_batch_matches_oracle(name, prec, B):
+    """The benchmarked configurations themselves against the CPU oracle: at >= 148*128 positions the big layers run the
+    cta_group::2 pair kernel (ws_gemm_tc3.cu), which the small golden cases never reach.  6 utterances spread over the
+    batch are compared with oracle.models_torch on the same features (the oracle is pinned by tests/test_oracle_golden.py)."""
+    T = 200
+    m = from_synthetic(name, 0, precision=prec)
+    feats = torch.from_numpy(syn.make_feats(B, T, 80, seed=23))
+    emb = m.embed(feats.to(DEV)).cpu().numpy()
+    sel = sorted({0, 1, B // 3, B // 2, B - 2, B - 1})
+    ref = models_torch.forward(name, syn.make_state_dict(name, 0), feats[sel]).numpy()
+    rel = rel_l2(emb[sel], ref)
+    tol = 1e-4 if prec in ("fp32", "tf32x3") else TC_TOL[prec]
+    print(f"bench-size {name} {prec} B{B}: rel-L2 max {rel.max():.3e} (bar {tol:g}), launches {m.last_launches()}")
+    assert np.isfinite(emb).all() and rel.max() <= tol, (name, prec, rel)
+
+
+def test_ecapa1024_bf16_matches_reference_golden():
+    """BASELINE.json configs[1]'s model in its benchmarked precision against the reference golden (non-GLOB c1024)."""
+    key = [k for k in G_MODELS.files if k.startswith("ECAPA_TDNN_c1024__")][0]
+    name, seed, B, T = parse_case(key)
+    m = from_synthetic(name, seed, precision="bf16")
+    feats = torch.from_numpy(syn.make_feats(B, T, 80, seed=seed + 17 * T)).to(DEV)
+    emb = m.embed(feats).cpu().numpy()
+    rel = rel_l2(emb, G_MODELS[key])
+    print(f"{key} bf16: rel-L2 max {rel.max():.3e}")
+    assert rel.max() <= TC_TOL["bf16"], rel
 
 
 def test_config1_ecapa512_16utts_wav_to_embedding():
