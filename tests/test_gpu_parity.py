@@ -150,6 +150,86 @@ def test_conv_operator(case, mode):
 
 
 
+C3_CASES = [
+    # name, B, F, T, C: geometry cases of the halo-resident 3x3 kernel (ws_conv3x3.cu)
+    ("l1_T200_2tiles", 2, 9, 200, 32),       # ResNet layer1 shape: one utterance per slot, two M tiles, 64-byte operand rows
+    ("l1_T100_1tile", 3, 7, 100, 32),
+    ("l2_T100_c64", 2, 11, 100, 64),         # layer2: 128-byte rows, resident weights
+    ("l3_T50_c128_nb2", 5, 20, 50, 128),     # layer3: two utterances share an M tile (odd B), streamed weights, two K panels
+    ("T25_c128_nb4", 6, 10, 25, 128),        # four utterances per tile
+    ("T64_c64_nb2", 3, 5, 64, 64),           # largest pitch of the side-by-side case (P = 66)
+    ("T65_c32", 2, 4, 65, 32),               # smallest one-utterance-per-slot pitch
+    ("T255_multibox", 1, 4, 255, 32),        # slot needs 258 rows: two 128-row boxes + the 2-row tail box
+    ("T256_multibox", 1, 3, 256, 64),
+    ("T300_ttiles128", 1, 5, 300, 32),       # t tiles of 128
+    ("T500_ttiles256", 1, 3, 500, 32),       # t tiles of 256, ragged last tile
+    ("T998_c32", 1, 6, 998, 32),             # CAM++ FCM head at 10 s
+    ("F1_single_row", 2, 1, 77, 64),
+    ("many_steps", 9, 40, 100, 64),          # more steps than SMs: CTAs cross utterance boundaries mid-range
+]
+
+
+@pytest.mark.parametrize("case", C3_CASES, ids=[c[0] for c in C3_CASES])
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("variant", ["relu", "res_relu", "plain"])
+def test_conv3x3_halo_kernel(case, prec, variant):
+    """use_tc = 4 routes stride-1 3x3 convs to ws_conv3x3.cu (input rows resident in a shared-memory ring, taps as
+    row-shifted UMMA operand reads).  Checked against fp64 conv2d on the rounded operands, and against the generic
+    conv-GEMM kernel (same operands, same fp32 accumulation: differences only from summation order)."""
+    name, B, F, T, Cc = case
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)
+    x = torch.randn(B, F, T, Cc, generator=g)
+    w = torch.randn(Cc, Cc, 3, 3, generator=g) / np.sqrt(9 * Cc)
+    bias = 0.1 * torch.randn(Cc, generator=g)
+    res = torch.randn(B, F, T, Cc, generator=g) if variant == "res_relu" else None
+    act1 = 1 if variant == "relu" else 0
+    act2 = 1 if variant == "res_relu" else 0
+    args = (x, w, bias, None, None, res, prec)
+    geo = (3, 3, (1, 1), (1, 1), (1, 1), act1, act2)
+    out = run_conv(*args, 4, *geo)
+    ref = ref_conv(x, w, bias, None, None, res, DT[prec][1], *geo)
+    err = (out.double() - ref).abs().max().item()
+    tol = {"bf16": 1.2e-2, "fp16": 2e-3}[prec] * max(1.0, ref.abs().max().item())
+    print(f"conv3x3 {name} {prec} {variant}: max|err|={err:.3e} (tol {tol:.1e})")
+    assert err <= tol, (name, prec, variant, err, tol)
+    if B * F * T <= 20000:
+        gen = run_conv(*args, 2, *geo)
+        assert (out - gen).abs().max().item() <= tol
+
+
+def test_conv3x3_ring_depths_agree():
+    """Ring depth only changes the pipelining (WS_C3_RING caps it): identical bits for depths 4..8."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 30, 100, 32, generator=g)
+    w = torch.randn(32, 32, 3, 3, generator=g) / np.sqrt(288)
+    bias = 0.1 * torch.randn(32, generator=g)
+    res = torch.randn(3, 30, 100, 32, generator=g)
+    outs = []
+    for depth in ("4", "5", "8"):
+        os.environ["WS_C3_RING"] = depth
+        try:
+            outs.append(run_conv(x, w, bias, None, None, res, "fp16", 4, 3, 3, (1, 1), (1, 1), (1, 1), 0, 1))
+        finally:
+            os.environ.pop("WS_C3_RING", None)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("name,prec,B,T", [("ResNet34", "fp16", 3, 200), ("ResNet34", "bf16", 2, 99), ("ResNet18", "fp16", 2, 57),
+                                           ("CAMPPlus", "bf16", 2, 198), ("ResNet34", "fp16", 2, 612)])
+def test_conv3x3_engine_path_matches_generic_path(name, prec, B, T):
+    """Whole models with the halo-resident kernel on (default) and off (`conv3x3` = 0): same operands and roundings, so the
+    embeddings agree to summation-order level, and fewer launches are not the point (same count +- shortcut convs)."""
+    feats = torch.from_numpy(syn.make_feats(B, T, 80, seed=9)).to(DEV)
+    m1 = from_synthetic(name, 0, precision=prec)
+    m1.set_option("conv3x3", 1)
+    m0 = from_synthetic(name, 0, precision=prec)
+    m0.set_option("conv3x3", 0)
+    e1, e0 = m1.embed(feats).cpu().numpy(), m0.embed(feats).cpu().numpy()
+    rel = rel_l2(e1, e0).max()
+    print(f"conv3x3 on/off {name} {prec} B{B} T{T}: rel {rel:.2e}, launches {m1.last_launches()} vs {m0.last_launches()}")
+    assert np.isfinite(e1).all() and rel <= 3e-3
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["bf16-tc2", "fp16-tc2", "tf32-tc2", "tf32x3-tc2", "bf16-tc3", "fp16-tc3", "tf32-tc3", "tf32x3-tc3"])
 @pytest.mark.parametrize("variant", ["bias_relu", "bn", "bn_res_relu"])

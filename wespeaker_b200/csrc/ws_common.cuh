@@ -331,6 +331,38 @@ struct WsRes2Params {
     int grid, smem_bytes;
 };
 
+// halo-resident 3x3 stride-1 conv (ws_conv3x3.cu): input rows of F live in a shared-memory ring, the 9 taps are row-shifted
+// UMMA operand reads of that ring
+#define WS_C3_MAX_RING 8
+#define WS_C3_MAX_WSTAGES 4
+struct WsC3Params {
+    CUtensorMap amap;       // input  (C, T, F, B): box (kc, box_t, 1, box_b), swizzle = row_bytes
+    CUtensorMap amap_tail;  // same tensor, box (kc, 2, 1, 1): the last two halo columns when a slot needs > 256 rows
+    CUtensorMap wmap;       // weights [Cout][9*Cin] K-major: box (kc, N)
+    CUtensorMap omap;       // output (Cout, T, F, B): box (panel_cols, obox_t, 1, obox_b), swizzle = panel_bytes
+    const void* res;        // residual (same geometry as the output) read with direct global loads, or null
+    long long res_ld;
+    const float* bias;      // [Cout]
+    int relu;
+    int B, F, T, Cin, Cout, dtype;
+    int row_bytes, npan, kc;       // bytes per smem operand row per K panel (64 / 128), K panels per tap, channels per panel
+    int P, tb, n_tt;               // padded pitch (tb + 2), output columns per t tile, number of t tiles
+    int nb, n_bg;                  // utterances per slot (case B: several short utterances share one M tile), b groups
+    int n_mt;                      // M tiles (128 rows) per step; tile mt starts 128*mt rows into the slot
+    int single_box;                // slot filled by one TMA box (rows = box_t * box_b) instead of n_mt x 128 rows + 2-row tail
+    int rows_loaded, slot_rows;    // rows written per slot per panel / allocated rows per slot per panel (multiple of 8)
+    int R;                         // ring depth in slots (>= 4)
+    int N, n_nt;                   // output channels per CTA tile, number of n tiles
+    int w_resident, w_stages;      // all 9*npan weight blocks resident in smem, or streamed through a ring
+    int panel_bytes, panel_cols;   // output staging panel row bytes (128, or 64 when N == 32) and columns
+    int stg_rows;                  // allocated rows per staging panel (128, or 136 in case B)
+    int case_b;
+    uint32_t idesc;
+    int total_steps;               // n_nt * n_tt * n_bg * F output-row steps, split contiguously over the CTAs
+    int grid, smem_bytes;
+    long long* prof;               // tuning aid (WS_C3_PROF=1): per-CTA wait-cycle counters, 16 slots per CTA; else null
+};
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are PER DEVICE: init guards are keyed by the current
 // device so that a second engine on another GPU of the same process gets its opt-in too (one bit per device ordinal).
 inline bool ws_dev_needs_init(unsigned long long* mask, int* dev_out) {
@@ -360,6 +392,9 @@ extern "C" {
 #endif
 const char* ws_res2_init(void);
 const char* ws_res2_launch(const WsRes2Params* p, cudaStream_t s);
+const char* ws_c3_init(void);
+int ws_c3_max_smem(void);
+const char* ws_c3_launch(const WsC3Params* p, cudaStream_t s);
 const char* ws_tc3_init(void);
 int ws_tc3_max_smem(void);
 const char* ws_tc3_launch(const WsTc2Params* p, cudaStream_t s);

@@ -406,6 +406,127 @@ bool make_res2_op(const View& x, const View& out, const void* W7, const float* b
     return true;
 }
 
+bool make_conv3x3_op(const View& x, const View& out, const void* W, const float* bias, const View* res, bool relu,
+                     Op* op, bool* unsupported) {
+    *unsupported = false;
+    const int Cin = x.C, Cout = out.C, T = x.T, F = x.F, B = x.B;
+    auto chan_ok = [](int c) { return c == 32 || c == 64 || c == 128; };
+    if (x.dt == WS_F32 || out.dt != x.dt || !chan_ok(Cin) || !chan_ok(Cout) || out.B != B || out.F != F || out.T != T ||
+        T < 1 || F < 1 || (x.ld * 2) % 16 != 0 || (out.ld * 2) % 16 != 0 || (res && (res->ld * 2) % 16 != 0) ||
+        getenv("WS_NO_CONV3X3")) {
+        *unsupported = true;
+        return false;
+    }
+    auto q = std::make_shared<WsC3Params>();
+    memset(q.get(), 0, sizeof(WsC3Params));
+    q->B = B; q->F = F; q->T = T; q->Cin = Cin; q->Cout = Cout; q->dtype = x.dt;
+    q->row_bytes = Cin * 2 >= 128 ? 128 : Cin * 2;
+    q->kc = q->row_bytes / 2;
+    q->npan = Cin / q->kc;
+    q->N = Cout; q->n_nt = 1;
+    // ---- geometry of one ring slot / one step: first candidate whose ring (>= 4 slots) fits in shared memory
+    const int budget = ws_c3_max_smem();
+    auto try_geom = [&](bool case_b, int tb, int n_mt) -> bool {
+        q->case_b = case_b ? 1 : 0;
+        q->tb = tb; q->n_mt = n_mt;
+        q->n_tt = (T + tb - 1) / tb;
+        q->P = tb + 2;
+        if (case_b) {             // several short utterances side by side in one M tile (pitch P = T + 2)
+            q->nb = std::min(B, 130 / q->P);   // nb * P - 2 <= 128
+            q->single_box = 1;
+            q->rows_loaded = q->nb * q->P;
+        } else {                  // one utterance per slot, 1-2 M tiles along t
+            q->nb = 1;
+            q->single_box = q->P <= 256;
+            q->rows_loaded = q->single_box ? q->P : 128 * n_mt + 2;
+        }
+        q->n_bg = (B + q->nb - 1) / q->nb;
+        q->slot_rows = (std::max(q->rows_loaded, 128 * n_mt + 2) + 7) & ~7;
+        if (2 * n_mt * q->N > 512) return false;
+        q->panel_bytes = q->N * 2 >= 128 ? 128 : q->N * 2;
+        q->panel_cols = q->panel_bytes / 2;
+        q->stg_rows = case_b ? 136 : 128;
+        const int slot_bytes = q->npan * q->slot_rows * q->row_bytes;
+        const int wblk = q->N * q->row_bytes, nwblk = 9 * q->npan;
+        const int stg_bytes = n_mt * (q->N / q->panel_cols) * q->stg_rows * q->panel_bytes;
+        const int fixed = stg_bytes + q->N * 4 + 2048 /* alignment slack */;
+        q->w_resident = (budget - fixed - nwblk * wblk) / slot_bytes >= 5;
+        q->w_stages = q->w_resident ? 0 : 3;
+        int R = (budget - fixed - (q->w_resident ? nwblk : q->w_stages) * wblk) / slot_bytes;
+        if (R > WS_C3_MAX_RING) R = WS_C3_MAX_RING;
+        if (const char* er = getenv("WS_C3_RING")) R = std::min(R, atoi(er));
+        if (R < 4) return false;
+        q->R = R;
+        q->smem_bytes = R * slot_bytes + (q->w_resident ? nwblk : q->w_stages) * wblk + fixed;
+        return true;
+    };
+    bool ok = false;
+    if (T + 2 <= 66) ok = try_geom(true, T, 1);
+    if (!ok && T <= 256) ok = try_geom(false, T, (T + 127) / 128);
+    if (!ok) {   // t tiles of 256 (2 M tiles) or 128 (1 M tile): fewer 128-row tiles first, 256 on a tie (fewer halo columns)
+        const bool pref256 = 2 * ((T + 255) / 256) <= (T + 127) / 128;
+        ok = pref256 ? (try_geom(false, 256, 2) || try_geom(false, 128, 1)) : (try_geom(false, 128, 1) || try_geom(false, 256, 2));
+    }
+    if (!ok) { *unsupported = true; return false; }
+    const uint32_t fmt = x.dt == WS_BF16 ? 1u : 0u;
+    q->idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(q->N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    q->total_steps = q->n_nt * q->n_tt * q->n_bg * F;
+    const int sms = ws_num_sms();
+    q->grid = q->total_steps < sms ? q->total_steps : sms;
+    // ---- tensor maps
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)T, (cuuint64_t)F, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)x.ld * 2, (cuuint64_t)T * x.ld * 2, (cuuint64_t)F * T * x.ld * 2};
+        cuuint32_t box[4] = {(cuuint32_t)q->kc, (cuuint32_t)(q->single_box ? q->P : 128), 1, (cuuint32_t)q->nb};
+        if (!encode_map(&q->amap, x.dt, x.p, 4, dims, str, box, q->row_bytes)) return false;
+        cuuint32_t boxt[4] = {(cuuint32_t)q->kc, 2, 1, 1};
+        if (!encode_map(&q->amap_tail, x.dt, x.p, 4, dims, str, boxt, q->row_bytes)) return false;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)(9 * Cin), (cuuint64_t)Cout};
+        cuuint64_t str[1] = {(cuuint64_t)(9 * Cin) * 2};
+        cuuint32_t box[2] = {(cuuint32_t)q->kc, (cuuint32_t)q->N};
+        if (!encode_map(&q->wmap, x.dt, W, 2, dims, str, box, q->row_bytes)) return false;
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)T, (cuuint64_t)F, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)out.ld * 2, (cuuint64_t)T * out.ld * 2, (cuuint64_t)F * T * out.ld * 2};
+        cuuint32_t box[4] = {(cuuint32_t)q->panel_cols, (cuuint32_t)(q->case_b ? q->P : 128), 1, (cuuint32_t)(q->case_b ? q->nb : 1)};
+        if (!encode_map(&q->omap, x.dt, out.p, 4, dims, str, box, q->panel_bytes)) return false;
+    }
+    q->res = res ? res->p : nullptr;
+    q->res_ld = res ? res->ld : 0;
+    q->bias = bias;
+    q->relu = relu ? 1 : 0;
+    if (getenv("WS_C3_PROF")) {   // tuning aid: synchronous launch + per-role wait-cycle summary on stderr
+        long long* prof = nullptr;
+        if (cudaMalloc((void**)&prof, (size_t)q->grid * 16 * 8) != cudaSuccess) { set_err("conv3x3: prof buffer"); return false; }
+        cudaMemset(prof, 0, (size_t)q->grid * 16 * 8);
+        q->prof = prof;
+        *op = [q](cudaStream_t s) -> const char* {
+            const char* m = ws_c3_launch(q.get(), s);
+            if (m) return m;
+            cudaStreamSynchronize(s);
+            std::vector<long long> h((size_t)q->grid * 16);
+            cudaMemcpy(h.data(), q->prof, h.size() * 8, cudaMemcpyDeviceToHost);
+            static const char* names[12] = {"prod.wait_aempty", "prod.total", "mma.wait_afull", "mma.wait_tempty", "mma.wait_wfull",
+                                            "mma.total", "epi.wait_store", "epi.wait_tfull", "epi.res_issue", "epi.body", "epi.total", "steps"};
+            fprintf(stderr, "[c3 prof] grid %d R %d n_mt %d nb %d N %d Cin %d w_res %d steps %d:", q->grid, q->R, q->n_mt, q->nb, q->N, q->Cin,
+                    q->w_resident, q->total_steps);
+            for (int k = 0; k < 12; ++k) {
+                double acc = 0;
+                for (int c = 0; c < q->grid; ++c) acc += (double)h[(size_t)c * 16 + k];
+                fprintf(stderr, " %s=%.0f", names[k], acc / q->grid);
+            }
+            fprintf(stderr, "\n");
+            return nullptr;
+        };
+        return true;
+    }
+    *op = [q](cudaStream_t s) { return ws_c3_launch(q.get(), s); };
+    return true;
+}
+
 }  // namespace ws
 
 // ------------------------------------------------------------------------------------------------ C ABI: ws_conv
@@ -432,8 +553,19 @@ extern "C" int ws_conv(const ws_conv_desc* d, void* stream) {
     s.epi.res = d->res; s.epi.res_ld = d->res_ld; s.epi.act2 = d->act2;
     s.epi.colsum = d->colsum; s.epi.colsum_T = d->colsum ? To : 0;
     Op op;
-    if (d->use_tc) { WS_CKS(ws_tc_init()); WS_CKS(ws_tc2_init()); WS_CKS(ws_tc3_init()); }
-    if (!make_conv_op(s, d->use_tc, &op)) return 1;
+    if (d->use_tc) { WS_CKS(ws_tc_init()); WS_CKS(ws_tc2_init()); WS_CKS(ws_tc3_init()); WS_CKS(ws_c3_init()); }
+    bool done = false;
+    if (d->use_tc >= 4 && d->kf == 3 && d->kt == 3 && d->dil_f == 1 && d->dil_t == 1 && d->pad_f == 1 && d->pad_t == 1 &&
+        d->stride_f == 1 && d->stride_t == 1 && d->scale == nullptr && d->x_lo == nullptr && d->colsum == nullptr &&
+        (d->act1 == 0 || d->res == nullptr) && d->act1 <= 1 && d->act2 <= 1) {
+        // halo-resident 3x3 kernel: act(conv + bias [+ res]); with a residual the activation is act2, else act1 (or act2)
+        View r = o;
+        r.p = const_cast<void*>(d->res); r.ld = d->res_ld;
+        bool unsupported = false;
+        if (make_conv3x3_op(x, o, d->w, d->bias, d->res ? &r : nullptr, (d->act1 | d->act2) != 0, &op, &unsupported)) done = true;
+        else if (!unsupported) return 1;
+    }
+    if (!done && !make_conv_op(s, d->use_tc >= 4 ? 3 : d->use_tc, &op)) return 1;
     const char* m = op((cudaStream_t)stream);
     if (m != nullptr) { set_err(std::string("ws_conv launch: ") + m); return 1; }
     return 0;

@@ -531,11 +531,54 @@ View basic_block(Builder& b, const std::string& p, const View& x, int cout, int 
     const int Fo = (x.F + 2 - 3) / sf + 1, To = (x.T + 2 - 3) / st_ + 1;
     View h = hbuf; h.B = x.B; h.F = Fo; h.T = To; h.C = cout; h.ld = cout;
     View o = obuf; o.B = x.B; o.F = Fo; o.T = To; o.C = cout; o.ld = cout;
-    WsEpi e1{};
-    e1.bias = b.w.f32("bnh:" + p + ".bn1", h1);
-    e1.act1 = WS_ACT_RELU;
-    b.conv_simple(x, h, b.w.act("w:" + p + ".conv1", w1), 3, 3, 1, 1, 1, 1, sf, st_, e1);
+    // stride-1 3x3 convs of the low-channel stages run the halo-resident kernel (ws_conv3x3.cu): every input row crosses
+    // L2 -> SM once instead of once per tap
+    const bool c3 = b.e.use_tc >= 2 && b.e.act_dt != WS_F32 && b.e.opt("conv3x3", 0) != 0;
+    auto try_c3 = [&](const View& in, const View& outv, const void* Wd, const float* bias, const View* res) -> int {
+        if (!c3) return 0;
+        Op op;
+        bool unsupported = false;
+        if (make_conv3x3_op(in, outv, Wd, bias, res, true, &op, &unsupported)) { b.push(std::move(op)); return 1; }
+        if (!unsupported) { b.ok = false; return -1; }
+        return 0;
+    };
+    {
+        const float* b1 = b.w.f32("bnh:" + p + ".bn1", h1);
+        const void* W1 = b.w.act("w:" + p + ".conv1", w1);
+        int r = (sf == 1 && st_ == 1) ? try_c3(x, h, W1, b1, nullptr) : 0;
+        if (r < 0) return none;
+        if (r == 0) {
+            WsEpi e1{};
+            e1.bias = b1;
+            e1.act1 = WS_ACT_RELU;
+            b.conv_simple(x, h, W1, 3, 3, 1, 1, 1, 1, sf, st_, e1);
+        }
+    }
     if (!b.good()) return none;
+    const bool has_sc0 = b.e.sd.count(p + ".shortcut.0.weight") != 0;
+    if (c3 && (cout == 32 || cout == 64 || cout == 128)) {
+        // conv2 on the halo-resident kernel: the 1x1 strided shortcut conv (+ its BN) is written to `o` first and then
+        // read back as the residual, in place (each output element is read and written by the same CTA step)
+        const float* b2 = b.w.f32("bnh:" + p + ".bn2", h2);
+        const void* W2 = b.w.act("w:" + p + ".conv2", w2);
+        // build conv2's launch first: if the shape is outside the kernel's envelope nothing has been emitted yet
+        View resv = has_sc0 ? o : x;
+        Op op2;
+        bool unsupported = false;
+        if (make_conv3x3_op(h, o, W2, b2, &resv, true, &op2, &unsupported)) {
+            if (has_sc0) {
+                std::vector<float> ss, hs, wsv;
+                if (!b.w.bn(p + ".shortcut.1", true, ss, hs) || !b.w.pack_conv(p + ".shortcut.0.weight", &ss, wsv, &co, &ci, &nt)) return none;
+                WsEpi es{};
+                es.bias = b.w.f32("bnh:" + p + ".shortcut", hs);
+                b.conv_simple(x, o, b.w.act("w:" + p + ".shortcut", wsv), 1, 1, 1, 1, 0, 0, sf, st_, es);
+                if (!b.good()) return none;
+            }
+            b.push(std::move(op2));
+            return o;
+        }
+        if (!unsupported) { b.ok = false; return none; }
+    }
     ConvSpec cs;
     cs.dt = b.e.act_dt;
     int F2, T2;
@@ -991,6 +1034,7 @@ int ws_engine_create(const char* model_name, const char* precision, int feat_dim
     WS_CKS(ws_tc2_init());
     WS_CKS(ws_res2_init());
     WS_CKS(ws_tc3_init());
+    WS_CKS(ws_c3_init());
     WS_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     WS_CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
     WS_CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
@@ -1003,7 +1047,7 @@ int ws_engine_set_option(ws_engine* e, const char* key, long long value) {
     const std::string k = key;
     if (k == "force_simt") { if (value) e->use_tc = 0; }
     else if (k == "tc_version") { if (e->use_tc) e->use_tc = value >= 3 ? 3 : (value >= 2 || e->split ? 2 : 1); }
-    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused" && k != "se_fused" && k != "se_colsum") { set_err("unknown option " + k); return 1; }
+    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused" && k != "se_fused" && k != "se_colsum" && k != "conv3x3") { set_err("unknown option " + k); return 1; }
     e->opts[k] = value;
     e->plans.clear();
     return 0;
