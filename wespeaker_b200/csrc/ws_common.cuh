@@ -340,8 +340,10 @@ struct WsC3Params {
     CUtensorMap amap_tail;  // same tensor, box (kc, 2, 1, 1): the last two halo columns when a slot needs > 256 rows
     CUtensorMap wmap;       // weights [Cout][9*Cin] K-major: box (kc, N)
     CUtensorMap omap;       // output (Cout, T, F, B): box (panel_cols, obox_t, 1, obox_b), swizzle = panel_bytes
-    const void* res;        // residual (same geometry as the output) read with direct global loads, or null
+    CUtensorMap rmap;       // residual tensor, same geometry and box as omap (TMA-loaded into the output staging tile)
+    const void* res;        // residual base pointer (null = no residual)
     long long res_ld;
+    int stg_bufs;           // output staging tiles: 2 = the residual of step s+1 is prefetched while step s drains, 1 = in line
     const float* bias;      // [Cout]
     int relu;
     int B, F, T, Cin, Cout, dtype;
@@ -361,6 +363,7 @@ struct WsC3Params {
     int total_steps;               // n_nt * n_tt * n_bg * F output-row steps, split contiguously over the CTAs
     int grid, smem_bytes;
     long long* prof;               // tuning aid (WS_C3_PROF=1): per-CTA wait-cycle counters, 16 slots per CTA; else null
+    int dbg;                       // tuning aid (WS_C3_DBG): knock-out bits 1 = no epilogue work, 2 = no input TMA loads, 8 = no MMAs
 };
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are PER DEVICE: init guards are keyed by the current

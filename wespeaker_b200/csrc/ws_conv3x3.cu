@@ -41,29 +41,47 @@ __device__ __forceinline__ void umma_commit_c3(uint32_t bar) {
 #define C3_T0() const long long t0__ = p.prof ? clock64() : 0
 #define C3_ACC(var) do { if (p.prof) var += clock64() - t0__; } while (0)
 
+// Walk over this CTA's contiguous range of output-row steps.  The (f, b group, t tile, n tile) decomposition costs integer
+// divisions only once; every role advances it incrementally (a 64-bit div/mod per step and role was ~5k cycles per step of
+// pure overhead in the first version of this kernel).
 struct C3Step {
     int f, bg, tt, nt;
     bool first, last;
 };
-__device__ __forceinline__ C3Step c3_step(const WsC3Params& p, long long s, long long s_beg, long long s_end) {
-    C3Step x;
-    x.f = (int)(s % p.F);
-    long long img = s / p.F;
-    x.bg = (int)(img % p.n_bg); img /= p.n_bg;
-    x.tt = (int)(img % p.n_tt);
-    x.nt = (int)(img / p.n_tt);
-    x.first = (s == s_beg) || (x.f == 0);
-    x.last = (s + 1 == s_end) || (x.f == p.F - 1);
-    return x;
-}
+struct C3Iter {
+    int s, s_beg, s_end, f, bg, tt, nt;
+    __device__ __forceinline__ C3Iter(const WsC3Params& p, int beg, int end) : s(beg), s_beg(beg), s_end(end) {
+        f = beg % p.F;
+        int img = beg / p.F;
+        bg = img % p.n_bg; img /= p.n_bg;
+        tt = img % p.n_tt;
+        nt = img / p.n_tt;
+    }
+    __device__ __forceinline__ bool done() const { return s >= s_end; }
+    __device__ __forceinline__ C3Step cur(const WsC3Params& p) const {
+        C3Step x;
+        x.f = f; x.bg = bg; x.tt = tt; x.nt = nt;
+        x.first = (s == s_beg) || (f == 0);
+        x.last = (s + 1 == s_end) || (f == p.F - 1);
+        return x;
+    }
+    __device__ __forceinline__ void next(const WsC3Params& p) {
+        ++s;
+        if (++f == p.F) {
+            f = 0;
+            if (++bg == p.n_bg) { bg = 0; if (++tt == p.n_tt) { tt = 0; ++nt; } }
+        }
+    }
+};
 
-template <int DT>
+template <int DT, int ROWB, int NPAN, int NMT>
 __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_constant__ WsC3Params p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_bar[2 * WS_C3_MAX_RING + 2 * WS_C3_MAX_WSTAGES + 5];
+    __shared__ __align__(8) uint64_t s_bar[2 * WS_C3_MAX_RING + 2 * WS_C3_MAX_WSTAGES + 11];
     __shared__ uint32_t s_tmem;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then knows the role branches are warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int slot_bytes = p.npan * p.slot_rows * p.row_bytes;
     const int wblk_bytes = p.N * p.row_bytes;
@@ -74,7 +92,8 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
     const int npanels_out = p.N / p.panel_cols;
     const int panel_stride = p.stg_rows * p.panel_bytes;
     const int tile_bytes = npanels_out * panel_stride;
-    const uint32_t s_par = stg + (uint32_t)(p.n_mt * tile_bytes);
+    const int obuf_bytes = p.n_mt * tile_bytes;                    // one staging buffer = the n_mt output tiles of a step
+    const uint32_t s_par = stg + (uint32_t)(p.stg_bufs * obuf_bytes);
     const uint32_t bar_afull = smem_u32(&s_bar[0]);
     const uint32_t bar_aempty = smem_u32(&s_bar[WS_C3_MAX_RING]);
     const uint32_t bar_wfull = smem_u32(&s_bar[2 * WS_C3_MAX_RING]);
@@ -82,20 +101,22 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
     const uint32_t bar_wres = smem_u32(&s_bar[2 * WS_C3_MAX_RING + 2 * WS_C3_MAX_WSTAGES]);
     const uint32_t bar_tfull = smem_u32(&s_bar[2 * WS_C3_MAX_RING + 2 * WS_C3_MAX_WSTAGES + 1]);   // [2]
     const uint32_t bar_tempty = smem_u32(&s_bar[2 * WS_C3_MAX_RING + 2 * WS_C3_MAX_WSTAGES + 3]);  // [2]
+    const uint32_t bar_rfull = smem_u32(&s_bar[2 * WS_C3_MAX_RING + 2 * WS_C3_MAX_WSTAGES + 5]);   // [set][buffer] residual panels landed
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < 2 * p.n_mt * p.N) tmem_cols <<= 1;
 
-    const long long s_beg = (long long)p.total_steps * blockIdx.x / gridDim.x;
-    const long long s_end = (long long)p.total_steps * (blockIdx.x + 1) / gridDim.x;
+    const int s_beg = (int)((long long)p.total_steps * blockIdx.x / gridDim.x);
+    const int s_end = (int)((long long)p.total_steps * (blockIdx.x + 1) / gridDim.x);
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&p.amap); prefetch_tmap(&p.amap_tail); prefetch_tmap(&p.wmap); prefetch_tmap(&p.omap);
+        prefetch_tmap(&p.amap); prefetch_tmap(&p.amap_tail); prefetch_tmap(&p.wmap); prefetch_tmap(&p.omap); prefetch_tmap(&p.rmap);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.R; ++i) { mbar_init(bar_afull + 8 * i, 1); mbar_init(bar_aempty + 8 * i, 1); }
         for (int i = 0; i < WS_C3_MAX_WSTAGES; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wempty + 8 * i, 1); }
         mbar_init(bar_wres, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
+        for (int i = 0; i < 6; ++i) mbar_init(bar_rfull + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -116,9 +137,11 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
             int j = 0;
             long long pw_aempty = 0;
             const long long tstart = p.prof ? clock64() : 0;
+            int slot = 0;
+            uint32_t sphase = 1;                             // waits on the "previous" phase of a fresh barrier pass at once
             auto load_row = [&](int frow, int bg, int tt) {
-                const int slot = j % p.R;
-                { C3_T0(); mbar_wait(bar_aempty + 8 * slot, (((uint32_t)(j / p.R)) & 1u) ^ 1u); C3_ACC(pw_aempty); }
+                { C3_T0(); mbar_wait(bar_aempty + 8 * slot, sphase); C3_ACC(pw_aempty); }
+                if (p.dbg & 2) { mbar_arrive(bar_afull + 8 * slot); if (++slot == p.R) { slot = 0; sphase ^= 1u; } ++j; return; }
                 mbar_expect_tx(bar_afull + 8 * slot, tx);
                 const int tc = tt * p.tb - 1, b0 = bg * p.nb;
                 for (int kp = 0; kp < p.npan; ++kp) {
@@ -133,10 +156,11 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
                                     kp * p.kc, tc + 128 * p.n_mt, frow, b0);
                     }
                 }
+                if (++slot == p.R) { slot = 0; sphase ^= 1u; }
                 ++j;
             };
-            for (long long s = s_beg; s < s_end; ++s) {
-                const C3Step st = c3_step(p, s, s_beg, s_end);
+            for (C3Iter it(p, s_beg, s_end); !it.done(); it.next(p)) {
+                const C3Step st = it.cur(p);
                 if (st.first) { load_row(st.f - 1, st.bg, st.tt); load_row(st.f, st.bg, st.tt); }
                 load_row(st.f + 1, st.bg, st.tt);
             }
@@ -152,121 +176,206 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
                         tma_load_2d(wbuf + (uint32_t)((tap * p.npan + kp) * wblk_bytes), &p.wmap, bar_wres,
                                     tap * p.Cin + kp * p.kc, 0);
             } else {
-                int wit = 0;
-                for (long long s = s_beg; s < s_end; ++s) {
-                    const C3Step st = c3_step(p, s, s_beg, s_end);
+                int ws = 0;
+                uint32_t wphase = 1;
+                for (C3Iter it(p, s_beg, s_end); !it.done(); it.next(p)) {
+                    const C3Step st = it.cur(p);
                     for (int tap = 0; tap < 9; ++tap)
-                        for (int kp = 0; kp < p.npan; ++kp, ++wit) {
-                            const int ws = wit % p.w_stages;
-                            mbar_wait(bar_wempty + 8 * ws, (((uint32_t)(wit / p.w_stages)) & 1u) ^ 1u);
+                        for (int kp = 0; kp < p.npan; ++kp) {
+                            mbar_wait(bar_wempty + 8 * ws, wphase);
                             mbar_expect_tx(bar_wfull + 8 * ws, (uint32_t)wblk_bytes);
                             tma_load_2d(wbuf + (uint32_t)(ws * wblk_bytes), &p.wmap, bar_wfull + 8 * ws,
                                         tap * p.Cin + kp * p.kc, st.nt * p.N);
+                            if (++ws == p.w_stages) { ws = 0; wphase ^= 1u; }
                         }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0 && s_beg < s_end) {
-            const int kper = p.row_bytes / 32;
-            int j = 0, wit = 0, step = 0;
+        // One elected lane issues every tcgen05.mma of the CTA, but the WHOLE warp runs this loop with warp-uniform values:
+        // inside an `if (lane == 0)` region the compiler has to move every descriptor into uniform registers through an
+        // ELECT / R2UR.BROADCAST convergence loop in front of each UTCHMMA (~20 instructions, 65-80 cycles per MMA measured
+        // with tools/experimental/mma_rate_probe.cu — more than a 128 x N x 16 MMA with N <= 128 takes).  Descriptor
+        // arithmetic is hoisted to once per step / k-block; the k loop is a compile-time unroll of 64-bit adds.
+        if (s_beg < s_end) {
+            uint32_t elected;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+            constexpr int KPER = ROWB / 32;
+            const uint64_t dhi = umma_desc(0u, ROWB);                                 // descriptor without the address field
+            const uint32_t dt_off = (uint32_t)ROWB >> 4;                              // one operand row, in 16-byte units
+            const uint32_t kp_off = (uint32_t)(p.slot_rows * ROWB) >> 4;
+            const uint32_t mt_off = (uint32_t)(128 * ROWB) >> 4;
+            const uint32_t wb_off = (uint32_t)wblk_bytes >> 4;
+            const uint64_t wdesc0 = dhi | (uint64_t)((wbuf & 0x3FFFFu) >> 4);
+            const int R = p.R, N = p.N;
+            int j = 0, wst = 0, step = 0;
+            uint32_t wph = 0;
             long long mw_afull = 0, mw_tempty = 0, mw_wfull = 0;
             const long long tstart = p.prof ? clock64() : 0;
             if (p.w_resident) mbar_wait(bar_wres, 0);
-            for (long long s = s_beg; s < s_end; ++s, ++step) {
-                const C3Step st = c3_step(p, s, s_beg, s_end);
+            int jslot = 0;                                   // == j % R and (j / R) & 1, kept incrementally
+            uint32_t jphase = 0;
+            for (C3Iter it(p, s_beg, s_end); !it.done(); it.next(p), ++step) {
+                const C3Step st = it.cur(p);
                 const int nnew = st.first ? 3 : 1;           // a new image segment starts with rows f-1, f, f+1
                 j += nnew;                                   // rows f-1, f, f+1 are loads j-3, j-2, j-1
-                { C3_T0(); for (int i = j - nnew; i < j; ++i) mbar_wait(bar_afull + 8 * (i % p.R), ((uint32_t)(i / p.R)) & 1u); C3_ACC(mw_afull); }
+                {   // wait for the newly loaded rows: slot / phase of load i follow incrementally from (jslot, jphase)
+                    C3_T0();
+                    for (int i = 0; i < nnew; ++i) {
+                        mbar_wait(bar_afull + 8 * jslot, jphase);
+                        if (++jslot == R) { jslot = 0; jphase ^= 1u; }
+                    }
+                    C3_ACC(mw_afull);
+                }
                 const int buf = step & 1;
                 { C3_T0(); mbar_wait(bar_tempty + 8 * buf, ((((uint32_t)step) >> 1) & 1u) ^ 1u); C3_ACC(mw_tempty); }
                 tc_fence_after();
+                // compact tap loop (a full 9-way unroll made the issuing warp run ~9 KB of straight-line code once per step,
+                // far beyond the 6 KB L0 instruction cache): df / dt advance incrementally, only the k loop is unrolled
+                int sl0 = jslot - 3 < 0 ? jslot - 3 + R : jslot - 3;        // slot of row f-1 (= load j-3)
+                const int slot_first = sl0;
+                uint64_t a_df = dhi | (uint64_t)(((ring + (uint32_t)(sl0 * slot_bytes)) & 0x3FFFFu) >> 4);
+                const uint64_t a_ring0 = dhi | (uint64_t)((ring & 0x3FFFFu) >> 4);
+                const uint32_t slot_off = (uint32_t)slot_bytes >> 4;
+                const uint32_t tacc0 = tmem_base + (uint32_t)(buf * NMT * N);
+                uint64_t bd = wdesc0;
+                uint32_t accum = 0;
+                // one runtime loop over the 9 taps; everything inside (K panels, M tiles, k steps) is a compile-time unroll,
+                // so the scalar work between two MMAs is a couple of uniform adds
+                int dtc = 0;
+                uint64_t a_dt = a_df;
+#pragma unroll 1
                 for (int tap = 0; tap < 9; ++tap) {
-                    const int df = tap / 3, dt = tap % 3;               // 0..2 (= offset + 1)
-                    const int slot = (j - 3 + df) % p.R;
-                    for (int kp = 0; kp < p.npan; ++kp) {
-                        uint32_t wb;
-                        int ws = 0;
-                        if (p.w_resident) {
-                            wb = wbuf + (uint32_t)((tap * p.npan + kp) * wblk_bytes);
-                        } else {
-                            ws = wit % p.w_stages;
-                            { C3_T0(); mbar_wait(bar_wfull + 8 * ws, ((uint32_t)(wit / p.w_stages)) & 1u); C3_ACC(mw_wfull); }
+#pragma unroll
+                    for (int kp = 0; kp < NPAN; ++kp) {
+                        if (!p.w_resident) {
+                            { C3_T0(); mbar_wait(bar_wfull + 8 * wst, wph); C3_ACC(mw_wfull); }
                             tc_fence_after();
-                            wb = wbuf + (uint32_t)(ws * wblk_bytes);
+                            bd = wdesc0 + (uint64_t)(wst * wb_off);
                         }
-                        const uint64_t bdesc = umma_desc(wb, p.row_bytes);
-                        for (int mt = 0; mt < p.n_mt; ++mt) {
-                            const uint32_t arow = ring + (uint32_t)(((slot * p.npan + kp) * p.slot_rows + dt + mt * 128) * p.row_bytes);
-                            const uint64_t adesc = umma_desc(arow, p.row_bytes);
-                            const uint32_t tacc = tmem_base + (uint32_t)((buf * p.n_mt + mt) * p.N);
-                            for (int k = 0; k < kper; ++k)
-                                umma_f16_c3(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                                            (uint32_t)((tap | kp | k) != 0));
+                        if (elected && !(p.dbg & 8)) {
+#pragma unroll
+                            for (int mt = 0; mt < NMT; ++mt) {
+#pragma unroll
+                                for (int k = 0; k < KPER; ++k)
+                                    umma_f16_c3(tacc0 + (uint32_t)(mt * N), a_dt + (uint64_t)(kp * kp_off + mt * mt_off + 2 * k),
+                                                bd + (uint64_t)(2 * k), p.idesc, (kp == 0 && k == 0) ? accum : 1u);
+                            }
                         }
-                        if (!p.w_resident) { umma_commit_c3(bar_wempty + 8 * ws); ++wit; }
+                        accum = 1u;
+                        if (p.w_resident) {
+                            bd += wb_off;
+                        } else {
+                            if (elected) umma_commit_c3(bar_wempty + 8 * wst);
+                            if (++wst == p.w_stages) { wst = 0; wph ^= 1u; }
+                        }
+                    }
+                    if (++dtc == 3) {           // next input row: slot of row f-1 -> f -> f+1 (ring wrap)
+                        dtc = 0;
+                        if (++sl0 == R) { sl0 = 0; a_df = a_ring0; } else a_df += slot_off;
+                        a_dt = a_df;
+                    } else {
+                        a_dt += dt_off;
                     }
                 }
-                umma_commit_c3(bar_tfull + 8 * buf);
-                umma_commit_c3(bar_aempty + 8 * ((j - 3) % p.R));       // row f-1 is not needed by later steps
-                if (st.last) {                                           // end of this image segment: release f and f+1 too
-                    umma_commit_c3(bar_aempty + 8 * ((j - 2) % p.R));
-                    umma_commit_c3(bar_aempty + 8 * ((j - 1) % p.R));
+                int sl[3];
+                sl[0] = slot_first;
+                sl[1] = slot_first + 1 == R ? 0 : slot_first + 1;
+                sl[2] = sl[1] + 1 == R ? 0 : sl[1] + 1;
+                if (elected) {
+                    umma_commit_c3(bar_tfull + 8 * buf);
+                    umma_commit_c3(bar_aempty + 8 * sl[0]);              // row f-1 is not needed by later steps
+                    if (st.last) {                                       // end of this image segment: release f and f+1 too
+                        umma_commit_c3(bar_aempty + 8 * sl[1]);
+                        umma_commit_c3(bar_aempty + 8 * sl[2]);
+                    }
                 }
+                __syncwarp();
             }
-            if (p.prof) {
+            if (p.prof && lane == 0) {
                 p.prof[blockIdx.x * 16 + 2] = mw_afull; p.prof[blockIdx.x * 16 + 3] = mw_tempty;
                 p.prof[blockIdx.x * 16 + 4] = mw_wfull; p.prof[blockIdx.x * 16 + 5] = clock64() - tstart;
             }
+            (void)j;
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
+        // Two independent warp sets (w4..w7, w8..w11), each covering the 128 accumulator rows.  The store units of a step
+        // ((M tile, column panel) pairs = one TMA box each) alternate between the sets; a set has its own named barrier,
+        // its own elected TMA thread (stores, residual loads and bulk-group waits are per thread) and its own staging
+        // panels, so the two halves of a step's epilogue never wait for each other.
         const int q = warp & 3, r = q * 32 + lane, set = (warp - 4) >> 2, et = threadIdx.x - 128;
+        const bool tma_thread = (et == 128 * set);
         float* spar = reinterpret_cast<float*>(smem_raw + (s_par - smem_u32(smem_raw)));
-        const int nchunks = p.N / 32, njobs = p.n_mt * nchunks;
-        constexpr int MAXJ = 4;                                          // n_mt * N <= 256  =>  <= 8 jobs, 4 per warp set
+        const int nunits = p.n_mt * npanels_out, cpp = p.panel_cols / 32;      // store units per step, 32-column chunks per panel
+        auto set_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + set) : "memory"); };
         int step = 0, last_nt = -1;
         long long ew_store = 0, ew_tfull = 0, ew_res = 0, ew_body = 0;
         const long long tstart = p.prof ? clock64() : 0;
-        for (long long s = s_beg; s < s_end; ++s, ++step) {
-            const C3Step st = c3_step(p, s, s_beg, s_end);
-            const int n0 = st.nt * p.N, t0 = st.tt * p.tb, b0 = st.bg * p.nb, buf = step & 1;
-            { C3_T0(); if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); C3_ACC(ew_store); }   // staging free again
-            if (st.nt != last_nt) {
-                for (int c = et; c < p.N; c += 256) spar[c] = p.bias ? __ldg(p.bias + n0 + c) : 0.f;
-                last_nt = st.nt;
+        const bool has_res = p.res != nullptr && !(p.dbg & 1);
+        const int nbuf = p.stg_bufs;
+        // The residual panel of a unit is TMA-loaded INTO that unit's output staging panel (same box geometry and swizzle);
+        // the epilogue reads it from there and overwrites it in place.  With three staging buffers the load for step s+1 is
+        // issued at the START of step s (its buffer was last read by the store of step s-2, long drained): a full step of
+        // lead time.  With two it can only be issued at the end of step s, with one in line.
+        const uint32_t unit_tx = (uint32_t)(p.panel_bytes * (p.case_b ? p.P * p.nb : 128));
+        int nmine = 0;
+        for (int u = set; u < nunits; u += 2) ++nmine;
+        auto issue_res = [&](const C3Step& x, int ob) {
+            mbar_expect_tx(bar_rfull + 8 * (3 * set + ob), unit_tx * (uint32_t)nmine);
+            for (int u = set; u < nunits; u += 2) {
+                const int mt = u / npanels_out, pn = u - mt * npanels_out;
+                tma_load_4d(stg + (uint32_t)(ob * obuf_bytes + mt * tile_bytes + pn * panel_stride), &p.rmap,
+                            bar_rfull + 8 * (3 * set + ob), x.nt * p.N + pn * p.panel_cols, p.case_b ? 0 : x.tt * p.tb + 128 * mt,
+                            x.f, x.bg * p.nb);
             }
-            epi_bar_sync();
-            // residual rows are fetched before the accumulator wait (their latency overlaps the MMAs of this step)
-            uint4 rr[MAXJ][4];
-            const long long tres = p.prof ? clock64() : 0;
-#pragma unroll
-            for (int jj = 0; jj < MAXJ; ++jj) {
-                const int job = set + 2 * jj;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) rr[jj][i] = make_uint4(0u, 0u, 0u, 0u);
-                if (job < njobs) {
-                    const int mt = job / nchunks, c = (job % nchunks) * 32;
-                    const int i = mt * 128 + r, u = i / p.P, tti = i - u * p.P;
-                    const bool ok = u < p.nb && tti < p.tb && (t0 + tti) < p.T && (b0 + u) < p.B;
-                    if (ok && p.res != nullptr) {
-                        const long long pos = ((long long)(b0 + u) * p.F + st.f) * p.T + t0 + tti;
-                        const uint4* src = reinterpret_cast<const uint4*>((const unsigned short*)p.res + pos * p.res_ld + n0 + c);
-#pragma unroll
-                        for (int i2 = 0; i2 < 4; ++i2) rr[jj][i2] = __ldg(src + i2);
-                    }
+        };
+        if (has_res && nbuf >= 2 && tma_thread && nmine > 0 && s_beg < s_end) issue_res(C3Iter(p, s_beg, s_end).cur(p), 0);
+        int ob = 0;                                          // == step % nbuf
+        uint32_t rph = 0;                                    // == (step / nbuf) & 1
+        for (C3Iter it(p, s_beg, s_end); !it.done(); it.next(p), ++step) {
+            const C3Step st = it.cur(p);
+            const int n0 = st.nt * p.N, t0 = st.tt * p.tb, b0 = st.bg * p.nb, buf = step & 1;
+            const uint32_t sbuf = stg + (uint32_t)(ob * obuf_bytes);
+            const int ob_next = ob + 1 == nbuf ? 0 : ob + 1;
+            if (nbuf == 1) {   // single staging buffer: free once this set's previous store has read it
+                C3_T0();
+                if (tma_thread) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (has_res && nmine > 0) issue_res(st, 0);
+                }
+                C3_ACC(ew_store);
+            } else if (nbuf == 3 && tma_thread) {   // buffer of step s+1 == buffer of step s-2: drained unless 2 stores pend
+                C3_T0();
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                C3_ACC(ew_store);
+                if (has_res && nmine > 0) {
+                    C3Iter nx = it;
+                    nx.next(p);
+                    if (!nx.done()) issue_res(nx.cur(p), ob_next);
                 }
             }
-            if (p.prof) ew_res += clock64() - tres;
+            if (st.nt != last_nt) {     // (all 256 epilogue threads: both sets walk the same steps)
+                if (last_nt >= 0) epi_bar_sync();
+                for (int c = et; c < p.N; c += 256) spar[c] = p.bias ? __ldg(p.bias + n0 + c) : 0.f;
+                last_nt = st.nt;
+                epi_bar_sync();
+            }
+            set_bar();
             { C3_T0(); mbar_wait(bar_tfull + 8 * buf, (((uint32_t)step) >> 1) & 1u); C3_ACC(ew_tfull); }
             tc_fence_after();
+            if (has_res && nmine > 0) {
+                C3_T0();
+                mbar_wait(bar_rfull + 8 * (3 * set + ob), rph);
+                C3_ACC(ew_res);
+            }
             const long long tbody = p.prof ? clock64() : 0;
-#pragma unroll
-            for (int jj = 0; jj < MAXJ; ++jj) {
-                const int job = set + 2 * jj;
-                if (job < njobs) {
-                    const int mt = job / nchunks, c = (job % nchunks) * 32;
+            for (int u = set; u < nunits && !(p.dbg & 1); u += 2) {
+                const int mt = u / npanels_out, pn = u - mt * npanels_out;
+                const uint32_t pbase = sbuf + (uint32_t)(mt * tile_bytes + pn * panel_stride);
+                for (int cc = 0; cc < cpp; ++cc) {
+                    const int c = pn * p.panel_cols + cc * 32;
                     uint32_t raw[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.n_mt + mt) * p.N + c), raw);
                     tmem_ld_wait();
@@ -278,39 +387,50 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
                         v[4 * i] = __uint_as_float(raw[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + b4.y;
                         v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + b4.w;
                     }
-                    if (p.res != nullptr) {
+                    if (has_res) {
+                        float rin[32];
+                        stage_load32(pbase, r, p.panel_bytes, cc * 32, DT, rin);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float x8[8];
-                            ws_unpack8(rr[jj][i], DT, x8);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) v[8 * i + k] += x8[k];
-                        }
+                        for (int i = 0; i < 32; ++i) v[i] += rin[i];
                     }
                     if (p.relu) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
                     // rows that are no output position (halo columns, rows past T or B) hold junk: the TMA store clips them
-                    stage_store32(stg + (uint32_t)(mt * tile_bytes + (c / p.panel_cols) * panel_stride), r, p.panel_bytes,
-                                  c % p.panel_cols, DT, v);
+                    stage_store32(pbase, r, p.panel_bytes, cc * 32, DT, v);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            epi_bar_sync();
-            if (et == 0) {
-                for (int mt = 0; mt < p.n_mt; ++mt)
-                    for (int pn = 0; pn < npanels_out; ++pn)
-                        tma_store_4d(&p.omap, stg + (uint32_t)(mt * tile_bytes + pn * panel_stride), n0 + pn * p.panel_cols,
+            set_bar();
+            if (tma_thread) {
+                if (!(p.dbg & 1)) {
+                    for (int u = set; u < nunits; u += 2) {
+                        const int mt = u / npanels_out, pn = u - mt * npanels_out;
+                        tma_store_4d(&p.omap, sbuf + (uint32_t)(mt * tile_bytes + pn * panel_stride), n0 + pn * p.panel_cols,
                                      p.case_b ? 0 : t0 + 128 * mt, st.f, b0);
+                    }
+                }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (nbuf == 2) {   // the other buffer (this set's store of step s-1) must be drained before anything lands in it
+                    C3_T0();
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    C3_ACC(ew_store);
+                    if (has_res && nmine > 0) {
+                        C3Iter nx = it;
+                        nx.next(p);
+                        if (!nx.done()) issue_res(nx.cur(p), ob_next);
+                    }
+                }
             }
+            ob = ob_next;
+            if (ob == 0) rph ^= 1u;
             if (p.prof) ew_body += clock64() - tbody;
         }
-        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (tma_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (p.prof && et == 0) {
             p.prof[blockIdx.x * 16 + 6] = ew_store; p.prof[blockIdx.x * 16 + 7] = ew_tfull; p.prof[blockIdx.x * 16 + 8] = ew_res;
             p.prof[blockIdx.x * 16 + 9] = ew_body; p.prof[blockIdx.x * 16 + 10] = clock64() - tstart;
@@ -328,14 +448,39 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
 
 }  // namespace
 
+namespace {
+template <int DT, int ROWB, int NPAN, int NMT>
+const char* c3_launch_one(const WsC3Params* p, cudaStream_t s, bool attr_only) {
+    if (attr_only) {
+        cudaError_t e = cudaFuncSetAttribute(ws_conv3x3_kernel<DT, ROWB, NPAN, NMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC3MaxSmem);
+        return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+    }
+    ws_conv3x3_kernel<DT, ROWB, NPAN, NMT><<<p->grid, kC3Threads, p->smem_bytes, s>>>(*p);
+    return nullptr;
+}
+// (operand row bytes, K panels per tap, M tiles per step): 64-byte rows only exist with one panel (C = 32)
+template <int DT>
+const char* c3_dispatch(const WsC3Params* p, cudaStream_t s, bool attr_only, int rowb, int npan, int nmt) {
+    if (rowb == 64 && npan == 1 && nmt == 1) return c3_launch_one<DT, 64, 1, 1>(p, s, attr_only);
+    if (rowb == 64 && npan == 1 && nmt == 2) return c3_launch_one<DT, 64, 1, 2>(p, s, attr_only);
+    if (rowb == 128 && npan == 1 && nmt == 1) return c3_launch_one<DT, 128, 1, 1>(p, s, attr_only);
+    if (rowb == 128 && npan == 1 && nmt == 2) return c3_launch_one<DT, 128, 1, 2>(p, s, attr_only);
+    if (rowb == 128 && npan == 2 && nmt == 1) return c3_launch_one<DT, 128, 2, 1>(p, s, attr_only);
+    if (rowb == 128 && npan == 2 && nmt == 2) return c3_launch_one<DT, 128, 2, 2>(p, s, attr_only);
+    return "conv3x3: unsupported (row bytes, K panels, M tiles) combination";
+}
+}  // namespace
+
 extern "C" const char* ws_c3_init(void) {
     static unsigned long long done = 0;
     int dev = 0;
     if (!ws_dev_needs_init(&done, &dev)) return nullptr;
-    cudaError_t e = cudaFuncSetAttribute(ws_conv3x3_kernel<WS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC3MaxSmem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(ws_conv3x3_kernel<WS_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC3MaxSmem);
-    if (e != cudaSuccess) { cudaGetLastError(); return cudaGetErrorString(e); }
+    const int combos[6][3] = {{64, 1, 1}, {64, 1, 2}, {128, 1, 1}, {128, 1, 2}, {128, 2, 1}, {128, 2, 2}};
+    for (auto& c : combos) {
+        const char* m = c3_dispatch<WS_BF16>(nullptr, nullptr, true, c[0], c[1], c[2]);
+        if (!m) m = c3_dispatch<WS_F16>(nullptr, nullptr, true, c[0], c[1], c[2]);
+        if (m) { cudaGetLastError(); return m; }
+    }
     ws_dev_mark_init(&done, dev);
     return nullptr;
 }
@@ -343,9 +488,11 @@ extern "C" const char* ws_c3_init(void) {
 extern "C" int ws_c3_max_smem(void) { return kC3MaxSmem; }
 
 extern "C" const char* ws_c3_launch(const WsC3Params* p, cudaStream_t s) {
-    if (p->dtype == WS_BF16) ws_conv3x3_kernel<WS_BF16><<<p->grid, kC3Threads, p->smem_bytes, s>>>(*p);
-    else if (p->dtype == WS_F16) ws_conv3x3_kernel<WS_F16><<<p->grid, kC3Threads, p->smem_bytes, s>>>(*p);
+    const char* m;
+    if (p->dtype == WS_BF16) m = c3_dispatch<WS_BF16>(p, s, false, p->row_bytes, p->npan, p->n_mt);
+    else if (p->dtype == WS_F16) m = c3_dispatch<WS_F16>(p, s, false, p->row_bytes, p->npan, p->n_mt);
     else return "conv3x3: 16-bit activations only";
+    if (m) return m;
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -443,22 +443,31 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
         q->n_bg = (B + q->nb - 1) / q->nb;
         q->slot_rows = (std::max(q->rows_loaded, 128 * n_mt + 2) + 7) & ~7;
         if (2 * n_mt * q->N > 512) return false;
-        q->panel_bytes = q->N * 2 >= 128 ? 128 : q->N * 2;
-        q->panel_cols = q->panel_bytes / 2;
+        // output panels (= TMA store units): 64 columns, or 32 when that is what it takes to give each of the two epilogue
+        // warp sets its own unit
+        q->panel_cols = std::min(64, q->N);
+        if (q->panel_cols == 64 && n_mt * (q->N / 64) < 2) q->panel_cols = 32;
+        q->panel_bytes = q->panel_cols * 2;
         q->stg_rows = case_b ? 136 : 128;
         const int slot_bytes = q->npan * q->slot_rows * q->row_bytes;
         const int wblk = q->N * q->row_bytes, nwblk = 9 * q->npan;
         const int stg_bytes = n_mt * (q->N / q->panel_cols) * q->stg_rows * q->panel_bytes;
-        const int fixed = stg_bytes + q->N * 4 + 2048 /* alignment slack */;
-        q->w_resident = (budget - fixed - nwblk * wblk) / slot_bytes >= 5;
-        q->w_stages = q->w_resident ? 0 : 3;
-        int R = (budget - fixed - (q->w_resident ? nwblk : q->w_stages) * wblk) / slot_bytes;
-        if (R > WS_C3_MAX_RING) R = WS_C3_MAX_RING;
-        if (const char* er = getenv("WS_C3_RING")) R = std::min(R, atoi(er));
-        if (R < 4) return false;
-        q->R = R;
-        q->smem_bytes = R * slot_bytes + (q->w_resident ? nwblk : q->w_stages) * wblk + fixed;
-        return true;
+        // three output staging buffers with a residual (its TMA load then leads its use by a full step), two without (stores
+        // are never waited for), as long as a ring of >= 5 slots still fits beside them; else one
+        for (int bufs = (res != nullptr && !getenv("WS_C3_NO_3BUF")) ? 3 : 2; bufs >= 1; --bufs) {
+            const int fixed = bufs * stg_bytes + q->N * 4 + 2048 /* alignment slack */;
+            q->w_resident = (budget - fixed - nwblk * wblk) / slot_bytes >= 5;
+            q->w_stages = q->w_resident ? 0 : 3;
+            int R = (budget - fixed - (q->w_resident ? nwblk : q->w_stages) * wblk) / slot_bytes;
+            if (R > WS_C3_MAX_RING) R = WS_C3_MAX_RING;
+            if (const char* er = getenv("WS_C3_RING")) R = std::min(R, atoi(er));
+            if (R < (bufs >= 2 ? 5 : 4)) continue;
+            q->R = R;
+            q->stg_bufs = bufs;
+            q->smem_bytes = R * slot_bytes + (q->w_resident ? nwblk : q->w_stages) * wblk + fixed;
+            return true;
+        }
+        return false;
     };
     bool ok = false;
     if (T + 2 <= 66) ok = try_geom(true, T, 1);
@@ -494,10 +503,18 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
         cuuint32_t box[4] = {(cuuint32_t)q->panel_cols, (cuuint32_t)(q->case_b ? q->P : 128), 1, (cuuint32_t)(q->case_b ? q->nb : 1)};
         if (!encode_map(&q->omap, x.dt, out.p, 4, dims, str, box, q->panel_bytes)) return false;
     }
+    q->rmap = q->omap;
+    if (res) {
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)T, (cuuint64_t)F, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)res->ld * 2, (cuuint64_t)T * res->ld * 2, (cuuint64_t)F * T * res->ld * 2};
+        cuuint32_t box[4] = {(cuuint32_t)q->panel_cols, (cuuint32_t)(q->case_b ? q->P : 128), 1, (cuuint32_t)(q->case_b ? q->nb : 1)};
+        if (!encode_map(&q->rmap, x.dt, res->p, 4, dims, str, box, q->panel_bytes)) return false;
+    }
     q->res = res ? res->p : nullptr;
     q->res_ld = res ? res->ld : 0;
     q->bias = bias;
     q->relu = relu ? 1 : 0;
+    if (const char* dbg = getenv("WS_C3_DBG")) q->dbg = atoi(dbg);
     if (getenv("WS_C3_PROF")) {   // tuning aid: synchronous launch + per-role wait-cycle summary on stderr
         long long* prof = nullptr;
         if (cudaMalloc((void**)&prof, (size_t)q->grid * 16 * 8) != cudaSuccess) { set_err("conv3x3: prof buffer"); return false; }
@@ -511,8 +528,8 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
             cudaMemcpy(h.data(), q->prof, h.size() * 8, cudaMemcpyDeviceToHost);
             static const char* names[12] = {"prod.wait_aempty", "prod.total", "mma.wait_afull", "mma.wait_tempty", "mma.wait_wfull",
                                             "mma.total", "epi.wait_store", "epi.wait_tfull", "epi.res_issue", "epi.body", "epi.total", "steps"};
-            fprintf(stderr, "[c3 prof] grid %d R %d n_mt %d nb %d N %d Cin %d w_res %d steps %d:", q->grid, q->R, q->n_mt, q->nb, q->N, q->Cin,
-                    q->w_resident, q->total_steps);
+            fprintf(stderr, "[c3 prof] grid %d R %d n_mt %d nb %d N %d Cin %d w_res %d stg_bufs %d res %d steps %d:", q->grid, q->R, q->n_mt, q->nb,
+                    q->N, q->Cin, q->w_resident, q->stg_bufs, q->res != nullptr, q->total_steps);
             for (int k = 0; k < 12; ++k) {
                 double acc = 0;
                 for (int c = 0; c < q->grid; ++c) acc += (double)h[(size_t)c * 16 + k];

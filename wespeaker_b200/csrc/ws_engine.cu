@@ -533,7 +533,7 @@ View basic_block(Builder& b, const std::string& p, const View& x, int cout, int 
     View o = obuf; o.B = x.B; o.F = Fo; o.T = To; o.C = cout; o.ld = cout;
     // stride-1 3x3 convs of the low-channel stages run the halo-resident kernel (ws_conv3x3.cu): every input row crosses
     // L2 -> SM once instead of once per tap
-    const bool c3 = b.e.use_tc >= 2 && b.e.act_dt != WS_F32 && b.e.opt("conv3x3", 0) != 0;
+    const bool c3 = b.e.use_tc >= 2 && b.e.act_dt != WS_F32 && b.e.opt("conv3x3", 1) != 0;
     auto try_c3 = [&](const View& in, const View& outv, const void* Wd, const float* bias, const View* res) -> int {
         if (!c3) return 0;
         Op op;

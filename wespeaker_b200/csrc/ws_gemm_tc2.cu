@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
     __shared__ __align__(8) uint64_t s_bar[2 * WS_TC_MAX_STAGES + 6];
     __shared__ uint32_t s_tmem;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int a_bytes = 128 * p.bk_bytes, b_bytes = p.bn * p.bk_bytes;
     const int stage_bytes = a_bytes + b_bytes;
@@ -136,17 +136,20 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        // all 32 lanes run the loop with warp-uniform values; only the tcgen05 instructions are predicated on the elected
+        // lane (see elect_one() in ws_tc_common.cuh)
+        {
+            const uint32_t elected = elect_one();
             const int kper = p.bk_bytes / 32;
-            int it = 0, j = 0;
+            int s = 0, j = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
                 const int buf = j & 1;
                 mbar_wait(bar_tempty + 8 * buf, (((uint32_t)j >> 1) & 1u) ^ 1u);  // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * p.bn);
-                for (int kit = 0; kit < p.nk_total * p.nsplit; ++kit, ++it) {
-                    const int s = it % p.nstages;
-                    const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+                const int nkit = p.nk_total * p.nsplit;
+                for (int kit = 0; kit < nkit; ++kit) {
                     mbar_wait(bar_full + 8 * s, ph);
                     tc_fence_after();
                     const uint32_t sa = ring + (uint32_t)(s * stage_bytes);
@@ -154,12 +157,16 @@ __global__ void __launch_bounds__(kThreads2, 1) ws_conv_gemm_tc2_kernel(const __
                     if (p.dbg_shift >= 0)  // row-shifted operand read: start one row in, base_offset field [49,52)
                         adesc = umma_desc(sa + (uint32_t)p.bk_bytes, p.bk_bytes) | ((uint64_t)(p.dbg_shift & 7) << 49);
                     const uint64_t bdesc = umma_desc(sa + (uint32_t)a_bytes, p.bk_bytes);
-                    for (int k = 0; k < kper; ++k)
-                        umma<KIND>(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                                   (uint32_t)((kit | k) != 0));
-                    umma_commit(bar_empty + 8 * s);
+                    if (elected) {
+                        for (int k = 0; k < kper; ++k)
+                            umma<KIND>(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                                       (uint32_t)((kit | k) != 0));
+                        umma_commit(bar_empty + 8 * s);
+                    }
+                    if (++s == p.nstages) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(bar_tfull + 8 * buf);
+                if (elected) umma_commit(bar_tfull + 8 * buf);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {

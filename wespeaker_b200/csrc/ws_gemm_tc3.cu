@@ -23,7 +23,7 @@
 #ifdef WS_TC3_PROFILE
 __device__ unsigned long long g_prof[16];
 #define PROF_T(x) const long long x = clock64()
-#define PROF_ADD(i, v) do { if (blockIdx.x == 0) atomicAdd(&g_prof[i], (unsigned long long)(v)); } while (0)
+#define PROF_ADD(i, v) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_prof[i], (unsigned long long)(v)); } while (0)
 #else
 #define PROF_T(x)
 #define PROF_ADD(i, v)
@@ -101,7 +101,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads3, 1) ws_con
     __shared__ __align__(8) uint64_t s_bar[2 * WS_TC_MAX_STAGES + 6];
     __shared__ uint32_t s_tmem;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
@@ -196,9 +196,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads3, 1) ws_con
         }
     } else if (warp == 1) {
         // ================================ MMA issuer (leader CTA only) ================================
-        if (lane == 0 && leader) {
+        // all 32 lanes run the loop with warp-uniform values; only the tcgen05 instructions are predicated on the elected
+        // lane (see elect_one() in ws_tc_common.cuh)
+        if (leader) {
+            const uint32_t elected = elect_one();
             const int kper = p.bk_bytes / 32;
-            int it = 0, j = 0;
+            int s = 0, j = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x >> 1; tile < p.num_tiles; tile += gridDim.x >> 1, ++j) {
                 const int buf = j & 1;
                 PROF_T(m0);
@@ -207,20 +211,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads3, 1) ws_con
                 PROF_ADD(8, m1 - m0);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * p.bn);
-                for (int kit = 0; kit < p.nk_total * p.nsplit; ++kit, ++it) {
-                    const int s = it % p.nstages;
-                    const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+                const int nkit = p.nk_total * p.nsplit;
+                for (int kit = 0; kit < nkit; ++kit) {
                     mbar_wait(bar_full + 8 * s, ph);
                     tc_fence_after();
                     const uint32_t sa = ring + (uint32_t)(s * stage_bytes);
                     const uint64_t adesc = umma_desc(sa, p.bk_bytes);
                     const uint64_t bdesc = umma_desc(sa + (uint32_t)a_bytes, p.bk_bytes);
-                    for (int k = 0; k < kper; ++k)
-                        umma<KIND>(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                                   (uint32_t)((kit | k) != 0));
-                    umma_commit(bar_empty + 8 * s);
+                    if (elected) {
+                        for (int k = 0; k < kper; ++k)
+                            umma<KIND>(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                                       (uint32_t)((kit | k) != 0));
+                        umma_commit(bar_empty + 8 * s);
+                    }
+                    if (++s == p.nstages) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(bar_tfull + 8 * buf);
+                if (elected) umma_commit(bar_tfull + 8 * buf);
+                __syncwarp();
                 PROF_T(m2);
                 PROF_ADD(9, m2 - m1);
                 PROF_ADD(10, 1);

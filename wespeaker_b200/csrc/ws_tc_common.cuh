@@ -55,6 +55,17 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// Warp index through a shuffle (the compiler then treats the role branches as warp-uniform) and one elected lane.  The MMA
+// issuer warp runs its whole loop on all 32 lanes with warp-uniform values and predicates only the tcgen05 instructions on
+// the elected lane: inside an `if (lane == 0)` region every descriptor has to be moved into uniform registers through an
+// ELECT / R2UR.BROADCAST convergence loop in front of each UTCHMMA (~20 SASS instructions, 65-80 cycles per MMA measured
+// with tools/experimental/mma_rate_probe.cu - longer than a 128 x N x 16 MMA with N <= 128 occupies the tensor pipe).
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t elected;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+    return elected;
+}
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int bk_bytes) {
     const uint64_t layout = bk_bytes == 128 ? 2ull : (bk_bytes == 64 ? 4ull : 6ull);
