@@ -230,6 +230,26 @@ def test_conv3x3_engine_path_matches_generic_path(name, prec, B, T):
     assert np.isfinite(e1).all() and rel <= 3e-3
 
 
+@pytest.mark.parametrize("prec,B,T,block", [("bf16", 3, 198, 0), ("fp16", 2, 455, 0), ("bf16", 2, 98, 0), ("bf16", 1, 998, 0),
+                                            ("bf16", 5, 300, 1), ("fp16", 2, 200, 1)])
+def test_campplus_fused_dense_layers_match_unfused(prec, B, T, block):
+    """ws_cam_dense.cu (BN-ReLU on load, 1x1 conv, context gate and dilated conv of a CAMDenseTDNNLayer in one launch; with
+    `cam_block` all layers of a dense block in one launch) against the 4-launch path: same roundings of h and of the new
+    channels, so the embeddings agree to summation-order level; and both against the oracle."""
+    feats = torch.from_numpy(syn.make_feats(B, T, 80, seed=13))
+    mf = from_synthetic("CAMPPlus", 0, precision=prec)
+    mf.set_option("cam_block", block)
+    mu = from_synthetic("CAMPPlus", 0, precision=prec)
+    mu.set_option("cam_fused", 0)
+    ef, eu = mf.embed(feats.to(DEV)).cpu().numpy(), mu.embed(feats.to(DEV)).cpu().numpy()
+    ref = models_torch.forward("CAMPPlus", syn.make_state_dict("CAMPPlus", 0), feats).numpy()
+    print(f"cam fused vs unfused {prec} B{B} T{T} block={block}: rel {rel_l2(ef, eu).max():.2e}; vs oracle fused {rel_l2(ef, ref).max():.2e} "
+          f"unfused {rel_l2(eu, ref).max():.2e}; launches {mf.last_launches()} vs {mu.last_launches()}")
+    assert np.isfinite(ef).all() and rel_l2(ef, eu).max() <= 3e-3
+    assert rel_l2(ef, ref).max() <= TC_TOL[prec]
+    assert mf.last_launches() < mu.last_launches() - 100
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["bf16-tc2", "fp16-tc2", "tf32-tc2", "tf32x3-tc2", "bf16-tc3", "fp16-tc3", "tf32-tc3", "tf32x3-tc3"])
 @pytest.mark.parametrize("variant", ["bias_relu", "bn", "bn_res_relu"])

@@ -366,6 +366,33 @@ struct WsC3Params {
     int dbg;                       // tuning aid (WS_C3_DBG): knock-out bits 1 = no epilogue work, 2 = no input TMA loads, 8 = no MMAs
 };
 
+// fused CAM++ dense layer (ws_cam_dense.cu).  One descriptor per CAMDenseTDNNLayer, device-resident (the tensor maps are
+// read by the TMA unit from global memory), 64-byte aligned.
+struct alignas(64) WsCamLayer {
+    CUtensorMap w1map;        // linear1 weights with nonlinear2's BN folded in: [128][Cin] K-major, box (64, 128), SWIZZLE_128B
+    CUtensorMap wlmap;        // cam_layer.linear_local weights [32][3*128] tap-major, box (64, 32), SWIZZLE_128B
+    const float* bn1_scale;   // nonlinear1 (BN + ReLU on the growing concat), [Cin]
+    const float* bn1_shift;
+    const float* bias2;       // nonlinear2 shift, [128]
+    const float* w1c_t;       // cam_layer.linear1 weight transposed to [128][64]
+    const float* b1c;         // [64]
+    const float* w2c_t;       // cam_layer.linear2 weight transposed to [64][32]
+    const float* b2c;         // [32]
+    int cin, dil;
+    int pad_[12];
+};
+struct WsCamParams {
+    CUtensorMap xmap;         // concat buffer (Cmax, T, B): box (64, 128, 1), SWIZZLE_128B (operand panels of the 1x1 conv)
+    CUtensorMap omap;         // same buffer: box (32, 128, 1), SWIZZLE_64B (the layer's 32 new channels)
+    const WsCamLayer* layers;
+    int l0, l1;               // layers [l0, l1) run back to back inside one launch
+    int B, T, nmt, seg_len, dtype;
+    uint32_t idesc1, idesc2;  // UMMA instruction descriptors: M=128 N=128 / N=32
+    int nstages, hrows;       // ring stages (32 KB each); rows per panel of the hidden operand buffer (16 + 128 * nmt)
+    int grid, smem_bytes;
+    long long* prof;          // tuning aid (WS_CAM_PROF=1): phase timestamps of CTA 0, first layer; else null
+};
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are PER DEVICE: init guards are keyed by the current
 // device so that a second engine on another GPU of the same process gets its opt-in too (one bit per device ordinal).
 inline bool ws_dev_needs_init(unsigned long long* mask, int* dev_out) {
@@ -395,6 +422,9 @@ extern "C" {
 #endif
 const char* ws_res2_init(void);
 const char* ws_res2_launch(const WsRes2Params* p, cudaStream_t s);
+const char* ws_cam_init(void);
+int ws_cam_max_smem(void);
+const char* ws_cam_launch(const WsCamParams* p, cudaStream_t s);
 const char* ws_c3_init(void);
 int ws_c3_max_smem(void);
 const char* ws_c3_launch(const WsC3Params* p, cudaStream_t s);

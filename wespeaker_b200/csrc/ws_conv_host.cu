@@ -544,6 +544,81 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
     return true;
 }
 
+extern "C" int ws_cam_smem_bytes(int nmt, int nstages);
+
+bool cam_layer_fill(WsCamLayer* L, int dt, const void* W1, const void* Wl, const float* bn1_scale, const float* bn1_shift,
+                    const float* bias2, const float* w1c_t, const float* b1c, const float* w2c_t, const float* b2c, int cin,
+                    int dil) {
+    memset(L, 0, sizeof(*L));
+    if (cin % 32 != 0 || cin > 1024 || dil < 1 || dil > 8) { set_err("cam_dense: cin must be a multiple of 32 (<= 1024), dilation <= 8"); return false; }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)cin, 128};
+        cuuint64_t str[1] = {(cuuint64_t)cin * 2};
+        cuuint32_t box[2] = {64, 128};
+        if (!encode_map(&L->w1map, dt, W1, 2, dims, str, box, 128)) return false;
+    }
+    {
+        cuuint64_t dims[2] = {384, 32};
+        cuuint64_t str[1] = {384 * 2};
+        cuuint32_t box[2] = {64, 32};
+        if (!encode_map(&L->wlmap, dt, Wl, 2, dims, str, box, 128)) return false;
+    }
+    L->bn1_scale = bn1_scale; L->bn1_shift = bn1_shift; L->bias2 = bias2;
+    L->w1c_t = w1c_t; L->b1c = b1c; L->w2c_t = w2c_t; L->b2c = b2c;
+    L->cin = cin; L->dil = dil;
+    return true;
+}
+
+bool make_cam_dense_op(const View& X, const WsCamLayer* layers_dev, int l0, int l1, Op* op, bool* unsupported) {
+    *unsupported = false;
+    const int T = X.T, B = X.B;
+    if (X.dt == WS_F32 || X.F != 1 || T < 1 || T > 512 || (X.ld * 2) % 16 != 0 || getenv("WS_NO_CAM_FUSED")) {
+        *unsupported = true;
+        return false;
+    }
+    auto q = std::make_shared<WsCamParams>();
+    memset(q.get(), 0, sizeof(WsCamParams));
+    q->layers = layers_dev; q->l0 = l0; q->l1 = l1;
+    q->B = B; q->T = T; q->nmt = (T + 127) / 128; q->seg_len = 100; q->dtype = X.dt;
+    q->hrows = 16 + 128 * q->nmt;
+    int nst = 6;
+    while (nst >= 2 && ws_cam_smem_bytes(q->nmt, nst) > ws_cam_max_smem()) --nst;
+    if (nst < 2) { *unsupported = true; return false; }
+    q->nstages = nst;
+    q->smem_bytes = ws_cam_smem_bytes(q->nmt, nst);
+    const uint32_t fmt = X.dt == WS_BF16 ? 1u : 0u;
+    q->idesc1 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    q->idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    q->grid = B;
+    cuuint64_t dims[3] = {(cuuint64_t)X.C, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t str[2] = {(cuuint64_t)X.ld * 2, (cuuint64_t)T * X.ld * 2};
+    cuuint32_t boxx[3] = {64, 128, 1}, boxo[3] = {32, 128, 1};
+    if (!encode_map(&q->xmap, X.dt, X.p, 3, dims, str, boxx, 128)) return false;
+    if (!encode_map(&q->omap, X.dt, X.p, 3, dims, str, boxo, 64)) return false;
+    if (getenv("WS_CAM_PROF")) {   // tuning aid: synchronous launch + phase timestamps (cycles since kernel start) of CTA 0
+        long long* prof = nullptr;
+        if (cudaMalloc((void**)&prof, 16 * 8) != cudaSuccess) { set_err("cam_dense: prof buffer"); return false; }
+        cudaMemset(prof, 0, 16 * 8);
+        q->prof = prof;
+        *op = [q](cudaStream_t s) -> const char* {
+            const char* m = ws_cam_launch(q.get(), s);
+            if (m) return m;
+            cudaStreamSynchronize(s);
+            long long h[16];
+            cudaMemcpy(h, q->prof, sizeof h, cudaMemcpyDeviceToHost);
+            static const char* names[12] = {"params", "transform_done", "acc1", "epi1", "colsums", "ctx", "hid_partial", "hid", "gate",
+                                            "acc2", "stored", "complete"};
+            fprintf(stderr, "[cam prof] B %d T %d l0 %d nst %d:", q->B, q->T, q->l0, q->nstages);
+            for (int k = 0; k < 12; ++k) fprintf(stderr, " %s=%lld", names[k], h[k]);
+            fprintf(stderr, "\n");
+            return nullptr;
+        };
+        return true;
+    }
+    *op = [q](cudaStream_t s) { return ws_cam_launch(q.get(), s); };
+    return true;
+}
+
 }  // namespace ws
 
 // ------------------------------------------------------------------------------------------------ C ABI: ws_conv

@@ -776,8 +776,49 @@ bool build_campplus(Builder& b) {
     }
     const int dt = e.act_dt;
     const long long npos = (long long)B * Tp;
+    // Fused dense layers (ws_cam_dense.cu): one launch per CAMDenseTDNNLayer (or per block with cam_block = 1) instead of four
+    const bool cam_fused = e.use_tc >= 2 && e.act_dt != WS_F32 && e.opt("cam_fused", 1) != 0 && Tp <= 512;
     for (int bl = 0; bl < 3 && b.good(); ++bl) {
-        for (int j = 1; j <= nl[bl] && b.good(); ++j) {
+        bool fused_done = false;
+        if (cam_fused) {
+            std::vector<WsCamLayer> hl((size_t)nl[bl]);
+            bool okl = true;
+            for (int j = 1; j <= nl[bl] && okl; ++j) {
+                const std::string p = "xvector.block" + std::to_string(bl + 1) + ".tdnnd" + std::to_string(j);
+                const int cin = c0[bl] + (j - 1) * growth;
+                std::vector<float> s1, h1, s2, h2, w1, wl;
+                int co, ci2, nt;
+                const HostT* c1w = b.w.get(p + ".cam_layer.linear1.weight");
+                const HostT* c2w = b.w.get(p + ".cam_layer.linear2.weight");
+                okl = c1w && c2w && b.w.bn(p + ".nonlinear1.batchnorm", true, s1, h1) && b.w.bn(p + ".nonlinear2.batchnorm", true, s2, h2) &&
+                      b.w.pack_conv(p + ".linear1.weight", &s2, w1, &co, &ci2, &nt) &&
+                      b.w.pack_conv(p + ".cam_layer.linear_local.weight", nullptr, wl, &co, &ci2, &nt);
+                if (!okl) break;
+                std::vector<float> w1ct((size_t)bnc * (bnc / 2)), w2ct((size_t)(bnc / 2) * growth);
+                for (int o = 0; o < bnc / 2; ++o)
+                    for (int c = 0; c < bnc; ++c) w1ct[(size_t)c * (bnc / 2) + o] = c1w->v[(size_t)o * bnc + c];
+                for (int g = 0; g < growth; ++g)
+                    for (int o = 0; o < bnc / 2; ++o) w2ct[(size_t)o * growth + g] = c2w->v[(size_t)g * (bnc / 2) + o];
+                okl = cam_layer_fill(&hl[(size_t)j - 1], e.act_dt, b.w.act("w:" + p + ".linear1", w1), b.w.act("w:" + p + ".local", wl),
+                                     b.w.f32("bns:" + p + ".n1", s1), b.w.f32("bnh:" + p + ".n1", h1), b.w.f32("bnh:" + p + ".n2", h2),
+                                     b.w.f32("w1ct:" + p, w1ct), b.w.vec(p + ".cam_layer.linear1.bias"), b.w.f32("w2ct:" + p, w2ct),
+                                     b.w.vec(p + ".cam_layer.linear2.bias"), cin, dil[bl]);
+            }
+            if (!okl || !b.good()) { b.ok = false; break; }
+            const WsCamLayer* ldev = (const WsCamLayer*)b.w.upload("camlayers:" + std::to_string(bl), hl.data(), hl.size() * sizeof(WsCamLayer));
+            if (!b.good()) break;
+            const bool whole = e.opt("cam_block", 1) != 0;
+            fused_done = true;
+            for (int j = 0; j < nl[bl]; j += whole ? nl[bl] : 1) {
+                Op op;
+                bool unsupported = false;
+                if (make_cam_dense_op(X[bl], ldev, j, whole ? nl[bl] : j + 1, &op, &unsupported)) b.push(std::move(op));
+                else if (unsupported && j == 0) { fused_done = false; break; }
+                else { b.ok = false; break; }
+            }
+            if (!b.good()) break;
+        }
+        for (int j = 1; j <= nl[bl] && b.good() && !fused_done; ++j) {
             const std::string p = "xvector.block" + std::to_string(bl + 1) + ".tdnnd" + std::to_string(j);
             const int cin = c0[bl] + (j - 1) * growth;
             std::vector<float> s1, h1, s2, h2, w1, wl;
@@ -1035,6 +1076,7 @@ int ws_engine_create(const char* model_name, const char* precision, int feat_dim
     WS_CKS(ws_res2_init());
     WS_CKS(ws_tc3_init());
     WS_CKS(ws_c3_init());
+    WS_CKS(ws_cam_init());
     WS_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     WS_CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
     WS_CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
@@ -1047,7 +1089,7 @@ int ws_engine_set_option(ws_engine* e, const char* key, long long value) {
     const std::string k = key;
     if (k == "force_simt") { if (value) e->use_tc = 0; }
     else if (k == "tc_version") { if (e->use_tc) e->use_tc = value >= 3 ? 3 : (value >= 2 || e->split ? 2 : 1); }
-    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused" && k != "se_fused" && k != "se_colsum" && k != "conv3x3") { set_err("unknown option " + k); return 1; }
+    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused" && k != "se_fused" && k != "se_colsum" && k != "conv3x3" && k != "cam_fused" && k != "cam_block") { set_err("unknown option " + k); return 1; }
     e->opts[k] = value;
     e->plans.clear();
     return 0;

@@ -88,4 +88,13 @@ bool make_res2_op(const View& x, const View& out, const void* W7, const float* b
 bool make_conv3x3_op(const View& x, const View& out, const void* W, const float* bias, const View* res, bool relu,
                      Op* op, bool* unsupported);
 
+// Fused CAM++ dense layers (ws_cam_dense.cu).  cam_layer_fill builds one host-side layer descriptor (weights are device
+// pointers in the activation dtype: W1 [128][cin] with BN2 folded, Wl [32][3*128] tap-major; everything else fp32 device
+// arrays).  make_cam_dense_op launches layers [l0, l1) of a device-resident descriptor array over the concat buffer X
+// (B,1,T,Cmax).  *unsupported = true when the shape is outside the kernel's envelope (T > 512, fp32 activations).
+bool cam_layer_fill(WsCamLayer* L, int dt, const void* W1, const void* Wl, const float* bn1_scale, const float* bn1_shift,
+                    const float* bias2, const float* w1c_t, const float* b1c, const float* w2c_t, const float* b2c, int cin,
+                    int dil);
+bool make_cam_dense_op(const View& X, const WsCamLayer* layers_dev, int l0, int l1, Op* op, bool* unsupported);
+
 }  // namespace ws
