@@ -11,6 +11,7 @@
 // magnitude ~256 have ulp 3e-5).  B200 runs DFMA at half the FFMA rate, so this is DFMA-bound, not HBM-bound:
 // 128x64 block tile, 8x4 register tile per thread, K streamed through shared memory.
 #include "ws_kernels.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -78,6 +79,118 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(const double* __restrict_
             const double v = acc[i][j] + rc + (colc != nullptr ? colc[c] : 0.0);
             if (out_is_f64) ((double*)out)[r * out_ld + c] = v;
             else ((float*)out)[r * out_ld + c] = (float)v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- DMMA variant
+// Same GEMM on the fp64 tensor path (mma.sync.m8n8k4.f64): one instruction = 8x8x4 FMAs per warp instead of 32, which is
+// what lets a kernel approach the DFMA peak (the FFMA-style loop above is instruction-issue bound at ~0.4 of it).
+// 128x128 block tile, 8 warps of 32x64 (4 x 8 m8n8 tiles, 64 accumulator doubles per thread), K streamed in chunks of 16
+// through a cp.async double buffer; shared rows are padded to 20 doubles so the 8-row x 4-column fragment loads of a
+// half-warp hit 32 distinct banks.
+constexpr int DBM = 128, DBN = 128, DBK = 16, DPITCH = 20;
+constexpr int kDmmaSmem = 2 * (DBM + DBN) * DPITCH * 8;
+
+__device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <int OUT_F64>
+__global__ void __launch_bounds__(256) dgemm_nt_dmma_kernel(const double* __restrict__ A, const double* __restrict__ Bm,
+                                                            const double* __restrict__ rowc, const double* __restrict__ colc,
+                                                            void* __restrict__ out, long long M, long long N, int K,
+                                                            long long out_ld) {
+    extern __shared__ __align__(16) double dsm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp & 3, wn = warp >> 2;               // 4 warps along M (32 rows each) x 2 along N (64 columns each)
+    const long long m0 = (long long)blockIdx.y * DBM, n0 = (long long)blockIdx.x * DBN;
+    // loader: (128 + 128) rows x 8 chunks of 2 doubles per stage; rows past M / N are clamped (their outputs are never stored)
+    const double* src[8];
+    int dst[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = tid + 256 * (i & 3), row = idx >> 3, ch = idx & 7;
+        if (i < 4) {
+            const long long g = m0 + row < M ? m0 + row : M - 1;
+            src[i] = A + g * (long long)K + ch * 2;
+            dst[i] = row * DPITCH + ch * 2;
+        } else {
+            const long long g = n0 + row < N ? n0 + row : N - 1;
+            src[i] = Bm + g * (long long)K + ch * 2;
+            dst[i] = (DBM + row) * DPITCH + ch * 2;
+        }
+    }
+    auto load_stage = [&](int st, int k0) {
+        double* base = dsm + st * (DBM + DBN) * DPITCH;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cp_async16(base + dst[i], src[i] + k0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int nk = K / DBK;
+    load_stage(0, 0);
+    const int fr = lane >> 2, fk = lane & 3;                // fragment row (A: m, B: n) and k of this lane
+    for (int kc = 0; kc < nk; ++kc) {
+        if (kc + 1 < nk) {
+            load_stage((kc + 1) & 1, (kc + 1) * DBK);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double* As = dsm + (kc & 1) * (DBM + DBN) * DPITCH + (wm * 32 + fr) * DPITCH + fk;
+        const double* Bs = dsm + (kc & 1) * (DBM + DBN) * DPITCH + (DBM + wn * 64 + fr) * DPITCH + fk;
+#pragma unroll
+        for (int k4 = 0; k4 < DBK / 4; ++k4) {
+            double a[4], b[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[i * 8 * DPITCH + k4 * 4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = Bs[j * 8 * DPITCH + k4 * 4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma_8x8x4(acc[i][j], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+    // accumulator fragment: rows lane/4 of each m8 tile, columns 2*(lane%4) + {0,1} of each n8 tile -> 8-byte (fp32) or
+    // 16-byte (fp64) stores, one full 32-byte sector per row and tile
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long r = m0 + wm * 32 + i * 8 + fr;
+        if (r >= M) continue;
+        const double rc = rowc != nullptr ? rowc[r] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long long c = n0 + wn * 64 + j * 8 + fk * 2;
+            if (c >= N) continue;
+            const double v0 = acc[i][j][0] + rc + (colc != nullptr ? colc[c] : 0.0);
+            if (c + 1 < N) {
+                const double v1 = acc[i][j][1] + rc + (colc != nullptr ? colc[c + 1] : 0.0);
+                if (OUT_F64) {
+                    double* o = (double*)out + r * out_ld + c;
+                    if ((((uintptr_t)o) & 15) == 0) *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
+                    else { o[0] = v0; o[1] = v1; }
+                } else {
+                    float* o = (float*)out + r * out_ld + c;
+                    if ((((uintptr_t)o) & 7) == 0) *reinterpret_cast<float2*>(o) = make_float2((float)v0, (float)v1);
+                    else { o[0] = (float)v0; o[1] = (float)v1; }
+                }
+            } else {
+                if (OUT_F64) ((double*)out)[r * out_ld + c] = v0;
+                else ((float*)out)[r * out_ld + c] = (float)v0;
+            }
         }
     }
 }
@@ -193,6 +306,23 @@ const char* ws_launch_dgemm_nt(const double* A, const double* Bm, const double* 
     if (M <= 0 || N <= 0) return nullptr;
     const long long gy = (M + TM - 1) / TM, gx = (N + TN - 1) / TN;
     if (gy > 65535) return "dgemm_nt: M too large for one launch (tile the enroll rows)";
+    // fp64 tensor path (mma.sync m8n8k4) whenever K is a multiple of the 16-deep k chunk and the operand rows are 16-byte
+    // aligned; WS_PLDA_SIMT=1 keeps the FFMA-style kernel as a cross-check
+    if (K % DBK == 0 && K >= DBK && ((uintptr_t)A & 15) == 0 && ((uintptr_t)Bm & 15) == 0 && getenv("WS_PLDA_SIMT") == nullptr) {
+        static unsigned long long attr = 0;
+        int dev = 0;
+        if (ws_dev_needs_init(&attr, &dev)) {
+            cudaFuncSetAttribute(dgemm_nt_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDmmaSmem);
+            cudaFuncSetAttribute(dgemm_nt_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDmmaSmem);
+            ws_dev_mark_init(&attr, dev);
+        }
+        const long long dy = (M + DBM - 1) / DBM, dx = (N + DBN - 1) / DBN;
+        if (dy > 65535) return "dgemm_nt: M too large for one launch (tile the enroll rows)";
+        dim3 dgrid((unsigned)dx, (unsigned)dy);
+        if (out_is_f64) dgemm_nt_dmma_kernel<1><<<dgrid, 256, kDmmaSmem, s>>>(A, Bm, rowc, colc, out, M, N, K, out_ld);
+        else dgemm_nt_dmma_kernel<0><<<dgrid, 256, kDmmaSmem, s>>>(A, Bm, rowc, colc, out, M, N, K, out_ld);
+        return last_err();
+    }
     dim3 grid((unsigned)gx, (unsigned)gy);
     dgemm_nt_kernel<<<grid, 256, 0, s>>>(A, Bm, rowc, colc, out, out_is_f64, M, N, K, out_ld);
     return last_err();
