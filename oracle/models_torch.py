@@ -127,14 +127,28 @@ def _basic_block(x, sd, p, stride):
     return F.relu(out + sc)
 
 
+def _bottleneck(x, sd, p, stride):
+    """`wespeaker/models/resnet.py:72-107`: 1x1 -> 3x3 (stride) -> 1x1 (x4), BN after each, shortcut, ReLU."""
+    out = F.relu(_bn(F.conv2d(x, _t(sd, p + ".conv1.weight", x)), sd, p + ".bn1"))
+    out = F.relu(_bn(F.conv2d(out, _t(sd, p + ".conv2.weight", x), None, stride=stride, padding=1), sd, p + ".bn2"))
+    out = _bn(F.conv2d(out, _t(sd, p + ".conv3.weight", x)), sd, p + ".bn3")
+    if (p + ".shortcut.0.weight") in sd:
+        sc = _bn(F.conv2d(x, _t(sd, p + ".shortcut.0.weight", x), None, stride=stride), sd, p + ".shortcut.1")
+    else:
+        sc = x
+    return F.relu(out + sc)
+
+
 def resnet_forward(sd, feats, num_blocks=(3, 4, 6, 3), two_emb_layer=False, return_taps=False):
-    """`wespeaker/models/resnet.py:171-204`.  feats (B,T,F) -> (tensor(0.), embed_a)."""
+    """`wespeaker/models/resnet.py:171-204`.  feats (B,T,F) -> (tensor(0.), embed_a).  The block type (BasicBlock or
+    Bottleneck) follows from the checkpoint (`conv3` exists only in Bottlenecks)."""
     x = feats.permute(0, 2, 1).unsqueeze(1)
     out = F.relu(_bn(F.conv2d(x, _t(sd, "conv1.weight", x), None, padding=1), sd, "bn1"))
     taps = dict(stem=out)
+    block = _bottleneck if "layer1.0.conv3.weight" in sd else _basic_block
     for li, (nb, stride) in enumerate(zip(num_blocks, (1, 2, 2, 2)), 1):
         for bi in range(nb):
-            out = _basic_block(out, sd, f"layer{li}.{bi}", stride if bi == 0 else 1)
+            out = block(out, sd, f"layer{li}.{bi}", stride if bi == 0 else 1)
         taps[f"layer{li}"] = out
     stats = tstp(out)
     emb = F.linear(stats, _t(sd, "seg_1.weight", x), _t(sd, "seg_1.bias", x))
@@ -209,11 +223,26 @@ def campplus_forward(sd, feats, return_taps=False):
     return taps if return_taps else emb
 
 
+# --------------------------------------------------------------------------- XVEC
+def xvec_forward(sd, feats):
+    """`wespeaker/models/tdnn.py:23-117`: TdnnLayer = BN(ReLU(Conv1d(x))) without padding (T shrinks by 4 + 4 + 6),
+    BN affine=False; TSTP; seg_1 -> ReLU -> seg_bn_1 -> seg_2.  Returns (embed_a, embed_b)."""
+    x = feats.permute(0, 2, 1)
+    for i, dil in enumerate((1, 2, 3, 1, 1), 1):
+        p = f"frame_{i}"
+        x = F.conv1d(x, _t(sd, p + ".conv_1d.weight", x), _t(sd, p + ".conv_1d.bias", x), dilation=dil)
+        x = _bn(F.relu(x), sd, p + ".bn", affine=False)
+    stats = tstp(x)
+    emb_a = F.linear(stats, _t(sd, "seg_1.weight", x), _t(sd, "seg_1.bias", x))
+    o = _bn(F.relu(emb_a), sd, "seg_bn_1", affine=False)
+    return emb_a, F.linear(o, _t(sd, "seg_2.weight", x), _t(sd, "seg_2.bias", x))
+
+
 # --------------------------------------------------------------------------- dispatch
 def forward(model_name: str, sd, feats, **kw):
     """Embedding (B,E) for a reference model name; same call convention as the reference
     callers' ``outputs[-1] if isinstance(outputs, tuple) else outputs`` (extract.py:133-134)."""
-    from wespeaker_b200.synthetic import ECAPA_NAMES, RESNET_NAMES
+    from wespeaker_b200.synthetic import ECAPA_NAMES, RESNET_NAMES, XVEC_NAMES
     feats = torch.as_tensor(feats)
     with torch.no_grad():
         if model_name in ECAPA_NAMES:
@@ -222,6 +251,8 @@ def forward(model_name: str, sd, feats, **kw):
             return resnet_forward(sd, feats, RESNET_NAMES[model_name], **kw)[-1]
         if model_name == "CAMPPlus":
             return campplus_forward(sd, feats, **kw)
+        if model_name in XVEC_NAMES:
+            return xvec_forward(sd, feats)[-1]
     raise ValueError(model_name)
 
 

@@ -81,3 +81,49 @@ def test_default_device_is_the_gpu():
         pytest.skip("CPU-only check")
     with pytest.raises(RuntimeError):
         ep.EmbeddingProcessingChain("length-norm")
+
+
+def test_loads_chains_pickled_by_the_reference_classes(tmp_path):
+    """A chain saved by the reference is a pickle of `wespeaker.utils.embedding_processing.<Class>` objects holding numpy
+    arrays; it must load here (by attribute) and a chain saved here carries no device handle."""
+    import pickle
+    import sys
+    import types
+    fake = types.ModuleType("wespeaker.utils.embedding_processing")
+    for name in ("Lda", "Length_norm", "MeanSubtraction"):
+        cls = type(name, (), {})
+        cls.__module__ = fake.__name__
+        setattr(fake, name, cls)
+    saved = {k: sys.modules.get(k) for k in ("wespeaker", "wespeaker.utils", fake.__name__)}
+    sys.modules.setdefault("wespeaker", types.ModuleType("wespeaker"))
+    sys.modules.setdefault("wespeaker.utils", types.ModuleType("wespeaker.utils"))
+    sys.modules[fake.__name__] = fake
+    try:
+        rng = np.random.default_rng(0)
+        ms, ln, lda = fake.MeanSubtraction(), fake.Length_norm(), fake.Lda()
+        ms.mean = rng.standard_normal(6)
+        lda.m, lda.lda = rng.standard_normal(6), rng.standard_normal((6, 3))
+        p = tmp_path / "ref_chain.pkl"
+        with open(p, "wb") as f:
+            pickle.dump([ms, ln, lda], f)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    with contextlib.redirect_stdout(io.StringIO()):
+        c = ep.EmbeddingProcessingChain(None, device="cpu")
+        c.load(str(p))
+    x = rng.standard_normal((5, 6))
+    y = x - ms.mean
+    y = y / np.sqrt((y ** 2).sum(1, keepdims=True))
+    y = (y - lda.m) @ lda.lda
+    assert [type(l).__name__ for l in c.chain_of_classes] == ["MeanSubtraction", "Length_norm", "Lda"]
+    assert np.abs(c(x) - y).max() < 1e-12
+    yt = c(torch.from_numpy(x))                     # tensor in -> tensor out (stays on its device)
+    assert torch.is_tensor(yt) and np.abs(yt.numpy() - y).max() < 1e-12
+    with contextlib.redirect_stdout(io.StringIO()):
+        c.save(str(tmp_path / "ours.pkl"))
+    blob = (tmp_path / "ours.pkl").read_bytes()
+    assert b"cuda" not in blob and b"torch" not in blob

@@ -23,7 +23,17 @@ from wespeaker_b200.plda import TwoCovPLDA
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-G_MODELS = np.load(os.path.join(HERE, "golden", "models.npz"))
+class _Goldens(dict):
+    """models.npz (hot-path families) + models_f4.npz (section 8(f) rank-4 families) behind the NpzFile interface."""
+    @property
+    def files(self):
+        return list(self.keys())
+
+
+G_MODELS = _Goldens()
+for _f in ("models.npz", "models_f4.npz"):
+    with np.load(os.path.join(HERE, "golden", _f)) as _z:
+        G_MODELS.update({k: _z[k] for k in _z.files})
 G_FBANK = np.load(os.path.join(HERE, "golden", "fbank.npz"))
 G_PLDA = np.load(os.path.join(HERE, "golden", "plda.npz"))
 DEV = "cuda:0"
@@ -446,7 +456,8 @@ def test_tc_v1_kernel_still_matches():
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16", "fp16"])
 @pytest.mark.parametrize("key", ["ECAPA_TDNN_c512__s0_B4_T198", "ECAPA_TDNN_GLOB_c1024__s1_B2_T200",
-                                 "ResNet34__s0_B2_T99", "CAMPPlus__s0_B2_T455"])
+                                 "ResNet34__s0_B2_T99", "CAMPPlus__s0_B2_T455", "ResNet50__s0_B2_T99", "ResNet101__s0_B1_T120",
+                                 "XVEC__s0_B3_T200"])
 def test_model_tensor_core_precisions(key, prec):
     name, seed, B, T = parse_case(key)
     m = from_synthetic(name, seed, precision=prec)

@@ -9,7 +9,17 @@ from oracle import fbank_np, models_torch, plda_np
 from wespeaker_b200 import synthetic as syn
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-G_MODELS = np.load(os.path.join(HERE, "golden", "models.npz"))
+class _Goldens(dict):
+    """models.npz (hot-path families) + models_f4.npz (section 8(f) rank-4 families) behind the NpzFile interface."""
+    @property
+    def files(self):
+        return list(self.keys())
+
+
+G_MODELS = _Goldens()
+for _f in ("models.npz", "models_f4.npz"):
+    with np.load(os.path.join(HERE, "golden", _f)) as _z:
+        G_MODELS.update({k: _z[k] for k in _z.files})
 G_FBANK = np.load(os.path.join(HERE, "golden", "fbank.npz"))
 G_PLDA = np.load(os.path.join(HERE, "golden", "plda.npz"))
 

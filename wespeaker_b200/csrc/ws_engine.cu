@@ -84,6 +84,7 @@ struct ws_engine {
     // model hyper-parameters
     int channels = 512;
     bool glob = false;
+    bool bottleneck = false;   // ResNet50..293: Bottleneck blocks (expansion 4) instead of BasicBlocks
     std::vector<int> num_blocks;
     ~ws_engine() {
         plans.clear();
@@ -611,6 +612,77 @@ View basic_block(Builder& b, const std::string& p, const View& x, int cout, int 
     return o;
 }
 
+// Bottleneck (resnet.py:72-107): 1x1 -> BN -> ReLU -> 3x3 (stride) -> BN -> ReLU -> 1x1 (x4) -> BN, + shortcut, ReLU.  BNs are
+// folded into the conv weights; the 1x1 strided shortcut conv (+ BN) is merged into conv3's GEMM as one extra K range (same
+// output positions), an identity shortcut is the residual input of conv3's epilogue.
+View bottleneck_block(Builder& b, const std::string& p, const View& x, int planes, int s, View h1buf, View h2buf, View obuf) {
+    std::vector<float> s1, h1, s2, h2, s3, h3, w1, w2, w3;
+    int co, ci, nt;
+    View none;
+    if (!b.w.bn(p + ".bn1", true, s1, h1) || !b.w.bn(p + ".bn2", true, s2, h2) || !b.w.bn(p + ".bn3", true, s3, h3) ||
+        !b.w.pack_conv(p + ".conv1.weight", &s1, w1, &co, &ci, &nt) || !b.w.pack_conv(p + ".conv2.weight", &s2, w2, &co, &ci, &nt) ||
+        !b.w.pack_conv(p + ".conv3.weight", &s3, w3, &co, &ci, &nt))
+        return none;
+    const int cout = 4 * planes;
+    const int Fo = (x.F + 2 - 3) / s + 1, To = (x.T + 2 - 3) / s + 1;
+    View a = h1buf; a.B = x.B; a.F = x.F; a.T = x.T; a.C = planes; a.ld = planes;
+    View c = h2buf; c.B = x.B; c.F = Fo; c.T = To; c.C = planes; c.ld = planes;
+    View o = obuf; o.B = x.B; o.F = Fo; o.T = To; o.C = cout; o.ld = cout;
+    WsEpi e1{};
+    e1.bias = b.w.f32("bnh:" + p + ".bn1", h1);
+    e1.act1 = WS_ACT_RELU;
+    b.conv_simple(x, a, b.w.act("w:" + p + ".conv1", w1), 1, 1, 1, 1, 0, 0, 1, 1, e1);
+    if (!b.good()) return none;
+    {   // 3x3: halo-resident kernel when stride 1 and planes <= 128, else the generic conv-GEMM
+        const float* b2 = b.w.f32("bnh:" + p + ".bn2", h2);
+        const void* W2 = b.w.act("w:" + p + ".conv2", w2);
+        bool done = false;
+        if (s == 1 && b.e.use_tc >= 2 && b.e.act_dt != WS_F32 && b.e.opt("conv3x3", 1) != 0) {
+            Op op;
+            bool unsupported = false;
+            if (make_conv3x3_op(a, c, W2, b2, nullptr, true, &op, &unsupported)) { b.push(std::move(op)); done = true; }
+            else if (!unsupported) { b.ok = false; return none; }
+        }
+        if (!done) {
+            WsEpi e2{};
+            e2.bias = b2;
+            e2.act1 = WS_ACT_RELU;
+            b.conv_simple(a, c, W2, 3, 3, 1, 1, 1, 1, s, s, e2);
+        }
+    }
+    if (!b.good()) return none;
+    ConvSpec cs;
+    cs.dt = b.e.act_dt;
+    int F3, T3;
+    int K = add_conv_taps(cs, c, 1, 1, 1, 1, 0, 0, 1, 1, 0, &F3, &T3);
+    std::vector<float> bias3 = h3;
+    if (b.e.sd.count(p + ".shortcut.0.weight") != 0) {
+        std::vector<float> ss, hs, wsv;
+        if (!b.w.bn(p + ".shortcut.1", true, ss, hs) || !b.w.pack_conv(p + ".shortcut.0.weight", &ss, wsv, &co, &ci, &nt)) return none;
+        int F4, T4;
+        const int K2 = add_conv_taps(cs, x, 1, 1, 1, 1, 0, 0, s, s, K, &F4, &T4);
+        if (K2 < 0 || F4 != Fo || T4 != To) { set_err("internal: shortcut shape mismatch"); b.ok = false; return none; }
+        std::vector<float> wm((size_t)cout * (K + K2));
+        for (int r = 0; r < cout; ++r) {
+            memcpy(&wm[(size_t)r * (K + K2)], &w3[(size_t)r * K], (size_t)K * 4);
+            memcpy(&wm[(size_t)r * (K + K2) + K], &wsv[(size_t)r * K2], (size_t)K2 * 4);
+        }
+        w3.swap(wm);
+        K += K2;
+        for (int i = 0; i < cout; ++i) bias3[i] += hs[i];
+    } else {
+        cs.epi.res = x.p;
+        cs.epi.res_ld = x.ld;
+        cs.dense_pointwise = true;
+    }
+    cs.W = b.w.act("w:" + p + ".conv3m", w3); cs.Ktot = K; cs.Cout = cout; cs.B = x.B; cs.F = Fo; cs.T = To;
+    cs.epi.bias = b.w.f32("bnh:" + p + ".bn3m", bias3);
+    cs.epi.act2 = WS_ACT_RELU;
+    fill_epi_out(cs.epi, o);
+    b.conv(cs);
+    return o;
+}
+
 View stem(Builder& b, const std::string& convkey, const std::string& bnkey, View outbuf) {
     std::vector<float> s, h, w9;
     int co, ci, nt;
@@ -633,9 +705,10 @@ View stem(Builder& b, const std::string& convkey, const std::string& bnkey, View
 bool build_resnet(Builder& b) {
     ws_engine& e = b.e;
     const int B = b.p.B, T = b.p.T, Fd = e.feat_dim, E = e.embed_dim, m = 32;
-    const size_t big = (size_t)B * Fd * T * m;
-    View bufs[3];
-    for (int i = 0; i < 3; ++i) {
+    // largest activation map: the layer-1 output (m channels, x4 with Bottleneck blocks) at full (F, T)
+    const size_t big = (size_t)B * Fd * T * m * (e.bottleneck ? 4 : 1);
+    View bufs[4];
+    for (int i = 0; i < (e.bottleneck ? 4 : 3); ++i) {
         bufs[i].dt = e.act_dt; bufs[i].p = b.raw(big * ws_esize(e.act_dt));
         if (e.split) bufs[i].plo = b.raw(big * 4);
     }
@@ -647,6 +720,12 @@ bool build_resnet(Builder& b) {
         for (int bi = 0; bi < e.num_blocks[li - 1] && b.good(); ++bi) {
             const int s = (bi == 0 && li > 1) ? 2 : 1;
             const std::string p = "layer" + std::to_string(li) + "." + std::to_string(bi);
+            if (e.bottleneck) {   // x lives in bufs[ci]; the two intermediates and the output rotate through the other three
+                View o = bottleneck_block(b, p, cur, cout, s, bufs[(ci + 1) % 4], bufs[(ci + 2) % 4], bufs[(ci + 3) % 4]);
+                ci = (ci + 3) % 4;
+                cur = o;
+                continue;
+            }
             View o = basic_block(b, p, cur, cout, s, s, bufs[(ci + 1) % 3], bufs[(ci + 2) % 3]);
             ci = (ci + 2) % 3;
             cur = o;
@@ -680,6 +759,77 @@ bool build_resnet(Builder& b) {
     } else {
         b.linear(stats, 2 * sd, nullptr, 0, 1, b.w.vec("seg_1.weight"), b.w.vec("seg_1.bias"), b.p.emb, E, B, 2 * sd, E, WS_ACT_NONE);
     }
+    return b.good();
+}
+
+// ----------------------------------------------------------------------------------------------- XVEC
+// tdnn.py:23-117: five TdnnLayers BN(ReLU(Conv1d(x) + b)) WITHOUT padding (the sequence shrinks by 4 + 4 + 6 frames) and
+// BatchNorm affine=False, TSTP, seg_1 -> ReLU -> seg_bn_1 -> seg_2; callers take the last element (embed_b).
+bool build_xvec(Builder& b) {
+    ws_engine& e = b.e;
+    const int B = b.p.B, T = b.p.T, Fd = e.feat_dim, E = e.embed_dim;
+    if (T < 15) { set_err("XVEC needs at least 15 frames (valid convolutions of context 5, 3x2, 3x3)"); return false; }
+    const HostT* w5 = b.w.get("frame_5.conv_1d.weight");
+    const HostT* w1h = b.w.get("frame_1.conv_1d.weight");
+    if (!w5 || !w1h) return false;
+    const int hid = (int)w1h->shape[0], sdim = (int)w5->shape[0];
+    const int sdim_pad = (sdim + 31) / 32 * 32;          // tensor-core tiles want Cout % 32 == 0: zero rows behind the 1500
+    View x0 = b.act(B, 1, T, Fd);
+    {
+        const float* fin = b.p.feats_in;
+        void* xo = x0.p;
+        float* xlo = (float*)x0.plo;
+        const int dt = e.act_dt;
+        const long long n = (long long)B * T * Fd;
+        b.push([=](cudaStream_t s) { return ws_launch_convert(fin, xo, xlo, dt, n, s); });
+    }
+    const int ks[5] = {5, 3, 3, 1, 1}, dils[5] = {1, 2, 3, 1, 1};
+    View cur = x0;
+    for (int i = 1; i <= 5 && b.good(); ++i) {
+        const std::string p = "frame_" + std::to_string(i);
+        std::vector<float> wp, s, h;
+        int co, ci, nt;
+        const HostT* bias = b.w.get(p + ".conv_1d.bias");
+        if (!bias || !b.w.pack_conv(p + ".conv_1d.weight", nullptr, wp, &co, &ci, &nt) || !b.w.bn(p + ".bn", false, s, h)) return false;
+        const int cop = i == 5 ? sdim_pad : co;
+        std::vector<float> bv(bias->v);
+        if (cop != co) {   // padded output channels: zero weights, zero bias, BN scale / shift 0 -> exact zeros
+            wp.resize((size_t)cop * nt * ci, 0.f);
+            bv.resize(cop, 0.f); s.resize(cop, 0.f); h.resize(cop, 0.f);
+        }
+        const int To = cur.T - dils[i - 1] * (ks[i - 1] - 1);
+        View out = b.act(B, 1, To, cop);
+        WsEpi ep{};
+        ep.bias = b.w.f32("b:" + p, bv);
+        ep.act1 = WS_ACT_RELU;
+        ep.scale = b.w.f32("bns:" + p, s);
+        ep.shift = b.w.f32("bnh:" + p, h);
+        b.conv_simple(cur, out, b.w.act("w:" + p, wp), 1, ks[i - 1], 1, dils[i - 1], 0, 0, 1, 1, ep);
+        cur = out;
+        (void)hid;
+    }
+    if (!b.good()) return false;
+    float* stats = b.f32((size_t)B * 2 * sdim);
+    View sv = cur; sv.C = sdim;                           // statistics over the real 1500 channels only
+    b.tstats(sv, nullptr, nullptr, stats, 2 * sdim, sdim);
+    float* ea = b.f32((size_t)B * E);
+    std::vector<float> s, h;
+    const HostT* w1 = b.w.get("seg_1.weight");
+    const HostT* w2 = b.w.get("seg_2.weight");
+    const HostT* b2 = b.w.get("seg_2.bias");
+    if (!w1 || !w2 || !b2 || !b.w.bn("seg_bn_1", false, s, h)) return false;
+    if ((int)w1->shape[1] != 2 * sdim || (int)w1->shape[0] != E) { set_err("seg_1.weight shape mismatch"); return false; }
+    std::vector<float> wf((size_t)E * E), bf(E);
+    for (int o = 0; o < E; ++o) {
+        double acc = b2->v[o];
+        for (int i = 0; i < E; ++i) {
+            wf[(size_t)o * E + i] = w2->v[(size_t)o * E + i] * s[i];
+            acc += (double)w2->v[(size_t)o * E + i] * h[i];
+        }
+        bf[o] = (float)acc;
+    }
+    b.linear(stats, 2 * sdim, nullptr, 0, 1, b.w.vec("seg_1.weight"), b.w.vec("seg_1.bias"), ea, E, B, 2 * sdim, E, WS_ACT_RELU);
+    b.linear(ea, E, nullptr, 0, 1, b.w.f32("w:seg_2.folded", wf), b.w.f32("b:seg_2.folded", bf), b.p.emb, E, B, E, E, WS_ACT_NONE);
     return b.good();
 }
 
@@ -912,6 +1062,7 @@ Plan* get_plan(ws_engine* e, int B, int T) {
     if (ok) {
         if (e->model.rfind("ECAPA", 0) == 0) ok = build_ecapa(b);
         else if (e->model.rfind("ResNet", 0) == 0) ok = build_resnet(b);
+        else if (e->model == "XVEC") ok = build_xvec(b);
         else ok = build_campplus(b);
     }
     if (!ok) return nullptr;
@@ -1061,6 +1212,12 @@ int ws_engine_create(const char* model_name, const char* precision, int feat_dim
     else if (m == "ECAPA_TDNN_GLOB_c1024") { e->channels = 1024; e->glob = true; }
     else if (m == "ResNet18") e->num_blocks = {2, 2, 2, 2};
     else if (m == "ResNet34") e->num_blocks = {3, 4, 6, 3};
+    else if (m == "ResNet50") { e->num_blocks = {3, 4, 6, 3}; e->bottleneck = true; }
+    else if (m == "ResNet101") { e->num_blocks = {3, 4, 23, 3}; e->bottleneck = true; }
+    else if (m == "ResNet152") { e->num_blocks = {3, 8, 36, 3}; e->bottleneck = true; }
+    else if (m == "ResNet221") { e->num_blocks = {6, 16, 48, 3}; e->bottleneck = true; }
+    else if (m == "ResNet293") { e->num_blocks = {10, 20, 64, 3}; e->bottleneck = true; }
+    else if (m == "XVEC") {}
     else if (m == "CAMPPlus") {}
     else { set_err("unknown / out-of-scope model name: " + m); return 1; }
     const std::string p = e->prec;

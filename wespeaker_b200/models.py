@@ -20,10 +20,10 @@ import numpy as np
 import torch
 
 from . import lib as _lib
-from .synthetic import CAMPP_NAMES, DEFAULT_MODEL_ARGS, ECAPA_NAMES, RESNET_NAMES, state_dict_spec
+from .synthetic import CAMPP_NAMES, DEFAULT_MODEL_ARGS, ECAPA_NAMES, RESNET_NAMES, XVEC_NAMES, state_dict_spec
 
 _IncompatibleKeys = namedtuple("IncompatibleKeys", ["missing_keys", "unexpected_keys"])
-SUPPORTED_MODELS = tuple(ECAPA_NAMES) + tuple(RESNET_NAMES) + tuple(CAMPP_NAMES)
+SUPPORTED_MODELS = tuple(ECAPA_NAMES) + tuple(RESNET_NAMES) + tuple(CAMPP_NAMES) + tuple(XVEC_NAMES)
 
 
 class B200SpeakerModel(torch.nn.Module):

@@ -28,8 +28,16 @@ ECAPA_NAMES = {
 RESNET_NAMES = {
     "ResNet18": [2, 2, 2, 2],
     "ResNet34": [3, 4, 6, 3],
+    # Bottleneck variants (`wespeaker/models/resnet.py:72-107,223-260`), SURVEY.md section 8(f) rank 4
+    "ResNet50": [3, 4, 6, 3],
+    "ResNet101": [3, 4, 23, 3],
+    "ResNet152": [3, 8, 36, 3],
+    "ResNet221": [6, 16, 48, 3],
+    "ResNet293": [10, 20, 64, 3],
 }
+RESNET_BOTTLENECK = ("ResNet50", "ResNet101", "ResNet152", "ResNet221", "ResNet293")
 CAMPP_NAMES = {"CAMPPlus": {}}
+XVEC_NAMES = {"XVEC": {}}   # Kaldi-style x-vector TDNN (`wespeaker/models/tdnn.py:57-117`), section 8(f) rank 4
 
 DEFAULT_MODEL_ARGS = {
     # examples/voxceleb/v2/conf/{ecapa_tdnn,resnet,campplus}.yaml
@@ -40,6 +48,12 @@ DEFAULT_MODEL_ARGS = {
     "ResNet18": dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False),
     "ResNet34": dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False),
     "CAMPPlus": dict(feat_dim=80, embed_dim=512, pooling_func="TSTP"),
+    "ResNet50": dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False),
+    "ResNet101": dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False),
+    "ResNet152": dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False),
+    "ResNet221": dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False),
+    "ResNet293": dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False),
+    "XVEC": dict(feat_dim=80, embed_dim=512, pooling_func="TSTP"),   # examples/voxceleb/v2/conf/xvec.yaml
 }
 
 
@@ -102,19 +116,36 @@ def _basic_block(s, p, cin, cout, stride):
         _bn(s, f"{p}.shortcut.1", cout)
 
 
+def _bottleneck(s, p, cin, planes, stride):
+    """`wespeaker/models/resnet.py:72-107` (expansion 4)."""
+    s[f"{p}.conv1.weight"] = (planes, cin, 1, 1)
+    _bn(s, f"{p}.bn1", planes)
+    s[f"{p}.conv2.weight"] = (planes, planes, 3, 3)
+    _bn(s, f"{p}.bn2", planes)
+    s[f"{p}.conv3.weight"] = (4 * planes, planes, 1, 1)
+    _bn(s, f"{p}.bn3", 4 * planes)
+    if stride != 1 or cin != 4 * planes:
+        s[f"{p}.shortcut.0.weight"] = (4 * planes, cin, 1, 1)
+        _bn(s, f"{p}.shortcut.1", 4 * planes)
+
+
 def resnet_spec(num_blocks, m_channels=32, feat_dim=80, embed_dim=256,
-                pooling_func="TSTP", two_emb_layer=False):
+                pooling_func="TSTP", two_emb_layer=False, bottleneck=False):
     assert pooling_func == "TSTP", "only TSTP is on the hot path for ResNet"
     s = OrderedDict()
     s["conv1.weight"] = (m_channels, 1, 3, 3)
     _bn(s, "bn1", m_channels)
     cin = m_channels
+    exp = 4 if bottleneck else 1
     for li, (nb, mult, stride) in enumerate(zip(num_blocks, (1, 2, 4, 8), (1, 2, 2, 2)), 1):
         cout = m_channels * mult
         for bi in range(nb):
-            _basic_block(s, f"layer{li}.{bi}", cin, cout, stride if bi == 0 else 1)
-            cin = cout
-    stats_dim = int(feat_dim / 8) * m_channels * 8
+            if bottleneck:
+                _bottleneck(s, f"layer{li}.{bi}", cin, cout, stride if bi == 0 else 1)
+            else:
+                _basic_block(s, f"layer{li}.{bi}", cin, cout, stride if bi == 0 else 1)
+            cin = cout * exp
+    stats_dim = int(feat_dim / 8) * m_channels * 8 * exp
     s["seg_1.weight"] = (embed_dim, stats_dim * 2)
     s["seg_1.bias"] = (embed_dim,)
     if two_emb_layer:
@@ -163,12 +194,31 @@ def campplus_spec(feat_dim=80, embed_dim=512, pooling_func="TSTP", growth_rate=3
     return s
 
 
+def xvec_spec(feat_dim=80, hid_dim=512, stats_dim=1500, embed_dim=512, pooling_func="TSTP"):
+    """`wespeaker/models/tdnn.py:57-86`: five TdnnLayers (Conv1d -> ReLU -> BN(affine=False)), TSTP, two segment layers."""
+    assert pooling_func == "TSTP", "only TSTP is on the hot path for XVEC"
+    s = OrderedDict()
+    for i, (cin, cout, k) in enumerate(((feat_dim, hid_dim, 5), (hid_dim, hid_dim, 3), (hid_dim, hid_dim, 3),
+                                        (hid_dim, hid_dim, 1), (hid_dim, stats_dim, 1)), 1):
+        s[f"frame_{i}.conv_1d.weight"] = (cout, cin, k)
+        s[f"frame_{i}.conv_1d.bias"] = (cout,)
+        _bn(s, f"frame_{i}.bn", cout, affine=False)
+    s["seg_1.weight"] = (embed_dim, stats_dim * 2)
+    s["seg_1.bias"] = (embed_dim,)
+    _bn(s, "seg_bn_1", embed_dim, affine=False)
+    s["seg_2.weight"] = (embed_dim, embed_dim)
+    s["seg_2.bias"] = (embed_dim,)
+    return s
+
+
 def state_dict_spec(model_name: str, **model_args):
     """key -> shape for a reference model name (`wespeaker/models/speaker_model.py:31-62`)."""
     if model_name in ECAPA_NAMES:
         return ecapa_spec(**ECAPA_NAMES[model_name], **model_args)
     if model_name in RESNET_NAMES:
-        return resnet_spec(RESNET_NAMES[model_name], **model_args)
+        return resnet_spec(RESNET_NAMES[model_name], bottleneck=model_name in RESNET_BOTTLENECK, **model_args)
+    if model_name in XVEC_NAMES:
+        return xvec_spec(**model_args)
     if model_name in CAMPP_NAMES:
         return campplus_spec(**model_args)
     raise ValueError(f"model {model_name!r} is not on the B200 hot path")
@@ -194,7 +244,7 @@ def make_state_dict(model_name: str, seed: int = 0, **model_args):
             sd[key] = g.uniform(0.5, 1.5, shape).astype(np.float32)
         elif ".bn" in key or "batchnorm" in key or key.startswith("bn") or "shortcut.1" in key \
                 or "seg_bn" in key:
-            if key.endswith(".bn2.weight") and "layer" in key:
+            if (key.endswith(".bn2.weight") or key.endswith(".bn3.weight")) and "layer" in key:
                 # residual-branch output BN of the 2-D BasicBlocks: keep the residual sum O(1)
                 # over 16 blocks (a trained net does; fp16 range matters for config 3)
                 sd[key] = g.uniform(0.2, 0.6, shape).astype(np.float32)
