@@ -59,7 +59,7 @@ def test_wrapper_state_dict_contract():
         m.load_state_dict(bad2, strict=False)
     assert m.to("cpu").eval() is m
     with pytest.raises(ValueError):
-        get_speaker_model("XVEC")
+        get_speaker_model("ReDimNetB0")   # a family outside SURVEY.md section 8
 
 
 def test_kaldi_vector_roundtrip(tmp_path):
