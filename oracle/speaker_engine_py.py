@@ -2,9 +2,10 @@
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Follows `runtime/core/speaker/speaker_engine.cc:62-75` (ApplyMean),
 `:77-139` (ExtractFeature, vector operations restated one for one on Python lists of frames) and `:141-159`
-(ExtractEmbedding).  The C++ runtime cannot be built offline (glog / gflags / onnxruntime are fetched by URL,
-`runtime/core/cmake/onnx.cmake`), so this restatement is checked by reading, not by goldens: "parity unpinned" for this
-row; the frontend and model it is composed with are the pinned oracles (fbank_np, models_torch).
+(ExtractEmbedding).  PINNED: the reference's own speaker_engine.cc / feature_pipeline.cc / fft.cc / fbank.h compile with a
+glog shim (`make -C oracle` -> oracle/_ref/libref_engine.so; the full CMake build needs onnxruntime by URL and is not
+used); tests/golden/ref_engine.npz holds its chunk composition, ApplyMean output and cosine values, and
+tests/test_speaker_engine.py checks this restatement (and oracle/fbank_np.py against the native fbank twin) on them.
 """
 from __future__ import annotations
 

@@ -654,8 +654,9 @@ def test_extract_dropin_and_speaker_api(tmp_path):
         lines.append(json.dumps({"key": f"utt{i}", "wav": str(tmp_path / f"u{i}.wav"), "spk": "s"}))
     (tmp_path / "raw.list").write_text("\n".join(lines) + "\n")
     ark = tmp_path / "emb" / "xvector.ark"
+    # batch_size 1 = whole utterances (extract.py:93 whole_utt), reader pool of 3 threads, pipelined through extract_stream
     n = extract(str(mdir / "config.yaml"), model_path=str(mdir / "avg_model.pt"), data_type="raw",
-                data_list=str(tmp_path / "raw.list"), embed_ark=str(ark), batch_size=2, precision="fp32")
+                data_list=str(tmp_path / "raw.list"), embed_ark=str(ark), batch_size=1, num_workers=3, precision="fp32")
     assert n == 6
     got = kaldi_io.read_vec_scp_file(str(ark)[:-3] + "scp")
     assert sorted(got) == [f"utt{i}" for i in range(6)]
@@ -669,6 +670,61 @@ def test_extract_dropin_and_speaker_api(tmp_path):
     fb = spk.compute_features(torch.from_numpy(wavs[:1]), cmn=True)[0].cpu().numpy()
     e_feats = spk.extract_embedding_from_feats([fb], batch_size=4, subseg_cmn=True)
     assert rel_l2(e_feats[0], got["utt0"]) <= 1e-5
+
+    # batch_size > 1 = one fixed-length chunk of num_frms frames per utterance (dataset.py:236-242, processor.py:315-347):
+    # random start (seeded here), short utterances tiled.  Same chunks rebuilt with the same generator for the oracle.
+    import random as _random
+    from wespeaker_b200.extract import get_random_chunk
+    cfg2 = dict(cfg, dataset_args=dict(cfg["dataset_args"], num_frms=150))
+    (mdir / "config2.yaml").write_text(yaml.safe_dump(cfg2))
+    ark2 = tmp_path / "emb2" / "xvector.ark"
+    n = extract(str(mdir / "config2.yaml"), model_path=str(mdir / "avg_model.pt"), data_type="raw", data_list=str(tmp_path / "raw.list"),
+                embed_ark=str(ark2), batch_size=4, num_workers=2, precision="fp32", seed=7)
+    got2 = kaldi_io.read_vec_scp_file(str(ark2)[:-3] + "scp")
+    assert n == 6 and len(got2) == 6
+    rng, clen = _random.Random(7), ((150 - 1) * 10 + 25) * 16
+    for i, nsamp in enumerate(lens):
+        chunk = get_random_chunk(wavs[i, :nsamp].astype(np.int16), clen, rng).astype(np.float32)
+        assert len(chunk) == clen
+        ref = models_torch.forward(name, sd_np, torch.from_numpy(fbank_np.cmn(fbank_np.fbank(chunk)))[None]).numpy()[0]
+        assert rel_l2(got2[f"utt{i}"], ref) <= 1e-3, (i, rel_l2(got2[f"utt{i}"], ref))
+
+    # shard list: tar members <key>.wav / <key>.spk grouped by prefix (processor.py:68-109); vad segments in a raw list
+    import tarfile
+    tar_path = tmp_path / "shard_000.tar"
+    with tarfile.open(tar_path, "w") as tf:
+        for i in range(3):
+            (tmp_path / f"utt{i}.spk").write_text("s\n")
+            tf.add(tmp_path / f"utt{i}.spk", arcname=f"utt{i}.spk")
+            tf.add(tmp_path / f"u{i}.wav", arcname=f"utt{i}.wav")
+    (tmp_path / "shards.list").write_text(str(tar_path) + "\n")
+    ark3 = tmp_path / "emb3" / "xvector.ark"
+    assert extract(str(mdir / "config.yaml"), model_path=str(mdir / "avg_model.pt"), data_type="shard", data_list=str(tmp_path / "shards.list"),
+                   embed_ark=str(ark3), batch_size=1, precision="fp32") == 3
+    got3 = kaldi_io.read_vec_scp_file(str(ark3)[:-3] + "scp")
+    for i in range(3):
+        assert rel_l2(got3[f"utt{i}"], got[f"utt{i}"]) <= 1e-6
+    (tmp_path / "vad.list").write_text(json.dumps({"key": "v0", "wav": str(tmp_path / "u0.wav"), "spk": "s", "vad": [[0.1, 0.9], [1.2, 1.9]]}) + "\n")
+    ark4 = tmp_path / "emb4" / "xvector.ark"
+    assert extract(str(mdir / "config.yaml"), model_path=str(mdir / "avg_model.pt"), data_type="raw", data_list=str(tmp_path / "vad.list"),
+                   embed_ark=str(ark4), batch_size=1, precision="fp32") == 1
+    wv = np.concatenate([wavs[0, 1600:14400], wavs[0, 19200:30400]]).astype(np.int16).astype(np.float32)
+    ref = models_torch.forward(name, sd_np, torch.from_numpy(fbank_np.cmn(fbank_np.fbank(wv)))[None]).numpy()[0]
+    assert rel_l2(kaldi_io.read_vec_scp_file(str(ark4)[:-3] + "scp")["v0"], ref) <= 1e-3
+
+    # feat list: Kaldi feature matrices by ark:offset (processor.py:169-196), CMN on the device, whole and chunked
+    flines = []
+    with kaldi_io.MatrixWriter(str(tmp_path / "feats.ark"), str(tmp_path / "feats.scp")) as mw:
+        for i, nsamp in enumerate(lens[:4]):
+            loc = mw(f"utt{i}", fbank_np.fbank(wavs[i, :nsamp]))
+            flines.append(json.dumps({"key": f"utt{i}", "feat": loc, "spk": "s"}))
+    (tmp_path / "feat.list").write_text("\n".join(flines) + "\n")
+    ark5 = tmp_path / "emb5" / "xvector.ark"
+    assert extract(str(mdir / "config.yaml"), model_path=str(mdir / "avg_model.pt"), data_type="feat", data_list=str(tmp_path / "feat.list"),
+                   embed_ark=str(ark5), batch_size=1, precision="fp32") == 4
+    got5 = kaldi_io.read_vec_scp_file(str(ark5)[:-3] + "scp")
+    for i in range(4):
+        assert rel_l2(got5[f"utt{i}"], got[f"utt{i}"]) <= 1e-3     # oracle fbank vs device fbank in front of the same model
 
 
 def test_plan_cache_eviction_many_shapes():

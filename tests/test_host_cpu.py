@@ -137,3 +137,45 @@ def test_speaker_register_recognize_similarity_host_logic(monkeypatch, capsys):
     r = spk.recognize("q.wav")
     assert r["name"] == "bob" and r["confidence"] == pytest.approx((0.8 + 1.0) / 2)
     assert Speaker(model=object()).recognize.__self__.table == {}
+
+
+def test_kaldi_matrix_formats_and_random_chunk(tmp_path):
+    """Kaldi matrix reader (`kaldiio.load_mat` analogue used by data_type=feat): FM / DM exactly, CM2 / CM3 / CM (compressed
+    matrix, compressed-matrix.h) against the values the format defines; get_random_chunk against processor.py:315-347."""
+    import random
+    import struct
+    from wespeaker_b200 import kaldi_io
+    from wespeaker_b200.extract import get_random_chunk
+    rng = np.random.default_rng(0)
+    m = rng.standard_normal((7, 5)).astype(np.float32)
+    with kaldi_io.MatrixWriter(str(tmp_path / "m.ark"), str(tmp_path / "m.scp")) as w:
+        loc = w("key1", m)
+        loc2 = w("key2", 2 * m)
+    assert np.array_equal(kaldi_io.load_mat(loc), m) and np.array_equal(kaldi_io.load_mat(loc2), 2 * m)
+    assert np.array_equal(kaldi_io.load_mat(str(tmp_path / "m.ark")), m)          # bare ark: first matrix
+    hdr = lambda tok, r, c: b"\0B" + tok + b"\4" + struct.pack("<i", r) + b"\4" + struct.pack("<i", c)  # noqa: E731
+    (tmp_path / "d.ark").write_bytes(hdr(b"DM ", 7, 5) + m.astype("<f8").tobytes())
+    assert np.array_equal(kaldi_io.load_mat(str(tmp_path / "d.ark")), m)
+    vmin, vrange = float(m.min()), float(m.max() - m.min())
+    q16 = np.round((m - vmin) / vrange * 65535).astype("<u2")
+    (tmp_path / "c2.ark").write_bytes(b"\0BCM2 " + struct.pack("<ffii", vmin, vrange, 7, 5) + q16.tobytes())
+    assert np.abs(kaldi_io.load_mat(str(tmp_path / "c2.ark")) - m).max() <= vrange / 65535
+    q8 = np.round((m - vmin) / vrange * 255).astype("u1")
+    (tmp_path / "c3.ark").write_bytes(b"\0BCM3 " + struct.pack("<ffii", vmin, vrange, 7, 5) + q8.tobytes())
+    assert np.abs(kaldi_io.load_mat(str(tmp_path / "c3.ark")) - m).max() <= vrange / 255
+    # CM: per-column percentile headers; bytes 0 / 64 / 192 / 255 decode to the 0th / 25th / 75th / 100th percentile values
+    ph = np.array([[0, 16384, 49152, 65535]] * 5, dtype="<u2")
+    codes = np.array([[0, 64, 192, 255, 32, 128, 224]] * 5, dtype="u1")           # (cols, rows): column-major bytes
+    (tmp_path / "c1.ark").write_bytes(b"\0BCM " + struct.pack("<ffii", -1.0, 2.0, 7, 5) + ph.tobytes() + codes.tobytes())
+    got = kaldi_io.load_mat(str(tmp_path / "c1.ark"))
+    p = -1.0 + 2.0 * ph[0].astype(np.float64) / 65535
+    want = [p[0], p[1], p[2], p[3], p[0] + (p[1] - p[0]) * 32 / 64, p[1] + (p[2] - p[1]) * 64 / 128, p[2] + (p[3] - p[2]) * 32 / 63]
+    assert got.shape == (7, 5) and np.abs(got[:, 0] - np.array(want)).max() < 1e-6 and np.array_equal(got[:, 0], got[:, 4])
+    # chunks: long input -> a window at the generator's start; short input -> tiled then cut
+    x = np.arange(1000)
+    r1, r2 = random.Random(3), random.Random(3)
+    s0 = r2.randint(0, 1000 - 300)
+    assert np.array_equal(get_random_chunk(x, 300, r1), x[s0:s0 + 300])
+    assert np.array_equal(get_random_chunk(np.arange(7), 17, r1), np.tile(np.arange(7), 3)[:17])
+    f = rng.standard_normal((5, 4))
+    assert np.array_equal(get_random_chunk(f, 12, r1), np.tile(f, (3, 1))[:12])

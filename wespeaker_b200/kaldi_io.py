@@ -186,3 +186,87 @@ def write_plda(path, mean, transform, psi, binary=True):
                 f.write(("  " + fmt(row) + (" ]\n" if i == transform.shape[0] - 1 else "\n")).encode())
             f.write((" [ " + fmt(psi) + " ]\n").encode())
             f.write(b"</Plda> ")
+
+
+# ---------------------------------------------------------------------------------------------- Kaldi matrices
+def _read_mat_binary(f):
+    """One binary Kaldi matrix after the '\\0B' marker: FM / DM (plain float / double) or CM / CM2 / CM3 (Kaldi's
+    compressed-matrix formats, compressed-matrix.h): what `kaldiio.load_mat` returns for `dataset/processor.py:190`."""
+    tok = f.read(3)
+    if tok in (b"FM ", b"DM "):
+        hdr = f.read(10)
+        if hdr[0:1] != b"\4" or hdr[5:6] != b"\4":
+            raise ValueError("bad Kaldi matrix header")
+        rows, cols = struct.unpack("<i", hdr[1:5])[0], struct.unpack("<i", hdr[6:10])[0]
+        if tok == b"FM ":
+            return np.frombuffer(f.read(4 * rows * cols), dtype="<f4").reshape(rows, cols).copy()
+        return np.frombuffer(f.read(8 * rows * cols), dtype="<f8").reshape(rows, cols).astype(np.float32)
+    if tok in (b"CM ", b"CM2", b"CM3"):
+        if tok != b"CM ":
+            f.read(1)                                     # the space after the 3-character token
+        vmin, vrange, rows, cols = struct.unpack("<ffii", f.read(16))
+        if tok == b"CM2":
+            d = np.frombuffer(f.read(2 * rows * cols), dtype="<u2").reshape(rows, cols)
+            return (vmin + vrange * (d.astype(np.float32) / 65535.0)).astype(np.float32)
+        if tok == b"CM3":
+            d = np.frombuffer(f.read(rows * cols), dtype="u1").reshape(rows, cols)
+            return (vmin + vrange * (d.astype(np.float32) / 255.0)).astype(np.float32)
+        # CM: per-column percentile headers (4 x uint16) then column-major bytes, piecewise-linear in three segments
+        ph = np.frombuffer(f.read(8 * cols), dtype="<u2").reshape(cols, 4).astype(np.float32)
+        p = vmin + vrange * (ph / 65535.0)                # (cols, 4): 0th, 25th, 75th, 100th percentile values
+        d = np.frombuffer(f.read(rows * cols), dtype="u1").reshape(cols, rows).astype(np.float32)
+        p0, p25, p75, p100 = (p[:, i:i + 1] for i in range(4))
+        out = np.where(d <= 64, p0 + (p25 - p0) * d / 64.0,
+                       np.where(d <= 192, p25 + (p75 - p25) * (d - 64.0) / 128.0, p75 + (p100 - p75) * (d - 192.0) / 63.0))
+        return np.ascontiguousarray(out.T.astype(np.float32))
+    raise ValueError(f"unsupported Kaldi matrix type {tok!r}")
+
+
+def load_mat(location: str) -> np.ndarray:
+    """`kaldiio.load_mat("file.ark:offset")` (or a file holding one matrix): (T, F) float32."""
+    path, sep, off = location.rpartition(":")
+    if not sep or not off.isdigit():
+        path, off = location, None
+    with open(path, "rb") as f:
+        if off is not None:
+            f.seek(int(off))
+        else:                                             # a key may precede the binary marker in a bare ark
+            head = f.read(2)
+            if head != b"\0B":
+                f.seek(0)
+                while f.read(1) not in (b" ", b""):
+                    pass
+                head = f.read(2)
+            f.seek(f.tell() - 2)
+        if f.read(2) != b"\0B":
+            raise ValueError(f"{location}: not a binary Kaldi object")
+        return _read_mat_binary(f)
+
+
+class MatrixWriter:
+    """``with MatrixWriter(ark, scp) as w: w(key, mat)`` — float matrices ('FM '), the feature ark/scp of Kaldi recipes."""
+
+    def __init__(self, ark_path: str, scp_path: str | None = None):
+        self.ark_path = os.path.abspath(ark_path)
+        self.ark = open(self.ark_path, "wb")
+        self.scp = open(scp_path, "w") if scp_path else None
+
+    def __call__(self, key: str, mat):
+        m = np.ascontiguousarray(np.asarray(mat), dtype=np.float32)
+        self.ark.write(key.encode() + b" ")
+        off = self.ark.tell()
+        self.ark.write(b"\0BFM \4" + struct.pack("<i", m.shape[0]) + b"\4" + struct.pack("<i", m.shape[1]) + m.tobytes())
+        if self.scp:
+            self.scp.write(f"{key} {self.ark_path}:{off}\n")
+        return f"{self.ark_path}:{off}"
+
+    def close(self):
+        self.ark.close()
+        if self.scp:
+            self.scp.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -291,6 +291,35 @@ class B200SpeakerModel(torch.nn.Module):
                 out[torch.as_tensor(sel, device=dev)] = self.extract_from_wav(x, window_type=window_type).to(dev)
         return out
 
+    def export_flat(self, path: str):
+        """Write the flat weights file the C++ back-end seam reads (`csrc/runtime/b200_speaker_model.h`, seam B4:
+        `wespeaker::B200SpeakerModel(path)` behind `runtime/core/speaker/speaker_model.h:25-32`)."""
+        import struct
+
+        def wstr(f, t: str):
+            b = t.encode()
+            f.write(struct.pack("<I", len(b)) + b)
+        opts = {k: int(v) for k, v in self.options.items()}
+        for opt in ("two_emb_layer", "emb_bn"):
+            if self.model_args.get(opt):
+                opts[opt] = 1
+        tensors = [(k, v) for k, v in self._sd.items() if not k.endswith("num_batches_tracked")]
+        with open(path, "wb") as f:
+            f.write(b"WSPKB200" + struct.pack("<I", 1))
+            wstr(f, self.model_name)
+            wstr(f, self.precision)
+            f.write(struct.pack("<ii", self.feat_dim, self.embed_dim))
+            f.write(struct.pack("<I", len(opts)))
+            for k, v in opts.items():
+                wstr(f, k)
+                f.write(struct.pack("<q", v))
+            f.write(struct.pack("<I", len(tensors)))
+            for k, v in tensors:
+                a = np.ascontiguousarray(v.detach().cpu().numpy(), dtype="<f4")
+                wstr(f, k)
+                f.write(struct.pack("<I", a.ndim) + struct.pack(f"<{a.ndim}q", *a.shape))
+                f.write(a.tobytes())
+
     def last_launches(self) -> int:
         return int(_lib.load().ws_engine_last_launches(self._engine)) if self._engine is not None else 0
 
