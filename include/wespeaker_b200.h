@@ -43,6 +43,16 @@ int ws_engine_embed_dim(const ws_engine* e);
 /* feats_dev: fp32 (B,T,feat_dim) already mean-normalised by the caller, as `model(features)` receives them
  * (extract.py:125-133); embs_dev: fp32 (B,embed_dim). */
 int ws_engine_forward(ws_engine* e, const float* feats_dev, int B, int T, float* embs_dev, void* stream);
+/* Variable-length jobs: one plan (and CUDA graph) per distinct (B, T); plans own disjoint buffers and are spread over a
+ * few internal streams, so the buckets of such a job overlap on the GPU when they are enqueued with the *_async variants
+ * (same arguments and semantics as ws_engine_forward / ws_engine_extract_wav, but `stream` is NOT made to wait for the
+ * result) and closed with ONE ws_engine_join(e, stream).  Inputs are ordered behind `stream` as usual; outputs and inputs
+ * must stay alive and untouched until the join.  The reference runs such sets at batch 1 (extract_vox.sh:31). */
+int ws_engine_forward_async(ws_engine* e, const float* feats_dev, int B, int T, float* embs_dev, void* stream);
+int ws_engine_extract_wav_async(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples, int B,
+                                const char* window_type, float* embs_dev, void* stream);
+int ws_engine_join(ws_engine* e, void* stream);
+
 /* same with HOST buffers (pinned or pageable): H2D + forward + D2H + stream sync; mirrors
  * `features.to(device)` ... `embeds.cpu()` (extract.py:116,135). */
 int ws_engine_forward_host(ws_engine* e, const float* feats_host, int B, int T, float* embs_host);

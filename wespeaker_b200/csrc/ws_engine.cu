@@ -48,7 +48,10 @@ struct Plan {
     float* emb = nullptr;       // fp32 [B][embed_dim]
     cudaGraphExec_t gexec = nullptr;
     bool graph_failed = false;
+    int lane = 0;               // which of the engine's streams runs this plan through the device-pointer entry points
+    cudaEvent_t done = nullptr; // recorded after every use: a later use on another stream waits for it
     ~Plan() {
+        if (done) cudaEventDestroy(done);
         if (gexec) cudaGraphExecDestroy(gexec);
         for (void* p : bufs) cudaFree(p);
     }
@@ -71,6 +74,12 @@ struct ws_engine {
     long long last_launches = 0;
     long long use_clock = 0;             // LRU clock for the plan cache
     cudaStream_t st = nullptr;
+    // Plans of different (B, T) own disjoint buffers, so the device-pointer entry points spread them over a few streams:
+    // the buckets of a variable-length job (one plan per distinct length) then overlap on the GPU instead of running one
+    // small batch at a time.  lanes[0] == st.
+    static constexpr int kLanes = 4;
+    cudaStream_t lanes[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+    int next_lane = 0;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     std::map<std::string, FbankTables> fb;
     void* wav_dev = nullptr;
@@ -101,6 +110,8 @@ struct ws_engine {
         if (copy_st) cudaStreamDestroy(copy_st);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
+        for (int i = 1; i < kLanes; ++i)
+            if (lanes[i]) cudaStreamDestroy(lanes[i]);
         if (st) cudaStreamDestroy(st);
     }
     long long opt(const char* k, long long dflt) const {
@@ -1075,11 +1086,13 @@ Plan* get_plan(ws_engine* e, int B, int T) {
         auto victim = e->plans.begin();
         for (auto i2 = e->plans.begin(); i2 != e->plans.end(); ++i2)
             if (i2->second->last_use < victim->second->last_use) victim = i2;
-        cudaStreamSynchronize(e->st);
+        cudaDeviceSynchronize();   // the victim may be in flight on any lane
         total -= victim->second->bytes;
         e->plans.erase(victim);
     }
     p->last_use = ++e->use_clock;
+    p->lane = e->opt("plan_lanes", 1) ? (e->next_lane++ % ws_engine::kLanes) : 0;
+    if (cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming) != cudaSuccess) { set_err("plan event creation failed"); return nullptr; }
     Plan* raw = p.get();
     e->plans[key] = std::move(p);
     return raw;
@@ -1177,16 +1190,21 @@ ws_engine* fbank_holder(int device) {
     return h;
 }
 
-int enter_stream(ws_engine* e, cudaStream_t user) {
+cudaStream_t lane_stream(ws_engine* e, const Plan* p) { return e->lanes[p->lane] ? e->lanes[p->lane] : e->st; }
+// the plan's buffers were last used on some stream: order this use behind it, and the user's stream in front
+int enter_stream(ws_engine* e, Plan* p, cudaStream_t work, cudaStream_t user) {
     WS_CK(cudaEventRecord(e->ev_in, user));
-    WS_CK(cudaStreamWaitEvent(e->st, e->ev_in, 0));
+    WS_CK(cudaStreamWaitEvent(work, e->ev_in, 0));
+    WS_CK(cudaStreamWaitEvent(work, p->done, 0));
     return 0;
 }
-int leave_stream(ws_engine* e, cudaStream_t user) {
-    WS_CK(cudaEventRecord(e->ev_out, e->st));
-    WS_CK(cudaStreamWaitEvent(user, e->ev_out, 0));
+int leave_stream(ws_engine* e, Plan* p, cudaStream_t work, cudaStream_t user) {
+    WS_CK(cudaEventRecord(p->done, work));
+    WS_CK(cudaStreamWaitEvent(user, p->done, 0));
     return 0;
 }
+int host_path_enter(ws_engine* e, Plan* p) { WS_CK(cudaStreamWaitEvent(e->st, p->done, 0)); return 0; }
+int host_path_leave(ws_engine* e, Plan* p) { WS_CK(cudaEventRecord(p->done, e->st)); return 0; }
 
 }  // namespace
 
@@ -1235,6 +1253,8 @@ int ws_engine_create(const char* model_name, const char* precision, int feat_dim
     WS_CKS(ws_c3_init());
     WS_CKS(ws_cam_init());
     WS_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    e->lanes[0] = e->st;
+    for (int i = 1; i < ws_engine::kLanes; ++i) WS_CK(cudaStreamCreateWithFlags(&e->lanes[i], cudaStreamNonBlocking));
     WS_CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
     WS_CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
     *out = e.release();
@@ -1246,7 +1266,7 @@ int ws_engine_set_option(ws_engine* e, const char* key, long long value) {
     const std::string k = key;
     if (k == "force_simt") { if (value) e->use_tc = 0; }
     else if (k == "tc_version") { if (e->use_tc) e->use_tc = value >= 3 ? 3 : (value >= 2 || e->split ? 2 : 1); }
-    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused" && k != "se_fused" && k != "se_colsum" && k != "conv3x3" && k != "cam_fused" && k != "cam_block") { set_err("unknown option " + k); return 1; }
+    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused" && k != "se_fused" && k != "se_colsum" && k != "conv3x3" && k != "cam_fused" && k != "cam_block" && k != "plan_lanes") { set_err("unknown option " + k); return 1; }
     e->opts[k] = value;
     e->plans.clear();
     return 0;
@@ -1277,18 +1297,37 @@ int ws_engine_finalize(ws_engine* e) {
 int ws_engine_embed_dim(const ws_engine* e) { return e ? e->embed_dim : -1; }
 long long ws_engine_last_launches(const ws_engine* e) { return e ? e->last_launches : -1; }
 
+static int forward_impl(ws_engine* e, const float* feats_dev, int B, int T, float* embs_dev, void* stream, bool join);
 int ws_engine_forward(ws_engine* e, const float* feats_dev, int B, int T, float* embs_dev, void* stream) {
+    return forward_impl(e, feats_dev, B, T, embs_dev, stream, true);
+}
+int ws_engine_forward_async(ws_engine* e, const float* feats_dev, int B, int T, float* embs_dev, void* stream) {
+    return forward_impl(e, feats_dev, B, T, embs_dev, stream, false);
+}
+// make `stream` wait for everything the engine has in flight on any of its lanes (closes a series of *_async calls)
+int ws_engine_join(ws_engine* e, void* stream) {
+    if (!e) { set_err("ws_engine_join: null engine"); return 1; }
+    WS_CK(cudaSetDevice(e->device));
+    for (int i = 0; i < ws_engine::kLanes; ++i) {
+        if (!e->lanes[i]) continue;
+        WS_CK(cudaEventRecord(e->ev_out, e->lanes[i]));
+        WS_CK(cudaStreamWaitEvent((cudaStream_t)stream, e->ev_out, 0));
+    }
+    return 0;
+}
+static int forward_impl(ws_engine* e, const float* feats_dev, int B, int T, float* embs_dev, void* stream, bool join) {
     if (!e || !feats_dev || !embs_dev) { set_err("ws_engine_forward: null argument"); return 1; }
     if (!e->finalized) { set_err("ws_engine_forward before ws_engine_finalize"); return 1; }
     WS_CK(cudaSetDevice(e->device));
     Plan* p = get_plan(e, B, T);
     if (!p) return 1;
-    cudaStream_t us = (cudaStream_t)stream;
-    if (enter_stream(e, us)) return 1;
-    WS_CK(cudaMemcpyAsync(p->feats_in, feats_dev, (size_t)B * T * e->feat_dim * 4, cudaMemcpyDeviceToDevice, e->st));
-    if (run_plan(e, p, e->st)) return 1;
-    WS_CK(cudaMemcpyAsync(embs_dev, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToDevice, e->st));
-    return leave_stream(e, us);
+    cudaStream_t us = (cudaStream_t)stream, ws = lane_stream(e, p);
+    if (enter_stream(e, p, ws, us)) return 1;
+    WS_CK(cudaMemcpyAsync(p->feats_in, feats_dev, (size_t)B * T * e->feat_dim * 4, cudaMemcpyDeviceToDevice, ws));
+    if (run_plan(e, p, ws)) return 1;
+    WS_CK(cudaMemcpyAsync(embs_dev, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToDevice, ws));
+    if (!join) { WS_CK(cudaEventRecord(p->done, ws)); return 0; }
+    return leave_stream(e, p, ws, us);
 }
 
 int ws_engine_forward_host(ws_engine* e, const float* feats_host, int B, int T, float* embs_host) {
@@ -1297,9 +1336,11 @@ int ws_engine_forward_host(ws_engine* e, const float* feats_host, int B, int T, 
     WS_CK(cudaSetDevice(e->device));
     Plan* p = get_plan(e, B, T);
     if (!p) return 1;
+    if (host_path_enter(e, p)) return 1;
     WS_CK(cudaMemcpyAsync(p->feats_in, feats_host, (size_t)B * T * e->feat_dim * 4, cudaMemcpyHostToDevice, e->st));
     if (run_plan(e, p, e->st)) return 1;
     WS_CK(cudaMemcpyAsync(embs_host, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToHost, e->st));
+    if (host_path_leave(e, p)) return 1;
     WS_CK(cudaStreamSynchronize(e->st));
     return 0;
 }
@@ -1325,8 +1366,18 @@ int ws_fbank(const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples
                       (cudaStream_t)stream);
 }
 
+static int extract_wav_impl(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples, int B,
+                            const char* window_type, float* embs_dev, float* feats_out_dev, void* stream, bool join);
 int ws_engine_extract_wav(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples, int B,
                           const char* window_type, float* embs_dev, float* feats_out_dev, void* stream) {
+    return extract_wav_impl(e, wav_dev, wav_is_i16, wav_ld, nsamples, B, window_type, embs_dev, feats_out_dev, stream, true);
+}
+int ws_engine_extract_wav_async(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples, int B,
+                                const char* window_type, float* embs_dev, void* stream) {
+    return extract_wav_impl(e, wav_dev, wav_is_i16, wav_ld, nsamples, B, window_type, embs_dev, nullptr, stream, false);
+}
+static int extract_wav_impl(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples, int B,
+                            const char* window_type, float* embs_dev, float* feats_out_dev, void* stream, bool join) {
     if (!e || !wav_dev || !embs_dev) { set_err("ws_engine_extract_wav: null argument"); return 1; }
     if (!e->finalized) { set_err("ws_engine_extract_wav before ws_engine_finalize"); return 1; }
     if (e->feat_dim != 80) { set_err("ws_engine_extract_wav: the fbank frontend produces 80 bins"); return 1; }
@@ -1335,15 +1386,17 @@ int ws_engine_extract_wav(ws_engine* e, const void* wav_dev, int wav_is_i16, lon
     if (T <= 0) { set_err("ws_engine_extract_wav: waveform shorter than one 25 ms frame"); return 1; }
     Plan* p = get_plan(e, B, T);
     if (!p) return 1;
-    cudaStream_t us = (cudaStream_t)stream;
-    if (enter_stream(e, us)) return 1;
-    if (fbank_into(e, wav_dev, wav_is_i16, wav_ld, nsamples, B, window_type, 1, p->feats_in, e->st)) return 1;
+    cudaStream_t us = (cudaStream_t)stream, ws = lane_stream(e, p);
+    if (fbank_tables(e, window_type) == nullptr) return 1;   // table upload (first use) before any lane work is enqueued
+    if (enter_stream(e, p, ws, us)) return 1;
+    if (fbank_into(e, wav_dev, wav_is_i16, wav_ld, nsamples, B, window_type, 1, p->feats_in, ws)) return 1;
     if (feats_out_dev)
-        WS_CK(cudaMemcpyAsync(feats_out_dev, p->feats_in, (size_t)B * T * 80 * 4, cudaMemcpyDeviceToDevice, e->st));
-    if (run_plan(e, p, e->st)) return 1;
+        WS_CK(cudaMemcpyAsync(feats_out_dev, p->feats_in, (size_t)B * T * 80 * 4, cudaMemcpyDeviceToDevice, ws));
+    if (run_plan(e, p, ws)) return 1;
     e->last_launches += 2;
-    WS_CK(cudaMemcpyAsync(embs_dev, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToDevice, e->st));
-    return leave_stream(e, us);
+    WS_CK(cudaMemcpyAsync(embs_dev, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToDevice, ws));
+    if (!join) { WS_CK(cudaEventRecord(p->done, ws)); return 0; }
+    return leave_stream(e, p, ws, us);
 }
 
 int ws_engine_extract_wav_host(ws_engine* e, const void* wav_host, int wav_is_i16, int nsamples, int B,
@@ -1362,11 +1415,13 @@ int ws_engine_extract_wav_host(ws_engine* e, const void* wav_host, int wav_is_i1
     }
     Plan* p = get_plan(e, B, T);
     if (!p) return 1;
+    if (host_path_enter(e, p)) return 1;
     WS_CK(cudaMemcpyAsync(e->wav_dev, wav_host, bytes, cudaMemcpyHostToDevice, e->st));
     if (fbank_into(e, e->wav_dev, wav_is_i16, nsamples, nsamples, B, window_type, 1, p->feats_in, e->st)) return 1;
     if (run_plan(e, p, e->st)) return 1;
     e->last_launches += 2;
     WS_CK(cudaMemcpyAsync(embs_host, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToHost, e->st));
+    if (host_path_leave(e, p)) return 1;
     WS_CK(cudaStreamSynchronize(e->st));
     return 0;
 }
@@ -1404,10 +1459,12 @@ int ws_engine_submit_wav_host(ws_engine* e, int slot, const void* wav_host, int 
     WS_CK(cudaMemcpyAsync(e->slot_wav[slot], wav_host, bytes, cudaMemcpyHostToDevice, e->copy_st));
     WS_CK(cudaEventRecord(e->slot_copied[slot], e->copy_st));
     WS_CK(cudaStreamWaitEvent(e->st, e->slot_copied[slot], 0));
+    if (host_path_enter(e, p)) return 1;
     if (fbank_into(e, e->slot_wav[slot], wav_is_i16, nsamples, nsamples, B, window_type, 1, p->feats_in, e->st)) return 1;
     if (run_plan(e, p, e->st)) return 1;
     e->last_launches += 2;
     WS_CK(cudaMemcpyAsync(embs_host, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToHost, e->st));
+    if (host_path_leave(e, p)) return 1;
     WS_CK(cudaEventRecord(e->slot_done[slot], e->st));
     return 0;
 }

@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(384, 1) ws_res2_fused_kernel(const __grid_cons
     __shared__ __align__(8) uint64_t s_bar[2 * kWStages + 5];
     __shared__ __align__(16) float s_par[3][128];
     __shared__ uint32_t s_tmem;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: role branches are warp-uniform for the compiler (see the MMA issuer below)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int npan = p.w8 >> 6;                       // K panels of 64 channels (128 B) per tap
     const int nmt = (p.T + 127) >> 7;                 // M tiles (128 rows) per utterance
@@ -182,30 +183,41 @@ __global__ void __launch_bounds__(384, 1) ws_res2_fused_kernel(const __grid_cons
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
-            int wit = 0, u = 0, g = 0;
+        // All 32 lanes run the loop with warp-uniform values and only the tcgen05 instructions are predicated on one elected
+        // lane: inside an `if (lane == 0)` region every UTCHMMA is preceded by an ELECT / R2UR.BROADCAST convergence loop
+        // (~20 SASS instructions, 65-80 cycles per MMA: tools/experimental/mma_rate_probe.cu), longer than these N = 64 / 128
+        // MMAs occupy the tensor pipe.
+        {
+            uint32_t elected;
+            asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(elected));
+            int ws = 0, u = 0, g = 0;
+            uint32_t wph = 0;
             for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++u) {
                 for (int i = 0; i < kNumConv; ++i, ++g) {
                     if (g > 0) mbar_wait(bar_sready, ((uint32_t)(g - 1)) & 1u);  // s_i written, TMEM drained
                     if (i == 0) mbar_wait(bar_x0, (uint32_t)u & 1u);
                     tc_fence_after();
                     for (int tap = 0; tap < 3; ++tap)
-                        for (int kp = 0; kp < npan; ++kp, ++wit) {
-                            const int s = wit % kWStages;
-                            mbar_wait(bar_wfull + 8 * s, ((uint32_t)(wit / kWStages)) & 1u);
+                        for (int kp = 0; kp < npan; ++kp) {
+                            mbar_wait(bar_wfull + 8 * ws, wph);
                             tc_fence_after();
-                            const uint64_t bdesc = umma_desc128(sW + (uint32_t)(s * wblk_bytes));
+                            const uint64_t bdesc = umma_desc128(sW + (uint32_t)(ws * wblk_bytes));
                             for (int mt = 0; mt < nmt; ++mt) {
                                 const int row = kPadRows + mt * 128 + (tap - 1) * p.dil;   // dilated tap = row shift
                                 const uint64_t adesc = umma_desc128(sS + (uint32_t)((kp * kSRows + row) * 128));
                                 const uint32_t tacc = tmem_base + (uint32_t)(mt * p.w8);
-                                for (int k = 0; k < 4; ++k)
-                                    umma_f16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                                             (uint32_t)((tap | kp | k) != 0));
+                                if (elected) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        umma_f16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                                                 (uint32_t)((tap | kp | k) != 0));
+                                }
                             }
-                            umma_commit(bar_wempty + 8 * s);
+                            if (elected) umma_commit(bar_wempty + 8 * ws);
+                            if (++ws == kWStages) { ws = 0; wph ^= 1u; }
                         }
-                    umma_commit(bar_acc);
+                    if (elected) umma_commit(bar_acc);
+                    __syncwarp();
                 }
             }
         }

@@ -256,40 +256,60 @@ class B200SpeakerModel(torch.nn.Module):
         return torch.from_numpy(t.numpy().copy())
 
     # ------------------------------------------------------------------ variable-length batches (BASELINE config 4)
+    def _run_buckets(self, items, key_fn, stack_fn, launch, max_batch, device):
+        """Bucket `items` by exact length, enqueue EVERY bucket through the *_async entry points (the engine spreads the
+        per-(B,T) plans over several streams, so small buckets overlap on the GPU) and close with one ws_engine_join."""
+        L = _lib.load()
+        buckets = {}
+        for i, it in enumerate(items):
+            buckets.setdefault(key_fn(it), []).append(i)
+        dev = torch.device(device) if device is not None else items[0].device
+        if dev.type != "cuda":
+            dev = torch.device("cuda", self._dev_index())
+        h = self._ensure_engine(dev.index)
+        out = torch.empty((len(items), self.embed_dim), dtype=torch.float32, device=dev)
+        keep = []
+        with torch.cuda.device(dev.index):
+            st = _lib.cur_stream_ptr(dev.index)
+            for _, idx in sorted(buckets.items()):
+                for s0 in range(0, len(idx), max_batch):
+                    sel = idx[s0:s0 + max_batch]
+                    x = stack_fn([items[i] for i in sel]).to(dev)
+                    o = torch.empty((len(sel), self.embed_dim), dtype=torch.float32, device=dev)
+                    keep.append((sel, launch(L, h, x, o, st), o))   # inputs stay alive until the join
+            _lib.check(L.ws_engine_join(h, st), "ws_engine_join")
+            for sel, _, o in keep:
+                out[torch.as_tensor(sel, device=dev)] = o
+        return out
+
     def embed_list(self, feats_list, max_batch: int = 64, device=None):
         """Embeddings for utterances of DIFFERENT lengths.  The reference has no length masking (test sets
-        run at batch 1), so padding would change results; instead utterances are bucketed by exact frame count and each
-        bucket runs as one batch (one cached plan / CUDA graph per (B,T)).  feats_list: list of (T_i, feat_dim) tensors.
-        Returns (N, embed_dim) in input order, on the device of the inputs (CUDA if `device` is given)."""
+        run at batch 1), so padding would change results; instead utterances are bucketed by exact frame count, each bucket
+        is one batch (one cached plan / CUDA graph per (B,T)) and the buckets run concurrently on the engine's streams.
+        feats_list: list of (T_i, feat_dim) tensors.  Returns (N, embed_dim) in input order on the CUDA device."""
         if len(feats_list) == 0:
             return torch.empty((0, self.embed_dim))
-        buckets = {}
-        for i, f in enumerate(feats_list):
-            buckets.setdefault(int(f.shape[0]), []).append(i)
-        dev = torch.device(device) if device is not None else feats_list[0].device
-        out = torch.empty((len(feats_list), self.embed_dim), dtype=torch.float32, device=dev)
-        for T, idx in sorted(buckets.items()):
-            for s0 in range(0, len(idx), max_batch):
-                sel = idx[s0:s0 + max_batch]
-                x = torch.stack([feats_list[i] for i in sel]).to(dev)
-                out[torch.as_tensor(sel, device=dev)] = self.embed(x).to(dev)
-        return out
+
+        def launch(L, h, x, o, st):
+            x = x.contiguous().float()
+            _lib.check(L.ws_engine_forward_async(h, x.data_ptr(), x.shape[0], x.shape[1], o.data_ptr(), st), "ws_engine_forward_async")
+            return x
+        return self._run_buckets(feats_list, lambda f: int(f.shape[0]), torch.stack, launch, max_batch, device)
 
     def extract_from_wav_list(self, wavs, window_type: str = "hamming", max_batch: int = 64, device=None):
         """Same bucketing for raw waveforms (1-D tensors of different lengths, int16 or int16-range float32)."""
         if len(wavs) == 0:
             return torch.empty((0, self.embed_dim))
-        buckets = {}
-        for i, w in enumerate(wavs):
-            buckets.setdefault(int(w.shape[-1]), []).append(i)
-        dev = torch.device(device) if device is not None else wavs[0].device
-        out = torch.empty((len(wavs), self.embed_dim), dtype=torch.float32, device=dev)
-        for n, idx in sorted(buckets.items()):
-            for s0 in range(0, len(idx), max_batch):
-                sel = idx[s0:s0 + max_batch]
-                x = torch.stack([wavs[i].reshape(-1) for i in sel]).to(dev)
-                out[torch.as_tensor(sel, device=dev)] = self.extract_from_wav(x, window_type=window_type).to(dev)
-        return out
+        wt = window_type.encode()
+
+        def launch(L, h, x, o, st):
+            is_i16 = 1 if x.dtype == torch.int16 else 0
+            x = x.contiguous() if is_i16 else x.float().contiguous()
+            _lib.check(L.ws_engine_extract_wav_async(h, x.data_ptr(), is_i16, x.shape[1], x.shape[1], x.shape[0], wt, o.data_ptr(), st),
+                       "ws_engine_extract_wav_async")
+            return x
+        return self._run_buckets(wavs, lambda w: int(w.shape[-1]), lambda ws: torch.stack([w.reshape(-1) for w in ws]), launch,
+                                 max_batch, device)
 
     def export_flat(self, path: str):
         """Write the flat weights file the C++ back-end seam reads (`csrc/runtime/b200_speaker_model.h`, seam B4:
