@@ -207,6 +207,39 @@ def test_conv3x3_halo_kernel(case, prec, variant):
         assert (out - gen).abs().max().item() <= tol
 
 
+C3_STRIDED = [
+    # name, B, F, T, Cin, Cout, stride_f, stride_t
+    ("r34_l2", 2, 20, 50, 32, 64, 2, 2),         # ResNet layer2 conv1: both strides, channel doubling, 64-byte operand rows
+    ("r34_l3", 3, 11, 37, 64, 128, 2, 2),        # odd extents
+    ("r34_l4in", 2, 10, 26, 128, 128, 2, 2),     # two K panels
+    ("fcm_s21", 2, 21, 150, 32, 32, 2, 1),       # CAM++ FCM: frequency-only stride
+    ("fcm_s21_long", 1, 10, 600, 32, 32, 2, 1),  # t tiles
+    ("s22_long", 1, 6, 700, 32, 64, 2, 2),       # stride-2 time planes with t tiles of 128 outputs
+    ("s12", 2, 5, 90, 64, 64, 1, 2),
+    ("many_steps_s22", 40, 20, 30, 32, 64, 2, 2),
+]
+
+
+@pytest.mark.parametrize("case", C3_STRIDED, ids=[c[0] for c in C3_STRIDED])
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_conv3x3_halo_kernel_strided(case, prec):
+    """Strided variants of ws_conv3x3.cu: stride 2 along F consumes two ring rows per step; stride 2 along T reads the even
+    and the shifted odd time plane of a row (two TMA views with a doubled t stride) as separate operand sub-slots."""
+    name, B, F, T, Cin, Cout, sf, st = case
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)
+    x = torch.randn(B, F, T, Cin, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / np.sqrt(9 * Cin)
+    bias = 0.1 * torch.randn(Cout, generator=g)
+    geo = (3, 3, (1, 1), (1, 1), (sf, st), 1, 0)
+    out = run_conv(x, w, bias, None, None, None, prec, 4, *geo)
+    ref = ref_conv(x, w, bias, None, None, None, DT[prec][1], *geo)
+    assert tuple(out.shape) == tuple(ref.shape)
+    err = (out.double() - ref).abs().max().item()
+    tol = {"bf16": 1.2e-2, "fp16": 2e-3}[prec] * max(1.0, ref.abs().max().item())
+    print(f"conv3x3 strided {name} {prec}: max|err|={err:.3e} (tol {tol:.1e})")
+    assert err <= tol, (name, prec, err, tol)
+
+
 def test_conv3x3_ring_depths_agree():
     """Ring depth only changes the pipelining (WS_C3_RING caps it): identical bits for depths 4..8."""
     g = torch.Generator().manual_seed(3)

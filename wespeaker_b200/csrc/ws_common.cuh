@@ -344,6 +344,9 @@ struct WsC3Params {
     const void* res;        // residual base pointer (null = no residual)
     long long res_ld;
     int stg_bufs;           // output staging tiles: 2 = the residual of step s+1 is prefetched while step s drains, 1 = in line
+    int sf, st;             // conv strides along F and T (1 or 2).  B, F, T below are OUTPUT extents.  st == 2: a slot holds the
+                            // even-t and the (shifted) odd-t plane of an input row (amap / amap_tail), sub_rows rows each
+    int sub_rows;
     const float* bias;      // [Cout]
     int relu;
     int B, F, T, Cin, Cout, dtype;

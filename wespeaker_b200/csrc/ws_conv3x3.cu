@@ -146,7 +146,10 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
                 const int tc = tt * p.tb - 1, b0 = bg * p.nb;
                 for (int kp = 0; kp < p.npan; ++kp) {
                     const uint32_t dst = ring + (uint32_t)((slot * p.npan + kp) * p.slot_rows * p.row_bytes);
-                    if (p.single_box) {
+                    if (p.st == 2) {      // even plane from output column t0, odd plane shifted by one (O'[k] = x[2k - 1])
+                        tma_load_4d(dst, &p.amap, bar_afull + 8 * slot, kp * p.kc, tc + 1, frow, b0);
+                        tma_load_4d(dst + (uint32_t)(p.sub_rows * p.row_bytes), &p.amap_tail, bar_afull + 8 * slot, kp * p.kc, tc, frow, b0);
+                    } else if (p.single_box) {
                         tma_load_4d(dst, &p.amap, bar_afull + 8 * slot, kp * p.kc, tc, frow, b0);
                     } else {
                         for (int m = 0; m < p.n_mt; ++m)
@@ -161,8 +164,10 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
             };
             for (C3Iter it(p, s_beg, s_end); !it.done(); it.next(p)) {
                 const C3Step st = it.cur(p);
-                if (st.first) { load_row(st.f - 1, st.bg, st.tt); load_row(st.f, st.bg, st.tt); }
-                load_row(st.f + 1, st.bg, st.tt);
+                const int fi = p.sf * st.f;                  // input row under the centre tap
+                if (st.first) load_row(fi - 1, st.bg, st.tt);
+                if (st.first || p.sf == 2) load_row(fi, st.bg, st.tt);
+                load_row(fi + 1, st.bg, st.tt);
             }
             if (p.prof) { p.prof[blockIdx.x * 16 + 0] = pw_aempty; p.prof[blockIdx.x * 16 + 1] = clock64() - tstart; }
         }
@@ -204,6 +209,11 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
             constexpr int KPER = ROWB / 32;
             const uint64_t dhi = umma_desc(0u, ROWB);                                 // descriptor without the address field
             const uint32_t dt_off = (uint32_t)ROWB >> 4;                              // one operand row, in 16-byte units
+            // operand start of the three time taps inside a slot: consecutive rows, or (stride 2 along t) the shifted-odd,
+            // even, shifted-odd+1 planes
+            const uint32_t sub_off = (uint32_t)(p.sub_rows * ROWB) >> 4;
+            const uint32_t tap_off0 = p.st == 2 ? sub_off : 0u, tap_off1 = p.st == 2 ? 0u : dt_off,
+                           tap_off2 = p.st == 2 ? sub_off + dt_off : 2u * dt_off;    // (scalars: a runtime-indexed array would live in local memory)
             const uint32_t kp_off = (uint32_t)(p.slot_rows * ROWB) >> 4;
             const uint32_t mt_off = (uint32_t)(128 * ROWB) >> 4;
             const uint32_t wb_off = (uint32_t)wblk_bytes >> 4;
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
             uint32_t jphase = 0;
             for (C3Iter it(p, s_beg, s_end); !it.done(); it.next(p), ++step) {
                 const C3Step st = it.cur(p);
-                const int nnew = st.first ? 3 : 1;           // a new image segment starts with rows f-1, f, f+1
+                const int nnew = st.first ? 3 : p.sf;        // a new image segment starts with rows f-1, f, f+1
                 j += nnew;                                   // rows f-1, f, f+1 are loads j-3, j-2, j-1
                 {   // wait for the newly loaded rows: slot / phase of load i follow incrementally from (jslot, jphase)
                     C3_T0();
@@ -241,43 +251,39 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
                 const uint32_t tacc0 = tmem_base + (uint32_t)(buf * NMT * N);
                 uint64_t bd = wdesc0;
                 uint32_t accum = 0;
-                // one runtime loop over the 9 taps; everything inside (K panels, M tiles, k steps) is a compile-time unroll,
-                // so the scalar work between two MMAs is a couple of uniform adds
-                int dtc = 0;
-                uint64_t a_dt = a_df;
+                // runtime loop over the three input rows, compile-time unroll of everything inside (time taps, K panels, M
+                // tiles, k steps): the scalar work between two MMAs is a couple of uniform adds, no selects or branches
 #pragma unroll 1
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int df = 0; df < 3; ++df) {
 #pragma unroll
-                    for (int kp = 0; kp < NPAN; ++kp) {
-                        if (!p.w_resident) {
-                            { C3_T0(); mbar_wait(bar_wfull + 8 * wst, wph); C3_ACC(mw_wfull); }
-                            tc_fence_after();
-                            bd = wdesc0 + (uint64_t)(wst * wb_off);
-                        }
-                        if (elected && !(p.dbg & 8)) {
+                    for (int dt = 0; dt < 3; ++dt) {
+                        const uint64_t a_dt = a_df + (uint64_t)(dt == 0 ? tap_off0 : (dt == 1 ? tap_off1 : tap_off2));
 #pragma unroll
-                            for (int mt = 0; mt < NMT; ++mt) {
+                        for (int kp = 0; kp < NPAN; ++kp) {
+                            if (!p.w_resident) {
+                                { C3_T0(); mbar_wait(bar_wfull + 8 * wst, wph); C3_ACC(mw_wfull); }
+                                tc_fence_after();
+                                bd = wdesc0 + (uint64_t)(wst * wb_off);
+                            }
+                            if (elected && !(p.dbg & 8)) {
 #pragma unroll
-                                for (int k = 0; k < KPER; ++k)
-                                    umma_f16_c3(tacc0 + (uint32_t)(mt * N), a_dt + (uint64_t)(kp * kp_off + mt * mt_off + 2 * k),
-                                                bd + (uint64_t)(2 * k), p.idesc, (kp == 0 && k == 0) ? accum : 1u);
+                                for (int mt = 0; mt < NMT; ++mt) {
+#pragma unroll
+                                    for (int k = 0; k < KPER; ++k)
+                                        umma_f16_c3(tacc0 + (uint32_t)(mt * N), a_dt + (uint64_t)(kp * kp_off + mt * mt_off + 2 * k),
+                                                    bd + (uint64_t)(2 * k), p.idesc, (kp == 0 && k == 0) ? accum : 1u);
+                                }
+                            }
+                            accum = 1u;
+                            if (p.w_resident) {
+                                bd += wb_off;
+                            } else {
+                                if (elected) umma_commit_c3(bar_wempty + 8 * wst);
+                                if (++wst == p.w_stages) { wst = 0; wph ^= 1u; }
                             }
                         }
-                        accum = 1u;
-                        if (p.w_resident) {
-                            bd += wb_off;
-                        } else {
-                            if (elected) umma_commit_c3(bar_wempty + 8 * wst);
-                            if (++wst == p.w_stages) { wst = 0; wph ^= 1u; }
-                        }
                     }
-                    if (++dtc == 3) {           // next input row: slot of row f-1 -> f -> f+1 (ring wrap)
-                        dtc = 0;
-                        if (++sl0 == R) { sl0 = 0; a_df = a_ring0; } else a_df += slot_off;
-                        a_dt = a_df;
-                    } else {
-                        a_dt += dt_off;
-                    }
+                    if (++sl0 == R) { sl0 = 0; a_df = a_ring0; } else a_df += slot_off;   // next input row (ring wrap)
                 }
                 int sl[3];
                 sl[0] = slot_first;
@@ -286,10 +292,8 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
                 if (elected) {
                     umma_commit_c3(bar_tfull + 8 * buf);
                     umma_commit_c3(bar_aempty + 8 * sl[0]);              // row f-1 is not needed by later steps
-                    if (st.last) {                                       // end of this image segment: release f and f+1 too
-                        umma_commit_c3(bar_aempty + 8 * sl[1]);
-                        umma_commit_c3(bar_aempty + 8 * sl[2]);
-                    }
+                    if (st.last || p.sf == 2) umma_commit_c3(bar_aempty + 8 * sl[1]);   // stride 2: neither is the centre row
+                    if (st.last) umma_commit_c3(bar_aempty + 8 * sl[2]);                 // end of this image segment
                 }
                 __syncwarp();
             }

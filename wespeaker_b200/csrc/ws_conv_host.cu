@@ -407,12 +407,13 @@ bool make_res2_op(const View& x, const View& out, const void* W7, const float* b
 }
 
 bool make_conv3x3_op(const View& x, const View& out, const void* W, const float* bias, const View* res, bool relu,
-                     Op* op, bool* unsupported) {
+                     Op* op, bool* unsupported, int stride_f, int stride_t) {
     *unsupported = false;
-    const int Cin = x.C, Cout = out.C, T = x.T, F = x.F, B = x.B;
+    const int Cin = x.C, Cout = out.C, Tin = x.T, Fin = x.F, B = x.B;
+    const int F = (Fin + 2 - 3) / stride_f + 1, T = (Tin + 2 - 3) / stride_t + 1;   // output extents
     auto chan_ok = [](int c) { return c == 32 || c == 64 || c == 128; };
     if (x.dt == WS_F32 || out.dt != x.dt || !chan_ok(Cin) || !chan_ok(Cout) || out.B != B || out.F != F || out.T != T ||
-        T < 1 || F < 1 || (x.ld * 2) % 16 != 0 || (out.ld * 2) % 16 != 0 || (res && (res->ld * 2) % 16 != 0) ||
+        (stride_f != 1 && stride_f != 2) || (stride_t != 1 && stride_t != 2) || T < 1 || F < 1 || (x.ld * 2) % 16 != 0 || (out.ld * 2) % 16 != 0 || (res && (res->ld * 2) % 16 != 0) ||
         getenv("WS_NO_CONV3X3")) {
         *unsupported = true;
         return false;
@@ -420,6 +421,7 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
     auto q = std::make_shared<WsC3Params>();
     memset(q.get(), 0, sizeof(WsC3Params));
     q->B = B; q->F = F; q->T = T; q->Cin = Cin; q->Cout = Cout; q->dtype = x.dt;
+    q->sf = stride_f; q->st = stride_t;
     q->row_bytes = Cin * 2 >= 128 ? 128 : Cin * 2;
     q->kc = q->row_bytes / 2;
     q->npan = Cin / q->kc;
@@ -442,6 +444,14 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
         }
         q->n_bg = (B + q->nb - 1) / q->nb;
         q->slot_rows = (std::max(q->rows_loaded, 128 * n_mt + 2) + 7) & ~7;
+        q->sub_rows = 0;
+        if (stride_t == 2) {      // even plane (tb rows) + shifted odd plane (tb + 1 rows), each in its own sub-slot
+            if (case_b || n_mt != 1) return false;
+            q->single_box = 1;
+            q->sub_rows = (128 + 1 + 7) & ~7;
+            q->slot_rows = 2 * q->sub_rows;
+            q->rows_loaded = tb + (tb + 1);
+        }
         if (2 * n_mt * q->N > 512) return false;
         // output panels (= TMA store units): 64 columns, or 32 when that is what it takes to give each of the two epilogue
         // warp sets its own unit
@@ -461,7 +471,7 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
             int R = (budget - fixed - (q->w_resident ? nwblk : q->w_stages) * wblk) / slot_bytes;
             if (R > WS_C3_MAX_RING) R = WS_C3_MAX_RING;
             if (const char* er = getenv("WS_C3_RING")) R = std::min(R, atoi(er));
-            if (R < (bufs >= 2 ? 5 : 4)) continue;
+            if (R < (bufs >= 2 ? 5 : 4) + (stride_f - 1)) continue;
             q->R = R;
             q->stg_bufs = bufs;
             q->smem_bytes = R * slot_bytes + (q->w_resident ? nwblk : q->w_stages) * wblk + fixed;
@@ -470,9 +480,11 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
         return false;
     };
     bool ok = false;
-    if (T + 2 <= 66) ok = try_geom(true, T, 1);
-    if (!ok && T <= 256) ok = try_geom(false, T, (T + 127) / 128);
-    if (!ok) {   // t tiles of 256 (2 M tiles) or 128 (1 M tile): fewer 128-row tiles first, 256 on a tie (fewer halo columns)
+    const bool strided = stride_f != 1 || stride_t != 1;
+    if (T + 2 <= 66 && !strided) ok = try_geom(true, T, 1);
+    if (!ok && stride_t == 2) ok = try_geom(false, std::min(T, 128), 1);
+    if (!ok && stride_t == 1 && T <= 256) ok = try_geom(false, T, (T + 127) / 128);
+    if (!ok && stride_t == 1) {   // t tiles of 256 (2 M tiles) or 128 (1 M tile): fewer 128-row tiles first, 256 on a tie
         const bool pref256 = 2 * ((T + 255) / 256) <= (T + 127) / 128;
         ok = pref256 ? (try_geom(false, 256, 2) || try_geom(false, 128, 1)) : (try_geom(false, 128, 1) || try_geom(false, 256, 2));
     }
@@ -483,9 +495,17 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
     const int sms = ws_num_sms();
     q->grid = q->total_steps < sms ? q->total_steps : sms;
     // ---- tensor maps
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)T, (cuuint64_t)F, (cuuint64_t)B};
-        cuuint64_t str[3] = {(cuuint64_t)x.ld * 2, (cuuint64_t)T * x.ld * 2, (cuuint64_t)F * T * x.ld * 2};
+    if (stride_t == 2) {   // even / odd time planes of the input as two tensors with a doubled t stride
+        cuuint64_t str[3] = {(cuuint64_t)x.ld * 4, (cuuint64_t)Tin * x.ld * 2, (cuuint64_t)Fin * Tin * x.ld * 2};
+        cuuint64_t de[4] = {(cuuint64_t)Cin, (cuuint64_t)((Tin + 1) / 2), (cuuint64_t)Fin, (cuuint64_t)B};
+        cuuint64_t dod[4] = {(cuuint64_t)Cin, (cuuint64_t)std::max(1, Tin / 2), (cuuint64_t)Fin, (cuuint64_t)B};
+        cuuint32_t be[4] = {(cuuint32_t)q->kc, (cuuint32_t)q->tb, 1, 1}, bo[4] = {(cuuint32_t)q->kc, (cuuint32_t)(q->tb + 1), 1, 1};
+        if (Tin < 2) { *unsupported = true; return false; }
+        if (!encode_map(&q->amap, x.dt, x.p, 4, de, str, be, q->row_bytes)) return false;
+        if (!encode_map(&q->amap_tail, x.dt, (const char*)x.p + (size_t)x.ld * 2, 4, dod, str, bo, q->row_bytes)) return false;
+    } else {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Tin, (cuuint64_t)Fin, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)x.ld * 2, (cuuint64_t)Tin * x.ld * 2, (cuuint64_t)Fin * Tin * x.ld * 2};
         cuuint32_t box[4] = {(cuuint32_t)q->kc, (cuuint32_t)(q->single_box ? q->P : 128), 1, (cuuint32_t)q->nb};
         if (!encode_map(&q->amap, x.dt, x.p, 4, dims, str, box, q->row_bytes)) return false;
         cuuint32_t boxt[4] = {(cuuint32_t)q->kc, 2, 1, 1};
@@ -648,13 +668,14 @@ extern "C" int ws_conv(const ws_conv_desc* d, void* stream) {
     if (d->use_tc) { WS_CKS(ws_tc_init()); WS_CKS(ws_tc2_init()); WS_CKS(ws_tc3_init()); WS_CKS(ws_c3_init()); }
     bool done = false;
     if (d->use_tc >= 4 && d->kf == 3 && d->kt == 3 && d->dil_f == 1 && d->dil_t == 1 && d->pad_f == 1 && d->pad_t == 1 &&
-        d->stride_f == 1 && d->stride_t == 1 && d->scale == nullptr && d->x_lo == nullptr && d->colsum == nullptr &&
+        d->stride_f >= 1 && d->stride_f <= 2 && d->stride_t >= 1 && d->stride_t <= 2 && d->scale == nullptr && d->x_lo == nullptr && d->colsum == nullptr &&
         (d->act1 == 0 || d->res == nullptr) && d->act1 <= 1 && d->act2 <= 1) {
         // halo-resident 3x3 kernel: act(conv + bias [+ res]); with a residual the activation is act2, else act1 (or act2)
         View r = o;
         r.p = const_cast<void*>(d->res); r.ld = d->res_ld;
         bool unsupported = false;
-        if (make_conv3x3_op(x, o, d->w, d->bias, d->res ? &r : nullptr, (d->act1 | d->act2) != 0, &op, &unsupported)) done = true;
+        if (make_conv3x3_op(x, o, d->w, d->bias, d->res ? &r : nullptr, (d->act1 | d->act2) != 0, &op, &unsupported, d->stride_f,
+                            d->stride_t)) done = true;
         else if (!unsupported) return 1;
     }
     if (!done && !make_conv_op(s, d->use_tc >= 4 ? 3 : d->use_tc, &op)) return 1;

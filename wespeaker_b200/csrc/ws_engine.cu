@@ -546,18 +546,18 @@ View basic_block(Builder& b, const std::string& p, const View& x, int cout, int 
     // stride-1 3x3 convs of the low-channel stages run the halo-resident kernel (ws_conv3x3.cu): every input row crosses
     // L2 -> SM once instead of once per tap
     const bool c3 = b.e.use_tc >= 2 && b.e.act_dt != WS_F32 && b.e.opt("conv3x3", 1) != 0;
-    auto try_c3 = [&](const View& in, const View& outv, const void* Wd, const float* bias, const View* res) -> int {
+    auto try_c3 = [&](const View& in, const View& outv, const void* Wd, const float* bias, const View* res, int s_f, int s_t) -> int {
         if (!c3) return 0;
         Op op;
         bool unsupported = false;
-        if (make_conv3x3_op(in, outv, Wd, bias, res, true, &op, &unsupported)) { b.push(std::move(op)); return 1; }
+        if (make_conv3x3_op(in, outv, Wd, bias, res, true, &op, &unsupported, s_f, s_t)) { b.push(std::move(op)); return 1; }
         if (!unsupported) { b.ok = false; return -1; }
         return 0;
     };
     {
         const float* b1 = b.w.f32("bnh:" + p + ".bn1", h1);
         const void* W1 = b.w.act("w:" + p + ".conv1", w1);
-        int r = (sf == 1 && st_ == 1) ? try_c3(x, h, W1, b1, nullptr) : 0;
+        int r = (b.e.opt("conv3x3_strided", 1) != 0 || (sf == 1 && st_ == 1)) ? try_c3(x, h, W1, b1, nullptr, sf, st_) : 0;
         if (r < 0) return none;
         if (r == 0) {
             WsEpi e1{};
@@ -648,10 +648,10 @@ View bottleneck_block(Builder& b, const std::string& p, const View& x, int plane
         const float* b2 = b.w.f32("bnh:" + p + ".bn2", h2);
         const void* W2 = b.w.act("w:" + p + ".conv2", w2);
         bool done = false;
-        if (s == 1 && b.e.use_tc >= 2 && b.e.act_dt != WS_F32 && b.e.opt("conv3x3", 1) != 0) {
+        if ((s == 1 || b.e.opt("conv3x3_strided", 1) != 0) && b.e.use_tc >= 2 && b.e.act_dt != WS_F32 && b.e.opt("conv3x3", 1) != 0) {
             Op op;
             bool unsupported = false;
-            if (make_conv3x3_op(a, c, W2, b2, nullptr, true, &op, &unsupported)) { b.push(std::move(op)); done = true; }
+            if (make_conv3x3_op(a, c, W2, b2, nullptr, true, &op, &unsupported, s, s)) { b.push(std::move(op)); done = true; }
             else if (!unsupported) { b.ok = false; return none; }
         }
         if (!done) {
@@ -874,10 +874,21 @@ bool build_campplus(Builder& b) {
         if (!b.w.bn("head.bn2", true, s, h) || !b.w.pack_conv("head.conv2.weight", &s, wp, &co, &cin, &nt)) return false;
         y = bufs[(ci + 1) % 3];
         y.B = B; y.F = (cur.F + 2 - 3) / 2 + 1; y.T = cur.T; y.C = m; y.ld = m;
-        WsEpi ep{};
-        ep.bias = b.w.f32("bnh:head.bn2", h);
-        ep.act1 = WS_ACT_RELU;
-        b.conv_simple(cur, y, b.w.act("w:head.conv2", wp), 3, 3, 1, 1, 1, 1, 2, 1, ep);
+        const float* hb = b.w.f32("bnh:head.bn2", h);
+        const void* Wh = b.w.act("w:head.conv2", wp);
+        bool done = false;
+        if (e.use_tc >= 2 && e.act_dt != WS_F32 && e.opt("conv3x3", 1) != 0 && e.opt("conv3x3_strided", 1) != 0) {
+            Op op;
+            bool unsupported = false;
+            if (make_conv3x3_op(cur, y, Wh, hb, nullptr, true, &op, &unsupported, 2, 1)) { b.push(std::move(op)); done = true; }
+            else if (!unsupported) return false;
+        }
+        if (!done) {
+            WsEpi ep{};
+            ep.bias = hb;
+            ep.act1 = WS_ACT_RELU;
+            b.conv_simple(cur, y, Wh, 3, 3, 1, 1, 1, 1, 2, 1, ep);
+        }
     }
     if (!b.good()) return false;
     // xvector.tdnn: Conv1d(C*F -> 128, k5, stride 2, pad 2) on the (B, C*F, T) reshape (channel = c*F + f),
@@ -1266,7 +1277,7 @@ int ws_engine_set_option(ws_engine* e, const char* key, long long value) {
     const std::string k = key;
     if (k == "force_simt") { if (value) e->use_tc = 0; }
     else if (k == "tc_version") { if (e->use_tc) e->use_tc = value >= 3 ? 3 : (value >= 2 || e->split ? 2 : 1); }
-    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused" && k != "se_fused" && k != "se_colsum" && k != "conv3x3" && k != "cam_fused" && k != "cam_block" && k != "plan_lanes") { set_err("unknown option " + k); return 1; }
+    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused" && k != "se_fused" && k != "se_colsum" && k != "conv3x3" && k != "cam_fused" && k != "cam_block" && k != "plan_lanes" && k != "conv3x3_strided") { set_err("unknown option " + k); return 1; }
     e->opts[k] = value;
     e->plans.clear();
     return 0;

@@ -82,11 +82,11 @@ void fill_epi_out(WsEpi& e, const View& out);
 bool make_res2_op(const View& x, const View& out, const void* W7, const float* bias, const float* scale,
                   const float* shift, int w8, int dil, Op* op, bool* unsupported);
 
-// Halo-resident 3x3 stride-1 pad-1 conv (ws_conv3x3.cu): out = act(conv(x, W) + bias [+ res]).  x/out/res: channels-last
-// 16-bit views with the same (B,F,T); W: [Cout][9*Cin] tap-major in the activation dtype.  Returns false with
+// Halo-resident 3x3 pad-1 conv (ws_conv3x3.cu), strides 1 or 2 per axis: out = act(conv(x, W) + bias [+ res]).  x/out/res:
+// channels-last 16-bit views (out / res with the strided extents); W: [Cout][9*Cin] tap-major in the activation dtype.  Returns false with
 // *unsupported = true when the shape is outside the kernel's envelope (the caller then uses make_conv_op).
 bool make_conv3x3_op(const View& x, const View& out, const void* W, const float* bias, const View* res, bool relu,
-                     Op* op, bool* unsupported);
+                     Op* op, bool* unsupported, int stride_f = 1, int stride_t = 1);
 
 // Fused CAM++ dense layers (ws_cam_dense.cu).  cam_layer_fill builds one host-side layer descriptor (weights are device
 // pointers in the activation dtype: W1 [128][cin] with BN2 folded, Wl [32][3*128] tap-major; everything else fp32 device

@@ -436,45 +436,64 @@ __global__ void bnrelu_kernel(const void* __restrict__ x, long long x_ld, const 
     }
 }
 
-// one thread per output position (b, f, t): 9 taps x Cout channels, weights in shared memory.
+// Stem conv (1 -> COUT channels, 3x3, pad 1) + folded BN + ReLU.  A block owns an 8 (F) x 128 (T) output tile of one
+// utterance.  The 10 x 130 input patch is staged through shared memory with F-contiguous (coalesced) global reads (the
+// input is [B][T][F]).  A thread owns ONE group of 8 output channels - its 72 weights sit in registers, so the inner loop is
+// 9 shared-memory reads per 72 FMAs instead of one read per FMA - and walks 4 x 8 positions; the COUT/8 channel groups of a
+// position are adjacent lanes, so a warp's store instruction covers whole 64- / 128-byte position records back to back.
 template <int COUT>
 __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ feats, const float* __restrict__ w9,
                                                    const float* __restrict__ shift, void* __restrict__ out,
                                                    float* __restrict__ lo, int dt, int B, int T, int Fdim) {
-    __shared__ float sw[COUT * 9];
-    __shared__ float sh[COUT];
-    for (int i = threadIdx.x; i < COUT * 9; i += blockDim.x) sw[i] = w9[i];
-    for (int i = threadIdx.x; i < COUT; i += blockDim.x) sh[i] = shift[i];
+    constexpr int NG = COUT / 8;            // channel groups per position (4 or 8)
+    constexpr int PL = 128 / NG;            // position lanes per block
+    __shared__ float sin_[10][132];
+    const int t0 = blockIdx.x * 128, f0 = blockIdx.y * 8, b = blockIdx.z;
+    for (int i = threadIdx.x; i < 10 * 130; i += 128) {
+        const int tl = i / 10, fl = i - tl * 10;           // consecutive threads: consecutive F of the same frame
+        const int tt = t0 + tl - 1, ff = f0 + fl - 1;
+        sin_[fl][tl] = (ff >= 0 && ff < Fdim && tt >= 0 && tt < T) ? __ldg(feats + ((long long)b * T + tt) * Fdim + ff) : 0.f;
+    }
+    const int cg = threadIdx.x % NG, pl = threadIdx.x / NG;
+    float w[8][9], sh8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sh8[j] = __ldg(shift + cg * 8 + j);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[j][k] = __ldg(w9 + (cg * 8 + j) * 9 + k);
+    }
     __syncthreads();
-    const long long n = (long long)B * Fdim * T;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    const int t = (int)(idx % T);
-    const int f = (int)((idx / T) % Fdim);
-    const int b = (int)(idx / ((long long)T * Fdim));
-    float in[9];
+#pragma unroll 1
+    for (int tl = pl; tl < 128; tl += PL) {
+        const int t = t0 + tl;
+        if (t >= T) break;
+        float r0[3], r1[3], r2[3];
 #pragma unroll
-    for (int df = 0; df < 3; ++df)
+        for (int k = 0; k < 3; ++k) { r0[k] = sin_[0][tl + k]; r1[k] = sin_[1][tl + k]; }
+#pragma unroll 1
+        for (int fl = 0; fl < 8; ++fl) {
+            const int f = f0 + fl;
+            if (f >= Fdim) break;
 #pragma unroll
-        for (int dtp = 0; dtp < 3; ++dtp) {
-            const int ff = f + df - 1, tt = t + dtp - 1;
-            in[df * 3 + dtp] = (ff >= 0 && ff < Fdim && tt >= 0 && tt < T) ? feats[((long long)b * T + tt) * Fdim + ff] : 0.f;
-        }
+            for (int k = 0; k < 3; ++k) r2[k] = sin_[fl + 2][tl + k];
+            const float in[9] = {r0[0], r0[1], r0[2], r1[0], r1[1], r1[2], r2[0], r2[1], r2[2]};
+            float v[8];
 #pragma unroll
-    for (int c0 = 0; c0 < COUT; c0 += 8) {
-        float v[8];
+            for (int j = 0; j < 8; ++j) {
+                float a = sh8[j];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float a = sh[c0 + j];
+                for (int k = 0; k < 9; ++k) a = fmaf(in[k], w[j][k], a);
+                v[j] = fmaxf(a, 0.f);
+            }
+            const long long idx = ((long long)b * Fdim + f) * T + t;
+            ws_stv8(out, dt, idx * COUT + cg * 8, v);
+            if (lo != nullptr) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) a = fmaf(in[k], sw[(c0 + j) * 9 + k], a);
-            v[j] = fmaxf(a, 0.f);
-        }
-        ws_stv<8>(out, dt, idx * COUT + c0, v);
-        if (lo != nullptr) {
+                for (int j = 0; j < 8; ++j) v[j] = ws_tf32_lo(v[j]);
+                ws_stv8(lo, WS_F32, idx * COUT + cg * 8, v);
+            }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = ws_tf32_lo(v[j]);
-            ws_stv<8>(lo, WS_F32, idx * COUT + c0, v);
+            for (int k = 0; k < 3; ++k) { r0[k] = r1[k]; r1[k] = r2[k]; }
         }
     }
 }
@@ -796,8 +815,8 @@ const char* ws_launch_bnrelu(const void* x, long long x_ld, const float* scale, 
 
 const char* ws_launch_stem(const float* feats, const float* w9, const float* shift, void* out, float* lo, int dt, int B,
                            int T, int Fdim, int Cout, cudaStream_t s) {
-    const long long n = (long long)B * Fdim * T;
-    const int grid = (int)((n + 127) / 128);
+    const dim3 grid((unsigned)((T + 127) / 128), (unsigned)((Fdim + 7) / 8), (unsigned)B);
+    if (B > 65535) return "stem conv: batch too large for one launch";
     if (Cout == 32) stem_kernel<32><<<grid, 128, 0, s>>>(feats, w9, shift, out, lo, dt, B, T, Fdim);
     else if (Cout == 64) stem_kernel<64><<<grid, 128, 0, s>>>(feats, w9, shift, out, lo, dt, B, T, Fdim);
     else return "stem conv supports 32 or 64 output channels";
