@@ -43,6 +43,17 @@ int ws_engine_embed_dim(const ws_engine* e);
 /* feats_dev: fp32 (B,T,feat_dim) already mean-normalised by the caller, as `model(features)` receives them
  * (extract.py:125-133); embs_dev: fp32 (B,embed_dim). */
 int ws_engine_forward(ws_engine* e, const float* feats_dev, int B, int T, float* embs_dev, void* stream);
+/* Length-masked batches (utterances of different lengths padded to a common T in ONE batch; the reference has no masking and
+ * runs such sets at batch 1, extract_vox.sh:31): the result of every utterance equals what it produces alone - rows behind
+ * its end stay zero wherever a convolution reads across time (the zero padding its own forward sees), SE / ASTP / TSTP /
+ * CAM++ context statistics use its own frame count, CAM++'s ceil-mode segment pooling its own segment count
+ * (campplus.py:117-135, pooling_layers.py:78-85,119-144).  n_frames_dev / n_samples_dev: int32[B] on the device.
+ * ECAPA, ResNet and CAM++ (16-bit precisions for CAM++); XVEC is refused. */
+int ws_engine_forward_masked(ws_engine* e, const float* feats_dev, const int* n_frames_dev, int B, int T, float* embs_dev,
+                             void* stream);
+int ws_engine_extract_wav_masked(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, const int* n_samples_dev,
+                                 int max_samples, int B, const char* window_type, float* embs_dev, void* stream);
+
 /* Variable-length jobs: one plan (and CUDA graph) per distinct (B, T); plans own disjoint buffers and are spread over a
  * few internal streams, so the buckets of such a job overlap on the GPU when they are enqueued with the *_async variants
  * (same arguments and semantics as ws_engine_forward / ws_engine_extract_wav, but `stream` is NOT made to wait for the

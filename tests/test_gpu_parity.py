@@ -760,6 +760,55 @@ def test_extract_dropin_and_speaker_api(tmp_path):
         assert rel_l2(got5[f"utt{i}"], got[f"utt{i}"]) <= 1e-3     # oracle fbank vs device fbank in front of the same model
 
 
+@pytest.mark.parametrize("name,prec,tol", [("ECAPA_TDNN_c512", "fp32", 1e-5), ("ECAPA_TDNN_GLOB_c512", "bf16", 4e-3),
+                                           ("ECAPA_TDNN_c1024", "bf16", 4e-3), ("ECAPA_TDNN_c512", "tf32x3", 1e-4),
+                                           ("ResNet34", "fp32", 1e-5), ("ResNet34", "fp16", 2e-3), ("ResNet50", "fp16", 2e-3),
+                                           ("CAMPPlus", "bf16", 4e-3), ("CAMPPlus", "fp16", 2e-3)])
+def test_length_masked_batch_equals_unpadded_utterances(name, prec, tol):
+    """ws_engine_forward_masked: utterances of different lengths padded to a common T in ONE batch must give what each gives
+    alone (the reference has no masking: campplus.py:117-135, pooling_layers.py:78-85,119-144 statistics over the true
+    frames, conv zero padding at the true end).  The padding rows are filled with large garbage to prove they are ignored;
+    also checked against the oracle run per utterance."""
+    lens = [200, 137, 163, 101, 256, 64] if name.startswith("ECAPA") else [200, 137, 163, 101, 301, 64]
+    Tmax = max(lens)
+    g = torch.Generator().manual_seed(5)
+    feats = [torch.from_numpy(syn.make_feats(1, n, 80, seed=40 + i))[0] for i, n in enumerate(lens)]
+    x = 50.0 * torch.randn(len(lens), Tmax, 80, generator=g)          # garbage everywhere ...
+    for i, f in enumerate(feats):
+        x[i, : lens[i]] = f                                            # ... except the valid frames
+    m = from_synthetic(name, 0, precision=prec)
+    got = m.embed_padded(x.to(DEV), lens).cpu().numpy()
+    sd = syn.make_state_dict(name, 0)
+    worst_self, worst_ref = 0.0, 0.0
+    for i, f in enumerate(feats):
+        alone = m.embed(f[None].to(DEV)).cpu().numpy()[0]
+        ref = models_torch.forward(name, sd, f[None]).numpy()[0]
+        worst_self = max(worst_self, float(rel_l2(got[i], alone)))
+        worst_ref = max(worst_ref, float(rel_l2(got[i], ref)))
+    print(f"masked batch {name} {prec}: vs alone {worst_self:.2e}, vs oracle {worst_ref:.2e}")
+    assert np.isfinite(got).all() and worst_self <= tol
+    assert worst_ref <= (1e-4 if prec in ("fp32", "tf32x3") else TC_TOL[prec])
+    # the list API built on it: any mix of lengths through a few padded plans
+    got2 = m.embed_list_padded(feats, max_batch=4, max_pad=0.3, device=DEV).cpu().numpy()
+    assert rel_l2(got2, got).max() <= tol
+
+
+def test_length_masked_wav_extraction():
+    """ws_engine_extract_wav_masked: padded waveforms + sample counts -> fbank, CMN over each utterance's own frames, masked
+    forward; equals per-utterance extraction."""
+    name = "ECAPA_TDNN_c512"
+    m = from_synthetic(name, 0, precision="fp32")
+    ns = [32000, 24000, 17000, 40000]
+    wavs = syn.make_wavs(4, 40000, seed=21)
+    pad = wavs.copy()
+    for i, n in enumerate(ns):
+        pad[i, n:] = 9999.0                                           # garbage behind the end
+    got = m.extract_from_wav_padded(torch.from_numpy(pad).to(DEV), ns).cpu().numpy()
+    for i, n in enumerate(ns):
+        alone = m.extract_from_wav(torch.from_numpy(wavs[i:i + 1, :n].copy()).to(DEV)).cpu().numpy()[0]
+        assert rel_l2(got[i], alone) <= 1e-5, (i, rel_l2(got[i], alone))
+
+
 def test_plan_cache_eviction_many_shapes():
     """More distinct (B,T) shapes than the plan cache holds (64): plans are evicted LRU and rebuilt transparently."""
     name = "ECAPA_TDNN_c512"

@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(kCamThreads, 1) ws_cam_dense_kernel(const __gr
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int b = blockIdx.x;
-    const int nmt = p.nmt, nst = p.nstages, T = p.T;
+    const int nmt = p.nmt, nst = p.nstages;
+    // frames of THIS utterance (length-masked batch) or of every utterance; memory extents stay p.T
+    const int T = p.lens != nullptr ? max(1, min(p.T, p.lens[b])) : p.T;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sH = base;                                          // [2 panels][hrows][128 B] hidden operand buffer
     const uint32_t hpanel = (uint32_t)(p.hrows * 128);

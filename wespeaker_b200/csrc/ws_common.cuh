@@ -329,6 +329,7 @@ struct WsRes2Params {
     int B, T, w8, dil, dtype;
     uint32_t idesc;
     int grid, smem_bytes;
+    const int* lens;    // length-masked batch: frames of each utterance (rows behind it are conv padding: kept zero), or null
 };
 
 // halo-resident 3x3 stride-1 conv (ws_conv3x3.cu): input rows of F live in a shared-memory ring, the 9 taps are row-shifted
@@ -366,6 +367,7 @@ struct WsC3Params {
     int total_steps;               // n_nt * n_tt * n_bg * F output-row steps, split contiguously over the CTAs
     int grid, smem_bytes;
     long long* prof;               // tuning aid (WS_C3_PROF=1): per-CTA wait-cycle counters, 16 slots per CTA; else null
+    const int* lens;               // length-masked batch: output frames of each utterance (rows behind are stored as zeros), or null
     int dbg;                       // tuning aid (WS_C3_DBG): knock-out bits 1 = no epilogue work, 2 = no input TMA loads, 8 = no MMAs
 };
 
@@ -394,6 +396,7 @@ struct WsCamParams {
     int nstages, hrows;       // ring stages (32 KB each); rows per panel of the hidden operand buffer (16 + 128 * nmt)
     int grid, smem_bytes;
     long long* prof;          // tuning aid (WS_CAM_PROF=1): phase timestamps of CTA 0, first layer; else null
+    const int* lens;          // length-masked batch: frames of each utterance (statistics and padding follow them), or null
 };
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are PER DEVICE: init guards are keyed by the current

@@ -401,6 +401,13 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
+                    if (p.lens != nullptr) {   // length-masked batch: frames behind the utterance's end are the next conv's padding
+                        const int i2 = mt * 128 + r, u = i2 / p.P, tti = i2 - u * p.P, bb = min(b0 + u, p.B - 1);
+                        if (t0 + tti >= p.lens[bb]) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                        }
+                    }
                     // rows that are no output position (halo columns, rows past T or B) hold junk: the TMA store clips them
                     stage_store32(pbase, r, p.panel_bytes, cc * 32, DT, v);
                 }

@@ -373,7 +373,7 @@ bool make_conv_op(const ConvSpec& spec, int use_tc, Op* out) {
 }
 
 bool make_res2_op(const View& x, const View& out, const void* W7, const float* bias, const float* scale,
-                  const float* shift, int w8, int dil, Op* op, bool* unsupported) {
+                  const float* shift, int w8, int dil, Op* op, bool* unsupported, const int* lens) {
     *unsupported = false;
     if (x.dt == WS_F32 || (w8 != 64 && w8 != 128) || x.T > 256 || x.F != 1 || dil < 1 || dil > 7 || getenv("WS_NO_RES2_FUSED")) {
         *unsupported = true;
@@ -394,7 +394,7 @@ bool make_res2_op(const View& x, const View& out, const void* W7, const float* b
         cuuint32_t box[2] = {64, (cuuint32_t)w8};
         if (!encode_map(&q->wmap, x.dt, W7, 2, dims, str, box, 128)) return false;
     }
-    q->x = x.p; q->ld = x.ld; q->bias = bias; q->scale = scale; q->shift = shift;
+    q->x = x.p; q->ld = x.ld; q->bias = bias; q->scale = scale; q->shift = shift; q->lens = lens;
     q->B = x.B; q->T = x.T; q->w8 = w8; q->dil = dil; q->dtype = x.dt;
     const uint32_t fmt = x.dt == WS_BF16 ? 1u : 0u;
     q->idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(w8 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -407,7 +407,7 @@ bool make_res2_op(const View& x, const View& out, const void* W7, const float* b
 }
 
 bool make_conv3x3_op(const View& x, const View& out, const void* W, const float* bias, const View* res, bool relu,
-                     Op* op, bool* unsupported, int stride_f, int stride_t) {
+                     Op* op, bool* unsupported, int stride_f, int stride_t, const int* lens) {
     *unsupported = false;
     const int Cin = x.C, Cout = out.C, Tin = x.T, Fin = x.F, B = x.B;
     const int F = (Fin + 2 - 3) / stride_f + 1, T = (Tin + 2 - 3) / stride_t + 1;   // output extents
@@ -534,6 +534,7 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
     q->res_ld = res ? res->ld : 0;
     q->bias = bias;
     q->relu = relu ? 1 : 0;
+    q->lens = lens;
     if (const char* dbg = getenv("WS_C3_DBG")) q->dbg = atoi(dbg);
     if (getenv("WS_C3_PROF")) {   // tuning aid: synchronous launch + per-role wait-cycle summary on stderr
         long long* prof = nullptr;
@@ -589,7 +590,8 @@ bool cam_layer_fill(WsCamLayer* L, int dt, const void* W1, const void* Wl, const
     return true;
 }
 
-bool make_cam_dense_op(const View& X, const WsCamLayer* layers_dev, int l0, int l1, Op* op, bool* unsupported) {
+bool make_cam_dense_op(const View& X, const WsCamLayer* layers_dev, int l0, int l1, Op* op, bool* unsupported,
+                       const int* lens) {
     *unsupported = false;
     const int T = X.T, B = X.B;
     if (X.dt == WS_F32 || X.F != 1 || T < 1 || T > 512 || (X.ld * 2) % 16 != 0 || getenv("WS_NO_CAM_FUSED")) {
@@ -598,7 +600,7 @@ bool make_cam_dense_op(const View& X, const WsCamLayer* layers_dev, int l0, int 
     }
     auto q = std::make_shared<WsCamParams>();
     memset(q.get(), 0, sizeof(WsCamParams));
-    q->layers = layers_dev; q->l0 = l0; q->l1 = l1;
+    q->layers = layers_dev; q->l0 = l0; q->l1 = l1; q->lens = lens;
     q->B = B; q->T = T; q->nmt = (T + 127) / 128; q->seg_len = 100; q->dtype = X.dt;
     q->hrows = 16 + 128 * q->nmt;
     int nst = 6;

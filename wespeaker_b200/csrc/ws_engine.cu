@@ -48,6 +48,8 @@ struct Plan {
     float* emb = nullptr;       // fp32 [B][embed_dim]
     cudaGraphExec_t gexec = nullptr;
     bool graph_failed = false;
+    bool masked = false;        // length-masked plan: per-utterance frame counts arrive with every run (see `lens`)
+    int* lens = nullptr;        // device [4][B]: frames per utterance at the input and behind each stride-2 level
     int lane = 0;               // which of the engine's streams runs this plan through the device-pointer entry points
     cudaEvent_t done = nullptr; // recorded after every use: a later use on another stream waits for it
     ~Plan() {
@@ -70,7 +72,7 @@ struct ws_engine {
     std::map<std::string, HostT> sd;
     bool finalized = false;
     std::map<std::string, void*> wcache;  // packed device weights by id
-    std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+    std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;   // key: (B, 2 * T + masked)
     long long last_launches = 0;
     long long use_clock = 0;             // LRU clock for the plan cache
     cudaStream_t st = nullptr;
@@ -252,6 +254,15 @@ struct Builder {
     }
     float* f32(size_t n) { return (float*)raw(n * 4); }
     void push(Op op) { p.ops.push_back(std::move(op)); }
+    // length-masked plans: frame counts of stride level k (nullptr in ordinary plans), and "zero the rows behind every
+    // utterance's end" for tensors a time-mixing op is about to read (the reference's unpadded forward sees zero padding)
+    const int* lens(int level) const { return p.masked ? p.lens + (size_t)level * p.B : nullptr; }
+    void zero_tail(const View& v, int level) {
+        if (!p.masked) return;
+        const View x = v;
+        const int* l = lens(level);
+        push([=](cudaStream_t s) { return ws_launch_zero_tail(x.p, (float*)x.plo, x.dt, x.B, x.F, x.T, x.C, x.ld, l, s); });
+    }
     void conv(const ConvSpec& s_in) {
         if (!good()) return;
         ConvSpec s = s_in;
@@ -286,11 +297,13 @@ struct Builder {
         fill_epi_out(s.epi, out);
         conv(s);
     }
-    void tstats(const View& x, const float* pre_scale, const float* pre_shift, float* out, long long out_ld, int std_off) {
+    void tstats(const View& x, const float* pre_scale, const float* pre_shift, float* out, long long out_ld, int std_off,
+                int level = 0) {
         View xv = x;
+        const int* l = lens(level);
         push([=](cudaStream_t s) {
             return ws_launch_tstats(xv.p, xv.dt, xv.B, xv.F, xv.T, xv.C, xv.ld, pre_scale, pre_shift, out, WS_F32, out_ld,
-                                    std_off, 1e-7f, s);
+                                    std_off, 1e-7f, s, l);
         });
     }
     void linear(const float* in, long long in_ld, const float* in2, long long in2_ld, int rows_per_b, const float* W,
@@ -333,6 +346,7 @@ bool build_ecapa(Builder& b) {
         const int dt = e.act_dt;
         const long long n = (long long)B * T * Fd;
         b.push([=](cudaStream_t s) { return ws_launch_convert(fin, xo, xlo, dt, n, s); });
+        b.zero_tail(x0, 0);   // (masked plans) the k=5 conv of layer1 must see zero padding behind each utterance
     }
     // Conv1dReluBn (ecapa_tdnn.py:85-106): bn(relu(conv(x)+bias))
     auto conv_relu_bn = [&](const std::string& pfx, const View& x, const View& out, int k, int dil, int pad) {
@@ -350,12 +364,13 @@ bool build_ecapa(Builder& b) {
     View xin = out1;
     float* se_colsum = nullptr;
     if (e.use_tc >= 2 && e.act_dt != WS_F32 && !e.split && T >= 128 && (C == 512 || C == 1024) && e.opt("se_fused", 1) &&
-        e.opt("se_colsum", 1) && getenv("WS_EPI_GENERIC") == nullptr)
+        e.opt("se_colsum", 1) && getenv("WS_EPI_GENERIC") == nullptr && !b.p.masked)   // (column sums would include padding rows)
         se_colsum = b.f32((size_t)2 * (((size_t)B * T + 63) / 64) * C);
     for (int L = 2; L <= 4 && b.good(); ++L) {
         const int d = L;
         const std::string pf = "layer" + std::to_string(L) + ".se_res2block";
         conv_relu_bn(pf + ".0", xin, tA, 1, 1, 0);
+        b.zero_tail(tA, 0);   // (masked plans) the dilated Res2 convs read tA across time
         // Res2Conv1dReluBn (ecapa_tdnn.py:29-78): 7 dependent dilated k=3 convs on w8-channel groups
         bool fused = false;
         if (e.use_tc >= 2 && e.act_dt != WS_F32 && e.opt("res2_fused", 1)) {
@@ -378,7 +393,7 @@ bool build_ecapa(Builder& b) {
             Op op;
             bool unsupported = false;
             if (make_res2_op(tA, tB, b.w.act("w7:" + pf, w7), b.w.f32("b7:" + pf, b7), b.w.f32("s7:" + pf, s7),
-                             b.w.f32("h7:" + pf, h7), w8, d, &op, &unsupported)) {
+                             b.w.f32("h7:" + pf, h7), w8, d, &op, &unsupported, b.lens(0))) {
                 b.push(std::move(op));
                 fused = true;
             } else if (!unsupported) {
@@ -403,6 +418,7 @@ bool build_ecapa(Builder& b) {
             }
             const View src = (i == 0) ? tA.ch(0, w8) : sc[(i - 1) & 1];
             b.conv_simple(src, tB.ch(i * w8, w8), b.w.act("w:" + cp, wp), 1, 3, 1, d, 0, d, 1, 1, ep);
+            if (i < 6) b.zero_tail(sc[i & 1], 0);   // (masked plans) s_{i+1} feeds the next dilated conv
         }
         if (!b.good()) break;
         {   // third block: 1x1 conv over cat[sp_0..sp_6, spx_7]: two K ranges from two buffers
@@ -443,7 +459,8 @@ bool build_ecapa(Builder& b) {
             View tc = tC;
             const int dt = e.act_dt;
             const float* cs_in = se_colsum;
-            b.push([=](cudaStream_t s) { return ws_launch_se_gate(tc.p, dt, B, T, C, tc.ld, w1d, b1d, w2d, b2d, 128, segate, cs_in, s); });
+            const int* l0 = b.lens(0);
+            b.push([=](cudaStream_t s) { return ws_launch_se_gate(tc.p, dt, B, T, C, tc.ld, w1d, b1d, w2d, b2d, 128, segate, cs_in, s, l0); });
         } else {
             b.tstats(tC, nullptr, nullptr, semean, C, -1);
             b.linear(semean, C, nullptr, 0, 1, b.w.vec(pf + ".3.linear1.weight"), b.w.vec(pf + ".3.linear1.bias"), sehid, 128, B,
@@ -505,7 +522,8 @@ bool build_ecapa(Builder& b) {
         ep2.bias = b.w.vec("pool.linear2.bias");
         b.conv_simple(hid, logits, b.w.act("w:pool.linear2", w2), 1, 1, 1, 1, 0, 0, 1, 1, ep2);
         View fr = frame, lg = logits;
-        b.push([=](cudaStream_t s) { return ws_launch_astp_stats(fr.p, lg.p, fr.dt, B, T, 1536, fr.ld, stats, s); });
+        const int* l0 = b.lens(0);
+        b.push([=](cudaStream_t s) { return ws_launch_astp_stats(fr.p, lg.p, fr.dt, B, T, 1536, fr.ld, stats, s, l0); });
     }
     {   // bn(3072) then linear (ecapa_tdnn.py:230-231): fold the affine into the linear; optional bn2 (emb_bn)
         std::vector<float> s, h;
@@ -533,7 +551,8 @@ bool build_ecapa(Builder& b) {
 // ----------------------------------------------------------------------------------------------- 2-D residual blocks
 // BasicBlock (resnet.py:35-69) / BasicResBlock (campplus.py:245-279): eval BN folded into the conv weights, the
 // 1x1 strided shortcut conv is merged into conv2's GEMM as one extra K range, residual/ReLU in the epilogue.
-View basic_block(Builder& b, const std::string& p, const View& x, int cout, int sf, int st_, View hbuf, View obuf) {
+// `lvl`: stride level of the block's OUTPUT (length-masked plans: frame counts b.lens(lvl)); the time stride st_ is 1 or 2
+View basic_block(Builder& b, const std::string& p, const View& x, int cout, int sf, int st_, View hbuf, View obuf, int lvl = 0) {
     std::vector<float> s1, h1, s2, h2, w1, w2;
     int co, ci, nt;
     View none;
@@ -550,7 +569,7 @@ View basic_block(Builder& b, const std::string& p, const View& x, int cout, int 
         if (!c3) return 0;
         Op op;
         bool unsupported = false;
-        if (make_conv3x3_op(in, outv, Wd, bias, res, true, &op, &unsupported, s_f, s_t)) { b.push(std::move(op)); return 1; }
+        if (make_conv3x3_op(in, outv, Wd, bias, res, true, &op, &unsupported, s_f, s_t, b.lens(lvl))) { b.push(std::move(op)); return 1; }
         if (!unsupported) { b.ok = false; return -1; }
         return 0;
     };
@@ -564,6 +583,7 @@ View basic_block(Builder& b, const std::string& p, const View& x, int cout, int 
             e1.bias = b1;
             e1.act1 = WS_ACT_RELU;
             b.conv_simple(x, h, W1, 3, 3, 1, 1, 1, 1, sf, st_, e1);
+            b.zero_tail(h, lvl);
         }
     }
     if (!b.good()) return none;
@@ -577,7 +597,7 @@ View basic_block(Builder& b, const std::string& p, const View& x, int cout, int 
         View resv = has_sc0 ? o : x;
         Op op2;
         bool unsupported = false;
-        if (make_conv3x3_op(h, o, W2, b2, &resv, true, &op2, &unsupported)) {
+        if (make_conv3x3_op(h, o, W2, b2, &resv, true, &op2, &unsupported, 1, 1, b.lens(lvl))) {
             if (has_sc0) {
                 std::vector<float> ss, hs, wsv;
                 if (!b.w.bn(p + ".shortcut.1", true, ss, hs) || !b.w.pack_conv(p + ".shortcut.0.weight", &ss, wsv, &co, &ci, &nt)) return none;
@@ -620,13 +640,15 @@ View basic_block(Builder& b, const std::string& p, const View& x, int cout, int 
     cs.epi.act2 = WS_ACT_RELU;
     fill_epi_out(cs.epi, o);
     b.conv(cs);
+    b.zero_tail(o, lvl);
     return o;
 }
 
 // Bottleneck (resnet.py:72-107): 1x1 -> BN -> ReLU -> 3x3 (stride) -> BN -> ReLU -> 1x1 (x4) -> BN, + shortcut, ReLU.  BNs are
 // folded into the conv weights; the 1x1 strided shortcut conv (+ BN) is merged into conv3's GEMM as one extra K range (same
 // output positions), an identity shortcut is the residual input of conv3's epilogue.
-View bottleneck_block(Builder& b, const std::string& p, const View& x, int planes, int s, View h1buf, View h2buf, View obuf) {
+View bottleneck_block(Builder& b, const std::string& p, const View& x, int planes, int s, View h1buf, View h2buf, View obuf,
+                      int lvl_in = 0, int lvl = 0) {
     std::vector<float> s1, h1, s2, h2, s3, h3, w1, w2, w3;
     int co, ci, nt;
     View none;
@@ -643,6 +665,7 @@ View bottleneck_block(Builder& b, const std::string& p, const View& x, int plane
     e1.bias = b.w.f32("bnh:" + p + ".bn1", h1);
     e1.act1 = WS_ACT_RELU;
     b.conv_simple(x, a, b.w.act("w:" + p + ".conv1", w1), 1, 1, 1, 1, 0, 0, 1, 1, e1);
+    b.zero_tail(a, lvl_in);   // (masked plans) the 3x3 conv reads `a` across time
     if (!b.good()) return none;
     {   // 3x3: halo-resident kernel when stride 1 and planes <= 128, else the generic conv-GEMM
         const float* b2 = b.w.f32("bnh:" + p + ".bn2", h2);
@@ -651,7 +674,7 @@ View bottleneck_block(Builder& b, const std::string& p, const View& x, int plane
         if ((s == 1 || b.e.opt("conv3x3_strided", 1) != 0) && b.e.use_tc >= 2 && b.e.act_dt != WS_F32 && b.e.opt("conv3x3", 1) != 0) {
             Op op;
             bool unsupported = false;
-            if (make_conv3x3_op(a, c, W2, b2, nullptr, true, &op, &unsupported, s, s)) { b.push(std::move(op)); done = true; }
+            if (make_conv3x3_op(a, c, W2, b2, nullptr, true, &op, &unsupported, s, s, b.lens(lvl))) { b.push(std::move(op)); done = true; }
             else if (!unsupported) { b.ok = false; return none; }
         }
         if (!done) {
@@ -708,7 +731,8 @@ View stem(Builder& b, const std::string& convkey, const std::string& bnkey, View
     const int dt = b.e.act_dt;
     void* op = o.p;
     float* olo = (float*)o.plo;
-    b.push([=](cudaStream_t st) { return ws_launch_stem(fin, wd, hd, op, olo, dt, B, T, Fd, co, st); });
+    const int* l0 = b.lens(0);
+    b.push([=](cudaStream_t st) { return ws_launch_stem(fin, wd, hd, op, olo, dt, B, T, Fd, co, st, l0); });
     return o;
 }
 
@@ -731,13 +755,14 @@ bool build_resnet(Builder& b) {
         for (int bi = 0; bi < e.num_blocks[li - 1] && b.good(); ++bi) {
             const int s = (bi == 0 && li > 1) ? 2 : 1;
             const std::string p = "layer" + std::to_string(li) + "." + std::to_string(bi);
+            const int lvl = li - 1, lvl_in = (s == 2) ? li - 2 : li - 1;   // stride level = number of stride-2 layers passed
             if (e.bottleneck) {   // x lives in bufs[ci]; the two intermediates and the output rotate through the other three
-                View o = bottleneck_block(b, p, cur, cout, s, bufs[(ci + 1) % 4], bufs[(ci + 2) % 4], bufs[(ci + 3) % 4]);
+                View o = bottleneck_block(b, p, cur, cout, s, bufs[(ci + 1) % 4], bufs[(ci + 2) % 4], bufs[(ci + 3) % 4], lvl_in, lvl);
                 ci = (ci + 3) % 4;
                 cur = o;
                 continue;
             }
-            View o = basic_block(b, p, cur, cout, s, s, bufs[(ci + 1) % 3], bufs[(ci + 2) % 3]);
+            View o = basic_block(b, p, cur, cout, s, s, bufs[(ci + 1) % 3], bufs[(ci + 2) % 3], lvl);
             ci = (ci + 2) % 3;
             cur = o;
         }
@@ -745,7 +770,7 @@ bool build_resnet(Builder& b) {
     if (!b.good()) return false;
     const int sd = cur.C * cur.F;  // stats_dim
     float* stats = b.f32((size_t)B * 2 * sd);
-    b.tstats(cur, nullptr, nullptr, stats, 2 * sd, sd);  // TSTP, index c*F' + f (pooling_layers.py:78-85)
+    b.tstats(cur, nullptr, nullptr, stats, 2 * sd, sd, 3);  // TSTP, index c*F' + f (pooling_layers.py:78-85); stride level 3
     const HostT* w1 = b.w.get("seg_1.weight");
     if (!w1) return false;
     if ((int)w1->shape[1] != 2 * sd || (int)w1->shape[0] != E) { set_err("seg_1.weight shape mismatch"); return false; }
@@ -780,6 +805,7 @@ bool build_xvec(Builder& b) {
     ws_engine& e = b.e;
     const int B = b.p.B, T = b.p.T, Fd = e.feat_dim, E = e.embed_dim;
     if (T < 15) { set_err("XVEC needs at least 15 frames (valid convolutions of context 5, 3x2, 3x3)"); return false; }
+    if (b.p.masked) { set_err("length-masked batches are not implemented for XVEC (its valid convolutions shrink every utterance differently)"); return false; }
     const HostT* w5 = b.w.get("frame_5.conv_1d.weight");
     const HostT* w1h = b.w.get("frame_1.conv_1d.weight");
     if (!w5 || !w1h) return false;
@@ -862,7 +888,7 @@ bool build_campplus(Builder& b) {
     for (int li = 1; li <= 2 && b.good(); ++li)
         for (int bi = 0; bi < 2 && b.good(); ++bi) {
             const std::string p = "head.layer" + std::to_string(li) + "." + std::to_string(bi);
-            View o = basic_block(b, p, cur, m, bi == 0 ? 2 : 1, 1, bufs[(ci + 1) % 3], bufs[(ci + 2) % 3]);
+            View o = basic_block(b, p, cur, m, bi == 0 ? 2 : 1, 1, bufs[(ci + 1) % 3], bufs[(ci + 2) % 3], 0);
             ci = (ci + 2) % 3;
             cur = o;
         }
@@ -880,7 +906,7 @@ bool build_campplus(Builder& b) {
         if (e.use_tc >= 2 && e.act_dt != WS_F32 && e.opt("conv3x3", 1) != 0 && e.opt("conv3x3_strided", 1) != 0) {
             Op op;
             bool unsupported = false;
-            if (make_conv3x3_op(cur, y, Wh, hb, nullptr, true, &op, &unsupported, 2, 1)) { b.push(std::move(op)); done = true; }
+            if (make_conv3x3_op(cur, y, Wh, hb, nullptr, true, &op, &unsupported, 2, 1, b.lens(0))) { b.push(std::move(op)); done = true; }
             else if (!unsupported) return false;
         }
         if (!done) {
@@ -888,6 +914,7 @@ bool build_campplus(Builder& b) {
             ep.bias = hb;
             ep.act1 = WS_ACT_RELU;
             b.conv_simple(cur, y, Wh, 3, 3, 1, 1, 1, 1, 2, 1, ep);
+            b.zero_tail(y, 0);
         }
     }
     if (!b.good()) return false;
@@ -984,12 +1011,13 @@ bool build_campplus(Builder& b) {
             for (int j = 0; j < nl[bl]; j += whole ? nl[bl] : 1) {
                 Op op;
                 bool unsupported = false;
-                if (make_cam_dense_op(X[bl], ldev, j, whole ? nl[bl] : j + 1, &op, &unsupported)) b.push(std::move(op));
+                if (make_cam_dense_op(X[bl], ldev, j, whole ? nl[bl] : j + 1, &op, &unsupported, b.lens(1))) b.push(std::move(op));
                 else if (unsupported && j == 0) { fused_done = false; break; }
                 else { b.ok = false; break; }
             }
             if (!b.good()) break;
         }
+        if (!fused_done && b.p.masked) { set_err("length-masked CAM++ plans need the fused dense-layer kernel (16-bit precision, T' <= 512)"); return false; }
         for (int j = 1; j <= nl[bl] && b.good() && !fused_done; ++j) {
             const std::string p = "xvector.block" + std::to_string(bl + 1) + ".tdnnd" + std::to_string(j);
             const int cin = c0[bl] + (j - 1) * growth;
@@ -1055,7 +1083,7 @@ bool build_campplus(Builder& b) {
         const int cf = Xf.C;
         if (!b.w.bn("xvector.out_nonlinear.batchnorm", true, s, h) || !b.w.bn("xvector.dense.nonlinear.batchnorm", false, sdn, hdn)) return false;
         float* stats = b.f32((size_t)B * 2 * cf);
-        b.tstats(Xf, b.w.f32("bns:out_nl", s), b.w.f32("bnh:out_nl", h), stats, 2 * cf, cf);
+        b.tstats(Xf, b.w.f32("bns:out_nl", s), b.w.f32("bnh:out_nl", h), stats, 2 * cf, cf, 1);
         const HostT* dw = b.w.get("xvector.dense.linear.weight");
         if (!dw) return false;
         if ((int)dw->shape[0] != E || (int)dw->shape[1] != 2 * cf) { set_err("xvector.dense.linear.weight shape mismatch"); return false; }
@@ -1067,8 +1095,8 @@ bool build_campplus(Builder& b) {
     return b.good();
 }
 
-Plan* get_plan(ws_engine* e, int B, int T) {
-    auto key = std::make_pair(B, T);
+Plan* get_plan(ws_engine* e, int B, int T, bool masked = false) {
+    auto key = std::make_pair(B, 2 * T + (masked ? 1 : 0));
     auto it = e->plans.find(key);
     if (it != e->plans.end()) {
         it->second->last_use = ++e->use_clock;
@@ -1076,8 +1104,13 @@ Plan* get_plan(ws_engine* e, int B, int T) {
     }
     if (B <= 0 || T <= 0) { set_err("forward: B and T must be positive"); return nullptr; }
     std::unique_ptr<Plan> p(new Plan());
-    p->B = B; p->T = T;
+    p->B = B; p->T = T; p->masked = masked;
     Builder b(*e, *p);
+    if (masked) {
+        p->lens = (int*)b.raw((size_t)4 * B * sizeof(int));
+        int* l = p->lens;
+        if (b.good()) b.push([=](cudaStream_t s) { return ws_launch_lens_derive(l, B, T, 4, s); });
+    }
     p->feats_in = b.f32((size_t)B * T * e->feat_dim);
     p->emb = b.f32((size_t)B * e->embed_dim);
     bool ok = b.good();
@@ -1338,6 +1371,52 @@ static int forward_impl(ws_engine* e, const float* feats_dev, int B, int T, floa
     if (run_plan(e, p, ws)) return 1;
     WS_CK(cudaMemcpyAsync(embs_dev, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToDevice, ws));
     if (!join) { WS_CK(cudaEventRecord(p->done, ws)); return 0; }
+    return leave_stream(e, p, ws, us);
+}
+
+// Length-masked batches: utterances of different lengths padded to a common T run as ONE batch and produce what each
+// utterance produces alone (the reference has no masking, extract_vox.sh:31 runs test sets at batch 1): rows behind an
+// utterance's end are kept zero wherever a convolution reads across time, and SE / ASTP / TSTP / CAM++ context statistics
+// use the utterance's own frame count.  n_frames_dev: int32[B] on the device; feats rows t >= n_frames[b] are ignored.
+int ws_engine_forward_masked(ws_engine* e, const float* feats_dev, const int* n_frames_dev, int B, int T, float* embs_dev,
+                             void* stream) {
+    if (!e || !feats_dev || !n_frames_dev || !embs_dev) { set_err("ws_engine_forward_masked: null argument"); return 1; }
+    if (!e->finalized) { set_err("ws_engine_forward_masked before ws_engine_finalize"); return 1; }
+    WS_CK(cudaSetDevice(e->device));
+    Plan* p = get_plan(e, B, T, true);
+    if (!p) return 1;
+    cudaStream_t us = (cudaStream_t)stream, ws = lane_stream(e, p);
+    if (enter_stream(e, p, ws, us)) return 1;
+    WS_CK(cudaMemcpyAsync(p->lens, n_frames_dev, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, ws));
+    WS_CK(cudaMemcpyAsync(p->feats_in, feats_dev, (size_t)B * T * e->feat_dim * 4, cudaMemcpyDeviceToDevice, ws));
+    if (run_plan(e, p, ws)) return 1;
+    WS_CK(cudaMemcpyAsync(embs_dev, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToDevice, ws));
+    return leave_stream(e, p, ws, us);
+}
+
+// Same from padded waveforms: wav_dev [B][wav_ld] with n_samples_dev[b] valid samples each (max_samples = the longest);
+// fbank of the padded rows, CMN over each utterance's own frames, masked forward.
+int ws_engine_extract_wav_masked(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, const int* n_samples_dev,
+                                 int max_samples, int B, const char* window_type, float* embs_dev, void* stream) {
+    if (!e || !wav_dev || !n_samples_dev || !embs_dev) { set_err("ws_engine_extract_wav_masked: null argument"); return 1; }
+    if (!e->finalized) { set_err("ws_engine_extract_wav_masked before ws_engine_finalize"); return 1; }
+    if (e->feat_dim != 80) { set_err("ws_engine_extract_wav_masked: the fbank frontend produces 80 bins"); return 1; }
+    WS_CK(cudaSetDevice(e->device));
+    const int T = ws_fbank_num_frames(max_samples);
+    if (T <= 0) { set_err("ws_engine_extract_wav_masked: waveforms shorter than one 25 ms frame"); return 1; }
+    Plan* p = get_plan(e, B, T, true);
+    if (!p) return 1;
+    const FbankTables* t = fbank_tables(e, window_type);
+    if (!t) return 1;
+    cudaStream_t us = (cudaStream_t)stream, ws = lane_stream(e, p);
+    if (enter_stream(e, p, ws, us)) return 1;
+    WS_CKS(ws_launch_frames_from_samples(n_samples_dev, p->lens, B, ws));
+    WS_CKS(ws_launch_fbank(wav_dev, wav_is_i16, wav_ld, max_samples, B, T, t->window, t->melw, t->melstart, t->mellen, t->maxlen,
+                           p->feats_in, ws));
+    WS_CKS(ws_launch_cmn(p->feats_in, B, T, 80, ws, p->lens));
+    if (run_plan(e, p, ws)) return 1;
+    e->last_launches += 3;
+    WS_CK(cudaMemcpyAsync(embs_dev, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToDevice, ws));
     return leave_stream(e, p, ws, us);
 }
 

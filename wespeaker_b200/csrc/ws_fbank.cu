@@ -288,12 +288,14 @@ __global__ void __launch_bounds__(256) fbank_kernel2(const void* __restrict__ wa
 }
 
 // block (32, 8): subtract the per-utterance mean over T from every bin (dataset_utils.py:19-26)
-__global__ void __launch_bounds__(256) cmn_kernel(float* __restrict__ feats, int T, int Fdim) {
+__global__ void __launch_bounds__(256) cmn_kernel(float* __restrict__ feats, int T, int Fdim, const int* __restrict__ lens) {
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     const int b = blockIdx.y;
     const bool cv = c < Fdim;
     float* p = feats + (long long)b * T * Fdim + c;
+    const int Tpad = T;
+    if (lens != nullptr) T = max(1, min(T, lens[b]));   // length-masked batch: mean over the utterance's own frames
     float s = 0.f;
     if (cv)
         for (int t = threadIdx.y; t < T; t += 8) s += p[(long long)t * Fdim];
@@ -303,8 +305,10 @@ __global__ void __launch_bounds__(256) cmn_kernel(float* __restrict__ feats, int
 #pragma unroll
     for (int i = 0; i < 8; ++i) mean += red[i][threadIdx.x];
     mean /= (float)T;
-    if (cv)
+    if (cv) {
         for (int t = threadIdx.y; t < T; t += 8) p[(long long)t * Fdim] -= mean;
+        for (int t = T + threadIdx.y; t < Tpad; t += 8) p[(long long)t * Fdim] = 0.f;   // padding frames
+    }
 }
 
 }  // namespace
@@ -323,10 +327,10 @@ const char* ws_launch_fbank(const void* wav, int wav_is_i16, long long wav_ld, i
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
-const char* ws_launch_cmn(float* feats, int B, int T, int Fdim, cudaStream_t s) {
+const char* ws_launch_cmn(float* feats, int B, int T, int Fdim, cudaStream_t s, const int* lens) {
     if (T <= 0 || B <= 0) return nullptr;
     dim3 grid((Fdim + 31) / 32, B), block(32, 8);
-    cmn_kernel<<<grid, block, 0, s>>>(feats, T, Fdim);
+    cmn_kernel<<<grid, block, 0, s>>>(feats, T, Fdim, lens);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -80,13 +80,13 @@ void fill_epi_out(WsEpi& e, const View& out);
 // the activation dtype; bias/scale/shift: [7][w8] fp32.  Returns false with *unsupported=true when the shape/dtype is
 // outside the fused kernel's envelope (16-bit activations, w8 in {64,128}, T <= 256).
 bool make_res2_op(const View& x, const View& out, const void* W7, const float* bias, const float* scale,
-                  const float* shift, int w8, int dil, Op* op, bool* unsupported);
+                  const float* shift, int w8, int dil, Op* op, bool* unsupported, const int* lens = nullptr);
 
 // Halo-resident 3x3 pad-1 conv (ws_conv3x3.cu), strides 1 or 2 per axis: out = act(conv(x, W) + bias [+ res]).  x/out/res:
 // channels-last 16-bit views (out / res with the strided extents); W: [Cout][9*Cin] tap-major in the activation dtype.  Returns false with
 // *unsupported = true when the shape is outside the kernel's envelope (the caller then uses make_conv_op).
 bool make_conv3x3_op(const View& x, const View& out, const void* W, const float* bias, const View* res, bool relu,
-                     Op* op, bool* unsupported, int stride_f = 1, int stride_t = 1);
+                     Op* op, bool* unsupported, int stride_f = 1, int stride_t = 1, const int* lens = nullptr);
 
 // Fused CAM++ dense layers (ws_cam_dense.cu).  cam_layer_fill builds one host-side layer descriptor (weights are device
 // pointers in the activation dtype: W1 [128][cin] with BN2 folded, Wl [32][3*128] tap-major; everything else fp32 device
@@ -95,6 +95,7 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
 bool cam_layer_fill(WsCamLayer* L, int dt, const void* W1, const void* Wl, const float* bn1_scale, const float* bn1_shift,
                     const float* bias2, const float* w1c_t, const float* b1c, const float* w2c_t, const float* b2c, int cin,
                     int dil);
-bool make_cam_dense_op(const View& X, const WsCamLayer* layers_dev, int l0, int l1, Op* op, bool* unsupported);
+bool make_cam_dense_op(const View& X, const WsCamLayer* layers_dev, int l0, int l1, Op* op, bool* unsupported,
+                       const int* lens = nullptr);
 
 }  // namespace ws

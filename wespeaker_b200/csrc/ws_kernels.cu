@@ -28,12 +28,16 @@ __global__ void convert_kernel(const float* __restrict__ in, void* __restrict__ 
 __global__ void __launch_bounds__(256) tstats_kernel(const void* __restrict__ x, int dt, int F, int T, int C,
                                                      long long ld, const float* __restrict__ pre_scale,
                                                      const float* __restrict__ pre_shift, void* __restrict__ out,
-                                                     int odt, long long out_ld, int std_off, float eps) {
+                                                     int odt, long long out_ld, int std_off, float eps,
+                                                     const int* __restrict__ lens) {
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     const int f = blockIdx.y, b = blockIdx.z;
     const bool cv = c < C;
     const long long base = ((long long)b * F + f) * T * ld + c;
+    const int Ts = T;                                   // memory stride between utterances stays the padded T
+    if (lens != nullptr) T = max(1, min(T, lens[b]));   // length-masked batch: statistics over this utterance's own frames
+    (void)Ts;
     float ps = 1.f, ph = 0.f;
     const bool pre = pre_scale != nullptr;
     if (pre && cv) { ps = pre_scale[c]; ph = pre_shift[c]; }
@@ -265,12 +269,14 @@ __global__ void scale_residual_kernel(const void* __restrict__ x, long long x_ld
 // block (32, 8), 2 channels per thread; ONE pass over (x, logits) with an online softmax per (b, c): running max m and
 // sums rescaled by exp(m_old - m_new); the 8 T-slices are merged through shared memory.
 __global__ void __launch_bounds__(256) astp_stats_kernel(const void* __restrict__ x, const void* __restrict__ lg,
-                                                         int dt, int T, int C, long long ld, float* __restrict__ out) {
+                                                         int dt, int T, int C, long long ld, float* __restrict__ out,
+                                                         const int* __restrict__ lens) {
     __shared__ float red[4][8][65];
     const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
     const int b = blockIdx.y;
     const bool cv = c < C;
     const long long base = (long long)b * T * ld + c;
+    if (lens != nullptr) T = max(1, min(T, lens[b]));   // softmax / weighted statistics over this utterance's own frames
     float m[2] = {-INFINITY, -INFINITY}, s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
     if (cv) {
         for (int t = threadIdx.y; t < T; t += 8) {   // this thread's slice maximum (logits only)
@@ -326,13 +332,15 @@ __global__ void __launch_bounds__(256) astp_stats_kernel(const void* __restrict_
 // per dtype and uses ex2.approx (__expf, ~1e-6 relative error: far below the 16-bit activation rounding it operates on).
 template <int dt>
 __global__ void __launch_bounds__(512, 2) astp_stats4_kernel(const void* __restrict__ x, const void* __restrict__ lg,
-                                                             int T, int C, long long ld, float* __restrict__ out) {
+                                                             int T, int C, long long ld, float* __restrict__ out,
+                                                             const int* __restrict__ lens) {
     __shared__ float red[16][4][64];
     const int cg = threadIdx.x, sl = threadIdx.y, warp = sl >> 1;   // a warp = 2 slices x 16 channel groups
     const int c = (blockIdx.x * 16 + cg) * 4;
     const int b = blockIdx.y;
     const bool cv = c < C;
     const long long base = (long long)b * T * ld + c;
+    if (lens != nullptr) T = max(1, min(T, lens[b]));   // softmax / weighted statistics over this utterance's own frames
     float m[4], s0[4], s1[4], s2[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { m[k] = -INFINITY; s0[k] = 0.f; s1[k] = 0.f; s2[k] = 0.f; }
@@ -444,15 +452,17 @@ __global__ void bnrelu_kernel(const void* __restrict__ x, long long x_ld, const 
 template <int COUT>
 __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ feats, const float* __restrict__ w9,
                                                    const float* __restrict__ shift, void* __restrict__ out,
-                                                   float* __restrict__ lo, int dt, int B, int T, int Fdim) {
+                                                   float* __restrict__ lo, int dt, int B, int T, int Fdim,
+                                                   const int* __restrict__ lens) {
     constexpr int NG = COUT / 8;            // channel groups per position (4 or 8)
     constexpr int PL = 128 / NG;            // position lanes per block
     __shared__ float sin_[10][132];
     const int t0 = blockIdx.x * 128, f0 = blockIdx.y * 8, b = blockIdx.z;
+    const int Tb = lens != nullptr ? min(T, lens[b]) : T;   // length-masked batch: frames past the utterance's end are padding
     for (int i = threadIdx.x; i < 10 * 130; i += 128) {
         const int tl = i / 10, fl = i - tl * 10;           // consecutive threads: consecutive F of the same frame
         const int tt = t0 + tl - 1, ff = f0 + fl - 1;
-        sin_[fl][tl] = (ff >= 0 && ff < Fdim && tt >= 0 && tt < T) ? __ldg(feats + ((long long)b * T + tt) * Fdim + ff) : 0.f;
+        sin_[fl][tl] = (ff >= 0 && ff < Fdim && tt >= 0 && tt < Tb) ? __ldg(feats + ((long long)b * T + tt) * Fdim + ff) : 0.f;
     }
     const int cg = threadIdx.x % NG, pl = threadIdx.x / NG;
     float w[8][9], sh8[8];
@@ -483,7 +493,7 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ fea
                 float a = sh8[j];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) a = fmaf(in[k], w[j][k], a);
-                v[j] = fmaxf(a, 0.f);
+                v[j] = t < Tb ? fmaxf(a, 0.f) : 0.f;        // zero rows behind the utterance: the next conv's padding
             }
             const long long idx = ((long long)b * Fdim + f) * T + t;
             ws_stv8(out, dt, idx * COUT + cg * 8, v);
@@ -537,7 +547,8 @@ __global__ void __launch_bounds__(512) se_gate_kernel(const void* __restrict__ x
                                                       const float* __restrict__ W1, const float* __restrict__ b1,
                                                       const float* __restrict__ W2t, const float* __restrict__ b2,
                                                       float* __restrict__ gate /*[B][C]*/,
-                                                      const float* __restrict__ colsum /* WsEpi::colsum or null */) {
+                                                      const float* __restrict__ colsum /* WsEpi::colsum or null */,
+                                                      const int* __restrict__ lens /* length-masked batch or null */) {
     extern __shared__ float sm[];
     float* mean = sm;              // [2][C]
     float* part = mean + 2 * C;    // [slices][2][C] partial sums of the T slices (slices * C = 4096 floats)
@@ -564,7 +575,8 @@ __global__ void __launch_bounds__(512) se_gate_kernel(const void* __restrict__ x
     for (int u = 0; u < nb && colsum == nullptr; ++u) {
         float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const long long base = (long long)(b0 + u) * T * ld + gi * 8;
-        for (int t = sl; t < T; t += slices) {
+        const int Tu = lens != nullptr ? max(1, min(T, lens[b0 + u])) : T;
+        for (int t = sl; t < Tu; t += slices) {
             float v[8];
             ws_ldv8(x, dt, base + (long long)t * ld, v);
 #pragma unroll
@@ -578,7 +590,7 @@ __global__ void __launch_bounds__(512) se_gate_kernel(const void* __restrict__ x
         const int u = i / C, c = i % C;
         float s = 0.f;
         for (int k = 0; k < slices; ++k) s += part[(k * 2 + u) * C + c];   // fixed order: deterministic
-        mean[u * C + c] = s / (float)T;
+        mean[u * C + c] = s / (float)(lens != nullptr ? max(1, min(T, lens[b0 + u])) : T);
     }
     __syncthreads();
     // fc1: two hidden units per warp pass, 16-byte weight loads (C % 128 == 0): 4x fewer dependent-latency steps
@@ -725,6 +737,38 @@ __global__ void __launch_bounds__(256) cam_gate_kernel(const void* __restrict__ 
     }
 }
 
+// Length-masked batches: zero the rows t >= lens[b] of a channels-last tensor [B][F][T][ld] (channels [0, C)) so that the
+// next time-mixing op sees the zero padding the reference's unpadded forward sees.  One block per (b, f) row strip; the
+// cost is proportional to the padding only.
+__global__ void __launch_bounds__(256) zero_tail_kernel(void* __restrict__ x, float* __restrict__ lo, int dt, int F, int T,
+                                                        int C, long long ld, const int* __restrict__ lens) {
+    const int b = blockIdx.y, f = blockIdx.x;
+    const int t0 = max(0, min(T, lens[b]));
+    const int es = dt == WS_F32 ? 4 : 2, cpr = C * es / 16;          // 16-byte chunks per row
+    const long long n = (long long)(T - t0) * cpr;
+    char* base = (char*)x + (((long long)b * F + f) * T + t0) * ld * es;
+    char* base_lo = lo ? (char*)lo + (((long long)b * F + f) * T + t0) * ld * 4 : nullptr;
+    for (long long i = threadIdx.x; i < n; i += 256) {
+        const long long r = i / cpr, c = i - r * cpr;
+        *reinterpret_cast<uint4*>(base + r * ld * es + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+        if (base_lo) *reinterpret_cast<uint4*>(base_lo + r * ld * 4 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+// lens[k + 1][b] = (lens[k][b] - 1) / 2 + 1 (stride-2 convs with kernel 3 / pad 1 or kernel 5 / pad 2), k < levels - 1;
+// level 0 is clamped to [1, T]
+__global__ void lens_derive_kernel(int* __restrict__ lens, int B, int T, int levels) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int l = max(1, min(T, lens[b]));
+    lens[b] = l;
+    for (int k = 1; k < levels; ++k) { l = (l - 1) / 2 + 1; lens[k * B + b] = l; }
+}
+// frames of an utterance of n samples (snip_edges, 25 ms / 10 ms at 16 kHz)
+__global__ void frames_from_samples_kernel(const int* __restrict__ nsamp, int* __restrict__ lens, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) lens[b] = nsamp[b] < 400 ? 0 : 1 + (nsamp[b] - 400) / 160;
+}
+
 inline const char* last_err() {
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
@@ -744,14 +788,14 @@ const char* ws_launch_convert(const float* in, void* out, float* lo, int dt, lon
 
 const char* ws_launch_tstats(const void* x, int dt, int B, int F, int T, int C, long long ld, const float* pre_scale,
                              const float* pre_shift, void* out, int odt, long long out_ld, int std_off, float eps,
-                             cudaStream_t s) {
-    if (std_off < 0 && F == 1 && pre_scale == nullptr && odt == WS_F32 && C % 8 == 0) {
+                             cudaStream_t s, const int* lens) {
+    if (std_off < 0 && F == 1 && pre_scale == nullptr && odt == WS_F32 && C % 8 == 0 && lens == nullptr) {
         dim3 g8((C + 511) / 512, B), b8(64, 8);
         tmean8_kernel<<<g8, b8, 0, s>>>(x, dt, T, C, ld, (float*)out, out_ld);
         return last_err();
     }
     dim3 grid((C + 31) / 32, F, B), block(32, 8);
-    tstats_kernel<<<grid, block, 0, s>>>(x, dt, F, T, C, ld, pre_scale, pre_shift, out, odt, out_ld, std_off, eps);
+    tstats_kernel<<<grid, block, 0, s>>>(x, dt, F, T, C, ld, pre_scale, pre_shift, out, odt, out_ld, std_off, eps, lens);
     return last_err();
 }
 
@@ -792,17 +836,32 @@ const char* ws_launch_scale_residual(const void* x, long long x_ld, const float*
 }
 
 const char* ws_launch_astp_stats(const void* x, const void* logits, int dt, int B, int T, int C, long long ld,
-                                 float* out, cudaStream_t s) {
+                                 float* out, cudaStream_t s, const int* lens) {
     if (C % 2 != 0) return "astp_stats: C must be even";
     static const int variant = getenv("WS_ASTP_VARIANT") ? atoi(getenv("WS_ASTP_VARIANT")) : 2;
     if (variant == 2 && C % 4 == 0 && ld % 4 == 0 && dt != WS_F32 && T <= 256) {
         dim3 grid((C + 63) / 64, B), block(16, 32);
-        if (dt == WS_BF16) astp_stats4_kernel<WS_BF16><<<grid, block, 0, s>>>(x, logits, T, C, ld, out);
-        else astp_stats4_kernel<WS_F16><<<grid, block, 0, s>>>(x, logits, T, C, ld, out);
+        if (dt == WS_BF16) astp_stats4_kernel<WS_BF16><<<grid, block, 0, s>>>(x, logits, T, C, ld, out, lens);
+        else astp_stats4_kernel<WS_F16><<<grid, block, 0, s>>>(x, logits, T, C, ld, out, lens);
         return last_err();
     }
     dim3 grid((C + 63) / 64, B), block(32, 8);
-    astp_stats_kernel<<<grid, block, 0, s>>>(x, logits, dt, T, C, ld, out);
+    astp_stats_kernel<<<grid, block, 0, s>>>(x, logits, dt, T, C, ld, out, lens);
+    return last_err();
+}
+
+const char* ws_launch_zero_tail(void* x, float* lo, int dt, int B, int F, int T, int C, long long ld, const int* lens,
+                                cudaStream_t s) {
+    if ((C * (dt == WS_F32 ? 4 : 2)) % 16 != 0 || (ld * (dt == WS_F32 ? 4 : 2)) % 16 != 0) return "zero_tail: rows must be 16-byte multiples";
+    zero_tail_kernel<<<dim3((unsigned)F, (unsigned)B), 256, 0, s>>>(x, lo, dt, F, T, C, ld, lens);
+    return last_err();
+}
+const char* ws_launch_lens_derive(int* lens, int B, int T, int levels, cudaStream_t s) {
+    lens_derive_kernel<<<(B + 127) / 128, 128, 0, s>>>(lens, B, T, levels);
+    return last_err();
+}
+const char* ws_launch_frames_from_samples(const int* nsamp, int* lens, int B, cudaStream_t s) {
+    frames_from_samples_kernel<<<(B + 127) / 128, 128, 0, s>>>(nsamp, lens, B);
     return last_err();
 }
 
@@ -814,11 +873,11 @@ const char* ws_launch_bnrelu(const void* x, long long x_ld, const float* scale, 
 }
 
 const char* ws_launch_stem(const float* feats, const float* w9, const float* shift, void* out, float* lo, int dt, int B,
-                           int T, int Fdim, int Cout, cudaStream_t s) {
+                           int T, int Fdim, int Cout, cudaStream_t s, const int* lens) {
     const dim3 grid((unsigned)((T + 127) / 128), (unsigned)((Fdim + 7) / 8), (unsigned)B);
     if (B > 65535) return "stem conv: batch too large for one launch";
-    if (Cout == 32) stem_kernel<32><<<grid, 128, 0, s>>>(feats, w9, shift, out, lo, dt, B, T, Fdim);
-    else if (Cout == 64) stem_kernel<64><<<grid, 128, 0, s>>>(feats, w9, shift, out, lo, dt, B, T, Fdim);
+    if (Cout == 32) stem_kernel<32><<<grid, 128, 0, s>>>(feats, w9, shift, out, lo, dt, B, T, Fdim, lens);
+    else if (Cout == 64) stem_kernel<64><<<grid, 128, 0, s>>>(feats, w9, shift, out, lo, dt, B, T, Fdim, lens);
     else return "stem conv supports 32 or 64 output channels";
     return last_err();
 }
@@ -842,7 +901,8 @@ const char* ws_launch_cam_gate(const void* x, int dt, int B, int T, int C, long 
 }
 
 const char* ws_launch_se_gate(const void* x, int dt, int B, int T, int C, long long ld, const float* W1, const float* b1,
-                              const float* W2t, const float* b2, int H, float* gate, const float* colsum, cudaStream_t s) {
+                              const float* W2t, const float* b2, int H, float* gate, const float* colsum, cudaStream_t s,
+                              const int* lens) {
     if (H != 128 || (C != 512 && C != 1024 && C != 2048 && C != 256)) return "se_gate: expected H=128 and C in {256,512,1024,2048}";
     const size_t smem = (size_t)(2 * C + 8192 + 2 * H) * sizeof(float);
     static unsigned long long attr = 0;   // per-device opt-in (ws_common.cuh)
@@ -853,6 +913,7 @@ const char* ws_launch_se_gate(const void* x, int dt, int B, int T, int C, long l
     }
     if (smem > 96 * 1024) return "se_gate: channel count too large for shared memory";
     if (colsum != nullptr && T < 128) return "se_gate: fused column sums need >= 128 frames per utterance";
-    se_gate_kernel<128><<<(B + 1) / 2, 512, smem, s>>>(x, dt, B, T, C, ld, W1, b1, W2t, b2, gate, colsum);
+    if (lens != nullptr && colsum != nullptr) return "se_gate: fused column sums are not available for length-masked batches";
+    se_gate_kernel<128><<<(B + 1) / 2, 512, smem, s>>>(x, dt, B, T, C, ld, W1, b1, W2t, b2, gate, colsum, lens);
     return last_err();
 }

@@ -11,7 +11,13 @@ const char* ws_launch_convert(const float* in, void* out, float* lo, int dt, lon
 //   mean -> out[b*out_ld + c*F + f],  std -> out[b*out_ld + std_off + c*F + f]   (std skipped if std_off < 0)
 const char* ws_launch_tstats(const void* x, int dt, int B, int F, int T, int C, long long ld, const float* pre_scale,
                              const float* pre_shift, void* out, int odt, long long out_ld, int std_off, float eps,
-                             cudaStream_t s);
+                             cudaStream_t s, const int* lens = nullptr);
+// length-masked batches (per-utterance frame counts `lens`, device int32): zero the rows t >= lens[b]; derive the frame
+// counts behind stride-2 layers (lens is [levels][B], level 0 = input); frames from sample counts
+const char* ws_launch_zero_tail(void* x, float* lo, int dt, int B, int F, int T, int C, long long ld, const int* lens,
+                                cudaStream_t s);
+const char* ws_launch_lens_derive(int* lens, int B, int T, int levels, cudaStream_t s);
+const char* ws_launch_frames_from_samples(const int* nsamp, int* lens, int B, cudaStream_t s);
 // out[r][o] = act( sum_i W[o][i] * (in[r][i] + in2[r / rows_per_b][i]) + bias[o] ),  fp32 in/out, W fp32 [O][I]
 bool ws_linear_rows_big(long long in_ld, const float* in2, long long in2_ld, int R, int I, int O);
 const char* ws_launch_linear_rows(const float* in, long long in_ld, const float* in2, long long in2_ld,
@@ -23,20 +29,21 @@ const char* ws_launch_scale_residual(const void* x, long long x_ld, const float*
                                      int C, cudaStream_t s);
 // ASTP statistics (pooling_layers.py:138-144): softmax over T of logits, weighted mean / std of x
 const char* ws_launch_astp_stats(const void* x, const void* logits, int dt, int B, int T, int C, long long ld,
-                                 float* out /*[B][2C]*/, cudaStream_t s);
+                                 float* out /*[B][2C]*/, cudaStream_t s, const int* lens = nullptr);
 // out[pos][c] = relu(x[pos][c]*scale[c] + shift[c])  (CAM++ pre-activation BN-ReLU, campplus.py:164-166,214)
 const char* ws_launch_bnrelu(const void* x, long long x_ld, const float* scale, const float* shift, void* out,
                              float* lo, long long out_ld, int dt, long long npos, int C, cudaStream_t s);
 // ResNet / FCM stem: Conv2d(1->Cout,3x3,pad 1) + folded BN + ReLU.  feats fp32 [B][T][Fdim] -> out [B][Fdim][T][Cout]
 const char* ws_launch_stem(const float* feats, const float* w9 /*[Cout][9]*/, const float* shift, void* out, float* lo,
-                           int dt, int B, int T, int Fdim, int Cout, cudaStream_t s);
+                           int dt, int B, int T, int Fdim, int Cout, cudaStream_t s, const int* lens = nullptr);
 // CAM context (campplus.py:108-135): mean over T and per-segment (seg_len) means with ceil-mode partial segment
 const char* ws_launch_seg_means(const void* x, int dt, int B, int T, int C, long long ld, int seg_len, float* mean,
                                 float* segmean /*[B][nseg][C]*/, cudaStream_t s);
 
 // fused SE gate: gate[b][c] = sigmoid(W2 relu(W1 mean_T(x[b]) + b1) + b2); W2t is W2 transposed to [H][C]
 const char* ws_launch_se_gate(const void* x, int dt, int B, int T, int C, long long ld, const float* W1, const float* b1,
-                              const float* W2t, const float* b2, int H, float* gate, const float* colsum, cudaStream_t s);
+                              const float* W2t, const float* b2, int H, float* gate, const float* colsum, cudaStream_t s,
+                              const int* lens = nullptr);
 // fused CAM context gate: gate[b][seg][g] = sigmoid(W2 relu(W1 (mean_T(x) + segmean(x)) + b1) + b2)
 const char* ws_launch_cam_gate(const void* x, int dt, int B, int T, int C, long long ld, int seg_len, const float* W1,
                                const float* b1, const float* W2, const float* b2, int H, int G, float* gate,
@@ -47,7 +54,7 @@ const char* ws_launch_cam_gate(const void* x, int dt, int B, int T, int C, long 
 const char* ws_launch_fbank(const void* wav, int wav_is_i16, long long wav_ld, int nsamples, int B, int T,
                             const float* window400, const float* melw, const int* melstart, const int* mellen,
                             int mel_maxlen, float* feats, cudaStream_t s);
-const char* ws_launch_cmn(float* feats, int B, int T, int Fdim, cudaStream_t s);
+const char* ws_launch_cmn(float* feats, int B, int T, int Fdim, cudaStream_t s, const int* lens = nullptr);
 
 // ---- PLDA (ws_plda.cu), fp64 arithmetic
 const char* ws_launch_f32_to_f64(const float* in, double* out, long long n, cudaStream_t s);

@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(384, 1) ws_res2_fused_kernel(const __grid_cons
         if (et == 0 && (int)blockIdx.x < p.B) load_xn(blockIdx.x, 1);
         int g = 0, xc = 0;
         for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+            const int Tb = p.lens != nullptr ? min(p.T, p.lens[b]) : p.T;   // rows t >= Tb are conv padding: stay zero everywhere
             for (int i = 0; i < kNumConv; ++i, ++g) {
                 if (et < p.w8) {
                     s_par[0][et] = p.bias[i * p.w8 + et];
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(384, 1) ws_res2_fused_kernel(const __grid_cons
 #pragma unroll 1
                 for (int mt = 0; mt < nmt; ++mt) {
                     const int t = mt * 128 + r;
-                    const bool valid = t < p.T;
+                    const bool valid = t < Tb;
                     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.w8);
 #pragma unroll 1
                     for (int c = c_beg; c < c_end; c += 32) {
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(384, 1) ws_res2_fused_kernel(const __grid_cons
                             uint32_t w[4], o[4];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const float a0 = v[8 * j + 2 * k], a1 = v[8 * j + 2 * k + 1];
+                                const float a0 = valid ? v[8 * j + 2 * k] : 0.f, a1 = valid ? v[8 * j + 2 * k + 1] : 0.f;
                                 w[k] = ws_pack2(a0, a1, DT);
                                 o[k] = ws_pack2(a0 + ws_16_to_f(xs[k] & 0xffffu, DT), a1 + ws_16_to_f(xs[k] >> 16, DT), DT);
                             }

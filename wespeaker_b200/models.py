@@ -282,6 +282,81 @@ class B200SpeakerModel(torch.nn.Module):
                 out[torch.as_tensor(sel, device=dev)] = o
         return out
 
+    # ------------------------------------------------------------------ length-masked batches
+    def embed_padded(self, features: torch.Tensor, lengths) -> torch.Tensor:
+        """(B, Tmax, feat_dim) features of utterances with `lengths[b]` valid frames each (rows behind are ignored, any
+        content) -> (B, embed_dim): every row equals what the utterance produces on its own, unpadded (the reference has no
+        masking and therefore extracts test sets at batch 1, extract_vox.sh:31)."""
+        L = _lib.load()
+        x = features.detach()
+        if not x.is_cuda:
+            x = x.to(torch.device("cuda", self._dev_index()))
+        x = x.contiguous().float()
+        B, T, _ = x.shape
+        idx = x.device.index
+        h = self._ensure_engine(idx)
+        n = torch.as_tensor(lengths, dtype=torch.int32).to(x.device).contiguous()
+        if n.numel() != B:
+            raise ValueError("lengths must have one entry per utterance")
+        out = torch.empty((B, self.embed_dim), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(idx):
+            _lib.check(L.ws_engine_forward_masked(h, x.data_ptr(), n.data_ptr(), B, T, out.data_ptr(), _lib.cur_stream_ptr(idx)),
+                       "ws_engine_forward_masked")
+        return out
+
+    def extract_from_wav_padded(self, wavs: torch.Tensor, n_samples, window_type: str = "hamming") -> torch.Tensor:
+        """(B, Nmax) waveforms (int16 or int16-range float32) with `n_samples[b]` valid samples each -> (B, embed_dim):
+        fbank, CMN over each utterance's own frames, masked forward."""
+        L = _lib.load()
+        w = wavs.detach()
+        if not w.is_cuda:
+            w = w.to(torch.device("cuda", self._dev_index()))
+        is_i16 = 1 if w.dtype == torch.int16 else 0
+        w = w.contiguous() if is_i16 else w.float().contiguous()
+        B, N = w.shape
+        idx = w.device.index
+        h = self._ensure_engine(idx)
+        n = torch.as_tensor(n_samples, dtype=torch.int32).to(w.device).contiguous()
+        nmax = int(n.max().item())
+        out = torch.empty((B, self.embed_dim), dtype=torch.float32, device=w.device)
+        with torch.cuda.device(idx):
+            _lib.check(L.ws_engine_extract_wav_masked(h, w.data_ptr(), is_i16, N, n.data_ptr(), nmax, B, window_type.encode(),
+                                                      out.data_ptr(), _lib.cur_stream_ptr(idx)), "ws_engine_extract_wav_masked")
+        return out
+
+    @staticmethod
+    def length_buckets(lengths, max_batch: int = 64, max_pad: float = 0.15):
+        """Greedy grouping for padded batches: longest first; a batch takes utterances down to (1 - max_pad) of its longest
+        member, at most max_batch of them.  Returns a list of index lists."""
+        order = sorted(range(len(lengths)), key=lambda i: -int(lengths[i]))
+        out, cur = [], []
+        for i in order:
+            if cur and (len(cur) >= max_batch or int(lengths[i]) < (1.0 - max_pad) * int(lengths[cur[0]])):
+                out.append(cur)
+                cur = []
+            cur.append(i)
+        if cur:
+            out.append(cur)
+        return out
+
+    def embed_list_padded(self, feats_list, max_batch: int = 64, max_pad: float = 0.15, device=None):
+        """Variable-length utterances through length-masked batches: a handful of (B, Tmax) plans serve ANY mix of lengths
+        (exact-length bucketing needs one plan per distinct length).  Returns (N, embed_dim) in input order."""
+        if len(feats_list) == 0:
+            return torch.empty((0, self.embed_dim))
+        dev = torch.device(device) if device is not None else feats_list[0].device
+        if dev.type != "cuda":
+            dev = torch.device("cuda", self._dev_index())
+        lens = [int(f.shape[0]) for f in feats_list]
+        out = torch.empty((len(feats_list), self.embed_dim), dtype=torch.float32, device=dev)
+        for sel in self.length_buckets(lens, max_batch, max_pad):
+            tmax = -(-lens[sel[0]] // 8) * 8                     # a few shapes, not one per length: round Tmax up to 8
+            x = torch.zeros((len(sel), tmax, self.feat_dim), dtype=torch.float32, device=dev)
+            for j, i in enumerate(sel):
+                x[j, : lens[i]] = feats_list[i].to(dev)
+            out[torch.as_tensor(sel, device=dev)] = self.embed_padded(x, [lens[i] for i in sel])
+        return out
+
     def embed_list(self, feats_list, max_batch: int = 64, device=None):
         """Embeddings for utterances of DIFFERENT lengths.  The reference has no length masking (test sets
         run at batch 1), so padding would change results; instead utterances are bucketed by exact frame count, each bucket
