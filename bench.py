@@ -394,8 +394,25 @@ def varlen_leg(steps, warmup, dev, rank, world, parallel, peaks, sampler, n_utts
            "ms_per_pass": ms / nrep, "passes": nrep,
            "step_tflops_per_gpu": gflop * nrep / (ms * 1e-3) / 1e3,
            "step_frac_of_sustained": gflop * nrep / (ms * 1e-3) / 1e3 / peaks["tf_sustained"]}
+    # the same job with CONTINUOUS durations (U[1, 10) s, arbitrary sample counts): exact-length bucketing would need one plan
+    # per utterance; the ragged / length-masked path runs it through the frame grid's bounded set of plans
+    nsamp = rng.integers(16000, 160000, n_utts)
+    cwavs = [torch.from_numpy(pool[i % 16, : int(n)].copy()).to(dev) for i, n in enumerate(nsamp)]
+    for _ in range(max(2, min(warmup, 3))):
+        model.extract_from_wav_list_ragged(cwavs, max_batch=64, device=dev)
+    cms, cemb = _timed(lambda: [model.extract_from_wav_list_ragged(cwavs, max_batch=64, device=dev) for _ in range(nrep)][-1],
+                       dev, parallel, world)
+    res["masked_continuous"] = {
+        "durations": "U[1, 10) s with arbitrary sample counts, concatenated PCM + offsets (ws_engine_extract_wav_ragged_async), "
+                     "length-masked buckets on the x1.15 frame grid, <= 64 per launch",
+        "value": world * n_utts * nrep / (cms * 1e-3), "unit": "utt/s",
+        "audio_s_per_s": world * float(nsamp.sum()) / 16000.0 * nrep / (cms * 1e-3), "ms_per_pass": cms / nrep}
     if rank == 0:
         from wespeaker_b200 import frontend
+        csel = [int(np.argmin(nsamp)), int(np.argsort(nsamp)[n_utts // 2]), int(np.argmax(nsamp))]
+        cfeats = [frontend.fbank_batch(cwavs[j][None], cmn=True)[0] for j in csel]
+        res["masked_continuous"]["parity_rel_l2"] = _parity(model_name, [cemb[j] for j in csel], cfeats)
+        res["masked_continuous"]["parity_bar"] = PARITY_BAR[prec]
         order = np.argsort(secs, kind="stable")
         sel = [int(order[int(round(j * (n_utts - 1) / max(1, parity_n - 1)))]) for j in range(parity_n)]
         feats = [frontend.fbank_batch(wavs[j][None], cmn=True)[0] for j in sel]

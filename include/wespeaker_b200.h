@@ -53,6 +53,16 @@ int ws_engine_forward_masked(ws_engine* e, const float* feats_dev, const int* n_
                              void* stream);
 int ws_engine_extract_wav_masked(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, const int* n_samples_dev,
                                  int max_samples, int B, const char* window_type, float* embs_dev, void* stream);
+/* The same from a RAGGED buffer: utterance b is the n_samples_dev[b] samples starting at wav_dev + offsets_dev[b] samples
+ * (int64[B] on the device) - concatenated PCM as a reader produces it, no padded copy.  max_samples >= every n_samples[b]
+ * (it fixes the plan's T); frames behind an utterance's end are neither read nor computed.  Every utterance must hold at
+ * least one 25 ms frame (400 samples; the reference's kaldi fbank fails below that too).  _async: see below. */
+int ws_engine_extract_wav_ragged(ws_engine* e, const void* wav_dev, int wav_is_i16, const long long* offsets_dev,
+                                 const int* n_samples_dev, int max_samples, int B, const char* window_type, float* embs_dev,
+                                 void* stream);
+int ws_engine_extract_wav_ragged_async(ws_engine* e, const void* wav_dev, int wav_is_i16, const long long* offsets_dev,
+                                       const int* n_samples_dev, int max_samples, int B, const char* window_type,
+                                       float* embs_dev, void* stream);
 
 /* Variable-length jobs: one plan (and CUDA graph) per distinct (B, T); plans own disjoint buffers and are spread over a
  * few internal streams, so the buckets of such a job overlap on the GPU when they are enqueued with the *_async variants

@@ -809,6 +809,29 @@ def test_length_masked_wav_extraction():
         assert rel_l2(got[i], alone) <= 1e-5, (i, rel_l2(got[i], alone))
 
 
+@pytest.mark.parametrize("name,prec,tol", [("ECAPA_TDNN_c512", "fp32", 1e-5), ("CAMPPlus", "bf16", 4e-3), ("ResNet34", "fp16", 2e-3)])
+def test_ragged_wav_list_any_lengths(name, prec, tol):
+    """ws_engine_extract_wav_ragged_async: concatenated PCM + offsets, arbitrary sample counts, a bounded set of masked plans;
+    every utterance equals its own unpadded extraction (odd offsets exercise the unaligned sample loads)."""
+    m = from_synthetic(name, 0, precision=prec)
+    rng = np.random.default_rng(9)
+    ns = [int(v) for v in rng.integers(6000, 52000, 21)] + [1680, 1999, 16001] + ([400, 560] if name.startswith("ECAPA") else [])
+    pool = syn.make_wavs(4, 52000, seed=33)
+    for dt in (torch.int16, torch.float32):
+        wavs = [torch.from_numpy(pool[i % 4, :n].copy()).to(dt).to(DEV) for i, n in enumerate(ns)]
+        got = m.extract_from_wav_list_ragged(wavs, max_batch=8, device=DEV).cpu().numpy()
+        assert got.shape == (len(ns), m.embed_dim) and np.isfinite(got).all()
+        worst = 0.0
+        for i, w in enumerate(wavs):
+            alone = m.extract_from_wav(w[None]).cpu().numpy()[0]
+            worst = max(worst, float(rel_l2(got[i], alone)))
+        print(f"ragged {name} {prec} {dt}: worst vs alone {worst:.2e}")
+        assert worst <= tol
+    assert m.frame_grid(200) >= 200 and m.frame_grid(17) == 24
+    with pytest.raises(ValueError):
+        m.extract_from_wav_list_ragged([torch.zeros(399)], device=DEV)
+
+
 def test_plan_cache_eviction_many_shapes():
     """More distinct (B,T) shapes than the plan cache holds (64): plans are evicted LRU and rebuilt transparently."""
     name = "ECAPA_TDNN_c512"

@@ -1396,28 +1396,52 @@ int ws_engine_forward_masked(ws_engine* e, const float* feats_dev, const int* n_
 
 // Same from padded waveforms: wav_dev [B][wav_ld] with n_samples_dev[b] valid samples each (max_samples = the longest);
 // fbank of the padded rows, CMN over each utterance's own frames, masked forward.
-int ws_engine_extract_wav_masked(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, const int* n_samples_dev,
-                                 int max_samples, int B, const char* window_type, float* embs_dev, void* stream) {
-    if (!e || !wav_dev || !n_samples_dev || !embs_dev) { set_err("ws_engine_extract_wav_masked: null argument"); return 1; }
-    if (!e->finalized) { set_err("ws_engine_extract_wav_masked before ws_engine_finalize"); return 1; }
-    if (e->feat_dim != 80) { set_err("ws_engine_extract_wav_masked: the fbank frontend produces 80 bins"); return 1; }
+// Length-masked extraction from waveforms.  Rectangular layout: utterance b at wav + b * wav_ld (offsets_dev == nullptr);
+// ragged layout: utterance b at wav + offsets_dev[b] samples (concatenated PCM, no padding copies).  Frames behind an
+// utterance's end are neither read nor computed.
+static int extract_wav_masked_impl(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, const long long* offsets_dev,
+                                   const int* n_samples_dev, int max_samples, int B, const char* window_type, float* embs_dev,
+                                   void* stream, bool join, const char* who) {
+    if (!e || !wav_dev || !n_samples_dev || !embs_dev) { set_err(std::string(who) + ": null argument"); return 1; }
+    if (!e->finalized) { set_err(std::string(who) + " before ws_engine_finalize"); return 1; }
+    if (e->feat_dim != 80) { set_err(std::string(who) + ": the fbank frontend produces 80 bins"); return 1; }
     WS_CK(cudaSetDevice(e->device));
     const int T = ws_fbank_num_frames(max_samples);
-    if (T <= 0) { set_err("ws_engine_extract_wav_masked: waveforms shorter than one 25 ms frame"); return 1; }
+    if (T <= 0) { set_err(std::string(who) + ": waveforms shorter than one 25 ms frame"); return 1; }
     Plan* p = get_plan(e, B, T, true);
     if (!p) return 1;
     const FbankTables* t = fbank_tables(e, window_type);
     if (!t) return 1;
     cudaStream_t us = (cudaStream_t)stream, ws = lane_stream(e, p);
     if (enter_stream(e, p, ws, us)) return 1;
-    WS_CKS(ws_launch_frames_from_samples(n_samples_dev, p->lens, B, ws));
+    WS_CKS(ws_launch_frames_from_samples(n_samples_dev, p->lens, B, T, ws));
     WS_CKS(ws_launch_fbank(wav_dev, wav_is_i16, wav_ld, max_samples, B, T, t->window, t->melw, t->melstart, t->mellen, t->maxlen,
-                           p->feats_in, ws));
+                           p->feats_in, ws, offsets_dev, p->lens));
     WS_CKS(ws_launch_cmn(p->feats_in, B, T, 80, ws, p->lens));
     if (run_plan(e, p, ws)) return 1;
     e->last_launches += 3;
     WS_CK(cudaMemcpyAsync(embs_dev, p->emb, (size_t)B * e->embed_dim * 4, cudaMemcpyDeviceToDevice, ws));
+    if (!join) { WS_CK(cudaEventRecord(p->done, ws)); return 0; }
     return leave_stream(e, p, ws, us);
+}
+int ws_engine_extract_wav_masked(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, const int* n_samples_dev,
+                                 int max_samples, int B, const char* window_type, float* embs_dev, void* stream) {
+    return extract_wav_masked_impl(e, wav_dev, wav_is_i16, wav_ld, nullptr, n_samples_dev, max_samples, B, window_type, embs_dev,
+                                   stream, true, "ws_engine_extract_wav_masked");
+}
+int ws_engine_extract_wav_ragged(ws_engine* e, const void* wav_dev, int wav_is_i16, const long long* offsets_dev,
+                                 const int* n_samples_dev, int max_samples, int B, const char* window_type, float* embs_dev,
+                                 void* stream) {
+    if (!offsets_dev) { set_err("ws_engine_extract_wav_ragged: null argument"); return 1; }
+    return extract_wav_masked_impl(e, wav_dev, wav_is_i16, 0, offsets_dev, n_samples_dev, max_samples, B, window_type, embs_dev,
+                                   stream, true, "ws_engine_extract_wav_ragged");
+}
+int ws_engine_extract_wav_ragged_async(ws_engine* e, const void* wav_dev, int wav_is_i16, const long long* offsets_dev,
+                                       const int* n_samples_dev, int max_samples, int B, const char* window_type,
+                                       float* embs_dev, void* stream) {
+    if (!offsets_dev) { set_err("ws_engine_extract_wav_ragged_async: null argument"); return 1; }
+    return extract_wav_masked_impl(e, wav_dev, wav_is_i16, 0, offsets_dev, n_samples_dev, max_samples, B, window_type, embs_dev,
+                                   stream, false, "ws_engine_extract_wav_ragged_async");
 }
 
 int ws_engine_forward_host(ws_engine* e, const float* feats_host, int B, int T, float* embs_host) {

@@ -153,7 +153,8 @@ __device__ __forceinline__ int zpad(int f) { return f + (f >> 3); }   // skewed 
 __global__ void __launch_bounds__(256) fbank_kernel2(const void* __restrict__ wav, int is_i16, long long wav_ld, int T,
                                                      const float* __restrict__ window, const float* __restrict__ melw,
                                                      const int* __restrict__ melstart, const int* __restrict__ mellen,
-                                                     int mel_maxlen, float* __restrict__ feats) {
+                                                     int mel_maxlen, float* __restrict__ feats,
+                                                     const long long* __restrict__ offs, const int* __restrict__ lens) {
     __shared__ float2 s_tw[256];        // W_512^k = exp(-2*pi*i*k/512)
     __shared__ float2 s_z[8][288];      // per-warp spectrum, index zpad(f)
     __shared__ float s_p[8][256];       // per-warp power spectrum (bins 0..255; Nyquist has zero mel weight)
@@ -173,7 +174,10 @@ __global__ void __launch_bounds__(256) fbank_kernel2(const void* __restrict__ wa
     const int b = blockIdx.y;
     const int frame = blockIdx.x * 8 + warp;
     if (frame >= T) return;
-    const long long base = (long long)b * wav_ld + (long long)frame * kFrameShift;
+    // ragged / length-masked input: utterance b starts at offs[b] (else b * wav_ld) and has lens[b] frames; frames behind
+    // the end are neither read nor written (cmn_kernel zeroes them), so a ragged buffer is never read past its last sample
+    if (lens != nullptr && frame >= lens[b]) return;
+    const long long base = (offs != nullptr ? offs[b] : (long long)b * wav_ld) + (long long)frame * kFrameShift;
 
     float2 x[7];
     float s = 0.f;
@@ -315,14 +319,14 @@ __global__ void __launch_bounds__(256) cmn_kernel(float* __restrict__ feats, int
 
 const char* ws_launch_fbank(const void* wav, int wav_is_i16, long long wav_ld, int nsamples, int B, int T,
                             const float* window400, const float* melw, const int* melstart, const int* mellen,
-                            int mel_maxlen, float* feats, cudaStream_t s) {
+                            int mel_maxlen, float* feats, cudaStream_t s, const long long* offs, const int* lens) {
     if (T <= 0 || B <= 0) return nullptr;
     if ((long long)(T - 1) * kFrameShift + kFrameLen > nsamples) return "fbank: T frames do not fit in nsamples";
     if (mel_maxlen > 20) return "fbank: mel filter wider than the shared-memory table";
     dim3 grid((T + 7) / 8, B);
     static const bool v1 = getenv("WS_FBANK_V1") != nullptr;   // A/B knob: the shared-memory radix-2 version
-    if (v1) fbank_kernel<<<grid, 256, 0, s>>>(wav, wav_is_i16, wav_ld, T, window400, melw, melstart, mellen, mel_maxlen, feats);
-    else fbank_kernel2<<<grid, 256, 0, s>>>(wav, wav_is_i16, wav_ld, T, window400, melw, melstart, mellen, mel_maxlen, feats);
+    if (v1 && !offs && !lens) fbank_kernel<<<grid, 256, 0, s>>>(wav, wav_is_i16, wav_ld, T, window400, melw, melstart, mellen, mel_maxlen, feats);
+    else fbank_kernel2<<<grid, 256, 0, s>>>(wav, wav_is_i16, wav_ld, T, window400, melw, melstart, mellen, mel_maxlen, feats, offs, lens);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
