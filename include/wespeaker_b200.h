@@ -93,6 +93,7 @@ int ws_engine_submit_wav_host(ws_engine* e, int slot, const void* wav_host, int 
 int ws_engine_collect(ws_engine* e, int slot);
 /* tuning aid: per-op device time (ms) of the (B,T) plan, measured with CUDA events in sequence context; returns #ops */
 int ws_engine_profile_ops(ws_engine* e, int B, int T, int iters, float* ms_out, int max_ops);
+const char* ws_engine_plan_op_name(ws_engine* e, int B, int T, int i, double* flops_out);   /* label + FLOPs of op i */
 /* number of this library's kernels launched by the most recent forward/extract call */
 long long ws_engine_last_launches(const ws_engine* e);
 void ws_engine_destroy(ws_engine* e);

@@ -1,4 +1,4 @@
-"""profiles/r01_sass_mnemonics.md: per-kernel SASS mnemonic counts of the shipped library (tcgen05 / TMEM / TMA evidence)."""
+"""profiles/r02_sass_mnemonics.md: per-kernel SASS mnemonic counts of the shipped library (tcgen05 / TMEM / TMA evidence)."""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "wespeaker_b200", "lib", "libwespeaker_b200.so")
@@ -15,16 +15,17 @@ for line in out.splitlines():
 def dem(n):
     r = subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()
     r = re.sub(r"\(anonymous namespace\)::", "", r); r = re.sub(r"\(.*$", "", r); return r.replace("void ", "")
-keys = ["UTC*MMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "SYNCS", "UCGABAR_ARV", "SHFL", "MUFU", "DFMA", "FFMA", "HFMA2"]
-lines = ["# r01 — SASS evidence: which kernels use tcgen05 / TMEM / TMA (cuobjdump -sass of the shipped .so)\n",
+keys = ["UTC*MMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "SYNCS", "UCGABAR_ARV", "SHFL", "MUFU", "DMMA", "DFMA", "FFMA", "HFMA2"]
+lines = ["# r02 — SASS evidence: which kernels use tcgen05 / TMEM / TMA (cuobjdump -sass of the shipped .so)\n",
          "Command: `python tools/sass_table.py` = `cuobjdump -sass wespeaker_b200/lib/libwespeaker_b200.so`, instruction mnemonics counted per",
          "kernel (B200_PROFILING.md: `tcgen05.mma` -> `UTC*MMA`, `tcgen05.ld` -> `LDTM`, TMA loads / stores -> `UTMALDG` / `UTMASTG`,",
          "`tcgen05.commit` -> `UTCBAR`, mbarrier -> `SYNCS`, cluster barrier -> `UCGABAR_ARV`).  Built with",
          "`-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo`.  Template arguments: conv-GEMM `<KIND (0 tf32, 1 f16/bf16), LEAN",
-         "(0 generic epilogue, dtype+1 lean)>`, Res2 / ASTP / scale_residual `<dtype>`.\n",
+         "(0 generic epilogue, dtype+1 lean)[, CL (CTAs per cluster, tc3)]>`, `ws_conv3x3_kernel<dtype, row bytes, K panels, M tiles>`,",
+         "`ws_cam_dense_kernel<dtype>`, Res2 / ASTP / scale_residual `<dtype>`; `dgemm_nt_dmma_kernel` shows its `mma.sync m8n8k4.f64` as DMMA.\n",
          "| kernel | SASS instr | " + " | ".join(keys) + " |", "|---|---|" + "---|" * len(keys)]
 for name, c in sorted(((dem(k), c) for k, c in stats.items() if c["_n"]), key=lambda r: -r[1]["_n"]):
     vals = [str(sum(v for kk, v in c.items() if kk.startswith("UTC") and kk.endswith("MMA"))) if k == "UTC*MMA" else str(c.get(k, 0)) for k in keys]
     lines.append(f"| `{name}` | {c['_n']} | " + " | ".join(vals) + " |")
-open(os.path.join(ROOT, "profiles", "r01_sass_mnemonics.md"), "w").write("\n".join(lines) + "\n")
+open(os.path.join(ROOT, "profiles", "r02_sass_mnemonics.md"), "w").write("\n".join(lines) + "\n")
 print("\n".join(lines[:16]))

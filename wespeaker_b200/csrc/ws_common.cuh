@@ -313,6 +313,7 @@ struct WsTc2Params {
     int epi_generic;     // test knob (WS_EPI_GENERIC=1): always run the generic epilogue instantiation
     int dbg_shift;       // -1 off; else experiment: A tile loaded one row early, MMA reads from row 1 with this base_offset
     int grid, smem_bytes;
+    int cl;              // ws_gemm_tc3: CTAs per cluster (2 = one cta_group::2 pair, 4 = two pairs sharing the weight tile by TMA multicast)
     WsEpi epi;
 };
 
@@ -436,6 +437,7 @@ int ws_c3_max_smem(void);
 const char* ws_c3_launch(const WsC3Params* p, cudaStream_t s);
 const char* ws_tc3_init(void);
 int ws_tc3_max_smem(void);
+int ws_tc3_max_clusters(int cl);   // co-resident clusters of `cl` CTAs on this device (0 = query failed)
 const char* ws_tc3_launch(const WsTc2Params* p, cudaStream_t s);
 const char* ws_tc2_init(void);
 int ws_tc2_max_smem(void);

@@ -14,6 +14,15 @@ namespace ws {
 
 static thread_local std::string g_err;
 void set_err(const std::string& msg) { g_err = msg; }
+static thread_local std::string g_op_label;
+static thread_local double g_op_flops = 0.0;
+static thread_local bool g_op_has = false;
+void set_op_label(const std::string& name, double flops) { g_op_label = name; g_op_flops = flops; g_op_has = true; }
+bool take_op_label(std::string* name, double* flops) {
+    if (!g_op_has) return false;
+    *name = g_op_label; *flops = g_op_flops; g_op_has = false;
+    return true;
+}
 const std::string& get_err() { return g_err; }
 
 void fill_epi_out(WsEpi& e, const View& out) {
@@ -208,7 +217,8 @@ static bool build_tc(const ConvSpec& s, WsTcParams* p) {
 
 
 // ---- v2 (persistent, TMA-store epilogue).  Returns false *without* error if the spec needs the v1 kernel.
-static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported, bool pair = false) {
+static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported, int cl = 1) {
+    const bool pair = cl >= 2;   // cl: CTAs per cluster (1 = ws_gemm_tc2; 2 / 4 = ws_gemm_tc3, see there)
     *unsupported = false;
     const WsEpi& e = s.epi;
     if ((e.res != nullptr && e.out2 != nullptr) || s.Cout % 32 != 0) { *unsupported = true; return false; }
@@ -259,7 +269,7 @@ static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported, bool
     q->bn = bn; q->nstages = nst;
     q->tiles_n = s.Cout / bn;
     const int mtiles = q->tiles_t * q->tiles_f * q->tiles_b;
-    q->num_tiles = q->tiles_n * (pair ? (mtiles + 1) / 2 : mtiles);
+    q->num_tiles = q->tiles_n * ((mtiles + cl - 1) / cl);
     const uint32_t fmt = s.dt == WS_F32 ? 2u : (s.dt == WS_BF16 ? 1u : 0u);
     q->idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((pair ? 256 : 128) >> 4) << 24);
     q->panel_bytes = bn * es >= 128 ? 128 : bn * es;
@@ -268,7 +278,7 @@ static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported, bool
     {   // weights map with the v2 N tile
         cuuint64_t dims[2] = {(cuuint64_t)s.Ktot, (cuuint64_t)s.Cout};
         cuuint64_t str[1] = {(cuuint64_t)s.Ktot * es};
-        cuuint32_t box[2] = {(cuuint32_t)bk_elems, (cuuint32_t)(pair ? bn / 2 : bn)};
+        cuuint32_t box[2] = {(cuuint32_t)bk_elems, (cuuint32_t)(bn / cl)};   // the rows ONE CTA loads per k-block
         if (!encode_map(&q->wmap, s.dt, s.W, 2, dims, str, box, q->bk_bytes)) return false;
         q->wmap_lo = q->wmap;
         if (s.split && !encode_map(&q->wmap_lo, s.dt, s.W_lo, 2, dims, str, box, q->bk_bytes)) return false;
@@ -309,9 +319,11 @@ static bool build_tc2(const ConvSpec& s, WsTc2Params* q, bool* unsupported, bool
     for (; oi < 4; ++oi) q->omap[oi] = q->omap[0];
     if (!q->has_epin) q->imap = q->omap[0];
     const int g_num_sms = ws_num_sms();
+    q->cl = cl;
     if (pair) {
-        const int pairs = g_num_sms / 2;
-        q->grid = 2 * (q->num_tiles < pairs ? q->num_tiles : pairs);
+        int ncl = ws_tc3_max_clusters(cl);
+        if (ncl <= 0) ncl = g_num_sms / cl;
+        q->grid = cl * (q->num_tiles < ncl ? q->num_tiles : ncl);
     } else {
         q->grid = q->num_tiles < g_num_sms ? q->num_tiles : g_num_sms;
     }
@@ -337,6 +349,12 @@ static bool build_simt(const ConvSpec& s, WsSimtParams* p) {
     return true;
 }
 
+static void label_conv(const char* kern, const ConvSpec& spec) {
+    const double pos = (double)spec.B * spec.F * spec.T;
+    char buf[160];
+    snprintf(buf, sizeof buf, "%s pos=%lld K=%d N=%d", kern, (long long)pos, spec.Ktot, spec.Cout);
+    set_op_label(buf, 2.0 * pos * spec.Ktot * spec.Cout);
+}
 bool make_conv_op(const ConvSpec& spec, int use_tc, Op* out) {
     const char* env_mp = getenv("WS_TC3_MIN_POS");
     const long long min_pos = env_mp ? atoll(env_mp) : 148LL * 128;
@@ -344,8 +362,16 @@ bool make_conv_op(const ConvSpec& spec, int use_tc, Op* out) {
         // big layers: CTA pairs (cta_group::2) halve the weight-operand traffic per CTA
         auto q = std::make_shared<WsTc2Params>();
         bool unsupported = false;
-        if (build_tc2(spec, q.get(), &unsupported, true)) {
+        // ... and clusters of two pairs share the weight tile by TMA multicast (WS_TC3_CL=2 keeps single pairs)
+        static const int cl_env = getenv("WS_TC3_CL") ? atoi(getenv("WS_TC3_CL")) : 2;
+        const int cl = (cl_env == 4 && (long long)spec.B * spec.F * spec.T >= 2LL * min_pos) ? 4 : 2;
+        if (build_tc2(spec, q.get(), &unsupported, cl)) {
             *out = [q](cudaStream_t s) { return ws_tc3_launch(q.get(), s); };
+            {
+                char kn[64];
+                snprintf(kn, sizeof kn, "conv_tc3 cl=%d grid=%d bn=%d st=%d", q->cl, q->grid, q->bn, q->nstages);
+                label_conv(kn, spec);
+            }
             return true;
         }
         if (!unsupported) return false;
@@ -355,6 +381,7 @@ bool make_conv_op(const ConvSpec& spec, int use_tc, Op* out) {
         bool unsupported = false;
         if (build_tc2(spec, q.get(), &unsupported)) {
             *out = [q](cudaStream_t s) { return ws_tc2_launch(q.get(), s); };
+            label_conv("conv_tc2", spec);
             return true;
         }
         if (!unsupported) return false;
@@ -364,10 +391,12 @@ bool make_conv_op(const ConvSpec& spec, int use_tc, Op* out) {
         auto p = std::make_shared<WsTcParams>();
         if (!build_tc(spec, p.get())) return false;
         *out = [p](cudaStream_t s) { return ws_tc_launch(p.get(), s); };
+        label_conv("conv_tc1", spec);
     } else {
         auto p = std::make_shared<WsSimtParams>();
         if (!build_simt(spec, p.get())) return false;
         *out = [p](cudaStream_t s) { return ws_simt_launch(p.get(), s); };
+        label_conv("conv_simt", spec);
     }
     return true;
 }
@@ -403,6 +432,11 @@ bool make_res2_op(const View& x, const View& out, const void* W7, const float* b
     const int npan = w8 / 64;
     q->smem_bytes = npan * 272 * 128 + 4 * w8 * 128 + npan * 256 * 128 + 1024;
     *op = [q](cudaStream_t s) { return ws_res2_launch(q.get(), s); };
+    {
+        char buf[160];
+        snprintf(buf, sizeof buf, "res2_fused B=%d T=%d C=%d", x.B, x.T, x.C);
+        set_op_label(buf, 2.0 * x.B * x.T * 7.0 * 3.0 * (x.C / 8.0) * (x.C / 8.0));
+    }
     return true;
 }
 
@@ -562,6 +596,12 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
         return true;
     }
     *op = [q](cudaStream_t s) { return ws_c3_launch(q.get(), s); };
+    {
+        char buf[200];
+        snprintf(buf, sizeof buf, "conv3x3 B=%d F=%d T=%d Cin=%d Cout=%d s=%dx%d caseB=%d nb=%d n_mt=%d R=%d res=%d", q->B, q->F, q->T,
+                 q->Cin, q->Cout, q->sf, q->st, q->case_b, q->nb, q->n_mt, q->R, q->res != nullptr);
+        set_op_label(buf, 2.0 * q->B * q->F * q->T * 9.0 * q->Cin * q->Cout);
+    }
     return true;
 }
 
@@ -638,6 +678,11 @@ bool make_cam_dense_op(const View& X, const WsCamLayer* layers_dev, int l0, int 
         return true;
     }
     *op = [q](cudaStream_t s) { return ws_cam_launch(q.get(), s); };
+    {
+        char buf[160];
+        snprintf(buf, sizeof buf, "cam_dense layers %d..%d B=%d T=%d", l0, l1 - 1, X.B, X.T);
+        set_op_label(buf, 0.0);
+    }
     return true;
 }
 

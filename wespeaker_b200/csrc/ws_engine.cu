@@ -40,6 +40,8 @@ struct FbankTables {
 struct Plan {
     int B = 0, T = 0;
     std::vector<Op> ops;
+    std::vector<std::string> op_names;   // tuning aid (ws_engine_profile_ops): label and FLOPs per op
+    std::vector<double> op_flops;
     std::vector<void*> bufs;
     int extra_launches = 0;     // ops that launch more than one kernel (split-K FC = 2)
     size_t bytes = 0;           // device memory held by this plan
@@ -253,7 +255,16 @@ struct Builder {
         return v;
     }
     float* f32(size_t n) { return (float*)raw(n * 4); }
-    void push(Op op) { p.ops.push_back(std::move(op)); }
+    void push(Op op, const char* name = nullptr) {
+        std::string label;
+        double flops = 0.0;
+        const bool had = take_op_label(&label, &flops);
+        if (name) { label = name; if (!had) flops = 0.0; }
+        else if (!had) label = "op";
+        p.ops.push_back(std::move(op));
+        p.op_names.push_back(label);
+        p.op_flops.push_back(flops);
+    }
     // length-masked plans: frame counts of stride level k (nullptr in ordinary plans), and "zero the rows behind every
     // utterance's end" for tensors a time-mixing op is about to read (the reference's unpadded forward sees zero padding)
     const int* lens(int level) const { return p.masked ? p.lens + (size_t)level * p.B : nullptr; }
@@ -261,7 +272,7 @@ struct Builder {
         if (!p.masked) return;
         const View x = v;
         const int* l = lens(level);
-        push([=](cudaStream_t s) { return ws_launch_zero_tail(x.p, (float*)x.plo, x.dt, x.B, x.F, x.T, x.C, x.ld, l, s); });
+        push([=](cudaStream_t s) { return ws_launch_zero_tail(x.p, (float*)x.plo, x.dt, x.B, x.F, x.T, x.C, x.ld, l, s); }, "zero_tail");
     }
     void conv(const ConvSpec& s_in) {
         if (!good()) return;
@@ -304,7 +315,7 @@ struct Builder {
         push([=](cudaStream_t s) {
             return ws_launch_tstats(xv.p, xv.dt, xv.B, xv.F, xv.T, xv.C, xv.ld, pre_scale, pre_shift, out, WS_F32, out_ld,
                                     std_off, 1e-7f, s, l);
-        });
+        }, "tstats");
     }
     void linear(const float* in, long long in_ld, const float* in2, long long in2_ld, int rows_per_b, const float* W,
                 const float* bias, float* out, long long out_ld, int R, int I, int O, int act) {
@@ -319,7 +330,7 @@ struct Builder {
         push([=](cudaStream_t s) {
             return ws_launch_linear_rows(in, in_ld, in2, in2_ld, rows_per_b, W, bias, out, out_ld, R, I, O, act, wsp,
                                          nsplit, s);
-        });
+        }, "linear_rows");
     }
 };
 
@@ -345,7 +356,7 @@ bool build_ecapa(Builder& b) {
         float* xlo = (float*)x0.plo;
         const int dt = e.act_dt;
         const long long n = (long long)B * T * Fd;
-        b.push([=](cudaStream_t s) { return ws_launch_convert(fin, xo, xlo, dt, n, s); });
+        b.push([=](cudaStream_t s) { return ws_launch_convert(fin, xo, xlo, dt, n, s); }, "convert");
         b.zero_tail(x0, 0);   // (masked plans) the k=5 conv of layer1 must see zero padding behind each utterance
     }
     // Conv1dReluBn (ecapa_tdnn.py:85-106): bn(relu(conv(x)+bias))
@@ -460,7 +471,7 @@ bool build_ecapa(Builder& b) {
             const int dt = e.act_dt;
             const float* cs_in = se_colsum;
             const int* l0 = b.lens(0);
-            b.push([=](cudaStream_t s) { return ws_launch_se_gate(tc.p, dt, B, T, C, tc.ld, w1d, b1d, w2d, b2d, 128, segate, cs_in, s, l0); });
+            b.push([=](cudaStream_t s) { return ws_launch_se_gate(tc.p, dt, B, T, C, tc.ld, w1d, b1d, w2d, b2d, 128, segate, cs_in, s, l0); }, "se_gate");
         } else {
             b.tstats(tC, nullptr, nullptr, semean, C, -1);
             b.linear(semean, C, nullptr, 0, 1, b.w.vec(pf + ".3.linear1.weight"), b.w.vec(pf + ".3.linear1.bias"), sehid, 128, B,
@@ -473,7 +484,7 @@ bool build_ecapa(Builder& b) {
             const int dt = e.act_dt;
             b.push([=](cudaStream_t s) {
                 return ws_launch_scale_residual(tc.p, tc.ld, segate, xi.p, xi.ld, o.p, (float*)o.plo, o.ld, dt, B, T, C, s);
-            });
+            }, "scale_residual");
             xin = o;
         }
     }
@@ -523,7 +534,7 @@ bool build_ecapa(Builder& b) {
         b.conv_simple(hid, logits, b.w.act("w:pool.linear2", w2), 1, 1, 1, 1, 0, 0, 1, 1, ep2);
         View fr = frame, lg = logits;
         const int* l0 = b.lens(0);
-        b.push([=](cudaStream_t s) { return ws_launch_astp_stats(fr.p, lg.p, fr.dt, B, T, 1536, fr.ld, stats, s, l0); });
+        b.push([=](cudaStream_t s) { return ws_launch_astp_stats(fr.p, lg.p, fr.dt, B, T, 1536, fr.ld, stats, s, l0); }, "astp_stats");
     }
     {   // bn(3072) then linear (ecapa_tdnn.py:230-231): fold the affine into the linear; optional bn2 (emb_bn)
         std::vector<float> s, h;
@@ -598,6 +609,9 @@ View basic_block(Builder& b, const std::string& p, const View& x, int cout, int 
         Op op2;
         bool unsupported = false;
         if (make_conv3x3_op(h, o, W2, b2, &resv, true, &op2, &unsupported, 1, 1, b.lens(lvl))) {
+            std::string lab2;
+            double fl2 = 0.0;
+            take_op_label(&lab2, &fl2);
             if (has_sc0) {
                 std::vector<float> ss, hs, wsv;
                 if (!b.w.bn(p + ".shortcut.1", true, ss, hs) || !b.w.pack_conv(p + ".shortcut.0.weight", &ss, wsv, &co, &ci, &nt)) return none;
@@ -606,6 +620,7 @@ View basic_block(Builder& b, const std::string& p, const View& x, int cout, int 
                 b.conv_simple(x, o, b.w.act("w:" + p + ".shortcut", wsv), 1, 1, 1, 1, 0, 0, sf, st_, es);
                 if (!b.good()) return none;
             }
+            set_op_label(lab2, fl2);
             b.push(std::move(op2));
             return o;
         }
@@ -732,7 +747,7 @@ View stem(Builder& b, const std::string& convkey, const std::string& bnkey, View
     void* op = o.p;
     float* olo = (float*)o.plo;
     const int* l0 = b.lens(0);
-    b.push([=](cudaStream_t st) { return ws_launch_stem(fin, wd, hd, op, olo, dt, B, T, Fd, co, st, l0); });
+    b.push([=](cudaStream_t st) { return ws_launch_stem(fin, wd, hd, op, olo, dt, B, T, Fd, co, st, l0); }, "stem");
     return o;
 }
 
@@ -818,7 +833,7 @@ bool build_xvec(Builder& b) {
         float* xlo = (float*)x0.plo;
         const int dt = e.act_dt;
         const long long n = (long long)B * T * Fd;
-        b.push([=](cudaStream_t s) { return ws_launch_convert(fin, xo, xlo, dt, n, s); });
+        b.push([=](cudaStream_t s) { return ws_launch_convert(fin, xo, xlo, dt, n, s); }, "convert");
     }
     const int ks[5] = {5, 3, 3, 1, 1}, dils[5] = {1, 2, 3, 1, 1};
     View cur = x0;
@@ -1032,7 +1047,7 @@ bool build_campplus(Builder& b) {
             View sv = scratch; sv.C = cin; sv.ld = cin;
             const float* s1d = b.w.f32("bns:" + p + ".n1", s1);
             const float* h1d = b.w.f32("bnh:" + p + ".n1", h1);
-            b.push([=](cudaStream_t st) { return ws_launch_bnrelu(xs.p, xs.ld, s1d, h1d, sv.p, (float*)sv.plo, sv.ld, dt, npos, cin, st); });
+            b.push([=](cudaStream_t st) { return ws_launch_bnrelu(xs.p, xs.ld, s1d, h1d, sv.p, (float*)sv.plo, sv.ld, dt, npos, cin, st); }, "bnrelu");
             // linear1 (1x1, no bias) + nonlinear2 (BN folded) + ReLU -> hid
             WsEpi e1{};
             e1.bias = b.w.f32("bnh:" + p + ".n2", h2);
@@ -1049,9 +1064,9 @@ bool build_campplus(Builder& b) {
                 if (cam_smem <= 48 * 1024) {
                     b.push([=](cudaStream_t st) {
                         return ws_launch_cam_gate(hv.p, dt, B, Tp, bnc, hv.ld, 100, w1c, b1c, w2c, b2c, bnc / 2, growth, cgate, st);
-                    });
+                    }, "cam_gate");
                 } else {  // very long utterances: unfused path
-                    b.push([=](cudaStream_t st) { return ws_launch_seg_means(hv.p, dt, B, Tp, bnc, hv.ld, 100, cmean, csegm, st); });
+                    b.push([=](cudaStream_t st) { return ws_launch_seg_means(hv.p, dt, B, Tp, bnc, hv.ld, 100, cmean, csegm, st); }, "seg_means");
                     b.linear(csegm, bnc, cmean, bnc, nseg, w1c, b1c, chid, bnc / 2, B * nseg, bnc, bnc / 2, WS_ACT_RELU);
                     b.linear(chid, bnc / 2, nullptr, 0, 1, w2c, b2c, cgate, growth, B * nseg, bnc / 2, growth, WS_ACT_SIGMOID);
                 }
@@ -1072,7 +1087,7 @@ bool build_campplus(Builder& b) {
         const float* sd_ = b.w.f32("bns:" + tp, s);
         const float* hd_ = b.w.f32("bnh:" + tp, h);
         const int cc = cmax[bl];
-        b.push([=](cudaStream_t st) { return ws_launch_bnrelu(xs.p, xs.ld, sd_, hd_, sv.p, (float*)sv.plo, sv.ld, dt, npos, cc, st); });
+        b.push([=](cudaStream_t st) { return ws_launch_bnrelu(xs.p, xs.ld, sd_, hd_, sv.p, (float*)sv.plo, sv.ld, dt, npos, cc, st); }, "bnrelu");
         WsEpi et{};
         View dst = (bl < 2) ? X[bl + 1].ch(0, cmax[bl] / 2) : Xf;
         b.conv_simple(sv, dst, b.w.act("w:" + tp, wt), 1, 1, 1, 1, 0, 0, 1, 1, et);
@@ -1109,7 +1124,7 @@ Plan* get_plan(ws_engine* e, int B, int T, bool masked = false) {
     if (masked) {
         p->lens = (int*)b.raw((size_t)4 * B * sizeof(int));
         int* l = p->lens;
-        if (b.good()) b.push([=](cudaStream_t s) { return ws_launch_lens_derive(l, B, T, 4, s); });
+        if (b.good()) b.push([=](cudaStream_t s) { return ws_launch_lens_derive(l, B, T, 4, s); }, "lens_derive");
     }
     p->feats_in = b.f32((size_t)B * T * e->feat_dim);
     p->emb = b.f32((size_t)B * e->embed_dim);
@@ -1619,6 +1634,15 @@ int ws_engine_profile_ops(ws_engine* e, int B, int T, int iters, float* ms_out, 
     for (int i = 0; i < n; ++i) ms_out[i] = (float)(acc[i] / iters);
     for (auto& x : ev) cudaEventDestroy(x);
     return n;
+}
+
+// label of op i of the (B,T) plan ("conv_tc3 pos=.. K=.. N=..", "conv3x3 ...", "tstats", ...) and its FLOPs (0 = not GEMM-like)
+const char* ws_engine_plan_op_name(ws_engine* e, int B, int T, int i, double* flops_out) {
+    if (!e || !e->finalized || cudaSetDevice(e->device) != cudaSuccess) return nullptr;
+    Plan* p = get_plan(e, B, T);
+    if (!p || i < 0 || i >= (int)p->op_names.size()) return nullptr;
+    if (flops_out) *flops_out = p->op_flops[i];
+    return p->op_names[i].c_str();
 }
 
 void ws_engine_destroy(ws_engine* e) {

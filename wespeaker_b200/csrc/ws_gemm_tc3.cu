@@ -5,6 +5,12 @@
 // L2-operand-bandwidth bound).  Completion is multicast to both CTAs' mbarriers; each CTA runs its own epilogue from its
 // own TMEM; accumulator buffers are handed back through the leader's barrier with remote (mapa) arrives.
 //
+// CL = 4: a cluster of TWO such pairs on adjacent position tiles and the same channel tile.  The CTAs with the same rank
+// inside their pair need the same half of the weight tile: each loads a QUARTER of the tile and TMA-multicasts it to both,
+// so a CTA pulls 16 KB (activations) + 8 KB (weights) per k-block from L2 instead of 16 + 16 (the round-1/2 profiles show
+// the mainloop pinned at the L2 -> SM operand rate, 9-11 TB/s).  Stage reuse then needs BOTH pairs to have consumed the
+// stage: each pair's MMA leader multicasts its tcgen05.commit to all four CTAs and the empty barriers count two arrivals.
+//
 // ---- original v2 header:
 // Persistent warp-specialised conv/GEMM on tcgen05 + TMEM + TMA (sm_100a), version 2.
 //
@@ -82,10 +88,20 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
     }
 }
 // completion of all prior MMAs -> arrive on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
+__device__ __forceinline__ void umma_commit(uint32_t bar, unsigned short mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"((unsigned short)3)
+                 "h"(mask)
                  : "memory");
+}
+// 2-SM TMA load multicast to the CTAs in `mask` (same smem offset in each; the bytes are credited to each destination's
+// pair-leader barrier, cute SM100_TMA_2SM_LOAD_MULTICAST)
+__device__ __forceinline__ void tma2_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                unsigned short mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
+        "{%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
 }
 constexpr int kThreads3 = 384;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4..w11 epilogue (2 warps per TMEM lane quadrant)
 constexpr int kMaxDynSmem3 = 220 * 1024;
@@ -95,16 +111,19 @@ constexpr int kMaxDynSmem3 = 220 * 1024;
 // tanh/sigmoid, every dtype) is ~100 KB of SASS of which a given layer executes a few KB scattered between never-taken
 // branches; ncu showed its warps stalled on instruction fetch (stall_no_inst) for half of their samples, which made the
 // short-K 1x1 convs epilogue-bound.  The lean chunk body is ~4 KB and stays in the 6 KB L0 instruction cache.
-template <int KIND, int LEAN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads3, 1) ws_conv_gemm_tc3_kernel(const __grid_constant__ WsTc2Params p) {
+template <int KIND, int LEAN, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kThreads3, 1) ws_conv_gemm_tc3_kernel(const __grid_constant__ WsTc2Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[2 * WS_TC_MAX_STAGES + 6];
     __shared__ uint32_t s_tmem;
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
+    const uint32_t rank = cluster_ctarank();            // 0..CL-1; pairs are (0,1) and (2,3)
+    const uint32_t r2 = rank & 1u, pr = rank >> 1;      // rank inside the pair, pair inside the cluster
+    const bool leader = r2 == 0;
+    const int ncl = (int)gridDim.x / CL, cid = (int)blockIdx.x / CL;
+    const unsigned short pair_mask = (unsigned short)(3u << (2 * pr)), all_mask = (unsigned short)((1u << CL) - 1u);
     const int a_bytes = 128 * p.bk_bytes, b_bytes = (p.bn / 2) * p.bk_bytes;   // own A tile + own HALF of the W tile
     const int stage_bytes = a_bytes + b_bytes;
     const int es = KIND == 0 ? 4 : 2;
@@ -133,7 +152,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads3, 1) ws_con
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.nstages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, CL / 2);   // one commit per pair
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
@@ -159,8 +178,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads3, 1) ws_con
         if (lane == 0) {
             const int bk_elems = p.bk_bytes / es;
             int it = 0, j = 0;
-            for (int tile = blockIdx.x >> 1; tile < p.num_tiles; tile += gridDim.x >> 1, ++j) {
-                int tt = (tile / p.tiles_n) * 2 + (int)rank;           // this CTA's position tile inside the pair
+            for (int tile = cid; tile < p.num_tiles; tile += ncl, ++j) {
+                int tt = (tile / p.tiles_n) * CL + (int)rank;           // this CTA's position tile inside the pair
                 const int n0 = (tile % p.tiles_n) * p.bn;
                 const int t0 = (tt % p.tiles_t) << p.bt_log2; tt /= p.tiles_t;
                 const int f0 = (tt % p.tiles_f) << p.bf_log2; tt /= p.tiles_f;
@@ -178,8 +197,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads3, 1) ws_con
                             const uint32_t sa = ring + (uint32_t)(s * stage_bytes);
                             tma2_load_4d(sa, ps == 0 ? &p.amap_lo[tap.map] : &p.amap[tap.map], bar_full + 8 * s,
                                          tap.c0 + kb * bk_elems, t0 + tap.dt, f0 + tap.df, b0);
-                            tma2_load_2d(sa + (uint32_t)a_bytes, ps == 1 ? &p.wmap_lo : &p.wmap, bar_full + 8 * s,
-                                         tap.wk + kb * bk_elems, n0 + (int)rank * (p.bn / 2));
+                            if (CL == 2)
+                                tma2_load_2d(sa + (uint32_t)a_bytes, ps == 1 ? &p.wmap_lo : &p.wmap, bar_full + 8 * s,
+                                             tap.wk + kb * bk_elems, n0 + (int)r2 * (p.bn / 2));
+                            else   // this CTA's quarter of the weight tile, to itself and to the same-rank CTA of the other pair
+                                tma2_load_2d_mc(sa + (uint32_t)(a_bytes + (int)pr * (b_bytes / 2)), ps == 1 ? &p.wmap_lo : &p.wmap,
+                                                bar_full + 8 * s, tap.wk + kb * bk_elems,
+                                                n0 + (int)r2 * (p.bn / 2) + (int)pr * (p.bn / 4),
+                                                (unsigned short)((1u << r2) | (4u << r2)));
                         }
                     }
                 }
@@ -203,7 +228,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads3, 1) ws_con
             const int kper = p.bk_bytes / 32;
             int s = 0, j = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x >> 1; tile < p.num_tiles; tile += gridDim.x >> 1, ++j) {
+            for (int tile = cid; tile < p.num_tiles; tile += ncl, ++j) {
                 const int buf = j & 1;
                 PROF_T(m0);
                 mbar_wait(bar_tempty + 8 * buf, (((uint32_t)j >> 1) & 1u) ^ 1u);  // epilogue drained this buffer
@@ -222,11 +247,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads3, 1) ws_con
                         for (int k = 0; k < kper; ++k)
                             umma<KIND>(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
                                        (uint32_t)((kit | k) != 0));
-                        umma_commit(bar_empty + 8 * s);
+                        umma_commit(bar_empty + 8 * s, all_mask);
                     }
                     if (++s == p.nstages) { s = 0; ph ^= 1u; }
                 }
-                if (elected) umma_commit(bar_tfull + 8 * buf);
+                if (elected) umma_commit(bar_tfull + 8 * buf, pair_mask);
                 __syncwarp();
                 PROF_T(m2);
                 PROF_ADD(9, m2 - m1);
@@ -246,8 +271,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads3, 1) ws_con
         const WsEpi& e = p.epi;
         float* spar = reinterpret_cast<float*>(smem_raw + (s_par - smem_u32(smem_raw)));
         int j = 0, last_n0 = -1;
-        for (int tile = blockIdx.x >> 1; tile < p.num_tiles; tile += gridDim.x >> 1, ++j) {
-            int tt = (tile / p.tiles_n) * 2 + (int)rank;
+        for (int tile = cid; tile < p.num_tiles; tile += ncl, ++j) {
+            int tt = (tile / p.tiles_n) * CL + (int)rank;
             const int n0 = (tile % p.tiles_n) * p.bn;
             const int t0 = (tt % p.tiles_t) << p.bt_log2; tt /= p.tiles_t;
             const int f0 = (tt % p.tiles_f) << p.bf_log2; tt /= p.tiles_f;
@@ -293,7 +318,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads3, 1) ws_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive_remote(bar_tempty + 8 * buf, 0);   // the MMA issuer lives in the leader CTA
+                mbar_arrive_remote(bar_tempty + 8 * buf, rank & ~1u);   // the MMA issuer lives in the pair's leader CTA
                 if (p.has_epin) mbar_arrive(bar_iempty);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -333,9 +358,19 @@ extern "C" void ws_tc3_prof_read(unsigned long long* out, int reset) {
 #endif
 
 namespace {
+template <int KIND, int LEAN, int CL>
+inline cudaError_t tc3_attr1() {
+    return cudaFuncSetAttribute(ws_conv_gemm_tc3_kernel<KIND, LEAN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem3);
+}
 template <int KIND, int LEAN>
 inline cudaError_t tc3_attr() {
-    return cudaFuncSetAttribute(ws_conv_gemm_tc3_kernel<KIND, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem3);
+    cudaError_t e = tc3_attr1<KIND, LEAN, 2>();
+    return e == cudaSuccess ? tc3_attr1<KIND, LEAN, 4>() : e;
+}
+template <int KIND, int LEAN>
+inline void tc3_go(const WsTc2Params* p, cudaStream_t s) {
+    if (p->cl == 4) ws_conv_gemm_tc3_kernel<KIND, LEAN, 4><<<p->grid, kThreads3, p->smem_bytes, s>>>(*p);
+    else ws_conv_gemm_tc3_kernel<KIND, LEAN, 2><<<p->grid, kThreads3, p->smem_bytes, s>>>(*p);
 }
 }  // namespace
 
@@ -355,14 +390,41 @@ extern "C" const char* ws_tc3_init(void) {
 
 extern "C" int ws_tc3_max_smem(void) { return kMaxDynSmem3; }
 
+// how many clusters of `cl` CTAs (at the kernel's maximum shared memory) the device keeps resident at once: GPCs whose SM
+// count is not a multiple of cl leave SMs idle, so this can be below num_sms / cl
+extern "C" int ws_tc3_max_clusters(int cl) {
+    static int cache[64][2];
+    static bool have[64][2];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || (cl != 2 && cl != 4)) return 0;
+    const int k = cl == 4;
+    if (have[dev][k]) return cache[dev][k];
+    if (ws_tc3_init() != nullptr) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ws_num_sms() / cl * cl));
+    cfg.blockDim = dim3(kThreads3);
+    cfg.dynamicSmemBytes = kMaxDynSmem3;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = (unsigned)cl; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e = cl == 4 ? cudaOccupancyMaxActiveClusters(&n, ws_conv_gemm_tc3_kernel<1, WS_BF16 + 1, 4>, &cfg)
+                            : cudaOccupancyMaxActiveClusters(&n, ws_conv_gemm_tc3_kernel<1, WS_BF16 + 1, 2>, &cfg);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    cache[dev][k] = n; have[dev][k] = true;
+    return n;
+}
+
 extern "C" const char* ws_tc3_launch(const WsTc2Params* p, cudaStream_t s) {
     const int lean = p->epi_generic ? 0 : ws_tc_lean_kind(p);
     if (const char* m = ws_tc_colsum_check(p, lean)) return m;
-    if (lean == WS_F32 + 1) ws_conv_gemm_tc3_kernel<0, WS_F32 + 1><<<p->grid, kThreads3, p->smem_bytes, s>>>(*p);
-    else if (lean == WS_BF16 + 1) ws_conv_gemm_tc3_kernel<1, WS_BF16 + 1><<<p->grid, kThreads3, p->smem_bytes, s>>>(*p);
-    else if (lean == WS_F16 + 1) ws_conv_gemm_tc3_kernel<1, WS_F16 + 1><<<p->grid, kThreads3, p->smem_bytes, s>>>(*p);
-    else if (p->kind == 0) ws_conv_gemm_tc3_kernel<0, 0><<<p->grid, kThreads3, p->smem_bytes, s>>>(*p);
-    else ws_conv_gemm_tc3_kernel<1, 0><<<p->grid, kThreads3, p->smem_bytes, s>>>(*p);
+    if (p->cl != 2 && p->cl != 4) return "ws_tc3_launch: cluster size must be 2 or 4";
+    if (lean == WS_F32 + 1) tc3_go<0, WS_F32 + 1>(p, s);
+    else if (lean == WS_BF16 + 1) tc3_go<1, WS_BF16 + 1>(p, s);
+    else if (lean == WS_F16 + 1) tc3_go<1, WS_F16 + 1>(p, s);
+    else if (p->kind == 0) tc3_go<0, 0>(p, s);
+    else tc3_go<1, 0>(p, s);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

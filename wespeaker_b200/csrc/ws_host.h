@@ -11,6 +11,9 @@
 namespace ws {
 
 void set_err(const std::string& msg);
+// tuning aid: op factories leave a label (+ FLOPs) for the op they just built; Builder::push() attaches it to the plan
+void set_op_label(const std::string& name, double flops = 0.0);
+bool take_op_label(std::string* name, double* flops);
 const std::string& get_err();
 
 #define WS_CK(call)                                                                               \
