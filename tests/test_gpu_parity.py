@@ -293,6 +293,29 @@ def test_campplus_fused_dense_layers_match_unfused(prec, B, T, block):
     assert mf.last_launches() < mu.last_launches() - 100
 
 
+@pytest.mark.parametrize("name,prec,B,T", [("ECAPA_TDNN_c512", "bf16", 5, 200), ("ECAPA_TDNN_GLOB_c512", "fp16", 3, 203),
+                                           ("ECAPA_TDNN_c1024", "bf16", 2, 256), ("ECAPA_TDNN_c512", "bf16", 3, 300),
+                                           ("ECAPA_TDNN_GLOB_c512", "bf16", 2, 998), ("ECAPA_TDNN_c512", "fp16", 300, 40),
+                                           ("ECAPA_TDNN_c512", "bf16", 1, 17)])
+def test_ecapa_fused_astp_matches_unfused(name, prec, B, T):
+    """ws_astp_fused.cu (linear2 + softmax over time + weighted mean/std in one launch, transposed logits in TMEM, online
+    softmax over 256-frame chunks) against the linear2-launch + statistics-launch path (pooling_layers.py:119-144), and both
+    against the oracle.  The fused path keeps the logits in fp32 (the unfused one rounds them to 16 bits), so the two agree
+    to 16-bit rounding level."""
+    feats = torch.from_numpy(syn.make_feats(B, T, 80, seed=17))
+    mf = from_synthetic(name, 0, precision=prec)
+    mu = from_synthetic(name, 0, precision=prec)
+    mu.set_option("astp_fused", 0)
+    ef, eu = mf.embed(feats.to(DEV)).cpu().numpy(), mu.embed(feats.to(DEV)).cpu().numpy()
+    nref = min(B, 4)
+    ref = models_torch.forward(name, syn.make_state_dict(name, 0), feats[:nref]).numpy()
+    print(f"astp fused vs unfused {name} {prec} B{B} T{T}: rel {rel_l2(ef, eu).max():.2e}; vs oracle fused {rel_l2(ef[:nref], ref).max():.2e} "
+          f"unfused {rel_l2(eu[:nref], ref).max():.2e}; launches {mf.last_launches()} vs {mu.last_launches()}")
+    assert np.isfinite(ef).all() and rel_l2(ef, eu).max() <= 3e-3
+    assert rel_l2(ef[:nref], ref).max() <= TC_TOL[prec]
+    assert mf.last_launches() == mu.last_launches() - 1
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["bf16-tc2", "fp16-tc2", "tf32-tc2", "tf32x3-tc2", "bf16-tc3", "fp16-tc3", "tf32-tc3", "tf32x3-tc3"])
 @pytest.mark.parametrize("variant", ["bias_relu", "bn", "bn_res_relu"])

@@ -317,6 +317,22 @@ struct WsTc2Params {
     WsEpi epi;
 };
 
+// fused ASTP tail (ws_astp_fused.cu): attention logits (linear2) + softmax over time + weighted mean / std
+struct WsAstpParams {
+    CUtensorMap hmap;   // H = tanh(linear1(x)) [B][T][128], 16-bit: dims (128, T, B), box (64, 256, 1), SWIZZLE_128B
+    CUtensorMap wmap;   // linear2 weight [C][128] K-major: dims (128, C), box (64, 128)
+    CUtensorMap xmap;   // x [B][T][x_ld]: dims (C, T, B), box (128, 128, 1), no swizzle (row pitch 256 B in smem)
+    const void* x;      // frame-level features [B][T][x_ld] (16-bit), the tensor the statistics are taken of
+    long long x_ld;
+    float* out;         // [B][2C]: weighted mean, then std
+    int B, T, C, dtype;
+    int g;              // channel blocks (of 128) per work unit: H is fetched once per unit
+    int grid;
+    const int* lens;    // length-masked batch: frames of each utterance, or null
+    int dbg;            // tuning knock-outs (WS_ASTP_DBG): 1 no x loads, 2 no exp, 4 no tcgen05.ld
+    long long* prof;    // WS_ASTP_PROF: [grid][16] wait-cycle counters per role
+};
+
 // fused Res2 chain (ws_res2_fused.cu)
 struct WsRes2Params {
     CUtensorMap xmap;   // block input  [B][T][C] (channels-last, 16-bit): dims (C, T, B), box (64, 128, 1), SWIZZLE_128B
@@ -427,6 +443,9 @@ inline int ws_num_sms() {
 #ifdef __cplusplus
 extern "C" {
 #endif
+const char* ws_astp_init(void);
+int ws_astp_smem(void);
+const char* ws_astp_launch(const WsAstpParams* p, cudaStream_t s);
 const char* ws_res2_init(void);
 const char* ws_res2_launch(const WsRes2Params* p, cudaStream_t s);
 const char* ws_cam_init(void);

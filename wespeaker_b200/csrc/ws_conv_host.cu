@@ -109,8 +109,8 @@ static bool encode_map(CUtensorMap* m, int dt, const void* ptr, int rank, const 
                                                : (dt == WS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                                 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
     const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                                       : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                                                              : CU_TENSOR_MAP_SWIZZLE_32B);
+                                  : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                     : (swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_32B));
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(m, t, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -440,6 +440,84 @@ bool make_res2_op(const View& x, const View& out, const void* W7, const float* b
     return true;
 }
 
+bool make_astp_op(const View& x, const View& h, const void* W2, float* stats, Op* op, bool* unsupported, const int* lens) {
+    *unsupported = false;
+    if (x.dt == WS_F32 || h.dt != x.dt || x.C % 128 != 0 || h.C != 128 || h.ld != 128 || x.F != 1 || h.F != 1 || h.T != x.T ||
+        h.B != x.B || getenv("WS_NO_ASTP_FUSED")) {
+        *unsupported = true;
+        return false;
+    }
+    auto q = std::make_shared<WsAstpParams>();
+    memset(q.get(), 0, sizeof(WsAstpParams));
+    {
+        cuuint64_t dims[3] = {128, (cuuint64_t)h.T, (cuuint64_t)h.B};
+        cuuint64_t str[2] = {128 * 2, (cuuint64_t)h.T * 128 * 2};
+        cuuint32_t box[3] = {64, 256, 1};
+        if (!encode_map(&q->hmap, h.dt, h.p, 3, dims, str, box, 128)) return false;
+    }
+    {
+        cuuint64_t dims[2] = {128, (cuuint64_t)x.C};
+        cuuint64_t str[1] = {128 * 2};
+        cuuint32_t box[2] = {64, 128};
+        if (!encode_map(&q->wmap, x.dt, W2, 2, dims, str, box, 128)) return false;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)x.C, (cuuint64_t)x.T, (cuuint64_t)x.B};
+        cuuint64_t str[2] = {(cuuint64_t)x.ld * 2, (cuuint64_t)x.T * x.ld * 2};
+        cuuint32_t box[3] = {128, 128, 1};
+        if (!encode_map(&q->xmap, x.dt, x.p, 3, dims, str, box, 0)) return false;
+    }
+    if (const char* d = getenv("WS_ASTP_DBG")) q->dbg = atoi(d);
+    q->x = x.p; q->x_ld = x.ld; q->out = stats; q->B = x.B; q->T = x.T; q->C = x.C; q->dtype = x.dt; q->lens = lens;
+    // channel blocks per unit: the largest g whose static round-robin over the SMs stays within 8 % of the best balance
+    const int nblk = x.C / 128, sms = ws_num_sms();
+    double best = 0.0;
+    int cand[6] = {12, 6, 4, 3, 2, 1};
+    auto eff = [&](int g) {
+        const long long units = (long long)x.B * (nblk / g);
+        const long long grid = units < sms ? units : sms;
+        return (double)units / (double)(((units + grid - 1) / grid) * grid);
+    };
+    for (int g : cand) if (nblk % g == 0 && eff(g) > best) best = eff(g);
+    q->g = 1;
+    for (int g : cand) if (nblk % g == 0 && eff(g) >= 0.92 * best) { q->g = g; break; }
+    if (const char* eg = getenv("WS_ASTP_G")) { const int g = atoi(eg); if (g > 0 && nblk % g == 0) q->g = g; }
+    const long long units = (long long)x.B * (nblk / q->g);
+    q->grid = (int)(units < sms ? units : sms);
+    if (getenv("WS_ASTP_PROF")) {   // tuning aid: synchronous launch + per-role wait-cycle summary on stderr
+        long long* prof = nullptr;
+        if (cudaMalloc((void**)&prof, (size_t)q->grid * 16 * 8) != cudaSuccess) { set_err("astp: prof buffer"); return false; }
+        q->prof = prof;
+        *op = [q](cudaStream_t s) -> const char* {
+            cudaMemsetAsync(q->prof, 0, (size_t)q->grid * 16 * 8, s);
+            const char* m = ws_astp_launch(q.get(), s);
+            if (m) return m;
+            cudaStreamSynchronize(s);
+            std::vector<long long> h((size_t)q->grid * 16);
+            cudaMemcpy(h.data(), q->prof, h.size() * 8, cudaMemcpyDeviceToHost);
+            static const char* names[11] = {"prod.wait_hempty", "prod.wait_wempty", "mma.wait_hfull", "mma.wait_wfull", "mma.wait_tempty",
+                                            "mma.tiles", "epi0.wait_tfull", "epi0.body", "epi1.wait_tfull", "epi1.body", "total"};
+            fprintf(stderr, "[astp prof] grid %d g %d:", q->grid, q->g);
+            for (int k = 0; k < 11; ++k) {
+                double acc = 0;
+                for (int c = 0; c < q->grid; ++c) acc += (double)h[(size_t)c * 16 + k];
+                fprintf(stderr, " %s=%.0f", names[k], acc / q->grid);
+            }
+            fprintf(stderr, "\n");
+            return nullptr;
+        };
+        set_op_label("astp_fused (profiled)", 0.0);
+        return true;
+    }
+    *op = [q](cudaStream_t s) { return ws_astp_launch(q.get(), s); };
+    {
+        char buf[160];
+        snprintf(buf, sizeof buf, "astp_fused B=%d T=%d C=%d g=%d grid=%d", x.B, x.T, x.C, q->g, q->grid);
+        set_op_label(buf, 2.0 * x.B * x.T * 128.0 * x.C);
+    }
+    return true;
+}
+
 bool make_conv3x3_op(const View& x, const View& out, const void* W, const float* bias, const View* res, bool relu,
                      Op* op, bool* unsupported, int stride_f, int stride_t, const int* lens) {
     *unsupported = false;
@@ -712,7 +790,7 @@ extern "C" int ws_conv(const ws_conv_desc* d, void* stream) {
     s.epi.res = d->res; s.epi.res_ld = d->res_ld; s.epi.act2 = d->act2;
     s.epi.colsum = d->colsum; s.epi.colsum_T = d->colsum ? To : 0;
     Op op;
-    if (d->use_tc) { WS_CKS(ws_tc_init()); WS_CKS(ws_tc2_init()); WS_CKS(ws_tc3_init()); WS_CKS(ws_c3_init()); }
+    if (d->use_tc) { WS_CKS(ws_tc_init()); WS_CKS(ws_tc2_init()); WS_CKS(ws_tc3_init()); WS_CKS(ws_c3_init()); WS_CKS(ws_astp_init()); }
     bool done = false;
     if (d->use_tc >= 4 && d->kf == 3 && d->kt == 3 && d->dil_f == 1 && d->dil_t == 1 && d->pad_f == 1 && d->pad_t == 1 &&
         d->stride_f >= 1 && d->stride_f <= 2 && d->stride_t >= 1 && d->stride_t <= 2 && d->scale == nullptr && d->x_lo == nullptr && d->colsum == nullptr &&

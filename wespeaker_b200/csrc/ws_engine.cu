@@ -344,7 +344,7 @@ bool build_ecapa(Builder& b) {
     View out1 = b.act(B, 1, T, C), cat = b.act(B, 1, T, 3 * C);
     View tA = b.act(B, 1, T, C), tB = b.act(B, 1, T, C), tC = b.act(B, 1, T, C);
     View sc[2] = {b.act(B, 1, T, w8), b.act(B, 1, T, w8)};
-    View frame = b.act(B, 1, T, 1536), hid = b.act(B, 1, T, 128), logits = b.act(B, 1, T, 1536);
+    View frame = b.act(B, 1, T, 1536), hid = b.act(B, 1, T, 128);
     float* semean = b.f32((size_t)B * C);
     float* sehid = b.f32((size_t)B * 128);
     float* segate = b.f32((size_t)B * C);
@@ -529,12 +529,24 @@ bool build_ecapa(Builder& b) {
         std::vector<float> w2;
         int co, ci, nt;
         if (!b.w.pack_conv("pool.linear2.weight", nullptr, w2, &co, &ci, &nt)) return false;
-        WsEpi ep2{};
-        ep2.bias = b.w.vec("pool.linear2.bias");
-        b.conv_simple(hid, logits, b.w.act("w:pool.linear2", w2), 1, 1, 1, 1, 0, 0, 1, 1, ep2);
-        View fr = frame, lg = logits;
+        const void* W2d = b.w.act("w:pool.linear2", w2);
         const int* l0 = b.lens(0);
-        b.push([=](cudaStream_t s) { return ws_launch_astp_stats(fr.p, lg.p, fr.dt, B, T, 1536, fr.ld, stats, s, l0); }, "astp_stats");
+        // linear2 + softmax over time + weighted statistics in one launch: the logits never leave the SM (ws_astp_fused.cu)
+        bool fused = false;
+        if (e.use_tc >= 2 && e.opt("astp_fused", 1) && b.good()) {
+            Op op;
+            bool unsupported = false;
+            if (make_astp_op(frame, hid, W2d, stats, &op, &unsupported, l0)) { b.push(std::move(op)); fused = true; }
+            else if (!unsupported) { b.ok = false; return false; }
+        }
+        if (!fused) {
+            View logits = b.act(B, 1, T, 1536);
+            WsEpi ep2{};
+            ep2.bias = b.w.vec("pool.linear2.bias");
+            b.conv_simple(hid, logits, W2d, 1, 1, 1, 1, 0, 0, 1, 1, ep2);
+            View fr = frame, lg = logits;
+            b.push([=](cudaStream_t s) { return ws_launch_astp_stats(fr.p, lg.p, fr.dt, B, T, 1536, fr.ld, stats, s, l0); }, "astp_stats");
+        }
     }
     {   // bn(3072) then linear (ecapa_tdnn.py:230-231): fold the affine into the linear; optional bn2 (emb_bn)
         std::vector<float> s, h;
@@ -1308,6 +1320,7 @@ int ws_engine_create(const char* model_name, const char* precision, int feat_dim
     WS_CKS(ws_tc_init());
     WS_CKS(ws_tc2_init());
     WS_CKS(ws_res2_init());
+    WS_CKS(ws_astp_init());
     WS_CKS(ws_tc3_init());
     WS_CKS(ws_c3_init());
     WS_CKS(ws_cam_init());
@@ -1325,7 +1338,7 @@ int ws_engine_set_option(ws_engine* e, const char* key, long long value) {
     const std::string k = key;
     if (k == "force_simt") { if (value) e->use_tc = 0; }
     else if (k == "tc_version") { if (e->use_tc) e->use_tc = value >= 3 ? 3 : (value >= 2 || e->split ? 2 : 1); }
-    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused" && k != "se_fused" && k != "se_colsum" && k != "conv3x3" && k != "cam_fused" && k != "cam_block" && k != "plan_lanes" && k != "conv3x3_strided") { set_err("unknown option " + k); return 1; }
+    else if (k != "two_emb_layer" && k != "emb_bn" && k != "cuda_graph" && k != "res2_fused" && k != "se_fused" && k != "se_colsum" && k != "conv3x3" && k != "cam_fused" && k != "cam_block" && k != "plan_lanes" && k != "conv3x3_strided" && k != "astp_fused") { set_err("unknown option " + k); return 1; }
     e->opts[k] = value;
     e->plans.clear();
     return 0;
