@@ -386,6 +386,7 @@ struct WsC3Params {
     long long* prof;               // tuning aid (WS_C3_PROF=1): per-CTA wait-cycle counters, 16 slots per CTA; else null
     const int* lens;               // length-masked batch: output frames of each utterance (rows behind are stored as zeros), or null
     int dbg;                       // tuning aid (WS_C3_DBG): knock-out bits 1 = no epilogue work, 2 = no input TMA loads, 8 = no MMAs
+    int cl;   // 2 = clusters of two CTAs multicast-share the weight ring (streamed weights, one channel tile), else 1
 };
 
 // fused CAM++ dense layer (ws_cam_dense.cu).  One descriptor per CAMDenseTDNNLayer, device-resident (the tensor maps are

@@ -33,6 +33,36 @@ __device__ __forceinline__ void umma_f16_c3(uint32_t tmem_d, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+// ---- 2-CTA cluster mode (p.cl == 2): the two CTAs walk different output rows but stream the SAME weight blocks, so each
+// fetches half of every block and TMA-multicasts it to both; a ring stage is reused once both CTAs' MMAs have read it
+__device__ __forceinline__ uint32_t c3_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void c3_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void c3_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void c3_tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                  unsigned short mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+        "%4}], [%2], %5;" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_c3_mc(uint32_t bar, unsigned short mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ void umma_commit_c3(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -105,15 +135,26 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < 2 * p.n_mt * p.N) tmem_cols <<= 1;
 
-    const int s_beg = (int)((long long)p.total_steps * blockIdx.x / gridDim.x);
-    const int s_end = (int)((long long)p.total_steps * (blockIdx.x + 1) / gridDim.x);
+    int s_beg = (int)((long long)p.total_steps * blockIdx.x / gridDim.x);
+    int s_end = (int)((long long)p.total_steps * (blockIdx.x + 1) / gridDim.x);
+    int w_rounds = s_end - s_beg;          // weight passes this CTA's ring goes through (one per step)
+    const bool mc = p.cl == 2;
+    const uint32_t crank = mc ? c3_cluster_rank() : 0u;
+    if (mc) {   // the cluster takes a contiguous range of steps and splits it in halves; both CTAs consume ceil(n / 2) weight passes
+        const int cid = (int)blockIdx.x >> 1, ncl = (int)gridDim.x >> 1;
+        const int c_beg = (int)((long long)p.total_steps * cid / ncl), c_end = (int)((long long)p.total_steps * (cid + 1) / ncl);
+        const int n0 = (c_end - c_beg + 1) >> 1;
+        s_beg = crank == 0 ? c_beg : c_beg + n0;
+        s_end = crank == 0 ? c_beg + n0 : c_end;
+        w_rounds = n0;
+    }
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.amap); prefetch_tmap(&p.amap_tail); prefetch_tmap(&p.wmap); prefetch_tmap(&p.omap); prefetch_tmap(&p.rmap);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.R; ++i) { mbar_init(bar_afull + 8 * i, 1); mbar_init(bar_aempty + 8 * i, 1); }
-        for (int i = 0; i < WS_C3_MAX_WSTAGES; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wempty + 8 * i, 1); }
+        for (int i = 0; i < WS_C3_MAX_WSTAGES; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wempty + 8 * i, mc ? 2 : 1); }
         mbar_init(bar_wres, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
         for (int i = 0; i < 6; ++i) mbar_init(bar_rfull + 8 * i, 1);
@@ -127,6 +168,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
     }
     tc_fence_before();
     __syncthreads();
+    if (mc) c3_cluster_sync();   // the peer's barriers are initialised before any multicast load / remote arrive reaches them
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
 
@@ -173,7 +215,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
         }
     } else if (warp == 3) {
         // ================================ weight producer ================================
-        if (lane == 0 && s_beg < s_end) {
+        if (lane == 0 && w_rounds > 0) {
             if (p.w_resident) {
                 mbar_expect_tx(bar_wres, (uint32_t)(nwblk * wblk_bytes));
                 for (int tap = 0; tap < 9; ++tap)
@@ -183,16 +225,22 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
             } else {
                 int ws = 0;
                 uint32_t wphase = 1;
-                for (C3Iter it(p, s_beg, s_end); !it.done(); it.next(p)) {
-                    const C3Step st = it.cur(p);
+                C3Iter it(p, s_beg, s_end);
+                for (int r = 0; r < w_rounds; ++r) {
+                    const int nt = mc ? 0 : it.cur(p).nt;      // cluster mode needs one channel tile (host guarantees n_nt == 1)
                     for (int tap = 0; tap < 9; ++tap)
                         for (int kp = 0; kp < p.npan; ++kp) {
                             mbar_wait(bar_wempty + 8 * ws, wphase);
                             mbar_expect_tx(bar_wfull + 8 * ws, (uint32_t)wblk_bytes);
-                            tma_load_2d(wbuf + (uint32_t)(ws * wblk_bytes), &p.wmap, bar_wfull + 8 * ws,
-                                        tap * p.Cin + kp * p.kc, st.nt * p.N);
+                            if (mc)   // this CTA's half of the block (N/2 rows), to both CTAs
+                                c3_tma_load_2d_mc(wbuf + (uint32_t)(ws * wblk_bytes) + crank * (uint32_t)(wblk_bytes >> 1), &p.wmap,
+                                                  bar_wfull + 8 * ws, tap * p.Cin + kp * p.kc, (int)crank * (p.N >> 1), (unsigned short)3);
+                            else
+                                tma_load_2d(wbuf + (uint32_t)(ws * wblk_bytes), &p.wmap, bar_wfull + 8 * ws,
+                                            tap * p.Cin + kp * p.kc, nt * p.N);
                             if (++ws == p.w_stages) { ws = 0; wphase ^= 1u; }
                         }
+                    if (!mc) it.next(p);
                 }
             }
         }
@@ -278,7 +326,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
                             if (p.w_resident) {
                                 bd += wb_off;
                             } else {
-                                if (elected) umma_commit_c3(bar_wempty + 8 * wst);
+                                if (elected) { if (mc) umma_commit_c3_mc(bar_wempty + 8 * wst, (unsigned short)3); else umma_commit_c3(bar_wempty + 8 * wst); }
                                 if (++wst == p.w_stages) { wst = 0; wph ^= 1u; }
                             }
                         }
@@ -296,6 +344,16 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
                     if (st.last) umma_commit_c3(bar_aempty + 8 * sl[2]);                 // end of this image segment
                 }
                 __syncwarp();
+            }
+            // cluster mode: a CTA with one step fewer than its peer still has to release the weight stages of the last pass
+            if (mc && !p.w_resident) {
+                for (int r = s_end - s_beg; r < w_rounds; ++r)
+                    for (int i = 0; i < 9 * NPAN; ++i) {
+                        mbar_wait(bar_wfull + 8 * wst, wph);
+                        if (elected) { mbar_arrive(bar_wempty + 8 * wst); c3_arrive_remote(bar_wempty + 8 * wst, crank ^ 1u); }
+                        __syncwarp();
+                        if (++wst == p.w_stages) { wst = 0; wph ^= 1u; }
+                    }
             }
             if (p.prof && lane == 0) {
                 p.prof[blockIdx.x * 16 + 2] = mw_afull; p.prof[blockIdx.x * 16 + 3] = mw_tempty;
@@ -451,6 +509,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
 
     tc_fence_before();
     __syncthreads();
+    if (mc) c3_cluster_sync();   // the peer may still multicast into this CTA's ring / arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -464,6 +523,16 @@ template <int DT, int ROWB, int NPAN, int NMT>
 const char* c3_launch_one(const WsC3Params* p, cudaStream_t s, bool attr_only) {
     if (attr_only) {
         cudaError_t e = cudaFuncSetAttribute(ws_conv3x3_kernel<DT, ROWB, NPAN, NMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC3MaxSmem);
+        return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+    }
+    if (p->cl == 2) {   // 2-CTA clusters (weight multicast): cluster dimension as a launch attribute
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)p->grid); cfg.blockDim = dim3(kC3Threads); cfg.dynamicSmemBytes = (size_t)p->smem_bytes; cfg.stream = s;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, ws_conv3x3_kernel<DT, ROWB, NPAN, NMT>, *p);
         return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
     }
     ws_conv3x3_kernel<DT, ROWB, NPAN, NMT><<<p->grid, kC3Threads, p->smem_bytes, s>>>(*p);

@@ -606,6 +606,12 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
     q->total_steps = q->n_nt * q->n_tt * q->n_bg * F;
     const int sms = ws_num_sms();
     q->grid = q->total_steps < sms ? q->total_steps : sms;
+    // streamed weights (they do not fit beside the input ring) and a single channel tile: clusters of two CTAs can share the
+    // weight stream by TMA multicast (each CTA fetches half of every block).  Measured on B200 (profiles/r02_conv3x3_layer3.md):
+    // no gain - the step is bound by shared-memory bandwidth (8 KB of operand reads + 4 KB of weight-ring fill per MMA), which
+    // multicast does not reduce - so it is opt-in (WS_C3_MC=1) and kept as a reproducible experiment.
+    q->cl = (!q->w_resident && q->n_nt == 1 && q->grid >= 2 && q->N % 16 == 0 && getenv("WS_C3_MC")) ? 2 : 1;
+    if (q->cl == 2) q->grid &= ~1;
     // ---- tensor maps
     if (stride_t == 2) {   // even / odd time planes of the input as two tensors with a doubled t stride
         cuuint64_t str[3] = {(cuuint64_t)x.ld * 4, (cuuint64_t)Tin * x.ld * 2, (cuuint64_t)Fin * Tin * x.ld * 2};
@@ -626,7 +632,7 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
     {
         cuuint64_t dims[2] = {(cuuint64_t)(9 * Cin), (cuuint64_t)Cout};
         cuuint64_t str[1] = {(cuuint64_t)(9 * Cin) * 2};
-        cuuint32_t box[2] = {(cuuint32_t)q->kc, (cuuint32_t)q->N};
+        cuuint32_t box[2] = {(cuuint32_t)q->kc, (cuuint32_t)(q->N / q->cl)};   // cluster mode: each CTA loads half of a block
         if (!encode_map(&q->wmap, x.dt, W, 2, dims, str, box, q->row_bytes)) return false;
     }
     {
@@ -676,8 +682,8 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
     *op = [q](cudaStream_t s) { return ws_c3_launch(q.get(), s); };
     {
         char buf[200];
-        snprintf(buf, sizeof buf, "conv3x3 B=%d F=%d T=%d Cin=%d Cout=%d s=%dx%d caseB=%d nb=%d n_mt=%d R=%d res=%d", q->B, q->F, q->T,
-                 q->Cin, q->Cout, q->sf, q->st, q->case_b, q->nb, q->n_mt, q->R, q->res != nullptr);
+        snprintf(buf, sizeof buf, "conv3x3 B=%d F=%d T=%d Cin=%d Cout=%d s=%dx%d caseB=%d nb=%d n_mt=%d R=%d res=%d cl=%d", q->B, q->F, q->T,
+                 q->Cin, q->Cout, q->sf, q->st, q->case_b, q->nb, q->n_mt, q->R, q->res != nullptr, q->cl);
         set_op_label(buf, 2.0 * q->B * q->F * q->T * 9.0 * q->Cin * q->Cout);
     }
     return true;

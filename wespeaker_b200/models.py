@@ -29,8 +29,9 @@ SUPPORTED_MODELS = tuple(ECAPA_NAMES) + tuple(RESNET_NAMES) + tuple(CAMPP_NAMES)
 class B200SpeakerModel(torch.nn.Module):
     """One reference speaker model executed by the B200 engine.
 
-    precision: "fp32" (exact fp32 FFMA path, embeddings <=1e-4 rel of the reference), "tf32", "bf16",
-    "fp16" (tcgen05 tensor-core paths).  Default from $WESPEAKER_B200_PRECISION or "fp32".
+    precision: "tf32x3" (default: tcgen05 tensor cores with three error-compensated TF32 passes, embeddings <= 1e-4 rel of
+    the reference - measured <= 4.9e-5), "fp32" (exact fp32 FFMA path, <= 6e-7), "tf32", "bf16", "fp16" (single-pass
+    tensor-core paths, 16-bit activations for the last two).  Default from $WESPEAKER_B200_PRECISION or "tf32x3".
     """
 
     def __init__(self, model_name: str, precision: str | None = None, **model_args):
@@ -41,7 +42,7 @@ class B200SpeakerModel(torch.nn.Module):
         args.update(model_args)
         self.model_name = model_name
         self.model_args = args
-        self.precision = precision or os.environ.get("WESPEAKER_B200_PRECISION", "fp32")
+        self.precision = precision or os.environ.get("WESPEAKER_B200_PRECISION", "tf32x3")
         self.feat_dim = int(args["feat_dim"])
         self.embed_dim = int(args["embed_dim"])
         self._spec = state_dict_spec(model_name, **args)
