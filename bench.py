@@ -534,7 +534,14 @@ def time_dominant_kernel(model, prec, B, T, iters=10, tc_version=3):
                 kernel=f"ws_conv_gemm_tc{tc_version}_kernel 1x1 {cin}->{cout} over {B * T} positions")
 
 
+def _quiet_nccl():
+    """NCCL prints its version banner to STDOUT at level VERSION; the driver reads ONE JSON line from stdout."""
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+
+
 def main():
+    _quiet_nccl()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
