@@ -347,6 +347,7 @@ struct WsRes2Params {
     uint32_t idesc;
     int grid, smem_bytes;
     const int* lens;    // length-masked batch: frames of each utterance (rows behind it are conv padding: kept zero), or null
+    int ew;             // epilogue warps: 8 (one CTA per SM) or 4 (256-thread CTAs, two per SM: w8 = 64)
 };
 
 // halo-resident 3x3 stride-1 conv (ws_conv3x3.cu): input rows of F live in a shared-memory ring, the 9 taps are row-shifted

@@ -428,9 +428,12 @@ bool make_res2_op(const View& x, const View& out, const void* W7, const float* b
     const uint32_t fmt = x.dt == WS_BF16 ? 1u : 0u;
     q->idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(w8 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int g_num_sms = ws_num_sms();
-    q->grid = x.B < g_num_sms ? x.B : g_num_sms;
     const int npan = w8 / 64;
     q->smem_bytes = npan * 272 * 128 + 4 * w8 * 128 + npan * 256 * 128 + 1024;
+    // 64-wide groups need ~100 KB: two 256-thread CTAs per SM, so that one utterance's MMAs run under another's epilogue
+    q->ew = (w8 == 64 && q->smem_bytes <= 112 * 1024 && !getenv("WS_RES2_EW8")) ? 4 : 8;
+    const int slots = g_num_sms * (q->ew == 4 ? 2 : 1);
+    q->grid = x.B < slots ? x.B : slots;
     *op = [q](cudaStream_t s) { return ws_res2_launch(q.get(), s); };
     {
         char buf[160];

@@ -62,7 +62,8 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int EW>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory"); }
 
 // K-major SWIZZLE_128B operand descriptor (rows 128 B apart, 8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc128(uint32_t saddr) {
@@ -105,8 +106,11 @@ constexpr int kNumConv = 7;
 // DT = activation dtype (compile-time so the epilogue carries one conversion path); 384 threads: w0 producer, w1 MMA,
 // w2 TMEM alloc, w4..w11 epilogue (warps w and w+4 share a TMEM lane quadrant and split the w8 columns).  The epilogue
 // sits on the serial conv_i -> conv_{i+1} chain, so its latency (not throughput) is what the kernel time is made of.
-template <int DT>
-__global__ void __launch_bounds__(384, 1) ws_res2_fused_kernel(const __grid_constant__ WsRes2Params p) {
+// EW = epilogue warps: 8 (384 threads, one CTA per SM: the 128-wide groups of ECAPA-1024 fill the shared memory), or 4 (256
+// threads at <= 128 registers, ~100 KB of shared memory: TWO CTAs per SM for the 64-wide groups of ECAPA-512, so that the MMAs
+// of one utterance run under the epilogue of another - inside one chain the two strictly alternate).
+template <int DT, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, EW == 4 ? 2 : 1) ws_res2_fused_kernel(const __grid_constant__ WsRes2Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[2 * kWStages + 5];
     __shared__ __align__(16) float s_par[3][128];
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(384, 1) ws_res2_fused_kernel(const __grid_cons
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kWStages; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
         mbar_init(bar_x0, 1);
-        mbar_init(bar_sready, 8);
+        mbar_init(bar_sready, EW);
         mbar_init(bar_acc, 1);
         mbar_init(bar_sfree, 1);
         mbar_init(bar_xn, 1);
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(384, 1) ws_res2_fused_kernel(const __grid_cons
         // overwrites it with sp_i (stored to HBM by TMA afterwards) and writes s_{i+1} = sp_i + x_{i+1} into the operand
         // buffer.  The elected thread re-arms XO with the following group as soon as the store has read it.
         const int q = warp & 3, r = q * 32 + lane, et = threadIdx.x - 128;   // et 0..255
-        const int c_beg = ((warp - 4) >> 2) * (p.w8 >> 1), c_end = c_beg + (p.w8 >> 1);
+        const int c_beg = EW == 8 ? ((warp - 4) >> 2) * (p.w8 >> 1) : 0, c_end = EW == 8 ? c_beg + (p.w8 >> 1) : p.w8;
         const uint32_t xo_bytes = (uint32_t)(npan * nmt * 128 * 128);
         auto load_xn = [&](int bb, int grp) {
             mbar_expect_tx(bar_xn, xo_bytes);
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(384, 1) ws_res2_fused_kernel(const __grid_cons
                     s_par[1][et] = p.scale[i * p.w8 + et];
                     s_par[2][et] = p.shift[i * p.w8 + et];
                 }
-                epi_bar_sync();
+                epi_bar_sync<EW>();
                 mbar_wait(bar_acc, (uint32_t)g & 1u);
                 tc_fence_after();
                 if (i == kNumConv - 1 && et == 0) mbar_arrive(bar_sfree);  // conv 6 done: S may take the next utterance
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(384, 1) ws_res2_fused_kernel(const __grid_cons
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_sready);
-                epi_bar_sync();
+                epi_bar_sync<EW>();
                 if (et == 0) {
                     for (int pn = 0; pn < npan; ++pn)
                         for (int mt = 0; mt < nmt; ++mt)
@@ -330,17 +334,26 @@ extern "C" const char* ws_res2_init(void) {
     static unsigned long long done = 0;
     int dev = 0;
     if (!ws_dev_needs_init(&done, &dev)) return nullptr;
-    cudaError_t e = cudaFuncSetAttribute(ws_res2_fused_kernel<WS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ws_res2_fused_kernel<WS_BF16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(ws_res2_fused_kernel<WS_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        e = cudaFuncSetAttribute(ws_res2_fused_kernel<WS_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    // the two-CTAs-per-SM variant: ~100 KB each, and the carveout must leave room for both
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ws_res2_fused_kernel<WS_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ws_res2_fused_kernel<WS_F16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ws_res2_fused_kernel<WS_BF16, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ws_res2_fused_kernel<WS_F16, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { cudaGetLastError(); return cudaGetErrorString(e); }
     ws_dev_mark_init(&done, dev);
     return nullptr;
 }
 
 extern "C" const char* ws_res2_launch(const WsRes2Params* p, cudaStream_t s) {
-    if (p->dtype == WS_BF16) ws_res2_fused_kernel<WS_BF16><<<p->grid, 384, p->smem_bytes, s>>>(*p);
-    else if (p->dtype == WS_F16) ws_res2_fused_kernel<WS_F16><<<p->grid, 384, p->smem_bytes, s>>>(*p);
+    if (p->ew == 4) {
+        if (p->dtype == WS_BF16) ws_res2_fused_kernel<WS_BF16, 4><<<p->grid, 256, p->smem_bytes, s>>>(*p);
+        else if (p->dtype == WS_F16) ws_res2_fused_kernel<WS_F16, 4><<<p->grid, 256, p->smem_bytes, s>>>(*p);
+        else return "res2_fused: 16-bit activations only";
+    } else if (p->dtype == WS_BF16) ws_res2_fused_kernel<WS_BF16, 8><<<p->grid, 384, p->smem_bytes, s>>>(*p);
+    else if (p->dtype == WS_F16) ws_res2_fused_kernel<WS_F16, 8><<<p->grid, 384, p->smem_bytes, s>>>(*p);
     else return "res2_fused: 16-bit activations only";
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
