@@ -197,9 +197,30 @@ __device__ __forceinline__ void epi_chunk(const WsTc2Params& p, const EpiTile& x
             v[4 * i] = __uint_as_float(raw[4 * i]) + x.x; v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + x.y;
             v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + x.z; v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + x.w;
         }
+        if (e.rowbias != nullptr && x.valid) {   // per-utterance bias row (ECAPA global-context attention)
+            const float4* rb = reinterpret_cast<const float4*>(e.rowbias + (long long)x.eb * e.rowbias_ld + x.n0 + c);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 x = __ldg(rb + i);
+                v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+            }
+        }
         if (e.act1 == WS_ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        } else if (e.act1 == WS_ACT_TANH) {
+            if constexpr (DT == WS_F32) {
+                ws_act_vec<32>(v, WS_ACT_TANH);
+            } else {
+                // 16-bit outputs: tanh(x) = 1 - 2 / (e^{2x} + 1) on ex2.approx + rcp.approx (abs error ~1e-7, far below
+                // the output rounding), 5 instructions per element instead of the ~25 of tanhf
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float ex;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(v[i] * 2.885390081777927f));
+                    v[i] = 1.f - __fdividef(2.f, ex + 1.f);
+                }
+            }
         }
         if (e.scale != nullptr) {
             const float4* ss = reinterpret_cast<const float4*>(x.spar + p.bn + c);
@@ -339,8 +360,8 @@ __device__ __forceinline__ void epi_colsum(const WsTc2Params& p, uint32_t stg_ou
 // 0 = generic epilogue, else activation dtype + 1 (see the LEAN template parameter)
 inline int ws_tc_lean_kind(const WsTc2Params* p) {
     const WsEpi& e = p->epi;
-    const bool common = !p->has_out2 && e.rowbias == nullptr && e.gate == nullptr &&
-                        (e.act1 == WS_ACT_NONE || e.act1 == WS_ACT_RELU) &&
+    const bool common = !p->has_out2 && e.gate == nullptr &&
+                        (e.act1 == WS_ACT_NONE || e.act1 == WS_ACT_RELU || e.act1 == WS_ACT_TANH) &&
                         (e.act2 == WS_ACT_NONE || e.act2 == WS_ACT_RELU) && p->panel_bytes == 128;
     if (!common) return 0;
     if (p->kind == 1 && p->nsplit == 1 && p->nout == 1 && p->bn >= 64 && (e.dtype == WS_BF16 || e.dtype == WS_F16))
