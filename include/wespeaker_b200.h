@@ -101,6 +101,12 @@ void ws_engine_destroy(ws_engine* e);
 /* ---- fbank + CMN: replaces torchaudio.compliance.kaldi.fbank as called at processor.py:518-525 /
  *      cli/speaker.py:92-99 and Fbank::Compute (runtime/core/frontend/fbank.h:138-198). */
 int ws_fbank_num_frames(int nsamples);
+/* Sinc resampling of (B, n_in) waveforms (int16 or float32) to new_freq: torchaudio.transforms.Resample(orig_freq, new_freq)
+ * with its defaults, as the reference applies it before fbank (dataset/processor.py:242-262, cli/speaker.py:157-159).
+ * out_dev: fp32 (B, out_ld), the first ws_resample_out_len(n_in, orig, new) = ceil(new * n_in / orig) samples of each row. */
+int ws_resample_out_len(int n_in, int orig_freq, int new_freq);
+int ws_resample(const void* wav_dev, int wav_is_i16, long long wav_ld, int n_in, int B, int orig_freq, int new_freq,
+                float* out_dev, long long out_ld, void* stream);
 int ws_fbank(const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples, int B, const char* window_type,
              int apply_cmn, float* feats_dev, void* stream);
 

@@ -686,6 +686,57 @@ def _write_wav(path, pcm_i16):
         w.writeframes(np.asarray(pcm_i16, dtype="<i2").tobytes())
 
 
+def test_resample_kernel_matches_torchaudio_goldens_and_feeds_the_extractors(tmp_path):
+    """ws_resample (device sinc resampler) against torchaudio.transforms.Resample outputs (goldens) for int16 and float input;
+    then the two call sites of the reference: Speaker.extract_embedding on an 8 kHz file (cli/speaker.py:157-159) and
+    extract() on a raw list with 8 kHz audio (processor.py:242-262) equal resample -> 16 kHz extraction."""
+    import json
+    import wave
+    import yaml
+    from oracle import resample_np
+    from wespeaker_b200 import frontend, kaldi_io
+    from wespeaker_b200.extract import extract
+    from wespeaker_b200.speaker import Speaker
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "resample.npz"))
+    for tag in ("8k_16k", "44k1_16k", "48k_16k", "22k05_16k", "16k_8k"):
+        o, n = (int(v) for v in g[f"{tag}_rates"])
+        x, y = g[f"{tag}_x"], g[f"{tag}_y"]
+        for dt in (torch.float32, torch.int16):
+            r = frontend.resample(torch.from_numpy(x).to(dt).to(DEV), o, n).cpu().numpy()
+            assert r.shape == y.shape
+            err = np.abs(r - y).max() / np.abs(y).max()
+            assert err <= 1e-5, (tag, dt, err)
+        one = frontend.resample(torch.from_numpy(x[0]).to(DEV), o, n)
+        assert one.dim() == 1 and one.shape[0] == y.shape[1]
+    name = "ECAPA_TDNN_c512"
+    sd_np = syn.make_state_dict(name, 0)
+    mdir = tmp_path / "model"
+    mdir.mkdir()
+    torch.save({k: torch.from_numpy(np.asarray(v)) for k, v in sd_np.items()}, mdir / "avg_model.pt")
+    cfg = {"model": name, "model_args": dict(syn.DEFAULT_MODEL_ARGS[name]),
+           "dataset_args": {"resample_rate": 16000, "fbank_args": {"num_mel_bins": 80}}}
+    (mdir / "config.yaml").write_text(yaml.safe_dump(cfg))
+    w8 = syn.make_wavs(2, 12000, seed=8).astype(np.int16)           # 1.5 s at 8 kHz
+    lines = []
+    for i in range(2):
+        with wave.open(str(tmp_path / f"n{i}.wav"), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(8000)
+            w.writeframes(w8[i].astype("<i2").tobytes())
+        lines.append(json.dumps({"key": f"nb{i}", "wav": str(tmp_path / f"n{i}.wav"), "spk": "s"}))
+    (tmp_path / "raw8k.list").write_text("\n".join(lines) + "\n")
+    ark = tmp_path / "emb8k" / "xvector.ark"
+    assert extract(str(mdir / "config.yaml"), model_path=str(mdir / "avg_model.pt"), data_type="raw", data_list=str(tmp_path / "raw8k.list"),
+                   embed_ark=str(ark), batch_size=1, precision="fp32") == 2
+    got = kaldi_io.read_vec_scp_file(str(ark)[:-3] + "scp")
+    spk = Speaker(str(mdir), precision="fp32")
+    for i in range(2):
+        up = resample_np.resample(w8[i:i + 1].astype(np.float32), 8000, 16000)[0]
+        ref = models_torch.forward(name, sd_np, torch.from_numpy(fbank_np.cmn(fbank_np.fbank(up)))[None]).numpy()[0]
+        assert rel_l2(got[f"nb{i}"], ref) <= 1e-3, rel_l2(got[f"nb{i}"], ref)
+        e = spk.extract_embedding(str(tmp_path / f"n{i}.wav")).numpy()
+        assert rel_l2(e, got[f"nb{i}"]) <= 1e-5
+
+
 def test_extract_dropin_and_speaker_api(tmp_path):
     """Seams B2/B3: extract(config, **kwargs) writes Kaldi ark/scp from a raw data list; Speaker.extract_embedding*
     returns the same vectors; both equal the oracle pipeline (fbank -> CMN -> forward) to fp32 accuracy."""

@@ -179,3 +179,17 @@ def test_kaldi_matrix_formats_and_random_chunk(tmp_path):
     assert np.array_equal(get_random_chunk(np.arange(7), 17, r1), np.tile(np.arange(7), 3)[:17])
     f = rng.standard_normal((5, 4))
     assert np.array_equal(get_random_chunk(f, 12, r1), np.tile(f, (3, 1))[:12])
+
+
+def test_resample_oracle_matches_torchaudio_goldens():
+    """oracle/resample_np.py (restated torchaudio sinc resampler) against outputs of torchaudio.transforms.Resample itself
+    (tests/golden/make_golden_resample.py): the call the reference makes in processor.py:258-259 / cli/speaker.py:158-159."""
+    from oracle import resample_np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "resample.npz"))
+    for tag in ("8k_16k", "44k1_16k", "48k_16k", "22k05_16k", "16k_8k"):
+        o, n = (int(v) for v in g[f"{tag}_rates"])
+        x, y = g[f"{tag}_x"], g[f"{tag}_y"]
+        r = resample_np.resample(x, o, n)
+        assert r.shape == y.shape
+        assert np.abs(r - y).max() <= 1e-5 * np.abs(y).max(), tag
+

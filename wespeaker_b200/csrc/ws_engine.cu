@@ -1508,6 +1508,62 @@ int ws_fbank(const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples
                       (cudaStream_t)stream);
 }
 
+// ---- resampling (torchaudio.transforms.Resample defaults: sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99)
+namespace {
+struct ResampleTaps { float* dev = nullptr; int of = 0, nf = 0, width = 0; };
+int gcd_i(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+// torchaudio/functional/functional.py::_get_sinc_resample_kernel, in fp64 then rounded to fp32 like there
+const ResampleTaps* resample_taps(int device, int orig, int neu) {
+    static std::map<std::tuple<int, int, int>, ResampleTaps> cache;
+    const auto key = std::make_tuple(device, orig, neu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return &it->second;
+    const int g = gcd_i(orig, neu), of = orig / g, nf = neu / g;
+    const double rolloff = 0.99, lpw = 6.0, pi = 3.14159265358979323846;
+    const double base = (double)(of < nf ? of : nf) * rolloff;
+    const int width = (int)std::ceil(lpw * of / base), klen = 2 * width + of;
+    std::vector<float> taps((size_t)nf * klen);
+    for (int i = 0; i < nf; ++i)
+        for (int k = 0; k < klen; ++k) {
+            double t = ((double)(-i) / nf + (double)(k - width) / of) * base;
+            t = t < -lpw ? -lpw : (t > lpw ? lpw : t);
+            const double c = std::cos(t * pi / lpw / 2.0), window = c * c;
+            const double tp = t * pi;
+            const double sinc = tp == 0.0 ? 1.0 : std::sin(tp) / tp;
+            taps[(size_t)i * klen + k] = (float)(sinc * window * (base / of));
+        }
+    ResampleTaps r;
+    r.of = of; r.nf = nf; r.width = width;
+    if (cudaMalloc((void**)&r.dev, taps.size() * 4) != cudaSuccess ||
+        cudaMemcpy(r.dev, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_err("ws_resample: tap table upload failed");
+        return nullptr;
+    }
+    return &(cache[key] = r);
+}
+}  // namespace
+
+int ws_resample_out_len(int n_in, int orig_freq, int new_freq) {
+    if (n_in <= 0 || orig_freq <= 0 || new_freq <= 0) return 0;
+    const int g = gcd_i(orig_freq, new_freq);
+    const long long of = orig_freq / g, nf = new_freq / g;
+    return (int)((nf * (long long)n_in + of - 1) / of);      // ceil(new * length / orig)
+}
+
+int ws_resample(const void* wav_dev, int wav_is_i16, long long wav_ld, int n_in, int B, int orig_freq, int new_freq,
+                float* out_dev, long long out_ld, void* stream) {
+    if (!wav_dev || !out_dev || n_in <= 0 || B <= 0 || orig_freq <= 0 || new_freq <= 0) { set_err("ws_resample: bad argument"); return 1; }
+    int dev = 0;
+    WS_CK(cudaGetDevice(&dev));
+    const ResampleTaps* t = resample_taps(dev, orig_freq, new_freq);
+    if (!t) return 1;
+    const int n_out = ws_resample_out_len(n_in, orig_freq, new_freq);
+    if (out_ld < n_out) { set_err("ws_resample: out_ld smaller than the output length"); return 1; }
+    WS_CKS(ws_launch_resample(wav_dev, wav_is_i16, wav_ld, n_in, B, t->dev, t->of, t->nf, t->width, out_dev, out_ld, n_out,
+                              (cudaStream_t)stream));
+    return 0;
+}
+
 static int extract_wav_impl(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples, int B,
                             const char* window_type, float* embs_dev, float* feats_out_dev, void* stream, bool join);
 int ws_engine_extract_wav(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples, int B,

@@ -331,6 +331,40 @@ const char* ws_launch_fbank(const void* wav, int wav_is_i16, long long wav_ld, i
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
+// ---- sinc resampling (torchaudio.transforms.Resample, the reference's `resample`: dataset/processor.py:242-262,
+// cli/speaker.py:157-159): out[j * nf + i] = sum_k x[j * of + k - width] * K[i][k], K = [nf][2 * width + of] polyphase taps
+// (Hann-windowed sinc built on the host in fp64 exactly as torchaudio builds it), samples outside [0, n_in) read as zero.
+namespace {
+__global__ void __launch_bounds__(256) resample_kernel(const void* __restrict__ wav, int is_i16, long long wav_ld, int n_in,
+                                                       const float* __restrict__ K, int of, int nf, int width, int klen,
+                                                       float* __restrict__ out, long long out_ld, int n_out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (n >= n_out) return;
+    const int j = n / nf, i = n - j * nf;
+    const long long base = (long long)j * of - width;
+    const float* k = K + (size_t)i * klen;
+    const long long row = (long long)b * wav_ld;
+    float acc = 0.f;
+    for (int t = 0; t < klen; ++t) {
+        const long long m = base + t;
+        if (m >= 0 && m < n_in) {
+            const float x = is_i16 ? (float)((const short*)wav)[row + m] : ((const float*)wav)[row + m];
+            acc = fmaf(x, k[t], acc);
+        }
+    }
+    out[(long long)b * out_ld + n] = acc;
+}
+}  // namespace
+
+const char* ws_launch_resample(const void* wav, int wav_is_i16, long long wav_ld, int n_in, int B, const float* taps, int of,
+                               int nf, int width, float* out, long long out_ld, int n_out, cudaStream_t s) {
+    if (B <= 0 || n_out <= 0) return nullptr;
+    dim3 grid((n_out + 255) / 256, B);
+    resample_kernel<<<grid, 256, 0, s>>>(wav, wav_is_i16, wav_ld, n_in, taps, of, nf, width, 2 * width + of, out, out_ld, n_out);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
 const char* ws_launch_cmn(float* feats, int B, int T, int Fdim, cudaStream_t s, const int* lens) {
     if (T <= 0 || B <= 0) return nullptr;
     dim3 grid((Fdim + 31) / 32, B), block(32, 8);

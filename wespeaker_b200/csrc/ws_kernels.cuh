@@ -56,6 +56,9 @@ const char* ws_launch_fbank(const void* wav, int wav_is_i16, long long wav_ld, i
                             int mel_maxlen, float* feats, cudaStream_t s, const long long* offs = nullptr,
                             const int* lens = nullptr);   // offs: utterance b starts at wav + offs[b]; lens: frames per utterance
 const char* ws_launch_cmn(float* feats, int B, int T, int Fdim, cudaStream_t s, const int* lens = nullptr);
+// polyphase sinc resampling: taps [nf][2*width+of] (device), out fp32 [B][out_ld]
+const char* ws_launch_resample(const void* wav, int wav_is_i16, long long wav_ld, int n_in, int B, const float* taps, int of,
+                               int nf, int width, float* out, long long out_ld, int n_out, cudaStream_t s);
 
 // ---- PLDA (ws_plda.cu), fp64 arithmetic
 const char* ws_launch_f32_to_f64(const float* in, double* out, long long n, cudaStream_t s);

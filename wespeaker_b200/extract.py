@@ -13,8 +13,9 @@ tiled) — that is what makes batches rectangular there.  What changes is where 
 DataLoader worker processes on the CPU and ships features to the GPU (`extract.py:99-134`); here a pool of reader threads
 only decodes PCM, batches go through ``B200SpeakerModel.extract_stream`` (pinned int16 H2D of batch i+1 overlapping fbank +
 CMN + forward of batch i on the device), and whole utterances of equal length are batched together.
-The augmentation pipeline (``reverb_data`` / ``noise_data`` / ``aug_prob``), ``speed_perturb`` and SSL frontends are
-training-side features outside SURVEY.md section 8: requesting them raises.
+Audio at another sample rate is resampled to ``resample_rate`` on the device (``frontend.resample`` = torchaudio's sinc
+resampler, `processor.py:242-262`).  The augmentation pipeline (``reverb_data`` / ``noise_data`` / ``aug_prob``),
+``speed_perturb`` and SSL frontends are training-side features outside SURVEY.md section 8: requesting them raises.
 """
 from __future__ import annotations
 
@@ -31,6 +32,7 @@ import numpy as np
 import torch
 import yaml
 
+from . import frontend
 from .kaldi_io import VectorWriter, load_mat
 from .models import get_speaker_model, load_checkpoint
 
@@ -185,16 +187,16 @@ def extract(config="conf/config.yaml", **kwargs):
                 pcm, sr = _read_audio(obj["wav"])
                 if "vad" in obj:
                     pcm = _apply_vad(pcm, sr, obj["vad"])
-            if sr != resample_rate:
-                raise NotImplementedError(f"{key}: {sr} Hz audio; resampling is outside the B200 hot path, provide {resample_rate} Hz")
-            return key, pcm
+            return key, pcm, sr
 
         def batches():
             """Rectangular (keys, int16 (B, N)) batches: fixed-length chunks, or whole utterances grouped by length."""
             src = _iter_raw(configs["data_list"]) if data_type == "raw" else _iter_shards(configs["data_list"])
             groups = {}
             with ThreadPoolExecutor(num_workers) as pool:       # the DataLoader-worker analogue: PCM decoding only
-                for key, pcm in pool.map(decode, src):
+                for key, pcm, sr in pool.map(decode, src):
+                    if sr != resample_rate:   # processor.py:242-262 (torchaudio Resample), on the device, before chunking
+                        pcm = frontend.resample(torch.from_numpy(np.array(pcm)), sr, resample_rate).cpu().numpy()
                     if not whole_utt:
                         pcm = get_random_chunk(pcm, chunk_samples, rng)
                     g = groups.setdefault(len(pcm), [])

@@ -65,3 +65,29 @@ def apply_cmvn(feats: torch.Tensor, norm_mean: bool = True, norm_var: bool = Fal
     if norm_var:
         feats = feats / torch.sqrt(torch.var(feats, dim=1, keepdim=True) + 1e-7)
     return feats
+
+
+def resample(waveform: torch.Tensor, orig_freq: int, new_freq: int) -> torch.Tensor:
+    """`torchaudio.transforms.Resample(orig_freq, new_freq)(waveform)` as the reference applies it before fbank
+    (`dataset/processor.py:242-262`, `cli/speaker.py:157-159`): (B, N) or (N,) int16 / float waveform -> float32 on the device,
+    ceil(new * N / orig) samples per row (Hann-windowed sinc, lowpass_filter_width 6, rolloff 0.99 = torchaudio's defaults)."""
+    if orig_freq == new_freq:
+        return waveform.float() if waveform.dtype != torch.int16 else waveform
+    L = _lib.load()
+    w = waveform.detach()
+    squeeze = w.dim() == 1
+    if squeeze:
+        w = w[None]
+    if not w.is_cuda:
+        w = w.cuda()
+    is_i16 = 1 if w.dtype == torch.int16 else 0
+    w = w.contiguous() if is_i16 else w.float().contiguous()
+    B, N = w.shape
+    n_out = int(L.ws_resample_out_len(N, int(orig_freq), int(new_freq)))
+    out = torch.empty((B, n_out), dtype=torch.float32, device=w.device)
+    idx = w.device.index if w.device.index is not None else torch.cuda.current_device()
+    with torch.cuda.device(idx):
+        _lib.check(L.ws_resample(w.data_ptr(), is_i16, N, N, B, int(orig_freq), int(new_freq), out.data_ptr(), n_out,
+                                 _lib.cur_stream_ptr(idx)), "ws_resample")
+    return out[0] if squeeze else out
+

@@ -50,6 +50,8 @@ _PROTOS = {
                                                C.c_char_p, C.c_void_p, C.c_void_p]),
     "ws_engine_extract_wav_ragged_async": (C.c_int, [c_engine_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                      C.c_char_p, C.c_void_p, C.c_void_p]),
+    "ws_resample_out_len": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "ws_resample": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
     "ws_engine_forward_async": (C.c_int, [c_engine_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ws_engine_extract_wav_async": (C.c_int, [c_engine_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int,
                                               C.c_char_p, C.c_void_p, C.c_void_p]),

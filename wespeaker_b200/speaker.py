@@ -12,6 +12,7 @@ import torch
 import yaml
 
 from .frontend import fbank_batch
+from . import frontend
 from .models import get_speaker_model, load_checkpoint
 
 
@@ -103,10 +104,12 @@ class Speaker:
 
     def extract_embedding_from_pcm(self, pcm: torch.Tensor, sample_rate: int):
         """`cli/speaker.py:130-167`: fused fbank + CMN + forward; returns a CPU (E,) tensor."""
-        if sample_rate != self.resample_rate:
-            raise NotImplementedError("resampling is out of scope; provide 16 kHz audio")
-        pcm = pcm.to(torch.float)
-        emb = self.model.extract_from_wav(pcm[:1].to(self._cuda_device()), window_type=self.window_type)
+        pcm = pcm.to(torch.float)[:1].to(self._cuda_device())
+        if sample_rate != self.resample_rate:   # cli/speaker.py:157-159: torchaudio.transforms.Resample, here on the device
+            if self.resample_rate != 16000:
+                raise NotImplementedError("the fbank kernel is built for 16 kHz features (resample_rate)")
+            pcm = frontend.resample(pcm, sample_rate, self.resample_rate)
+        emb = self.model.extract_from_wav(pcm, window_type=self.window_type)
         return emb[0].to(torch.device("cpu"))
 
     def extract_embedding_list(self, scp_path: str):
