@@ -338,6 +338,8 @@ struct WsRes2Params {
     CUtensorMap xmap;   // block input  [B][T][C] (channels-last, 16-bit): dims (C, T, B), box (64, 128, 1), SWIZZLE_128B
     CUtensorMap wmap;   // 7 packed conv weights [7*w8][3*w8] K-major: box (64, w8)
     CUtensorMap omap;   // block output [B][T][C]: same geometry as xmap
+    CUtensorMap omap64; // the same with 64-row boxes (time-tiled utterances store the exact inner rows of a tile)
+    int ntile;          // time tiles per utterance: 1 (T <= 256), else ceil(T / 192) tiles of 256 rows overlapping by 2 x 32
     const void* x;      // raw pointer of the block input (x_{i+1} groups are read directly in the epilogue)
     long long ld;       // row stride (elements) of the block input
     const float* bias;  // [7][w8]

@@ -404,7 +404,8 @@ bool make_conv_op(const ConvSpec& spec, int use_tc, Op* out) {
 bool make_res2_op(const View& x, const View& out, const void* W7, const float* bias, const float* scale,
                   const float* shift, int w8, int dil, Op* op, bool* unsupported, const int* lens) {
     *unsupported = false;
-    if (x.dt == WS_F32 || (w8 != 64 && w8 != 128) || x.T > 256 || x.F != 1 || dil < 1 || dil > 7 || getenv("WS_NO_RES2_FUSED")) {
+    // T > 256: time tiles with a 32-row halo per side cover the chain's receptive field (7 * dil rows) up to dilation 4
+    if (x.dt == WS_F32 || (w8 != 64 && w8 != 128) || (x.T > 256 && dil > 4) || x.F != 1 || dil < 1 || dil > 7 || getenv("WS_NO_RES2_FUSED")) {
         *unsupported = true;
         return false;
     }
@@ -417,6 +418,13 @@ bool make_res2_op(const View& x, const View& out, const void* W7, const float* b
         return encode_map(m, v.dt, v.p, 3, dims, str, box, 128);
     };
     if (!act_map(&q->xmap, x) || !act_map(&q->omap, out)) return false;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)out.C, (cuuint64_t)out.T, (cuuint64_t)out.B};
+        cuuint64_t str[2] = {(cuuint64_t)out.ld * 2, (cuuint64_t)out.T * out.ld * 2};
+        cuuint32_t box[3] = {64, 64, 1};
+        if (!encode_map(&q->omap64, out.dt, out.p, 3, dims, str, box, 128)) return false;
+    }
+    q->ntile = x.T <= 256 ? 1 : (x.T + 191) / 192;
     {
         cuuint64_t dims[2] = {(cuuint64_t)(3 * w8), (cuuint64_t)(7 * w8)};
         cuuint64_t str[1] = {(cuuint64_t)(3 * w8) * 2};
@@ -433,7 +441,8 @@ bool make_res2_op(const View& x, const View& out, const void* W7, const float* b
     // 64-wide groups need ~100 KB: two 256-thread CTAs per SM, so that one utterance's MMAs run under another's epilogue
     q->ew = (w8 == 64 && q->smem_bytes <= 112 * 1024 && !getenv("WS_RES2_EW8")) ? 4 : 8;
     const int slots = g_num_sms * (q->ew == 4 ? 2 : 1);
-    q->grid = x.B < slots ? x.B : slots;
+    const long long units = (long long)x.B * q->ntile;
+    q->grid = (int)(units < slots ? units : slots);
     *op = [q](cudaStream_t s) { return ws_res2_launch(q.get(), s); };
     {
         char buf[160];

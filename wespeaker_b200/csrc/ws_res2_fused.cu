@@ -11,7 +11,11 @@
 //   * weights stream through a TMA ring (they are L2-resident, shared by all CTAs); accumulators sit in TMEM;
 //   * the epilogue (bias, ReLU, BN affine) writes sp_i to the output buffer through a swizzled staging tile + TMA store
 //     and writes s_{i+1} = sp_i + x_{i+1} straight back into the operand buffer for the next conv.
-// Warp roles: w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4..w7 epilogue.
+//   * utterances longer than 256 frames are walked in time tiles of 256 rows that overlap by 2 x 32: the chain's receptive
+//     field is 7 x dilation <= 28 rows per side, so the inner 192 rows of a tile are exact and only those are stored (three
+//     64-row TMA boxes per channel panel); rows before t = 0 and behind the utterance's end are forced to zero in the operand
+//     buffer - they are the convs' zero padding.
+// Warp roles: w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4.. epilogue.
 #include "ws_common.cuh"
 
 namespace {
@@ -119,7 +123,9 @@ __global__ void __launch_bounds__(128 + 32 * EW, EW == 4 ? 2 : 1) ws_res2_fused_
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int npan = p.w8 >> 6;                       // K panels of 64 channels (128 B) per tap
-    const int nmt = (p.T + 127) >> 7;                 // M tiles (128 rows) per utterance
+    const int nmt = p.ntile > 1 ? 2 : (p.T + 127) >> 7;   // M tiles (128 rows) per work unit
+    // work unit = (utterance, time tile); tile k covers rows [k * tstride - halo, +256); single-tile utterances: halo 0
+    const int halo = p.ntile > 1 ? 32 : 0, tstride = 256 - 2 * halo, nunits = p.B * p.ntile;
     const int wblk_bytes = p.w8 * 128;                // one weight k-block: w8 output rows x 128 B
     const uint32_t sS = base;                                             // [npan][kSRows][128 B]
     const uint32_t sW = sS + (uint32_t)(npan * kSRows * 128);             // [kWStages][wblk_bytes]
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, EW == 4 ? 2 : 1) ws_res2_fused_
             asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sS + (uint32_t)(i * 16)), "r"(0u) : "memory");
     }
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&p.xmap); prefetch_tmap(&p.wmap); prefetch_tmap(&p.omap);
+        prefetch_tmap(&p.xmap); prefetch_tmap(&p.wmap); prefetch_tmap(&p.omap); prefetch_tmap(&p.omap64);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kWStages; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
@@ -167,13 +173,14 @@ __global__ void __launch_bounds__(128 + 32 * EW, EW == 4 ? 2 : 1) ws_res2_fused_
         // ================================ producer: x_0 tiles and the weight ring ================================
         if (lane == 0) {
             int wit = 0, u = 0;
-            for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++u) {
-                mbar_wait(bar_sfree, ((uint32_t)u & 1u) ^ 1u);   // previous utterance's last MMA no longer reads S
+            for (int un = blockIdx.x; un < nunits; un += gridDim.x, ++u) {
+                const int b = un / p.ntile, t0 = (un % p.ntile) * tstride - halo;
+                mbar_wait(bar_sfree, ((uint32_t)u & 1u) ^ 1u);   // previous unit's last MMA no longer reads S
                 mbar_expect_tx(bar_x0, (uint32_t)(npan * nmt * 128 * 128));
                 for (int kp = 0; kp < npan; ++kp)
                     for (int mt = 0; mt < nmt; ++mt)
                         tma_load_3d(sS + (uint32_t)((kp * kSRows + kPadRows + mt * 128) * 128), &p.xmap, bar_x0, kp * 64,
-                                    mt * 128, b);
+                                    t0 + mt * 128, b);
                 for (int i = 0; i < kNumConv; ++i)
                     for (int tap = 0; tap < 3; ++tap)
                         for (int kp = 0; kp < npan; ++kp, ++wit) {
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, EW == 4 ? 2 : 1) ws_res2_fused_
             asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(elected));
             int ws = 0, u = 0, g = 0;
             uint32_t wph = 0;
-            for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++u) {
+            for (int un = blockIdx.x; un < nunits; un += gridDim.x, ++u) {
                 for (int i = 0; i < kNumConv; ++i, ++g) {
                     if (g > 0) mbar_wait(bar_sready, ((uint32_t)(g - 1)) & 1u);  // s_i written, TMEM drained
                     if (i == 0) mbar_wait(bar_x0, (uint32_t)u & 1u);
@@ -233,16 +240,18 @@ __global__ void __launch_bounds__(128 + 32 * EW, EW == 4 ? 2 : 1) ws_res2_fused_
         const int q = warp & 3, r = q * 32 + lane, et = threadIdx.x - 128;   // et 0..255
         const int c_beg = EW == 8 ? ((warp - 4) >> 2) * (p.w8 >> 1) : 0, c_end = EW == 8 ? c_beg + (p.w8 >> 1) : p.w8;
         const uint32_t xo_bytes = (uint32_t)(npan * nmt * 128 * 128);
-        auto load_xn = [&](int bb, int grp) {
+        auto load_xn = [&](int un_, int grp) {
+            const int bb = un_ / p.ntile, tt0 = (un_ % p.ntile) * tstride - halo;
             mbar_expect_tx(bar_xn, xo_bytes);
             for (int kp = 0; kp < npan; ++kp)
                 for (int mt = 0; mt < nmt; ++mt)
-                    tma_load_3d(sO + (uint32_t)((kp * 256 + mt * 128) * 128), &p.xmap, bar_xn, grp * p.w8 + kp * 64, mt * 128, bb);
+                    tma_load_3d(sO + (uint32_t)((kp * 256 + mt * 128) * 128), &p.xmap, bar_xn, grp * p.w8 + kp * 64, tt0 + mt * 128, bb);
         };
-        if (et == 0 && (int)blockIdx.x < p.B) load_xn(blockIdx.x, 1);
+        if (et == 0 && (int)blockIdx.x < nunits) load_xn(blockIdx.x, 1);
         int g = 0, xc = 0;
-        for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-            const int Tb = p.lens != nullptr ? min(p.T, p.lens[b]) : p.T;   // rows t >= Tb are conv padding: stay zero everywhere
+        for (int un = blockIdx.x; un < nunits; un += gridDim.x) {
+            const int b = un / p.ntile, t0 = (un % p.ntile) * tstride - halo;
+            const int Tb = p.lens != nullptr ? min(p.T, p.lens[b]) : p.T;   // rows t >= Tb (and t < 0) are conv padding: stay zero everywhere
             for (int i = 0; i < kNumConv; ++i, ++g) {
                 if (et < p.w8) {
                     s_par[0][et] = p.bias[i * p.w8 + et];
@@ -257,8 +266,8 @@ __global__ void __launch_bounds__(128 + 32 * EW, EW == 4 ? 2 : 1) ws_res2_fused_
                 if (has_next) { mbar_wait(bar_xn, (uint32_t)xc & 1u); ++xc; }
 #pragma unroll 1
                 for (int mt = 0; mt < nmt; ++mt) {
-                    const int t = mt * 128 + r;
-                    const bool valid = t < Tb;
+                    const int t = mt * 128 + r;                       // row inside the tile (addresses the buffers)
+                    const bool valid = t0 + t >= 0 && t0 + t < Tb;    // frame of the utterance
                     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.w8);
 #pragma unroll 1
                     for (int c = c_beg; c < c_end; c += 32) {
@@ -308,13 +317,20 @@ __global__ void __launch_bounds__(128 + 32 * EW, EW == 4 ? 2 : 1) ws_res2_fused_
                 if (lane == 0) mbar_arrive(bar_sready);
                 epi_bar_sync<EW>();
                 if (et == 0) {
-                    for (int pn = 0; pn < npan; ++pn)
-                        for (int mt = 0; mt < nmt; ++mt)
-                            tma_store_3d(&p.omap, sO + (uint32_t)((pn * 256 + mt * 128) * 128), i * p.w8 + pn * 64, mt * 128, b);
+                    for (int pn = 0; pn < npan; ++pn) {
+                        if (p.ntile > 1) {   // only the exact inner rows [halo, 256 - halo) of the tile: three 64-row boxes
+                            for (int q3 = 0; q3 < 3; ++q3)
+                                tma_store_3d(&p.omap64, sO + (uint32_t)((pn * 256 + halo + 64 * q3) * 128), i * p.w8 + pn * 64,
+                                             t0 + halo + 64 * q3, b);
+                        } else {
+                            for (int mt = 0; mt < nmt; ++mt)
+                                tma_store_3d(&p.omap, sO + (uint32_t)((pn * 256 + mt * 128) * 128), i * p.w8 + pn * 64, mt * 128, b);
+                        }
+                    }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // XO has been read by the store
-                    if (i < kNumConv - 2) load_xn(b, i + 2);                          // group for the next conv's epilogue
-                    else if (i == kNumConv - 1 && b + (int)gridDim.x < p.B) load_xn(b + gridDim.x, 1);
+                    if (i < kNumConv - 2) load_xn(un, i + 2);                         // group for the next conv's epilogue
+                    else if (i == kNumConv - 1 && un + (int)gridDim.x < nunits) load_xn(un + gridDim.x, 1);
                 }
             }
         }
