@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+{
+timeout -k 10 200 python tools/op_times.py ECAPA_TDNN_GLOB_c512 bf16 256 200 2>&1 | grep -E "tstats|sum"
+timeout -k 10 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -4
+} > gpurun_out/r2ag.log 2>&1
+cut -c1-250 gpurun_out/r2ag.log

@@ -75,6 +75,86 @@ __global__ void __launch_bounds__(256) tstats_kernel(const void* __restrict__ x,
     }
 }
 
+// 16-bit activations: 8 channels per thread (16-byte loads), 16 T slices per block of 128 channels, ONE pass with the
+// utterance's first frame as a per-channel shift (sum (v - v0), sum (v - v0)^2: no cancellation for means far from zero).
+// The scalar two-pass kernel above ran at 1.3 TB/s on the ECAPA global-context statistics (157 MB); it stays for fp32.
+template <int DT>
+__global__ void __launch_bounds__(256) tstats8_kernel(const void* __restrict__ x, int F, int T, int C, long long ld,
+                                                      const float* __restrict__ pre_scale, const float* __restrict__ pre_shift,
+                                                      void* __restrict__ out, int odt, long long out_ld, int std_off, float eps,
+                                                      const int* __restrict__ lens) {
+    __shared__ float red[2][16][128 + 4];
+    __shared__ float shift[128];
+    const int cg = threadIdx.x, sl = threadIdx.y;             // 16 channel groups of 8, 16 T slices
+    const int c = blockIdx.x * 128 + cg * 8;
+    const int f = blockIdx.y, b = blockIdx.z;
+    const bool cv = c < C;
+    const long long base = ((long long)b * F + f) * T * ld + c;
+    if (lens != nullptr) T = max(1, min(T, lens[b]));
+    float ps[8], ph[8], v0[8], s1[8], s2[8];
+    const bool pre = pre_scale != nullptr;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ps[k] = 1.f; ph[k] = 0.f; s1[k] = 0.f; s2[k] = 0.f; v0[k] = 0.f; }
+    auto load8 = [&](int t, float* v) {
+        const uint4 r = *reinterpret_cast<const uint4*>((const unsigned short*)x + base + (long long)t * ld);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[2 * k] = ws_16_to_f(w[k] & 0xffffu, DT);
+            v[2 * k + 1] = ws_16_to_f(w[k] >> 16, DT);
+        }
+        if (pre) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], ps[k], ph[k]), 0.f);
+        }
+    };
+    if (cv) {
+        if (pre) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { ps[k] = pre_scale[c + k]; ph[k] = pre_shift[c + k]; }
+        }
+        load8(0, v0);
+        int t = sl;
+        for (; t + 48 < T; t += 64) {   // four independent 16-byte loads in flight per thread
+            float va[8], vb[8], vc[8], vd[8];
+            load8(t, va); load8(t + 16, vb); load8(t + 32, vc); load8(t + 48, vd);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float d0 = va[k] - v0[k], d1 = vb[k] - v0[k], d2 = vc[k] - v0[k], d3 = vd[k] - v0[k];
+                s1[k] += (d0 + d1) + (d2 + d3);
+                s2[k] = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2[k]))));
+            }
+        }
+        for (; t < T; t += 16) {
+            float v[8];
+            load8(t, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const float d = v[k] - v0[k]; s1[k] += d; s2[k] = fmaf(d, d, s2[k]); }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { red[0][sl][cg * 8 + k] = s1[k]; red[1][sl][cg * 8 + k] = s2[k]; }
+    if (sl == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) shift[cg * 8 + k] = v0[k];
+    }
+    __syncthreads();
+    const int tid = sl * 16 + cg;
+    if (tid < 128) {
+        const int cc = blockIdx.x * 128 + tid;
+        if (cc < C) {
+            float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { a1 += red[0][i][tid]; a2 += red[1][i][tid]; }
+            const float n = (float)T, dmean = a1 / n;
+            const long long o = (long long)b * out_ld + (long long)cc * F + f;
+            ws_st(out, odt, o, shift[tid] + dmean);
+            // sum (d - dmean)^2 = sum d^2 - dmean * sum d;  torch.var: unbiased
+            if (std_off >= 0) ws_st(out, odt, o + std_off, sqrtf(fmaxf(a2 - a1 * dmean, 0.f) / (n - 1.f) + eps));
+        }
+    }
+}
+
 // mean over T only, 8 channels per thread (16-byte loads): the SE squeeze (ecapa_tdnn.py:120) reads a full activation map
 // per stage.  block (64, 8): x = group of 8 channels, y = T slice.
 __global__ void __launch_bounds__(512) tmean8_kernel(const void* __restrict__ x, int dt, int T, int C, long long ld,
@@ -793,6 +873,12 @@ const char* ws_launch_tstats(const void* x, int dt, int B, int F, int T, int C, 
     if (std_off < 0 && F == 1 && pre_scale == nullptr && odt == WS_F32 && C % 8 == 0 && lens == nullptr) {
         dim3 g8((C + 511) / 512, B), b8(64, 8);
         tmean8_kernel<<<g8, b8, 0, s>>>(x, dt, T, C, ld, (float*)out, out_ld);
+        return last_err();
+    }
+    if (dt != WS_F32 && C % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && !getenv("WS_TSTATS_SCALAR")) {
+        dim3 g8((C + 127) / 128, F, B), b8(16, 16);
+        if (dt == WS_BF16) tstats8_kernel<WS_BF16><<<g8, b8, 0, s>>>(x, F, T, C, ld, pre_scale, pre_shift, out, odt, out_ld, std_off, eps, lens);
+        else tstats8_kernel<WS_F16><<<g8, b8, 0, s>>>(x, F, T, C, ld, pre_scale, pre_shift, out, odt, out_ld, std_off, eps, lens);
         return last_err();
     }
     dim3 grid((C + 31) / 32, F, B), block(32, 8);
