@@ -189,7 +189,8 @@ __device__ __forceinline__ void epi_chunk(const WsTc2Params& p, const EpiTile& x
     float v[32];
     if constexpr (LEAN != 0) {
         constexpr int DT = LEAN - 1;                          // activation dtype of this instantiation
-        constexpr int PCOLS = DT == WS_F32 ? 32 : 64;         // columns of one 128-byte staging panel
+        // staging panels: 128-byte rows (32 fp32 / 64 16-bit columns), or 64-byte rows for 32-channel 16-bit tiles (bn = 32)
+        const int PB = x.panel_bytes, PCOLS = x.panel_cols;
         const float4* sb = reinterpret_cast<const float4*>(x.spar + c);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -232,10 +233,10 @@ __device__ __forceinline__ void epi_chunk(const WsTc2Params& p, const EpiTile& x
                 v[4 * i + 2] = fmaf(v[4 * i + 2], a.z, d.z); v[4 * i + 3] = fmaf(v[4 * i + 3], a.w, d.w);
             }
         }
-        const uint32_t poff = (uint32_t)((c / PCOLS) * 128 * 128);
+        const uint32_t poff = (uint32_t)((c / PCOLS) * 128 * PB);
         if (p.has_epin) {  // residual
             float rin[32];
-            stage_load32(x.stg_in + poff, x.r, 128, c % PCOLS, DT, rin);
+            stage_load32(x.stg_in + poff, x.r, PB, c % PCOLS, DT, rin);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += rin[i];
         }
@@ -243,12 +244,12 @@ __device__ __forceinline__ void epi_chunk(const WsTc2Params& p, const EpiTile& x
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        stage_store32(x.stg_out + poff, x.r, 128, c % PCOLS, DT, v);
+        stage_store32(x.stg_out + poff, x.r, PB, c % PCOLS, DT, v);
         if constexpr (DT == WS_F32) {
             if (p.nsplit == 3) {  // 3xTF32: the low twin of the output feeds the next layer's x_lo pass
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = ws_tf32_lo(v[i]);
-                stage_store32(x.stg_out + (uint32_t)x.tile_out_bytes + poff, x.r, 128, c % PCOLS, DT, v);
+                stage_store32(x.stg_out + (uint32_t)x.tile_out_bytes + poff, x.r, PB, c % PCOLS, DT, v);
             }
         }
         return;
@@ -362,10 +363,14 @@ inline int ws_tc_lean_kind(const WsTc2Params* p) {
     const WsEpi& e = p->epi;
     const bool common = !p->has_out2 && e.gate == nullptr &&
                         (e.act1 == WS_ACT_NONE || e.act1 == WS_ACT_RELU || e.act1 == WS_ACT_TANH) &&
-                        (e.act2 == WS_ACT_NONE || e.act2 == WS_ACT_RELU) && p->panel_bytes == 128;
+                        (e.act2 == WS_ACT_NONE || e.act2 == WS_ACT_RELU);
     if (!common) return 0;
-    if (p->kind == 1 && p->nsplit == 1 && p->nout == 1 && p->bn >= 64 && (e.dtype == WS_BF16 || e.dtype == WS_F16))
+    // 16-bit: 128-byte panels, or the 64-byte panels of 32-channel tiles (CAM++ / ResNet 1x1 shortcut convs) when no column
+    // sums are asked for (they read whole 128-byte rows)
+    if (p->kind == 1 && p->nsplit == 1 && p->nout == 1 && (e.dtype == WS_BF16 || e.dtype == WS_F16) &&
+        ((p->bn >= 64 && p->panel_bytes == 128) || (p->bn == 32 && p->panel_bytes == 64 && e.colsum == nullptr)))
         return e.dtype + 1;
+    if (p->panel_bytes != 128) return 0;
     if (p->kind == 0 && e.dtype == WS_F32 && p->bn >= 32 &&
         ((p->nsplit == 1 && p->nout == 1) || (p->nsplit == 3 && p->nout == 2)))
         return WS_F32 + 1;
