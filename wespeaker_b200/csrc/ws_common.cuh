@@ -329,7 +329,6 @@ struct WsAstpParams {
     int g;              // channel blocks (of 128) per work unit: H is fetched once per unit
     int grid;
     const int* lens;    // length-masked batch: frames of each utterance, or null
-    int dbg;            // tuning knock-outs (WS_ASTP_DBG): 1 no x loads, 2 no exp, 4 no tcgen05.ld
     long long* prof;    // WS_ASTP_PROF: [grid][16] wait-cycle counters per role
 };
 

@@ -479,7 +479,6 @@ bool make_astp_op(const View& x, const View& h, const void* W2, float* stats, Op
         cuuint32_t box[3] = {128, 128, 1};
         if (!encode_map(&q->xmap, x.dt, x.p, 3, dims, str, box, 0)) return false;
     }
-    if (const char* d = getenv("WS_ASTP_DBG")) q->dbg = atoi(d);
     q->x = x.p; q->x_ld = x.ld; q->out = stats; q->B = x.B; q->T = x.T; q->C = x.C; q->dtype = x.dt; q->lens = lens;
     // channel blocks per unit: the largest g whose static round-robin over the SMs stays within 8 % of the best balance
     const int nblk = x.C / 128, sms = ws_num_sms();
