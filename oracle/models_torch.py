@@ -238,11 +238,94 @@ def xvec_forward(sd, feats):
     return emb_a, F.linear(o, _t(sd, "seg_2.weight", x), _t(sd, "seg_2.bias", x))
 
 
+# --------------------------------------------------------------------------- Res2Net / ERes2Net
+def _relu20(x):
+    """`wespeaker/models/eres2net.py:43-52`: the families' "ReLU" is Hardtanh(0, 20)."""
+    return torch.clamp(x, 0.0, 20.0)
+
+
+def _aff(x, y, sd, p):
+    """`wespeaker/models/eres2net.py:75-102` (AFF): att = 1 + tanh(BN(conv(SiLU(BN(conv([x | y])))))),
+    out = x * att + y * (2 - att)."""
+    xa = torch.cat((x, y), dim=1)
+    h = F.conv2d(xa, _t(sd, p + ".local_att.0.weight", x), _t(sd, p + ".local_att.0.bias", x))
+    h = F.silu(_bn(h, sd, p + ".local_att.1"))
+    a = F.conv2d(h, _t(sd, p + ".local_att.3.weight", x), _t(sd, p + ".local_att.3.bias", x))
+    att = 1.0 + torch.tanh(_bn(a, sd, p + ".local_att.4"))
+    return x * att + y * (2.0 - att)
+
+
+def _res2net_block(x, sd, p, stride, width, scale, kind):
+    """kind "res2net": `res2net.py:61-90` (scale - 1 chain convs, the last split passes through);
+    "eres2net": `eres2net.py:141-163` (scale chain convs, sp + spx[i] before conv i >= 1);
+    "eres2net_aff": `eres2net.py:203-224` (conv2_1 first, then AFF(sp, spx[i]) before conv i)."""
+    out = _relu20(_bn(F.conv2d(x, _t(sd, p + ".conv1.weight", x), None, stride=stride), sd, p + ".bn1"))
+    spx = torch.split(out, width, 1)
+    outs = []
+    if kind == "eres2net_aff":
+        sp = _relu20(_bn(F.conv2d(spx[0], _t(sd, p + ".conv2_1.weight", x), None, padding=1), sd, p + ".bn2_1"))
+        outs.append(sp)
+        for i in range(1, scale):
+            sp = _aff(sp, spx[i], sd, f"{p}.fuse_models.{i - 1}")
+            sp = _relu20(_bn(F.conv2d(sp, _t(sd, f"{p}.convs.{i - 1}.weight", x), None, padding=1), sd, f"{p}.bns.{i - 1}"))
+            outs.append(sp)
+    else:
+        nums = scale if kind == "eres2net" else scale - 1
+        sp = spx[0]
+        for i in range(nums):
+            if i >= 1:
+                sp = sp + spx[i]
+            sp = _relu20(_bn(F.conv2d(sp, _t(sd, f"{p}.convs.{i}.weight", x), None, padding=1), sd, f"{p}.bns.{i}"))
+            outs.append(sp)
+        if kind == "res2net":
+            outs.append(spx[nums])
+    out = _bn(F.conv2d(torch.cat(outs, 1), _t(sd, p + ".conv3.weight", x)), sd, p + ".bn3")
+    if (p + ".shortcut.0.weight") in sd:
+        sc = _bn(F.conv2d(x, _t(sd, p + ".shortcut.0.weight", x), None, stride=stride), sd, p + ".shortcut.1")
+    else:
+        sc = x
+    return _relu20(out + sc)
+
+
+def res2net_forward(sd, feats, m_channels=32, num_blocks=(3, 4, 6, 3), base_width=32, scale=2, expansion=2, fuse=False,
+                    two_emb_layer=False, return_taps=False):
+    """`wespeaker/models/res2net.py:153-199` (fuse=False) and `wespeaker/models/eres2net.py:354-391` (fuse=True: AFF blocks
+    in layers 3-4, stride-2 3x3 downsampling of the running fusion and an AFF with the next stage's output)."""
+    import math
+    x = feats.permute(0, 2, 1).unsqueeze(1)
+    out = F.relu(_bn(F.conv2d(x, _t(sd, "conv1.weight", x), None, padding=1), sd, "bn1"))   # plain ReLU here
+    taps = dict(stem=out)
+    stage = []
+    for li, (nb, mult, stride) in enumerate(zip(num_blocks, (1, 2, 4, 8), (1, 2, 2, 2)), 1):
+        width = int(math.floor(m_channels * mult * (base_width / 64.0)))
+        kind = "res2net" if not fuse else ("eres2net_aff" if li >= 3 else "eres2net")
+        for bi in range(nb):
+            out = _res2net_block(out, sd, f"layer{li}.{bi}", stride if bi == 0 else 1, width, scale, kind)
+        stage.append(out)
+        taps[f"layer{li}"] = out
+    if fuse:
+        f = stage[0]
+        for li, name in ((1, "fuse_mode12"), (2, "fuse_mode123"), (3, "fuse_mode1234")):
+            d = F.conv2d(f, _t(sd, f"layer{li}_downsample.weight", x), None, stride=2, padding=1)
+            f = _aff(stage[li], d, sd, name)
+            taps[name] = f
+        out = f
+    stats = tstp(out)
+    emb = F.linear(stats, _t(sd, "seg_1.weight", x), _t(sd, "seg_1.bias", x))
+    taps.update(stats=stats, emb=emb)
+    if two_emb_layer:
+        o = _bn(F.relu(emb), sd, "seg_bn_1", affine=False)
+        return emb, F.linear(o, _t(sd, "seg_2.weight", x), _t(sd, "seg_2.bias", x))
+    if return_taps:
+        return taps
+    return torch.tensor(0.0), emb
+
+
 # --------------------------------------------------------------------------- dispatch
 def forward(model_name: str, sd, feats, **kw):
     """Embedding (B,E) for a reference model name; same call convention as the reference
     callers' ``outputs[-1] if isinstance(outputs, tuple) else outputs`` (extract.py:133-134)."""
-    from wespeaker_b200.synthetic import ECAPA_NAMES, RESNET_NAMES, XVEC_NAMES
+    from wespeaker_b200.synthetic import ECAPA_NAMES, RES2NET_NAMES, RESNET_NAMES, XVEC_NAMES
     feats = torch.as_tensor(feats)
     with torch.no_grad():
         if model_name in ECAPA_NAMES:
@@ -253,6 +336,8 @@ def forward(model_name: str, sd, feats, **kw):
             return campplus_forward(sd, feats, **kw)
         if model_name in XVEC_NAMES:
             return xvec_forward(sd, feats)[-1]
+        if model_name in RES2NET_NAMES:
+            return res2net_forward(sd, feats, **RES2NET_NAMES[model_name], **kw)[-1]
     raise ValueError(model_name)
 
 

@@ -38,6 +38,15 @@ RESNET_NAMES = {
 RESNET_BOTTLENECK = ("ResNet50", "ResNet101", "ResNet152", "ResNet221", "ResNet293")
 CAMPP_NAMES = {"CAMPPlus": {}}
 XVEC_NAMES = {"XVEC": {}}   # Kaldi-style x-vector TDNN (`wespeaker/models/tdnn.py:57-117`), section 8(f) rank 4
+# Res2Net / ERes2Net (`wespeaker/models/res2net.py:202-221`, `wespeaker/models/eres2net.py:393-431`), section 8(f) rank 4.
+# fuse: ERes2Net's local (AFF inside the layer-3/4 blocks) and global (bottom-up AFF over the four stages) feature fusion.
+RES2NET_NAMES = {
+    "Res2Net34_Base": dict(m_channels=32, num_blocks=[3, 4, 6, 3], base_width=32, scale=2, expansion=2, fuse=False),
+    "Res2Net34_Large": dict(m_channels=64, num_blocks=[3, 4, 6, 3], base_width=32, scale=2, expansion=2, fuse=False),
+    "ERes2Net34_Base": dict(m_channels=32, num_blocks=[3, 4, 6, 3], base_width=32, scale=2, expansion=2, fuse=True),
+    "ERes2Net34_Large": dict(m_channels=64, num_blocks=[3, 4, 6, 3], base_width=32, scale=2, expansion=2, fuse=True),
+    "ERes2Net34_aug": dict(m_channels=64, num_blocks=[3, 4, 6, 3], base_width=24, scale=3, expansion=4, fuse=True),
+}
 
 DEFAULT_MODEL_ARGS = {
     # examples/voxceleb/v2/conf/{ecapa_tdnn,resnet,campplus}.yaml
@@ -54,6 +63,12 @@ DEFAULT_MODEL_ARGS = {
     "ResNet221": dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False),
     "ResNet293": dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False),
     "XVEC": dict(feat_dim=80, embed_dim=512, pooling_func="TSTP"),   # examples/voxceleb/v2/conf/xvec.yaml
+    # examples/voxceleb/v2/conf/{res2net,eres2net}.yaml
+    "Res2Net34_Base": dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False),
+    "Res2Net34_Large": dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False),
+    "ERes2Net34_Base": dict(feat_dim=80, embed_dim=512, pooling_func="TSTP", two_emb_layer=False),
+    "ERes2Net34_Large": dict(feat_dim=80, embed_dim=512, pooling_func="TSTP", two_emb_layer=False),
+    "ERes2Net34_aug": dict(feat_dim=80, embed_dim=512, pooling_func="TSTP", two_emb_layer=False),
 }
 
 
@@ -211,6 +226,80 @@ def xvec_spec(feat_dim=80, hid_dim=512, stats_dim=1500, embed_dim=512, pooling_f
     return s
 
 
+def _aff(s, p, channels, r=4):
+    """`wespeaker/models/eres2net.py:75-102`: Conv2d(2C -> C/r, 1x1, bias) -> BN -> SiLU -> Conv2d(C/r -> C, 1x1, bias) -> BN."""
+    inter = channels // r
+    s[f"{p}.local_att.0.weight"] = (inter, 2 * channels, 1, 1)
+    s[f"{p}.local_att.0.bias"] = (inter,)
+    _bn(s, f"{p}.local_att.1", inter)
+    s[f"{p}.local_att.3.weight"] = (channels, inter, 1, 1)
+    s[f"{p}.local_att.3.bias"] = (channels,)
+    _bn(s, f"{p}.local_att.4", channels)
+
+
+def res2net_width(planes, base_width):
+    return int(np.floor(planes * (base_width / 64.0)))
+
+
+def res2net_spec(m_channels=32, num_blocks=(3, 4, 6, 3), base_width=32, scale=2, expansion=2, fuse=False, feat_dim=80,
+                 embed_dim=256, pooling_func="TSTP", two_emb_layer=False):
+    """Key order of the reference modules' ``state_dict()``: `res2net.py:34-58,98-151` (BasicBlockRes2Net: scale - 1 chain
+    convs) and `eres2net.py:104-139,159-201,227-336` (BasicBlockERes2Net in layers 1-2: scale chain convs;
+    BasicBlockERes2Net_diff_AFF in layers 3-4: conv2_1/bn2_1 + (scale - 1) convs, bns and AFF fuse models; three stride-2
+    3x3 downsampling convs and three AFF modules for the bottom-up fusion)."""
+    assert pooling_func == "TSTP", "only TSTP is on the hot path for Res2Net / ERes2Net"
+    s = OrderedDict()
+    s["conv1.weight"] = (m_channels, 1, 3, 3)
+    _bn(s, "bn1", m_channels)
+    cin = m_channels
+    for li, (nb, mult, stride) in enumerate(zip(num_blocks, (1, 2, 4, 8), (1, 2, 2, 2)), 1):
+        planes = m_channels * mult
+        w = res2net_width(planes, base_width)
+        cout = planes * expansion
+        for bi in range(nb):
+            p = f"layer{li}.{bi}"
+            st = stride if bi == 0 else 1
+            s[f"{p}.conv1.weight"] = (w * scale, cin, 1, 1)
+            _bn(s, f"{p}.bn1", w * scale)
+            if fuse and li >= 3:
+                s[f"{p}.conv2_1.weight"] = (w, w, 3, 3)
+                _bn(s, f"{p}.bn2_1", w)
+                for i in range(scale - 1):
+                    s[f"{p}.convs.{i}.weight"] = (w, w, 3, 3)
+                for i in range(scale - 1):
+                    _bn(s, f"{p}.bns.{i}", w)
+                for i in range(scale - 1):
+                    _aff(s, f"{p}.fuse_models.{i}", w)
+            else:
+                nums = scale if fuse else scale - 1
+                for i in range(nums):
+                    s[f"{p}.convs.{i}.weight"] = (w, w, 3, 3)
+                for i in range(nums):
+                    _bn(s, f"{p}.bns.{i}", w)
+            s[f"{p}.conv3.weight"] = (cout, w * scale, 1, 1)
+            _bn(s, f"{p}.bn3", cout)
+            if st != 1 or cin != cout:
+                s[f"{p}.shortcut.0.weight"] = (cout, cin, 1, 1)
+                _bn(s, f"{p}.shortcut.1", cout)
+            cin = cout
+    if fuse:
+        me = m_channels * expansion
+        s["layer1_downsample.weight"] = (me * 2, me, 3, 3)
+        s["layer2_downsample.weight"] = (me * 4, me * 2, 3, 3)
+        s["layer3_downsample.weight"] = (me * 8, me * 4, 3, 3)
+        _aff(s, "fuse_mode12", me * 2)
+        _aff(s, "fuse_mode123", me * 4)
+        _aff(s, "fuse_mode1234", me * 8)
+    stats_dim = int(feat_dim / 8) * m_channels * 8 * expansion
+    s["seg_1.weight"] = (embed_dim, stats_dim * 2)
+    s["seg_1.bias"] = (embed_dim,)
+    if two_emb_layer:
+        _bn(s, "seg_bn_1", embed_dim, affine=False)
+        s["seg_2.weight"] = (embed_dim, embed_dim)
+        s["seg_2.bias"] = (embed_dim,)
+    return s
+
+
 def state_dict_spec(model_name: str, **model_args):
     """key -> shape for a reference model name (`wespeaker/models/speaker_model.py:31-62`)."""
     if model_name in ECAPA_NAMES:
@@ -219,6 +308,8 @@ def state_dict_spec(model_name: str, **model_args):
         return resnet_spec(RESNET_NAMES[model_name], bottleneck=model_name in RESNET_BOTTLENECK, **model_args)
     if model_name in XVEC_NAMES:
         return xvec_spec(**model_args)
+    if model_name in RES2NET_NAMES:
+        return res2net_spec(**RES2NET_NAMES[model_name], **model_args)
     if model_name in CAMPP_NAMES:
         return campplus_spec(**model_args)
     raise ValueError(f"model {model_name!r} is not on the B200 hot path")
@@ -243,7 +334,7 @@ def make_state_dict(model_name: str, seed: int = 0, **model_args):
         elif key.endswith("running_var"):
             sd[key] = g.uniform(0.5, 1.5, shape).astype(np.float32)
         elif ".bn" in key or "batchnorm" in key or key.startswith("bn") or "shortcut.1" in key \
-                or "seg_bn" in key:
+                or "seg_bn" in key or "local_att.1." in key or "local_att.4." in key:
             if (key.endswith(".bn2.weight") or key.endswith(".bn3.weight")) and "layer" in key:
                 # residual-branch output BN of the 2-D BasicBlocks: keep the residual sum O(1)
                 # over 16 blocks (a trained net does; fp16 range matters for config 3)
