@@ -30,6 +30,12 @@ const char* ws_last_error(void);
  *             fp32-grade accuracy), "tf32", "bf16", "fp16" (tcgen05 tensor cores). */
 int ws_engine_create(const char* model_name, const char* precision, int feat_dim, int embed_dim, int device,
                      ws_engine** out);
+/* Plan-check engine: needs NO device and never computes.  set_option / set_tensor / finalize / plan_op_name behave as on a
+ * real engine - the launch plan is built with placeholder addresses and every tensor map is checked against the
+ * cuTensorMapEncodeTiled rules - so a checkpoint (`load_checkpoint`, wespeaker/utils/checkpoint.py:20-85) can be validated
+ * against the plan builder (missing keys, shapes, kernel envelopes) on a host without a GPU.  Every compute entry point
+ * returns an error on such an engine. */
+int ws_engine_create_plan_check(const char* model_name, const char* precision, int feat_dim, int embed_dim, ws_engine** out);
 /* options: "two_emb_layer", "emb_bn" (model_args), "cuda_graph" (default 1), "force_simt" (debug cross-check),
  * "tc_version" (1: one-tile-per-CTA tcgen05 kernel, 2: persistent / TMA-store kernel, 3 (default): + cta_group::2 CTA pairs
  * on the large layers),

@@ -193,3 +193,47 @@ def test_resample_oracle_matches_torchaudio_goldens():
         assert r.shape == y.shape
         assert np.abs(r - y).max() <= 1e-5 * np.abs(y).max(), tag
 
+
+
+# ------------------------------------------------------------------------------------------ plan-check engine (no device)
+PLAN_CASES = [("ECAPA_TDNN_c1024", "bf16", 256, 200), ("ECAPA_TDNN_c512", "tf32x3", 256, 200), ("ECAPA_TDNN_GLOB_c512", "fp32", 3, 301),
+              ("ResNet34", "fp16", 64, 200), ("ResNet18", "tf32x3", 2, 99), ("ResNet50", "bf16", 2, 99), ("ResNet101", "fp32", 1, 64),
+              ("CAMPPlus", "bf16", 64, 200), ("CAMPPlus", "fp32", 2, 998), ("XVEC", "bf16", 3, 200)]
+
+
+@pytest.mark.parametrize("name,prec,B,T", PLAN_CASES)
+def test_plan_check_builds_every_family_without_a_device(name, prec, B, T):
+    """ws_engine_create_plan_check: the whole weight-ingest + plan-building path (key names, shapes, folding, kernel envelopes,
+    tensor-map rules) runs on a host without a GPU; nothing is computed."""
+    m = from_synthetic(name, precision=prec)
+    ops = m.plan_check(B, T)
+    assert len(ops) >= 5 and all(isinstance(n, str) and n for n, _ in ops)
+    gflop = sum(f for _, f in ops) / B / 1e9
+    assert gflop > 0.5, (name, gflop)                      # the conv / GEMM ops carry their algorithmic FLOPs
+    if name == "ECAPA_TDNN_c1024" and prec == "bf16":      # SURVEY section 8(d): 5.14 GFLOP per 200-frame utterance
+        assert abs(gflop - 5.14) < 0.05, gflop
+        assert any(n.startswith("conv_tc3") and "K=3072 N=1536" in n for n, _ in ops)
+        assert sum(n.startswith("res2_fused") for n, _ in ops) == 3 and sum(n.startswith("astp_fused") for n, _ in ops) == 1
+    if name == "ResNet34" and prec == "fp16":
+        assert sum(n.startswith("conv3x3") for n, _ in ops) >= 24   # layers 1-3 on the halo-resident kernel
+
+
+def test_plan_check_reports_missing_and_misshaped_tensors_and_never_computes():
+    m = from_synthetic("ResNet34", precision="fp16")
+    del m._sd["layer2.0.shortcut.0.weight"]
+    del m._sd["layer3.1.bn1.running_var"]
+    with pytest.raises(lib.B200Error, match="layer3.1.bn1.running_var"):
+        m.plan_check(2, 100)
+    # a plan-check engine refuses every compute entry point
+    import ctypes as C
+    L = lib.load()
+    h = lib.c_engine_p()
+    lib.check(L.ws_engine_create_plan_check(b"XVEC", b"bf16", 80, 512, C.byref(h)), "create")
+    try:
+        assert L.ws_engine_forward_host(h, None, 1, 200, None) != 0
+        buf = np.zeros((1, 200, 80), np.float32)
+        out = np.zeros((1, 512), np.float32)
+        assert L.ws_engine_forward_host(h, buf.ctypes.data, 1, 200, out.ctypes.data) != 0
+        assert b"plan-check engine" in L.ws_last_error()
+    finally:
+        L.ws_engine_destroy(h)

@@ -25,6 +25,18 @@ bool take_op_label(std::string* name, double* flops) {
 }
 const std::string& get_err() { return g_err; }
 
+static thread_local bool g_plan_check = false;
+bool plan_check_mode() { return g_plan_check; }
+PlanCheckScope::PlanCheckScope(bool on) : prev(g_plan_check) { g_plan_check = on; }
+PlanCheckScope::~PlanCheckScope() { g_plan_check = prev; }
+void* plan_check_alloc(size_t bytes) {
+    static thread_local unsigned long long next = 0x7000000000ull;   // far from anything a host allocator returns
+    void* p = (void*)next;
+    next += (bytes + 255) & ~255ull;
+    if (bytes == 0) next += 256;
+    return p;
+}
+
 void fill_epi_out(WsEpi& e, const View& out) {
     e.out = out.p;
     e.out_lo = out.plo;
@@ -100,6 +112,32 @@ static EncodeTiledFn get_encode() {
 
 static bool encode_map(CUtensorMap* m, int dt, const void* ptr, int rank, const cuuint64_t* dims,
                        const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes) {
+    if (plan_check_mode()) {
+        // no driver: check what cuTensorMapEncodeTiled would check (CUDA driver API, tensor map object management)
+        const int es = ws_esize(dt);
+        char buf[200];
+        const char* why = nullptr;
+        if (((unsigned long long)ptr & 15ull) != 0) why = "global address not 16-byte aligned";
+        if (rank < 1 || rank > 5) why = "rank outside 1..5";
+        for (int i = 0; i < rank && !why; ++i) {
+            if (dims[i] < 1 || dims[i] > (1ull << 32)) why = "dimension outside 1..2^32";
+            else if (box[i] < 1 || box[i] > 256) why = "box extent outside 1..256";
+            else if (i + 1 < rank && (strides_bytes[i] % 16 != 0 || strides_bytes[i] >= (1ull << 40))) why = "stride not a multiple of 16 bytes (or >= 2^40)";
+        }
+        if (!why) {
+            const unsigned inner = box[0] * (unsigned)es;
+            if (swizzle_bytes != 0 && inner > (unsigned)swizzle_bytes) why = "inner box extent exceeds the swizzle span";
+            else if (inner % 16 != 0) why = "inner box extent not a multiple of 16 bytes";
+        }
+        if (why) {
+            snprintf(buf, sizeof buf, "tensor map check failed: %s (rank %d dims [%llu %llu ..] box [%u %u ..] sw %d)", why, rank,
+                     (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0, swizzle_bytes);
+            set_err(buf);
+            return false;
+        }
+        memset(m, 0, sizeof(*m));
+        return true;
+    }
     EncodeTiledFn fn = get_encode();
     if (fn == nullptr) {
         set_err("cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)");

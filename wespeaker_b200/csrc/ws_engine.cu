@@ -54,10 +54,11 @@ struct Plan {
     int* lens = nullptr;        // device [4][B]: frames per utterance at the input and behind each stride-2 level
     int lane = 0;               // which of the engine's streams runs this plan through the device-pointer entry points
     cudaEvent_t done = nullptr; // recorded after every use: a later use on another stream waits for it
+    bool check = false;         // built by a plan-check engine: buffers are placeholder addresses, nothing to release
     ~Plan() {
         if (done) cudaEventDestroy(done);
         if (gexec) cudaGraphExecDestroy(gexec);
-        for (void* p : bufs) cudaFree(p);
+        if (!check) for (void* p : bufs) cudaFree(p);
     }
 };
 
@@ -73,6 +74,7 @@ struct ws_engine {
     std::map<std::string, long long> opts;
     std::map<std::string, HostT> sd;
     bool finalized = false;
+    bool plan_check = false;   // ws_engine_create_plan_check: builds launch plans without a device, never computes
     std::map<std::string, void*> wcache;  // packed device weights by id
     std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;   // key: (B, 2 * T + masked)
     long long last_launches = 0;
@@ -101,6 +103,7 @@ struct ws_engine {
     std::vector<int> num_blocks;
     ~ws_engine() {
         plans.clear();
+        if (plan_check) return;   // placeholder addresses only, no streams / events were created
         for (auto& kv : wcache) cudaFree(kv.second);
         for (auto& kv : fb) {
             cudaFree(kv.second.window); cudaFree(kv.second.melw); cudaFree(kv.second.melstart); cudaFree(kv.second.mellen);
@@ -145,7 +148,9 @@ struct Weights {
         auto it = e.wcache.find(id);
         if (it != e.wcache.end()) return it->second;
         void* d = nullptr;
-        if (cudaMalloc(&d, bytes ? bytes : 16) != cudaSuccess || cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        if (plan_check_mode()) {
+            d = plan_check_alloc(bytes);
+        } else if (cudaMalloc(&d, bytes ? bytes : 16) != cudaSuccess || cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
             if (ok) set_err("device allocation/copy failed for weight " + id);
             ok = false;
             return nullptr;
@@ -238,7 +243,9 @@ struct Builder {
 
     void* raw(size_t bytes) {
         void* d = nullptr;
-        if (cudaMalloc(&d, bytes ? bytes : 16) != cudaSuccess) {
+        if (plan_check_mode()) {
+            d = plan_check_alloc(bytes);
+        } else if (cudaMalloc(&d, bytes ? bytes : 16) != cudaSuccess) {
             if (ok) set_err("cudaMalloc failed for an activation buffer");
             ok = false;
             return nullptr;
@@ -1131,7 +1138,8 @@ Plan* get_plan(ws_engine* e, int B, int T, bool masked = false) {
     }
     if (B <= 0 || T <= 0) { set_err("forward: B and T must be positive"); return nullptr; }
     std::unique_ptr<Plan> p(new Plan());
-    p->B = B; p->T = T; p->masked = masked;
+    p->B = B; p->T = T; p->masked = masked; p->check = e->plan_check;
+    PlanCheckScope check_scope(e->plan_check);
     Builder b(*e, *p);
     if (masked) {
         p->lens = (int*)b.raw((size_t)4 * B * sizeof(int));
@@ -1157,13 +1165,13 @@ Plan* get_plan(ws_engine* e, int B, int T, bool masked = false) {
         auto victim = e->plans.begin();
         for (auto i2 = e->plans.begin(); i2 != e->plans.end(); ++i2)
             if (i2->second->last_use < victim->second->last_use) victim = i2;
-        cudaDeviceSynchronize();   // the victim may be in flight on any lane
+        if (!e->plan_check) cudaDeviceSynchronize();   // the victim may be in flight on any lane
         total -= victim->second->bytes;
         e->plans.erase(victim);
     }
     p->last_use = ++e->use_clock;
     p->lane = e->opt("plan_lanes", 1) ? (e->next_lane++ % ws_engine::kLanes) : 0;
-    if (cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming) != cudaSuccess) { set_err("plan event creation failed"); return nullptr; }
+    if (!e->plan_check && cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming) != cudaSuccess) { set_err("plan event creation failed"); return nullptr; }
     Plan* raw = p.get();
     e->plans[key] = std::move(p);
     return raw;
@@ -1280,19 +1288,17 @@ int host_path_leave(ws_engine* e, Plan* p) { WS_CK(cudaEventRecord(p->done, e->s
 }  // namespace
 
 // ================================================================================================= C ABI
+// why a compute entry point cannot run on this engine (nullptr = it can)
+static const char* not_runnable(const ws_engine* e) {
+    if (e->plan_check) return " on a plan-check engine (it builds launch plans without a device and never computes)";
+    if (!e->finalized) return " before ws_engine_finalize";
+    return nullptr;
+}
+
 extern "C" {
 
-int ws_engine_create(const char* model_name, const char* precision, int feat_dim, int embed_dim, int device,
-                     ws_engine** out) {
-    if (!model_name || !precision || !out) { set_err("ws_engine_create: null argument"); return 1; }
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        set_err("ws_engine_create: no CUDA device (this engine has no CPU fallback)");
-        return 1;
-    }
-    WS_CK(cudaSetDevice(device));
-    std::unique_ptr<ws_engine> e(new ws_engine());
+// model name + precision -> engine configuration (shared by ws_engine_create and ws_engine_create_plan_check)
+static int configure_engine(ws_engine* e, const char* model_name, const char* precision, int feat_dim, int embed_dim, int device) {
     e->model = model_name; e->prec = precision; e->feat_dim = feat_dim; e->embed_dim = embed_dim; e->device = device;
     const std::string m = e->model;
     if (m == "ECAPA_TDNN_c512") { e->channels = 512; e->glob = false; }
@@ -1317,6 +1323,21 @@ int ws_engine_create(const char* model_name, const char* precision, int feat_dim
     else if (p == "fp16") { e->act_dt = WS_F16; e->use_tc = 3; }
     else { set_err("unknown precision (fp32|tf32x3|tf32|bf16|fp16): " + p); return 1; }
     if (feat_dim % 8 != 0) { set_err("feat_dim must be a multiple of 8"); return 1; }
+    return 0;
+}
+
+int ws_engine_create(const char* model_name, const char* precision, int feat_dim, int embed_dim, int device,
+                     ws_engine** out) {
+    if (!model_name || !precision || !out) { set_err("ws_engine_create: null argument"); return 1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_err("ws_engine_create: no CUDA device (this engine has no CPU fallback)");
+        return 1;
+    }
+    WS_CK(cudaSetDevice(device));
+    std::unique_ptr<ws_engine> e(new ws_engine());
+    if (configure_engine(e.get(), model_name, precision, feat_dim, embed_dim, device)) return 1;
     WS_CKS(ws_tc_init());
     WS_CKS(ws_tc2_init());
     WS_CKS(ws_res2_init());
@@ -1329,6 +1350,19 @@ int ws_engine_create(const char* model_name, const char* precision, int feat_dim
     for (int i = 1; i < ws_engine::kLanes; ++i) WS_CK(cudaStreamCreateWithFlags(&e->lanes[i], cudaStreamNonBlocking));
     WS_CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
     WS_CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+    *out = e.release();
+    return 0;
+}
+
+// An engine that only BUILDS launch plans: no device is touched, nothing is computed, every compute entry point refuses.
+// ws_engine_set_tensor / ws_engine_set_option / ws_engine_finalize / ws_engine_plan_op_name work as on a real engine, so a
+// checkpoint can be validated against the plan builder (missing keys, shapes, kernel envelopes, tensor-map alignment rules)
+// on a host without a GPU.
+int ws_engine_create_plan_check(const char* model_name, const char* precision, int feat_dim, int embed_dim, ws_engine** out) {
+    if (!model_name || !precision || !out) { set_err("ws_engine_create_plan_check: null argument"); return 1; }
+    std::unique_ptr<ws_engine> e(new ws_engine());
+    e->plan_check = true;
+    if (configure_engine(e.get(), model_name, precision, feat_dim, embed_dim, 0)) return 1;
     *out = e.release();
     return 0;
 }
@@ -1357,7 +1391,7 @@ int ws_engine_set_tensor(ws_engine* e, const char* key, const float* host_data, 
 
 int ws_engine_finalize(ws_engine* e) {
     if (!e) { set_err("ws_engine_finalize: null engine"); return 1; }
-    WS_CK(cudaSetDevice(e->device));
+    if (!e->plan_check) WS_CK(cudaSetDevice(e->device));
     // Build (and drop) a nominal plan: this packs/folds/uploads every weight and reports missing keys.
     Plan* p = get_plan(e, 1, 200);
     if (p == nullptr) return 1;
@@ -1389,7 +1423,7 @@ int ws_engine_join(ws_engine* e, void* stream) {
 }
 static int forward_impl(ws_engine* e, const float* feats_dev, int B, int T, float* embs_dev, void* stream, bool join) {
     if (!e || !feats_dev || !embs_dev) { set_err("ws_engine_forward: null argument"); return 1; }
-    if (!e->finalized) { set_err("ws_engine_forward before ws_engine_finalize"); return 1; }
+    if (const char* nr = not_runnable(e)) { set_err(std::string("ws_engine_forward") + nr); return 1; }
     WS_CK(cudaSetDevice(e->device));
     Plan* p = get_plan(e, B, T);
     if (!p) return 1;
@@ -1409,7 +1443,7 @@ static int forward_impl(ws_engine* e, const float* feats_dev, int B, int T, floa
 int ws_engine_forward_masked(ws_engine* e, const float* feats_dev, const int* n_frames_dev, int B, int T, float* embs_dev,
                              void* stream) {
     if (!e || !feats_dev || !n_frames_dev || !embs_dev) { set_err("ws_engine_forward_masked: null argument"); return 1; }
-    if (!e->finalized) { set_err("ws_engine_forward_masked before ws_engine_finalize"); return 1; }
+    if (const char* nr = not_runnable(e)) { set_err(std::string("ws_engine_forward_masked") + nr); return 1; }
     WS_CK(cudaSetDevice(e->device));
     Plan* p = get_plan(e, B, T, true);
     if (!p) return 1;
@@ -1431,7 +1465,7 @@ static int extract_wav_masked_impl(ws_engine* e, const void* wav_dev, int wav_is
                                    const int* n_samples_dev, int max_samples, int B, const char* window_type, float* embs_dev,
                                    void* stream, bool join, const char* who) {
     if (!e || !wav_dev || !n_samples_dev || !embs_dev) { set_err(std::string(who) + ": null argument"); return 1; }
-    if (!e->finalized) { set_err(std::string(who) + " before ws_engine_finalize"); return 1; }
+    if (const char* nr = not_runnable(e)) { set_err(std::string(who) + nr); return 1; }
     if (e->feat_dim != 80) { set_err(std::string(who) + ": the fbank frontend produces 80 bins"); return 1; }
     WS_CK(cudaSetDevice(e->device));
     const int T = ws_fbank_num_frames(max_samples);
@@ -1474,7 +1508,7 @@ int ws_engine_extract_wav_ragged_async(ws_engine* e, const void* wav_dev, int wa
 
 int ws_engine_forward_host(ws_engine* e, const float* feats_host, int B, int T, float* embs_host) {
     if (!e || !feats_host || !embs_host) { set_err("ws_engine_forward_host: null argument"); return 1; }
-    if (!e->finalized) { set_err("ws_engine_forward_host before ws_engine_finalize"); return 1; }
+    if (const char* nr = not_runnable(e)) { set_err(std::string("ws_engine_forward_host") + nr); return 1; }
     WS_CK(cudaSetDevice(e->device));
     Plan* p = get_plan(e, B, T);
     if (!p) return 1;
@@ -1577,7 +1611,7 @@ int ws_engine_extract_wav_async(ws_engine* e, const void* wav_dev, int wav_is_i1
 static int extract_wav_impl(ws_engine* e, const void* wav_dev, int wav_is_i16, long long wav_ld, int nsamples, int B,
                             const char* window_type, float* embs_dev, float* feats_out_dev, void* stream, bool join) {
     if (!e || !wav_dev || !embs_dev) { set_err("ws_engine_extract_wav: null argument"); return 1; }
-    if (!e->finalized) { set_err("ws_engine_extract_wav before ws_engine_finalize"); return 1; }
+    if (const char* nr = not_runnable(e)) { set_err(std::string("ws_engine_extract_wav") + nr); return 1; }
     if (e->feat_dim != 80) { set_err("ws_engine_extract_wav: the fbank frontend produces 80 bins"); return 1; }
     WS_CK(cudaSetDevice(e->device));
     const int T = ws_fbank_num_frames(nsamples);
@@ -1600,7 +1634,7 @@ static int extract_wav_impl(ws_engine* e, const void* wav_dev, int wav_is_i16, l
 int ws_engine_extract_wav_host(ws_engine* e, const void* wav_host, int wav_is_i16, int nsamples, int B,
                                const char* window_type, float* embs_host) {
     if (!e || !wav_host || !embs_host) { set_err("ws_engine_extract_wav_host: null argument"); return 1; }
-    if (!e->finalized) { set_err("ws_engine_extract_wav_host before ws_engine_finalize"); return 1; }
+    if (const char* nr = not_runnable(e)) { set_err(std::string("ws_engine_extract_wav_host") + nr); return 1; }
     WS_CK(cudaSetDevice(e->device));
     const int T = ws_fbank_num_frames(nsamples);
     if (T <= 0) { set_err("ws_engine_extract_wav_host: waveform shorter than one 25 ms frame"); return 1; }
@@ -1631,7 +1665,7 @@ int ws_engine_extract_wav_host(ws_engine* e, const void* wav_host, int wav_is_i1
 int ws_engine_submit_wav_host(ws_engine* e, int slot, const void* wav_host, int wav_is_i16, int nsamples, int B,
                               const char* window_type, float* embs_host) {
     if (!e || !wav_host || !embs_host || slot < 0 || slot >= ws_engine::kSlots) { set_err("ws_engine_submit_wav_host: bad argument"); return 1; }
-    if (!e->finalized) { set_err("ws_engine_submit_wav_host before ws_engine_finalize"); return 1; }
+    if (const char* nr = not_runnable(e)) { set_err(std::string("ws_engine_submit_wav_host") + nr); return 1; }
     WS_CK(cudaSetDevice(e->device));
     const int T = ws_fbank_num_frames(nsamples);
     if (T <= 0) { set_err("ws_engine_submit_wav_host: waveform shorter than one 25 ms frame"); return 1; }
@@ -1676,7 +1710,7 @@ int ws_engine_collect(ws_engine* e, int slot) {
 // Tuning aid: run the (B,T) plan op by op (no CUDA graph) with CUDA events between ops, in sequence context (the L2 holds
 // what the previous op left there, unlike ncu's cold-cache replays).  ms_out[i] = duration of op i; returns the op count.
 int ws_engine_profile_ops(ws_engine* e, int B, int T, int iters, float* ms_out, int max_ops) {
-    if (!e || !ms_out || !e->finalized) { set_err("ws_engine_profile_ops: bad argument"); return -1; }
+    if (!e || !ms_out || !e->finalized || e->plan_check) { set_err("ws_engine_profile_ops: bad argument"); return -1; }
     if (cudaSetDevice(e->device) != cudaSuccess) return -1;
     Plan* p = get_plan(e, B, T);
     if (!p) return -1;
@@ -1707,7 +1741,7 @@ int ws_engine_profile_ops(ws_engine* e, int B, int T, int iters, float* ms_out, 
 
 // label of op i of the (B,T) plan ("conv_tc3 pos=.. K=.. N=..", "conv3x3 ...", "tstats", ...) and its FLOPs (0 = not GEMM-like)
 const char* ws_engine_plan_op_name(ws_engine* e, int B, int T, int i, double* flops_out) {
-    if (!e || !e->finalized || cudaSetDevice(e->device) != cudaSuccess) return nullptr;
+    if (!e || !e->finalized || (!e->plan_check && cudaSetDevice(e->device) != cudaSuccess)) return nullptr;
     Plan* p = get_plan(e, B, T);
     if (!p || i < 0 || i >= (int)p->op_names.size()) return nullptr;
     if (flops_out) *flops_out = p->op_flops[i];
@@ -1716,6 +1750,7 @@ const char* ws_engine_plan_op_name(ws_engine* e, int B, int T, int i, double* fl
 
 void ws_engine_destroy(ws_engine* e) {
     if (!e) return;
+    if (e->plan_check) { delete e; return; }
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     delete e;

@@ -33,6 +33,17 @@ const std::string& get_err();
         }                                                                                         \
     } while (0)
 
+// Plan-check mode (ws_engine_create_plan_check): launch plans are built without a device - buffers and weights get
+// placeholder addresses (never dereferenced), tensor maps are validated against the cuTensorMapEncodeTiled rules instead of
+// being encoded, nothing is launched.  Thread-local, set for the duration of a plan build.
+bool plan_check_mode();
+struct PlanCheckScope {
+    bool prev;
+    explicit PlanCheckScope(bool on);
+    ~PlanCheckScope();
+};
+void* plan_check_alloc(size_t bytes);   // 256-byte aligned placeholder address
+
 // channels-last activation view: element (b,f,t,c) at p[((b*F+f)*T+t)*ld + c]
 struct View {
     void* p = nullptr;

@@ -38,6 +38,7 @@ _PROTOS = {
     "ws_version": (C.c_int, []),
     "ws_last_error": (C.c_char_p, []),
     "ws_engine_create": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(c_engine_p)]),
+    "ws_engine_create_plan_check": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(c_engine_p)]),
     "ws_engine_set_option": (C.c_int, [c_engine_p, C.c_char_p, C.c_longlong]),
     "ws_engine_set_tensor": (C.c_int, [c_engine_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_longlong), C.c_int]),
     "ws_engine_finalize": (C.c_int, [c_engine_p]),

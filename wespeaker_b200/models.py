@@ -129,24 +129,50 @@ class B200SpeakerModel(torch.nn.Module):
         _lib.check(L.ws_engine_create(self.model_name.encode(), self.precision.encode(), self.feat_dim,
                                       self.embed_dim, dev_index, C.byref(h)), "ws_engine_create")
         try:
-            for opt in ("two_emb_layer", "emb_bn"):
-                if self.model_args.get(opt):
-                    _lib.check(L.ws_engine_set_option(h, opt.encode(), 1), "ws_engine_set_option")
-            for k, v in self.options.items():
-                _lib.check(L.ws_engine_set_option(h, k.encode(), v), "ws_engine_set_option")
-            for k, v in self._sd.items():
-                if k.endswith("num_batches_tracked"):
-                    continue
-                a = np.ascontiguousarray(v.detach().cpu().numpy(), dtype=np.float32)
-                shape = (C.c_longlong * a.ndim)(*a.shape)
-                _lib.check(L.ws_engine_set_tensor(h, k.encode(), a.ctypes.data, shape, a.ndim),
-                           "ws_engine_set_tensor")
-            _lib.check(L.ws_engine_finalize(h), "ws_engine_finalize")
+            self._configure(L, h)
         except Exception:
             L.ws_engine_destroy(h)
             raise
         self._engine, self._engine_device = h, dev_index
         return h
+
+    def _configure(self, L, h):
+        """options + reference state_dict -> engine handle, then finalize (packs / folds / converts the weights)."""
+        for opt in ("two_emb_layer", "emb_bn"):
+            if self.model_args.get(opt):
+                _lib.check(L.ws_engine_set_option(h, opt.encode(), 1), "ws_engine_set_option")
+        for k, v in self.options.items():
+            _lib.check(L.ws_engine_set_option(h, k.encode(), v), "ws_engine_set_option")
+        for k, v in self._sd.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            a = np.ascontiguousarray(v.detach().cpu().numpy(), dtype=np.float32)
+            shape = (C.c_longlong * a.ndim)(*a.shape)
+            _lib.check(L.ws_engine_set_tensor(h, k.encode(), a.ctypes.data, shape, a.ndim),
+                       "ws_engine_set_tensor")
+        _lib.check(L.ws_engine_finalize(h), "ws_engine_finalize")
+
+    def plan_check(self, batch: int = 1, frames: int = 200):
+        """Validate the loaded checkpoint against the engine's plan builder WITHOUT a device (ws_engine_create_plan_check:
+        nothing is computed): missing / mis-shaped tensors, kernel envelopes and tensor-map alignment rules raise B200Error.
+        Returns the launch plan of a (batch, frames) input as a list of (op label, FLOPs)."""
+        L = _lib.load()
+        h = _lib.c_engine_p()
+        _lib.check(L.ws_engine_create_plan_check(self.model_name.encode(), self.precision.encode(), self.feat_dim,
+                                                 self.embed_dim, C.byref(h)), "ws_engine_create_plan_check")
+        try:
+            self._configure(L, h)
+            ops, fl = [], C.c_double(0.0)
+            while True:
+                name = L.ws_engine_plan_op_name(h, batch, frames, len(ops), C.byref(fl))
+                if name is None:
+                    break
+                ops.append((name.decode(), fl.value))
+            if not ops:
+                _lib.check(1, "ws_engine_plan_op_name")
+            return ops
+        finally:
+            L.ws_engine_destroy(h)
 
     def _dev_index(self, t: torch.Tensor | None = None) -> int:
         if t is not None and t.is_cuda:
