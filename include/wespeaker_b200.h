@@ -100,6 +100,9 @@ int ws_engine_collect(ws_engine* e, int slot);
 /* tuning aid: per-op device time (ms) of the (B,T) plan, measured with CUDA events in sequence context; returns #ops */
 int ws_engine_profile_ops(ws_engine* e, int B, int T, int iters, float* ms_out, int max_ops);
 const char* ws_engine_plan_op_name(ws_engine* e, int B, int T, int i, double* flops_out);   /* label + FLOPs of op i */
+/* plan-check engines only: write the (B,T) launch plan as data (JSON op descriptions + placeholder allocation table + fp32
+ * weight sources) so that a test can re-evaluate the plan's arithmetic on the host (tests/plan_interp.py) */
+int ws_engine_plan_trace(ws_engine* e, int B, int T, const char* path);
 /* number of this library's kernels launched by the most recent forward/extract call */
 long long ws_engine_last_launches(const ws_engine* e);
 void ws_engine_destroy(ws_engine* e);
@@ -126,7 +129,7 @@ typedef struct {
     const void* w;            /* [Cout][kf*kt*Cin], tap-major (tap = jf*kt + jt), dtype below */
     int Cout, kf, kt, dil_f, dil_t, pad_f, pad_t, stride_f, stride_t;
     const float* bias;        /* added before act1 (or NULL) */
-    int act1;                 /* 0 none 1 relu 2 tanh 3 sigmoid */
+    int act1;                 /* 0 none 1 relu 2 tanh 3 sigmoid 4 hardtanh(0,20) 5 silu */
     const float* scale;       /* per-channel affine after act1 (or NULL) */
     const float* shift;
     const void* res;          /* residual added after the affine (or NULL), [positions][res_ld] */

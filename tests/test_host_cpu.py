@@ -237,3 +237,22 @@ def test_plan_check_reports_missing_and_misshaped_tensors_and_never_computes():
         assert b"plan-check engine" in L.ws_last_error()
     finally:
         L.ws_engine_destroy(h)
+
+
+@pytest.mark.parametrize("name,prec,B,T", [("ResNet34", "fp16", 2, 99), ("ResNet34", "tf32x3", 1, 40), ("ResNet50", "bf16", 1, 64),
+                                          ("XVEC", "bf16", 2, 40)])
+def test_plan_arithmetic_matches_oracle_on_the_host(name, prec, B, T, tmp_path):
+    """ws_engine_plan_trace + tests/plan_interp.py: the launch plan (BN folding, merged shortcut K ranges, strided convs as
+    parity planes, the halo-resident 3x3 ops with in-place residuals, TSTP index order, folded segment layers) re-evaluated on
+    the host equals the oracle; the kernels executing the same plan are checked on the GPU."""
+    from oracle import models_torch
+    from plan_interp import run_plan
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    m = from_synthetic(name, precision=prec)
+    path = str(tmp_path / "plan.bin")
+    m.plan_trace(path, B, T)
+    feats = syn.make_feats(B, T, 80, seed=5)
+    emb, meta = run_plan(path, feats)
+    ref = models_torch.forward(name, syn.make_state_dict(name, 0), feats).numpy()
+    rel = np.linalg.norm(emb - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert rel.max() < 1e-5, rel

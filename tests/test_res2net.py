@@ -46,3 +46,31 @@ def test_param_counts():
                    if not k.endswith(("running_mean", "running_var", "num_batches_tracked")))
     assert abs(nparams("Res2Net34_Base") / 1e6 - 4.69) < 0.01
     assert abs(nparams("ERes2Net34_Base") / 1e6 - 9.89) < 0.01
+
+
+# ------------------------------------------------------------------------------------------ plan builder, no device
+from plan_interp import run_plan  # noqa: E402  (tests/ is on sys.path under pytest's rootdir conftest)
+from wespeaker_b200.models import from_synthetic  # noqa: E402
+
+PLAN_CASES = [("Res2Net34_Base", "fp32", 1, 48, 1.0), ("Res2Net34_Base", "bf16", 2, 57, 6.0), ("Res2Net34_Large", "fp16", 1, 40, 1.0),
+              ("ERes2Net34_Base", "tf32x3", 1, 48, 1.0), ("ERes2Net34_Base", "bf16", 1, 56, 6.0), ("ERes2Net34_Large", "bf16", 1, 40, 3.0),
+              ("ERes2Net34_aug", "bf16", 1, 40, 1.0)]
+
+
+@pytest.mark.parametrize("name,prec,B,T,gain", PLAN_CASES)
+def test_plan_arithmetic_matches_oracle_on_the_host(name, prec, B, T, gain, tmp_path):
+    """The launch plan the engine builds for these families (channel padding to 32/64/128, split / cat as channel slices,
+    summed chain inputs as repeated-weight K ranges, AFF, merged shortcuts, folded BN, Hardtanh) re-evaluated on the host
+    from ws_engine_plan_trace equals the oracle - for the fp32 (FFMA), 3xTF32 and 16-bit (halo-resident 3x3 kernel) plan
+    variants, which differ in the ops they contain.  No device, nothing computed by the library."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    m = from_synthetic(name, precision=prec)
+    path = str(tmp_path / "plan.bin")
+    m.plan_trace(path, B, T)
+    feats = syn.make_feats(B, T, 80, seed=5) * np.float32(gain)
+    emb, meta = run_plan(path, feats)
+    assert meta["model"] == name and meta["precision"] == prec
+    kinds = {op["trace"]["kind"] for op in meta["ops"]}
+    assert ("conv3x3" in kinds) == (prec in ("bf16", "fp16")) and ("aff_combine" in kinds) == name.startswith("ERes2Net")
+    ref = models_torch.forward(name, syn.make_state_dict(name, 0), feats).numpy()
+    assert rel_l2(emb, ref).max() < 2e-5, rel_l2(emb, ref)   # float64 re-evaluation vs the fp32 oracle

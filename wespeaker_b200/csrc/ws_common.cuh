@@ -7,7 +7,8 @@
 #include <stdint.h>
 
 enum WsDType : int { WS_F32 = 0, WS_BF16 = 1, WS_F16 = 2 };
-enum WsAct : int { WS_ACT_NONE = 0, WS_ACT_RELU = 1, WS_ACT_TANH = 2, WS_ACT_SIGMOID = 3 };
+// RELU20 = Hardtanh(0, 20), the "ReLU" of the Res2Net / ERes2Net families (eres2net.py:43-52); SILU = v * sigmoid(v) (AFF)
+enum WsAct : int { WS_ACT_NONE = 0, WS_ACT_RELU = 1, WS_ACT_TANH = 2, WS_ACT_SIGMOID = 3, WS_ACT_RELU20 = 4, WS_ACT_SILU = 5 };
 
 __host__ __device__ inline int ws_esize(int dt) { return dt == WS_F32 ? 4 : 2; }
 
@@ -56,6 +57,8 @@ __device__ __forceinline__ float ws_act(float v, int act) {
         case WS_ACT_RELU: return fmaxf(v, 0.f);
         case WS_ACT_TANH: return tanhf(v);
         case WS_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        case WS_ACT_RELU20: return fminf(fmaxf(v, 0.f), 20.f);
+        case WS_ACT_SILU: return v / (1.f + expf(-v));
         default: return v;
     }
 }
@@ -72,9 +75,15 @@ __device__ __forceinline__ void ws_act_vec(float* v, int act) {
     } else if (act == WS_ACT_TANH) {
 #pragma unroll 4
         for (int j = 0; j < NV; ++j) v[j] = tanhf(v[j]);
-    } else {
+    } else if (act == WS_ACT_SIGMOID) {
 #pragma unroll 4
         for (int j = 0; j < NV; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+    } else if (act == WS_ACT_RELU20) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 20.f);
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < NV; ++j) v[j] = v[j] / (1.f + expf(-v[j]));
     }
 }
 
@@ -368,7 +377,7 @@ struct WsC3Params {
                             // even-t and the (shifted) odd-t plane of an input row (amap / amap_tail), sub_rows rows each
     int sub_rows;
     const float* bias;      // [Cout]
-    int relu;
+    int relu;               // 0 none, 1 ReLU, 2 Hardtanh(0, 20)
     int B, F, T, Cin, Cout, dtype;
     int row_bytes, npan, kc;       // bytes per smem operand row per K panel (64 / 128), K panels per tap, channels per panel
     int P, tb, n_tt;               // padded pitch (tb + 2), output columns per t tile, number of t tiles

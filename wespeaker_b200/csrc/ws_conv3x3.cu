@@ -458,6 +458,10 @@ __global__ void __launch_bounds__(kC3Threads, 1) ws_conv3x3_kernel(const __grid_
                     if (p.relu) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        if (p.relu == 2) {   // Hardtanh(0, 20): the Res2Net / ERes2Net "ReLU" (eres2net.py:43-52)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fminf(v[i], 20.f);
+                        }
                     }
                     if (p.lens != nullptr) {   // length-masked batch: frames behind the utterance's end are the next conv's padding
                         const int i2 = mt * 128 + r, u = i2 / p.P, tti = i2 - u * p.P, bb = min(b0 + u, p.B - 1);

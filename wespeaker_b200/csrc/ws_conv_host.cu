@@ -29,6 +29,44 @@ static thread_local bool g_plan_check = false;
 bool plan_check_mode() { return g_plan_check; }
 PlanCheckScope::PlanCheckScope(bool on) : prev(g_plan_check) { g_plan_check = on; }
 PlanCheckScope::~PlanCheckScope() { g_plan_check = prev; }
+static thread_local std::string g_op_trace;
+static thread_local bool g_op_trace_has = false;
+void set_op_trace(const std::string& json) {
+    if (!g_plan_check) return;
+    g_op_trace = json; g_op_trace_has = true;
+}
+bool take_op_trace(std::string* json) {
+    if (!g_op_trace_has) return false;
+    *json = g_op_trace; g_op_trace_has = false;
+    return true;
+}
+static std::string jp(const void* p) { char b[32]; snprintf(b, sizeof b, "%llu", (unsigned long long)p); return b; }
+static std::string jv(const char* name, long long v) { char b[96]; snprintf(b, sizeof b, "\"%s\":%lld", name, v); return b; }
+static std::string view_json(const View& v) {
+    return "{\"p\":" + jp(v.p) + "," + jv("B", v.B) + "," + jv("F", v.F) + "," + jv("T", v.T) + "," + jv("C", v.C) + "," + jv("ld", v.ld) + "}";
+}
+static std::string conv_trace(const ConvSpec& s) {
+    std::string j = "{\"kind\":\"conv\"," + jv("es", ws_esize(s.dt)) + ",\"src\":[";
+    for (int i = 0; i < s.nsrc; ++i) {
+        const WsSrc& v = s.src[i];
+        j += std::string(i ? "," : "") + "{\"p\":" + jp(v.ptr) + "," + jv("B", v.B) + "," + jv("F", v.F) + "," + jv("T", v.T) + "," + jv("C", v.C) + "," +
+             jv("sB", v.sB) + "," + jv("sF", v.sF) + "," + jv("sT", v.sT) + "}";
+    }
+    j += "],\"taps\":[";
+    for (size_t i = 0; i < s.taps.size(); ++i) {
+        const WsTap& t = s.taps[i];
+        j += std::string(i ? "," : "") + "[" + std::to_string(t.src) + "," + std::to_string(t.c0) + "," + std::to_string(t.dt) + "," + std::to_string(t.df) + "," +
+             std::to_string(t.wk) + "," + std::to_string(t.nch) + "]";
+    }
+    const WsEpi& e = s.epi;
+    j += "],\"W\":" + jp(s.W) + "," + jv("Ktot", s.Ktot) + "," + jv("Cout", s.Cout) + "," + jv("B", s.B) + "," + jv("F", s.F) + "," + jv("T", s.T) +
+         ",\"bias\":" + jp(e.bias) + ",\"rowbias\":" + jp(e.rowbias) + "," + jv("rowbias_ld", e.rowbias_ld) + "," + jv("act1", e.act1) + ",\"scale\":" + jp(e.scale) +
+         ",\"shift\":" + jp(e.shift) + ",\"gate\":" + jp(e.gate) + ",\"res\":" + jp(e.res) + "," + jv("res_ld", e.res_ld) + "," + jv("act2", e.act2) + ",\"out\":" + jp(e.out) +
+         "," + jv("out_ld", e.out_ld) + ",\"out2\":" + jp(e.out2) + "," + jv("out2_ld", e.out2_ld) + ",\"add2\":" + jp(e.add2) + "," + jv("add2_ld", e.add2_ld) +
+         ",\"colsum\":" + jp(e.colsum) + "}";
+    return j;
+}
+
 void* plan_check_alloc(size_t bytes) {
     static thread_local unsigned long long next = 0x7000000000ull;   // far from anything a host allocator returns
     void* p = (void*)next;
@@ -394,6 +432,7 @@ static void label_conv(const char* kern, const ConvSpec& spec) {
     set_op_label(buf, 2.0 * pos * spec.Ktot * spec.Cout);
 }
 bool make_conv_op(const ConvSpec& spec, int use_tc, Op* out) {
+    if (plan_check_mode()) set_op_trace(conv_trace(spec));
     const char* env_mp = getenv("WS_TC3_MIN_POS");
     const long long min_pos = env_mp ? atoll(env_mp) : 148LL * 128;
     if (use_tc >= 3 && spec.Cout % 128 == 0 && (long long)spec.B * spec.F * spec.T >= min_pos) {
@@ -567,7 +606,7 @@ bool make_astp_op(const View& x, const View& h, const void* W2, float* stats, Op
     return true;
 }
 
-bool make_conv3x3_op(const View& x, const View& out, const void* W, const float* bias, const View* res, bool relu,
+bool make_conv3x3_op(const View& x, const View& out, const void* W, const float* bias, const View* res, int relu,
                      Op* op, bool* unsupported, int stride_f, int stride_t, const int* lens) {
     *unsupported = false;
     const int Cin = x.C, Cout = out.C, Tin = x.T, Fin = x.F, B = x.B;
@@ -700,7 +739,7 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
     q->res = res ? res->p : nullptr;
     q->res_ld = res ? res->ld : 0;
     q->bias = bias;
-    q->relu = relu ? 1 : 0;
+    q->relu = relu;   // 0 none, 1 ReLU, 2 Hardtanh(0, 20)
     q->lens = lens;
     if (const char* dbg = getenv("WS_C3_DBG")) q->dbg = atoi(dbg);
     if (getenv("WS_C3_PROF")) {   // tuning aid: synchronous launch + per-role wait-cycle summary on stderr
@@ -729,6 +768,10 @@ bool make_conv3x3_op(const View& x, const View& out, const void* W, const float*
         return true;
     }
     *op = [q](cudaStream_t s) { return ws_c3_launch(q.get(), s); };
+    if (plan_check_mode())
+        set_op_trace("{\"kind\":\"conv3x3\",\"es\":2,\"x\":" + view_json(x) + ",\"out\":" + view_json(out) + ",\"W\":" + jp(W) + ",\"bias\":" + jp(bias) +
+                     ",\"res\":" + (res ? view_json(*res) : std::string("null")) + "," + jv("relu", relu) + "," + jv("sf", stride_f) + "," + jv("st", stride_t) +
+                     ",\"lens\":" + jp(lens) + "}");
     {
         char buf[200];
         snprintf(buf, sizeof buf, "conv3x3 B=%d F=%d T=%d Cin=%d Cout=%d s=%dx%d caseB=%d nb=%d n_mt=%d R=%d res=%d cl=%d", q->B, q->F, q->T,
@@ -849,12 +892,14 @@ extern "C" int ws_conv(const ws_conv_desc* d, void* stream) {
     bool done = false;
     if (d->use_tc >= 4 && d->kf == 3 && d->kt == 3 && d->dil_f == 1 && d->dil_t == 1 && d->pad_f == 1 && d->pad_t == 1 &&
         d->stride_f >= 1 && d->stride_f <= 2 && d->stride_t >= 1 && d->stride_t <= 2 && d->scale == nullptr && d->x_lo == nullptr && d->colsum == nullptr &&
-        (d->act1 == 0 || d->res == nullptr) && d->act1 <= 1 && d->act2 <= 1) {
+        (d->act1 == 0 || d->res == nullptr) && (d->act1 <= 1 || d->act1 == WS_ACT_RELU20) && (d->act2 <= 1 || d->act2 == WS_ACT_RELU20) &&
+        (d->act1 == 0 || d->act2 == 0 || d->act1 == d->act2)) {
         // halo-resident 3x3 kernel: act(conv + bias [+ res]); with a residual the activation is act2, else act1 (or act2)
         View r = o;
         r.p = const_cast<void*>(d->res); r.ld = d->res_ld;
         bool unsupported = false;
-        if (make_conv3x3_op(x, o, d->w, d->bias, d->res ? &r : nullptr, (d->act1 | d->act2) != 0, &op, &unsupported, d->stride_f,
+        const int a = d->act1 | d->act2;   // one of them is set, or both to the same (idempotent) activation
+        if (make_conv3x3_op(x, o, d->w, d->bias, d->res ? &r : nullptr, a == WS_ACT_RELU20 ? 2 : (a != 0 ? 1 : 0), &op, &unsupported, d->stride_f,
                             d->stride_t)) done = true;
         else if (!unsupported) return 1;
     }

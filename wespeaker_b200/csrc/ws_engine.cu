@@ -42,6 +42,7 @@ struct Plan {
     std::vector<Op> ops;
     std::vector<std::string> op_names;   // tuning aid (ws_engine_profile_ops): label and FLOPs per op
     std::vector<double> op_flops;
+    std::vector<std::string> op_traces;  // plan-check engines: JSON description of each op (ws_engine_plan_trace), else empty strings
     std::vector<void*> bufs;
     int extra_launches = 0;     // ops that launch more than one kernel (split-K FC = 2)
     size_t bytes = 0;           // device memory held by this plan
@@ -75,6 +76,10 @@ struct ws_engine {
     std::map<std::string, HostT> sd;
     bool finalized = false;
     bool plan_check = false;   // ws_engine_create_plan_check: builds launch plans without a device, never computes
+    // plan-check engines: every placeholder allocation (address, bytes) and the fp32 source of every weight upload, for
+    // ws_engine_plan_trace
+    std::vector<std::pair<unsigned long long, unsigned long long>> check_allocs;
+    std::map<unsigned long long, std::vector<float>> check_blobs;
     std::map<std::string, void*> wcache;  // packed device weights by id
     std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;   // key: (B, 2 * T + masked)
     long long last_launches = 0;
@@ -101,6 +106,9 @@ struct ws_engine {
     bool glob = false;
     bool bottleneck = false;   // ResNet50..293: Bottleneck blocks (expansion 4) instead of BasicBlocks
     std::vector<int> num_blocks;
+    // Res2Net / ERes2Net (res2net.py:202-221, eres2net.py:393-431): stem width, baseWidth, scale, expansion, AFF fusion
+    int r2_m = 0, r2_base_width = 32, r2_scale = 2, r2_expansion = 2;
+    bool r2_fuse = false;
     ~ws_engine() {
         plans.clear();
         if (plan_check) return;   // placeholder addresses only, no streams / events were created
@@ -144,12 +152,15 @@ struct Weights {
         }
         return &it->second;
     }
-    void* upload(const std::string& id, const void* host, size_t bytes) {
+    // f32src: the fp32 values `host` was converted from (kept by plan-check engines for ws_engine_plan_trace)
+    void* upload(const std::string& id, const void* host, size_t bytes, const std::vector<float>* f32src = nullptr) {
         auto it = e.wcache.find(id);
         if (it != e.wcache.end()) return it->second;
         void* d = nullptr;
         if (plan_check_mode()) {
             d = plan_check_alloc(bytes);
+            e.check_allocs.push_back({(unsigned long long)d, (unsigned long long)bytes});
+            if (f32src) e.check_blobs[(unsigned long long)d] = *f32src;
         } else if (cudaMalloc(&d, bytes ? bytes : 16) != cudaSuccess || cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
             if (ok) set_err("device allocation/copy failed for weight " + id);
             ok = false;
@@ -164,12 +175,12 @@ struct Weights {
         *out = it->second;
         return true;
     }
-    float* f32(const std::string& id, const std::vector<float>& v) { return (float*)upload(id, v.data(), v.size() * 4); }
+    float* f32(const std::string& id, const std::vector<float>& v) { return (float*)upload(id, v.data(), v.size() * 4, &v); }
     void* act(const std::string& id, const std::vector<float>& v) {
         void* c;
         if (cached(id, &c)) return c;
         if (e.act_dt == WS_F32) {
-            void* hi = upload(id, v.data(), v.size() * 4);
+            void* hi = upload(id, v.data(), v.size() * 4, &v);
             if (e.split && hi != nullptr) {
                 std::vector<float> lo(v.size());
                 for (size_t i = 0; i < v.size(); ++i) {
@@ -188,7 +199,7 @@ struct Weights {
         for (size_t i = 0; i < v.size(); ++i)
             h[i] = e.act_dt == WS_BF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v[i]))
                                        : __half_as_ushort(__float2half_rn(v[i]));
-        return upload(id, h.data(), h.size() * 2);
+        return upload(id, h.data(), h.size() * 2, &v);
     }
     const float* vec(const std::string& key) {
         void* c;
@@ -245,6 +256,7 @@ struct Builder {
         void* d = nullptr;
         if (plan_check_mode()) {
             d = plan_check_alloc(bytes);
+            e.check_allocs.push_back({(unsigned long long)d, (unsigned long long)bytes});
         } else if (cudaMalloc(&d, bytes ? bytes : 16) != cudaSuccess) {
             if (ok) set_err("cudaMalloc failed for an activation buffer");
             ok = false;
@@ -271,6 +283,15 @@ struct Builder {
         p.ops.push_back(std::move(op));
         p.op_names.push_back(label);
         p.op_flops.push_back(flops);
+        std::string tr;
+        take_op_trace(&tr);
+        p.op_traces.push_back(tr);
+    }
+    // plan-trace helpers (no-ops outside plan-check mode): "name":address / "name":integer fields of an op description
+    static std::string tp(const char* n, const void* q) { char bf[96]; snprintf(bf, sizeof bf, "\"%s\":%llu", n, (unsigned long long)q); return bf; }
+    static std::string ti(const char* n, long long v) { char bf[96]; snprintf(bf, sizeof bf, "\"%s\":%lld", n, v); return bf; }
+    static std::string tview(const char* n, const View& v) {
+        return std::string("\"") + n + "\":{" + tp("p", v.p) + "," + ti("B", v.B) + "," + ti("F", v.F) + "," + ti("T", v.T) + "," + ti("C", v.C) + "," + ti("ld", v.ld) + "}";
     }
     // length-masked plans: frame counts of stride level k (nullptr in ordinary plans), and "zero the rows behind every
     // utterance's end" for tensors a time-mixing op is about to read (the reference's unpadded forward sees zero padding)
@@ -319,6 +340,8 @@ struct Builder {
                 int level = 0) {
         View xv = x;
         const int* l = lens(level);
+        set_op_trace("{\"kind\":\"tstats\"," + ti("es", ws_esize(x.dt)) + "," + tview("x", x) + "," + tp("pre_scale", pre_scale) + "," + tp("pre_shift", pre_shift) + "," +
+                     tp("out", out) + "," + ti("out_ld", out_ld) + "," + ti("std_off", std_off) + "," + tp("lens", l) + "}");
         push([=](cudaStream_t s) {
             return ws_launch_tstats(xv.p, xv.dt, xv.B, xv.F, xv.T, xv.C, xv.ld, pre_scale, pre_shift, out, WS_F32, out_ld,
                                     std_off, 1e-7f, s, l);
@@ -334,6 +357,8 @@ struct Builder {
         else while (blocks * nsplit < 296 && I / (nsplit * 2) >= 128 && nsplit < 16) nsplit *= 2;
         float* wsp = nsplit > 1 ? f32((size_t)nsplit * R * O) : nullptr;
         if (nsplit > 1) p.extra_launches += 1;
+        set_op_trace("{\"kind\":\"linear\"," + tp("in", in) + "," + ti("in_ld", in_ld) + "," + tp("in2", in2) + "," + ti("in2_ld", in2_ld) + "," + ti("rows_per_b", rows_per_b) + "," +
+                     tp("W", W) + "," + tp("bias", bias) + "," + tp("out", out) + "," + ti("out_ld", out_ld) + "," + ti("R", R) + "," + ti("I", I) + "," + ti("O", O) + "," + ti("act", act) + "}");
         push([=](cudaStream_t s) {
             return ws_launch_linear_rows(in, in_ld, in2, in2_ld, rows_per_b, W, bias, out, out_ld, R, I, O, act, wsp,
                                          nsplit, s);
@@ -363,6 +388,7 @@ bool build_ecapa(Builder& b) {
         float* xlo = (float*)x0.plo;
         const int dt = e.act_dt;
         const long long n = (long long)B * T * Fd;
+        set_op_trace("{\"kind\":\"convert\"," + Builder::ti("es", ws_esize(dt)) + "," + Builder::tp("in", fin) + "," + Builder::tp("out", xo) + "," + Builder::ti("n", n) + "}");
         b.push([=](cudaStream_t s) { return ws_launch_convert(fin, xo, xlo, dt, n, s); }, "convert");
         b.zero_tail(x0, 0);   // (masked plans) the k=5 conv of layer1 must see zero padding behind each utterance
     }
@@ -628,9 +654,10 @@ View basic_block(Builder& b, const std::string& p, const View& x, int cout, int 
         Op op2;
         bool unsupported = false;
         if (make_conv3x3_op(h, o, W2, b2, &resv, true, &op2, &unsupported, 1, 1, b.lens(lvl))) {
-            std::string lab2;
+            std::string lab2, tr2;
             double fl2 = 0.0;
             take_op_label(&lab2, &fl2);
+            const bool had_tr2 = take_op_trace(&tr2);
             if (has_sc0) {
                 std::vector<float> ss, hs, wsv;
                 if (!b.w.bn(p + ".shortcut.1", true, ss, hs) || !b.w.pack_conv(p + ".shortcut.0.weight", &ss, wsv, &co, &ci, &nt)) return none;
@@ -640,6 +667,7 @@ View basic_block(Builder& b, const std::string& p, const View& x, int cout, int 
                 if (!b.good()) return none;
             }
             set_op_label(lab2, fl2);
+            if (had_tr2) set_op_trace(tr2);
             b.push(std::move(op2));
             return o;
         }
@@ -766,9 +794,47 @@ View stem(Builder& b, const std::string& convkey, const std::string& bnkey, View
     void* op = o.p;
     float* olo = (float*)o.plo;
     const int* l0 = b.lens(0);
+    set_op_trace("{\"kind\":\"stem\"," + Builder::ti("es", ws_esize(dt)) + "," + Builder::tp("feats", fin) + "," + Builder::tp("w9", wd) + "," + Builder::tp("shift", hd) + "," +
+                 Builder::tview("out", o) + "," + Builder::ti("Fdim", Fd) + "," + Builder::tp("lens", l0) + "}");
     b.push([=](cudaStream_t st) { return ws_launch_stem(fin, wd, hd, op, olo, dt, B, T, Fd, co, st, l0); }, "stem");
     return o;
 }
+
+// TSTP over the last feature map + the segment layer(s) (resnet.py:187-204; the same tail closes Res2Net / ERes2Net,
+// res2net.py:186-199, eres2net.py:379-391)
+bool resnet_tail(Builder& b, const View& cur, int E) {
+    ws_engine& e = b.e;
+    const int B = b.p.B;
+    const int sd = cur.C * cur.F;  // stats_dim
+    float* stats = b.f32((size_t)B * 2 * sd);
+    b.tstats(cur, nullptr, nullptr, stats, 2 * sd, sd, 3);  // TSTP, index c*F' + f (pooling_layers.py:78-85); stride level 3
+    const HostT* w1 = b.w.get("seg_1.weight");
+    if (!w1) return false;
+    if ((int)w1->shape[1] != 2 * sd || (int)w1->shape[0] != E) { set_err("seg_1.weight shape mismatch"); return false; }
+    if (e.opt("two_emb_layer", 0)) {
+        // embed_b = seg_2(seg_bn_1(relu(embed_a))) (resnet.py:196-200): BN (affine=False) folded into seg_2
+        float* ea = b.f32((size_t)B * E);
+        std::vector<float> s, h;
+        const HostT* w2 = b.w.get("seg_2.weight");
+        const HostT* b2 = b.w.get("seg_2.bias");
+        if (!w2 || !b2 || !b.w.bn("seg_bn_1", false, s, h)) return false;
+        std::vector<float> wf((size_t)E * E), bf(E);
+        for (int o = 0; o < E; ++o) {
+            double acc = b2->v[o];
+            for (int i = 0; i < E; ++i) {
+                wf[(size_t)o * E + i] = w2->v[(size_t)o * E + i] * s[i];
+                acc += (double)w2->v[(size_t)o * E + i] * h[i];
+            }
+            bf[o] = (float)acc;
+        }
+        b.linear(stats, 2 * sd, nullptr, 0, 1, b.w.vec("seg_1.weight"), b.w.vec("seg_1.bias"), ea, E, B, 2 * sd, E, WS_ACT_RELU);
+        b.linear(ea, E, nullptr, 0, 1, b.w.f32("w:seg_2.folded", wf), b.w.f32("b:seg_2.folded", bf), b.p.emb, E, B, E, E, WS_ACT_NONE);
+    } else {
+        b.linear(stats, 2 * sd, nullptr, 0, 1, b.w.vec("seg_1.weight"), b.w.vec("seg_1.bias"), b.p.emb, E, B, 2 * sd, E, WS_ACT_NONE);
+    }
+    return b.good();
+}
+
 
 // resnet.py:110-204
 bool build_resnet(Builder& b) {
@@ -802,34 +868,301 @@ bool build_resnet(Builder& b) {
         }
     }
     if (!b.good()) return false;
-    const int sd = cur.C * cur.F;  // stats_dim
-    float* stats = b.f32((size_t)B * 2 * sd);
-    b.tstats(cur, nullptr, nullptr, stats, 2 * sd, sd, 3);  // TSTP, index c*F' + f (pooling_layers.py:78-85); stride level 3
-    const HostT* w1 = b.w.get("seg_1.weight");
-    if (!w1) return false;
-    if ((int)w1->shape[1] != 2 * sd || (int)w1->shape[0] != E) { set_err("seg_1.weight shape mismatch"); return false; }
-    if (e.opt("two_emb_layer", 0)) {
-        // embed_b = seg_2(seg_bn_1(relu(embed_a))) (resnet.py:196-200): BN (affine=False) folded into seg_2
-        float* ea = b.f32((size_t)B * E);
-        std::vector<float> s, h;
-        const HostT* w2 = b.w.get("seg_2.weight");
-        const HostT* b2 = b.w.get("seg_2.bias");
-        if (!w2 || !b2 || !b.w.bn("seg_bn_1", false, s, h)) return false;
-        std::vector<float> wf((size_t)E * E), bf(E);
-        for (int o = 0; o < E; ++o) {
-            double acc = b2->v[o];
-            for (int i = 0; i < E; ++i) {
-                wf[(size_t)o * E + i] = w2->v[(size_t)o * E + i] * s[i];
-                acc += (double)w2->v[(size_t)o * E + i] * h[i];
-            }
-            bf[o] = (float)acc;
-        }
-        b.linear(stats, 2 * sd, nullptr, 0, 1, b.w.vec("seg_1.weight"), b.w.vec("seg_1.bias"), ea, E, B, 2 * sd, E, WS_ACT_RELU);
-        b.linear(ea, E, nullptr, 0, 1, b.w.f32("w:seg_2.folded", wf), b.w.f32("b:seg_2.folded", bf), b.p.emb, E, B, E, E, WS_ACT_NONE);
-    } else {
-        b.linear(stats, 2 * sd, nullptr, 0, 1, b.w.vec("seg_1.weight"), b.w.vec("seg_1.bias"), b.p.emb, E, B, 2 * sd, E, WS_ACT_NONE);
+    return resnet_tail(b, cur, E);
+}
+
+// ----------------------------------------------------------------------------------------------- Res2Net / ERes2Net
+// res2net.py:34-199 (BasicBlockRes2Net), eres2net.py:43-391 (Hardtanh(0,20) "ReLU", AFF, BasicBlockERes2Net in layers 1-2,
+// BasicBlockERes2Net_diff_AFF in layers 3-4, stride-2 3x3 downsampling + AFF bottom-up fusion of the four stage outputs).
+//
+// Channel padding: the split width w = floor(planes * baseWidth / 64) is 16 (or 24, 48, 96, 192 in ERes2Net34_aug); every
+// width-w tensor is carried as wp = max(32, next power of two >= w) channels whose extra channels are exact zeros (zero weight
+// rows and zero bias give Hardtanh(0) = 0 / SiLU(0) = 0, consumers have zero weight columns there), so every conv runs on the
+// 32 / 64 / 128-channel kernels.  torch.split / torch.cat are channel slices of two buffers: conv1 writes all `scale` chunks
+// into A, chain conv i writes chunk i of the concat buffer, conv3 reads the concat buffer (plus, in Res2Net, the last chunk of
+// A) as K ranges.  "sp + spx[i]" ahead of a chain conv is the same conv over two sources with the weights repeated (the sum
+// happens in the fp32 accumulator); BN is folded into the conv weights everywhere (conv -> BN -> Hardtanh order).
+struct Res2Cfg {
+    int m = 32, base_width = 32, scale = 2, expansion = 2;
+    bool fuse = false;
+};
+
+static int res2_pad(int w) {
+    int p = 32;
+    while (p < w) p <<= 1;
+    return p;
+}
+
+// rows [chunk c][j < w] of a [nchunk * w][K] matrix -> rows [c * wp + j] of a zero-initialised [nchunk * wp][K] matrix
+static std::vector<float> pad_rows(const std::vector<float>& m, int nchunk, int w, int wp, int K) {
+    std::vector<float> o((size_t)nchunk * wp * K, 0.f);
+    for (int c = 0; c < nchunk; ++c)
+        for (int j = 0; j < w; ++j)
+            memcpy(&o[((size_t)c * wp + j) * K], &m[((size_t)c * w + j) * K], (size_t)K * 4);
+    return o;
+}
+// columns [block g][chunk c][j < w] of a [R][G * nchunk * w] matrix -> columns [g][c * wp + j] of [R][G * nchunk * wp]
+static std::vector<float> pad_cols(const std::vector<float>& m, int R, int G, int nchunk, int w, int wp) {
+    const int Kin = G * nchunk * w, Kout = G * nchunk * wp;
+    std::vector<float> o((size_t)R * Kout, 0.f);
+    for (int r = 0; r < R; ++r)
+        for (int g = 0; g < G; ++g)
+            for (int c = 0; c < nchunk; ++c)
+                memcpy(&o[(size_t)r * Kout + ((size_t)g * nchunk + c) * wp], &m[(size_t)r * Kin + ((size_t)g * nchunk + c) * w], (size_t)w * 4);
+    return o;
+}
+
+// AFF (eres2net.py:75-102): out = x * att + y * (2 - att), att = 1 + tanh(BN(conv1x1(SiLU(BN(conv1x1([x | y]))))))
+// x, y: views of Cp channels of which the first Cr are real (the rest zero); hid / att: scratch buffers of >= the positions.
+static bool aff(Builder& b, const std::string& p, const View& x, const View& y, int Cr, View hidbuf, View attbuf, const View& out) {
+    const int Cp = x.C, inter = Cr / 4, ip = std::max(32, (inter + 31) / 32 * 32);
+    std::vector<float> sa, ha, sb, hb, wa, wb;
+    int co, ci, nt;
+    const HostT* ba = b.w.get(p + ".local_att.0.bias");
+    const HostT* bb = b.w.get(p + ".local_att.3.bias");
+    if (!ba || !bb || !b.w.bn(p + ".local_att.1", true, sa, ha) || !b.w.bn(p + ".local_att.4", true, sb, hb) ||
+        !b.w.pack_conv(p + ".local_att.0.weight", &sa, wa, &co, &ci, &nt) || !b.w.pack_conv(p + ".local_att.3.weight", &sb, wb, &co, &ci, &nt))
+        return false;
+    if ((int)wa.size() != inter * 2 * Cr || (int)wb.size() != Cr * inter || y.C != Cp || Cr > Cp) { set_err(p + ": AFF weight shape mismatch"); b.ok = false; return false; }
+    // conv a: rows inter -> ip, columns [x: Cr -> Cp | y: Cr -> Cp]
+    std::vector<float> wap = pad_rows(pad_cols(wa, inter, 2, 1, Cr, Cp), 1, inter, ip, 2 * Cp), bap(ip, 0.f);
+    for (int i = 0; i < inter; ++i) bap[i] = sa[i] * ba->v[i] + ha[i];
+    View hid = hidbuf; hid.B = x.B; hid.F = x.F; hid.T = x.T; hid.C = ip; hid.ld = ip;
+    {
+        ConvSpec cs;
+        cs.dt = b.e.act_dt;
+        int Fo, To;
+        const int K1 = add_conv_taps(cs, x, 1, 1, 1, 1, 0, 0, 1, 1, 0, &Fo, &To);
+        const int K2 = add_conv_taps(cs, y, 1, 1, 1, 1, 0, 0, 1, 1, K1, &Fo, &To);
+        if (K1 != Cp || K2 != Cp || y.B != x.B || y.F != x.F || y.T != x.T) { set_err(p + ": AFF operand shape mismatch"); b.ok = false; return false; }
+        cs.W = b.w.act("w:" + p + ".att0", wap); cs.Ktot = 2 * Cp; cs.Cout = ip; cs.B = x.B; cs.F = x.F; cs.T = x.T;
+        cs.dense_pointwise = true;
+        cs.epi.bias = b.w.f32("b:" + p + ".att0", bap);
+        cs.epi.act1 = WS_ACT_SILU;
+        fill_epi_out(cs.epi, hid);
+        b.conv(cs);
     }
+    // conv b: rows Cr -> Cp, columns inter -> ip; tanh in the epilogue
+    std::vector<float> wbp = pad_rows(pad_cols(wb, Cr, 1, 1, inter, ip), 1, Cr, Cp, ip), bbp(Cp, 0.f);
+    for (int i = 0; i < Cr; ++i) bbp[i] = sb[i] * bb->v[i] + hb[i];
+    View att = attbuf; att.B = x.B; att.F = x.F; att.T = x.T; att.C = Cp; att.ld = Cp;
+    WsEpi eb{};
+    eb.bias = b.w.f32("b:" + p + ".att3", bbp);
+    eb.act1 = WS_ACT_TANH;
+    b.conv_simple(hid, att, b.w.act("w:" + p + ".att3", wbp), 1, 1, 1, 1, 0, 0, 1, 1, eb);
+    if (!b.good()) return false;
+    const View xv = x, yv = y, av = att, ov = out;
+    const int dt = b.e.act_dt;
+    const long long npos = x.npos();
+    set_op_trace("{\"kind\":\"aff_combine\"," + Builder::ti("es", ws_esize(dt)) + "," + Builder::tview("x", xv) + "," + Builder::tview("y", yv) + "," + Builder::tview("t", av) + "," +
+                 Builder::tview("out", ov) + "}");
+    b.push([=](cudaStream_t s) {
+        return ws_launch_aff_combine(xv.p, xv.ld, yv.p, yv.ld, av.p, av.ld, ov.p, (float*)ov.plo, ov.ld, dt, npos, Cp, s);
+    }, "aff_combine");
     return b.good();
+}
+
+// 3x3 pad-1 conv (+ folded BN shift) -> act over `in` (and, when in2 != nullptr, over in + in2 with the weights repeated):
+// the halo-resident kernel where it applies, else the generic conv-GEMM.  act: WS_ACT_RELU20 or WS_ACT_NONE.
+static bool res2_conv3x3(Builder& b, const std::string& id, const View& in, const View* in2, const View& out, const std::vector<float>& w9,
+                         const std::vector<float>& bias, int act, int stride) {
+    const int Cin = in.C, Cout = out.C;
+    if ((int)w9.size() != Cout * 9 * Cin || (int)bias.size() != Cout) { set_err(id + ": 3x3 weight shape mismatch"); b.ok = false; return false; }
+    const float* bd = b.w.f32("b:" + id, bias);
+    if (in2 == nullptr) {
+        const void* W = b.w.act("w:" + id, w9);
+        if (b.e.use_tc >= 2 && b.e.act_dt != WS_F32 && b.e.opt("conv3x3", 1) != 0 && (stride == 1 || b.e.opt("conv3x3_strided", 1) != 0)) {
+            Op op;
+            bool unsupported = false;
+            if (make_conv3x3_op(in, out, W, bd, nullptr, act == WS_ACT_RELU20 ? 2 : 0, &op, &unsupported, stride, stride, nullptr)) {
+                b.push(std::move(op));
+                return b.good();
+            }
+            if (!unsupported) { b.ok = false; return false; }
+        }
+        WsEpi ep{};
+        ep.bias = bd;
+        ep.act1 = act;
+        b.conv_simple(in, out, W, 3, 3, 1, 1, 1, 1, stride, stride, ep);
+        return b.good();
+    }
+    // two summed inputs: K = [9 taps over in | 9 taps over in2], weight rows repeated
+    std::vector<float> w2((size_t)Cout * 18 * Cin);
+    for (int o = 0; o < Cout; ++o) {
+        memcpy(&w2[(size_t)o * 18 * Cin], &w9[(size_t)o * 9 * Cin], (size_t)9 * Cin * 4);
+        memcpy(&w2[(size_t)o * 18 * Cin + 9 * Cin], &w9[(size_t)o * 9 * Cin], (size_t)9 * Cin * 4);
+    }
+    ConvSpec cs;
+    cs.dt = b.e.act_dt;
+    int Fo, To, F2, T2;
+    const int K1 = add_conv_taps(cs, in, 3, 3, 1, 1, 1, 1, stride, stride, 0, &Fo, &To);
+    const int K2 = K1 < 0 ? -1 : add_conv_taps(cs, *in2, 3, 3, 1, 1, 1, 1, stride, stride, K1, &F2, &T2);
+    if (K1 != 9 * Cin || K2 != 9 * Cin || Fo != out.F || To != out.T || F2 != Fo || T2 != To) { set_err(id + ": summed-input conv shape mismatch"); b.ok = false; return false; }
+    cs.W = b.w.act("w:" + id + ".x2", w2); cs.Ktot = 18 * Cin; cs.Cout = Cout; cs.B = out.B; cs.F = Fo; cs.T = To;
+    cs.epi.bias = bd;
+    cs.epi.act1 = act;
+    fill_epi_out(cs.epi, out);
+    b.conv(cs);
+    return b.good();
+}
+
+struct Res2Bufs {   // per-stage scratch, sized for the stage's largest tensor of each kind
+    View A, cat, fz, hid, att, xo[2];
+};
+
+// one residual block; kind 0 = BasicBlockRes2Net, 1 = BasicBlockERes2Net, 2 = BasicBlockERes2Net_diff_AFF
+static View res2_block(Builder& b, const Res2Cfg& c, const std::string& p, const View& x, int planes, int stride, int kind, Res2Bufs& bf, View obuf) {
+    View none;
+    const int w = (int)std::floor(planes * (c.base_width / 64.0)), wp = res2_pad(w), s = c.scale, cout = planes * c.expansion, cin = x.C;
+    const int nconv = kind == 0 ? s - 1 : s;            // chain convs
+    const int ncat = kind == 0 ? s - 1 : s;             // chunks of the concat buffer (Res2Net's last chunk stays in A)
+    const int Fo = (x.F - 1) / stride + 1, To = (x.T - 1) / stride + 1;
+    std::vector<float> s1, h1, s3, h3, w1, w3;
+    int co, ci, nt;
+    if (!b.w.bn(p + ".bn1", true, s1, h1) || !b.w.bn(p + ".bn3", true, s3, h3) || !b.w.pack_conv(p + ".conv1.weight", &s1, w1, &co, &ci, &nt) ||
+        !b.w.pack_conv(p + ".conv3.weight", &s3, w3, &co, &ci, &nt))
+        return none;
+    if ((int)w1.size() != s * w * cin || (int)w3.size() != cout * s * w) { set_err(p + ": conv1 / conv3 weight shape mismatch"); b.ok = false; return none; }
+    View A = bf.A; A.B = x.B; A.F = Fo; A.T = To; A.C = s * wp; A.ld = s * wp;
+    View cat = bf.cat; cat.B = x.B; cat.F = Fo; cat.T = To; cat.C = ncat * wp; cat.ld = ncat * wp;
+    View o = obuf; o.B = x.B; o.F = Fo; o.T = To; o.C = cout; o.ld = cout;
+    {   // conv1 (1x1, stride) + bn1 + Hardtanh -> the `scale` chunks of A
+        std::vector<float> w1p = pad_rows(w1, s, w, wp, cin), b1p((size_t)s * wp, 0.f);
+        for (int k = 0; k < s; ++k)
+            for (int j = 0; j < w; ++j) b1p[(size_t)k * wp + j] = h1[(size_t)k * w + j];
+        WsEpi e1{};
+        e1.bias = b.w.f32("b:" + p + ".bn1", b1p);
+        e1.act1 = WS_ACT_RELU20;
+        b.conv_simple(x, A, b.w.act("w:" + p + ".conv1", w1p), 1, 1, 1, 1, 0, 0, stride, stride, e1);
+        if (!b.good()) return none;
+    }
+    for (int i = 0; i < nconv; ++i) {
+        const std::string ck = (kind == 2) ? (i == 0 ? p + ".conv2_1" : p + ".convs." + std::to_string(i - 1))
+                                           : p + ".convs." + std::to_string(i);
+        const std::string bk = (kind == 2) ? (i == 0 ? p + ".bn2_1" : p + ".bns." + std::to_string(i - 1))
+                                           : p + ".bns." + std::to_string(i);
+        std::vector<float> sc, sh, wc;
+        if (!b.w.bn(bk, true, sc, sh) || !b.w.pack_conv(ck + ".weight", &sc, wc, &co, &ci, &nt)) return none;
+        if (co != w || ci != w || nt != 9) { set_err(ck + ".weight: expected (w, w, 3, 3)"); b.ok = false; return none; }
+        // [w][9][w] -> [wp][9][wp]
+        std::vector<float> wcp = pad_rows(pad_cols(wc, w, 9, 1, w, wp), 1, w, wp, 9 * wp), bcp(wp, 0.f);
+        for (int j = 0; j < w; ++j) bcp[j] = sh[j];
+        const View dst = cat.ch(i * wp, wp), spx = A.ch(i * wp, wp);
+        if (i == 0) {
+            if (!res2_conv3x3(b, ck, spx, nullptr, dst, wcp, bcp, WS_ACT_RELU20, 1)) return none;
+        } else if (kind == 2) {
+            View fz = bf.fz; fz.B = x.B; fz.F = Fo; fz.T = To; fz.C = wp; fz.ld = wp;
+            if (!aff(b, p + ".fuse_models." + std::to_string(i - 1), cat.ch((i - 1) * wp, wp), spx, w, bf.hid, bf.att, fz)) return none;
+            if (!res2_conv3x3(b, ck, fz, nullptr, dst, wcp, bcp, WS_ACT_RELU20, 1)) return none;
+        } else {
+            const View prev = cat.ch((i - 1) * wp, wp);
+            if (!res2_conv3x3(b, ck, prev, &spx, dst, wcp, bcp, WS_ACT_RELU20, 1)) return none;
+        }
+    }
+    // conv3 (1x1) + bn3 over [concat chunks | (Res2Net) last chunk of A] (+ the strided 1x1 shortcut conv as one more K range,
+    // or the identity shortcut as the epilogue's residual), Hardtanh
+    ConvSpec cs;
+    cs.dt = b.e.act_dt;
+    int F3, T3;
+    int K = add_conv_taps(cs, cat, 1, 1, 1, 1, 0, 0, 1, 1, 0, &F3, &T3);
+    if (kind == 0 && K >= 0) {
+        const int K1 = add_conv_taps(cs, A.ch(ncat * wp, wp), 1, 1, 1, 1, 0, 0, 1, 1, K, &F3, &T3);
+        K = K1 < 0 ? -1 : K + K1;
+    }
+    if (K != s * wp) { set_err(p + ": conv3 operand mismatch"); b.ok = false; return none; }
+    std::vector<float> w3p = pad_cols(w3, cout, 1, s, w, wp), bias3 = h3;
+    const bool has_sc = b.e.sd.count(p + ".shortcut.0.weight") != 0;
+    if (has_sc) {
+        std::vector<float> ss, hs, wsv;
+        if (!b.w.bn(p + ".shortcut.1", true, ss, hs) || !b.w.pack_conv(p + ".shortcut.0.weight", &ss, wsv, &co, &ci, &nt)) return none;
+        int F4, T4;
+        const int K2 = add_conv_taps(cs, x, 1, 1, 1, 1, 0, 0, stride, stride, K, &F4, &T4);
+        if (K2 != cin || co != cout || F4 != Fo || T4 != To) { set_err(p + ": shortcut shape mismatch"); b.ok = false; return none; }
+        std::vector<float> wm((size_t)cout * (K + K2));
+        for (int r = 0; r < cout; ++r) {
+            memcpy(&wm[(size_t)r * (K + K2)], &w3p[(size_t)r * K], (size_t)K * 4);
+            memcpy(&wm[(size_t)r * (K + K2) + K], &wsv[(size_t)r * K2], (size_t)K2 * 4);
+        }
+        w3p.swap(wm);
+        K += K2;
+        for (int i = 0; i < cout; ++i) bias3[i] += hs[i];
+    } else {
+        if (cin != cout || stride != 1) { set_err(p + ": identity shortcut with a shape change"); b.ok = false; return none; }
+        cs.epi.res = x.p;
+        cs.epi.res_ld = x.ld;
+        cs.dense_pointwise = true;
+    }
+    cs.W = b.w.act("w:" + p + ".conv3m", w3p); cs.Ktot = K; cs.Cout = cout; cs.B = x.B; cs.F = Fo; cs.T = To;
+    cs.epi.bias = b.w.f32("b:" + p + ".bn3m", bias3);
+    cs.epi.act2 = WS_ACT_RELU20;
+    fill_epi_out(cs.epi, o);
+    b.conv(cs);
+    return b.good() ? o : none;
+}
+
+bool build_res2net(Builder& b, const Res2Cfg& c) {
+    ws_engine& e = b.e;
+    const int B = b.p.B, T = b.p.T, Fd = e.feat_dim, E = e.embed_dim, m = c.m;
+    if (b.p.masked) { set_err("length-masked batches are not implemented for Res2Net / ERes2Net"); return false; }
+    if (m != 32 && m != 64) { set_err("Res2Net / ERes2Net: m_channels must be 32 or 64"); return false; }
+    View stem_buf = b.act(B, Fd, T, m);
+    if (!b.good()) return false;
+    View cur = stem(b, "conv1.weight", "bn1", stem_buf);   // plain ReLU (res2net.py:158, eres2net.py:358)
+    if (!b.good() || cur.p == nullptr) return false;
+    View stage[4];
+    int stage_real[4];
+    for (int li = 1; li <= 4 && b.good(); ++li) {
+        const int planes = m << (li - 1), cout = planes * c.expansion;
+        const int w = (int)std::floor(planes * (c.base_width / 64.0)), wp = res2_pad(w);
+        const int stride = li == 1 ? 1 : 2;
+        const int Fo = (cur.F - 1) / stride + 1, To = (cur.T - 1) / stride + 1;
+        const int kind = !c.fuse ? 0 : (li >= 3 ? 2 : 1);
+        // conv1 of the first block runs at the output resolution already (the stride is on conv1), so every scratch tensor of
+        // the stage has Fo x To positions
+        Res2Bufs bf;
+        bf.A = b.act(B, Fo, To, c.scale * wp);
+        bf.cat = b.act(B, Fo, To, c.scale * wp);
+        if (kind == 2) {
+            bf.fz = b.act(B, Fo, To, wp);
+            bf.hid = b.act(B, Fo, To, std::max(32, (w / 4 + 31) / 32 * 32));
+            bf.att = b.act(B, Fo, To, wp);
+        }
+        bf.xo[0] = b.act(B, Fo, To, cout);
+        bf.xo[1] = b.act(B, Fo, To, cout);
+        if (!b.good()) return false;
+        for (int bi = 0; bi < e.num_blocks[li - 1] && b.good(); ++bi) {
+            const std::string p = "layer" + std::to_string(li) + "." + std::to_string(bi);
+            View o = res2_block(b, c, p, cur, planes, bi == 0 ? stride : 1, kind, bf, bf.xo[bi & 1]);
+            if (!b.good() || o.p == nullptr) return false;
+            cur = o;
+        }
+        stage[li - 1] = cur;
+        stage_real[li - 1] = cout;
+    }
+    if (!b.good()) return false;
+    if (c.fuse) {
+        // bottom-up fusion (eres2net.py:359-369): f = AFF(stage[k + 1], conv3x3_stride2(f)), f starting at stage 0
+        View f = stage[0];
+        const char* names[3] = {"fuse_mode12", "fuse_mode123", "fuse_mode1234"};
+        for (int k = 0; k < 3 && b.good(); ++k) {
+            const View& nx = stage[k + 1];
+            const int C2 = stage_real[k + 1];
+            const std::string dk = "layer" + std::to_string(k + 1) + "_downsample";
+            std::vector<float> wd;
+            int co, ci, nt;
+            if (!b.w.pack_conv(dk + ".weight", nullptr, wd, &co, &ci, &nt)) return false;
+            if (co != C2 || ci != f.C || nt != 9) { set_err(dk + ".weight shape mismatch"); return false; }
+            View d = b.act(B, nx.F, nx.T, C2), hid = b.act(B, nx.F, nx.T, std::max(32, (C2 / 4 + 31) / 32 * 32)), att = b.act(B, nx.F, nx.T, C2),
+                 fo = b.act(B, nx.F, nx.T, C2);
+            if (!b.good()) return false;
+            if (!res2_conv3x3(b, dk, f, nullptr, d, wd, std::vector<float>((size_t)C2, 0.f), WS_ACT_NONE, 2)) return false;
+            if (!aff(b, names[k], nx, d, C2, hid, att, fo)) return false;
+            f = fo;
+        }
+        cur = f;
+    }
+    if (!b.good()) return false;
+    return resnet_tail(b, cur, E);
 }
 
 // ----------------------------------------------------------------------------------------------- XVEC
@@ -852,6 +1185,7 @@ bool build_xvec(Builder& b) {
         float* xlo = (float*)x0.plo;
         const int dt = e.act_dt;
         const long long n = (long long)B * T * Fd;
+        set_op_trace("{\"kind\":\"convert\"," + Builder::ti("es", ws_esize(dt)) + "," + Builder::tp("in", fin) + "," + Builder::tp("out", xo) + "," + Builder::ti("n", n) + "}");
         b.push([=](cudaStream_t s) { return ws_launch_convert(fin, xo, xlo, dt, n, s); }, "convert");
     }
     const int ks[5] = {5, 3, 3, 1, 1}, dils[5] = {1, 2, 3, 1, 1};
@@ -1153,6 +1487,11 @@ Plan* get_plan(ws_engine* e, int B, int T, bool masked = false) {
         if (e->model.rfind("ECAPA", 0) == 0) ok = build_ecapa(b);
         else if (e->model.rfind("ResNet", 0) == 0) ok = build_resnet(b);
         else if (e->model == "XVEC") ok = build_xvec(b);
+        else if (e->r2_m != 0) {
+            Res2Cfg c;
+            c.m = e->r2_m; c.base_width = e->r2_base_width; c.scale = e->r2_scale; c.expansion = e->r2_expansion; c.fuse = e->r2_fuse;
+            ok = build_res2net(b, c);
+        }
         else ok = build_campplus(b);
     }
     if (!ok) return nullptr;
@@ -1313,6 +1652,11 @@ static int configure_engine(ws_engine* e, const char* model_name, const char* pr
     else if (m == "ResNet221") { e->num_blocks = {6, 16, 48, 3}; e->bottleneck = true; }
     else if (m == "ResNet293") { e->num_blocks = {10, 20, 64, 3}; e->bottleneck = true; }
     else if (m == "XVEC") {}
+    else if (m == "Res2Net34_Base") { e->num_blocks = {3, 4, 6, 3}; e->r2_m = 32; }
+    else if (m == "Res2Net34_Large") { e->num_blocks = {3, 4, 6, 3}; e->r2_m = 64; }
+    else if (m == "ERes2Net34_Base") { e->num_blocks = {3, 4, 6, 3}; e->r2_m = 32; e->r2_fuse = true; }
+    else if (m == "ERes2Net34_Large") { e->num_blocks = {3, 4, 6, 3}; e->r2_m = 64; e->r2_fuse = true; }
+    else if (m == "ERes2Net34_aug") { e->num_blocks = {3, 4, 6, 3}; e->r2_m = 64; e->r2_fuse = true; e->r2_base_width = 24; e->r2_scale = 3; e->r2_expansion = 4; }
     else if (m == "CAMPPlus") {}
     else { set_err("unknown / out-of-scope model name: " + m); return 1; }
     const std::string p = e->prec;
@@ -1746,6 +2090,48 @@ const char* ws_engine_plan_op_name(ws_engine* e, int B, int T, int i, double* fl
     if (!p || i < 0 || i >= (int)p->op_names.size()) return nullptr;
     if (flops_out) *flops_out = p->op_flops[i];
     return p->op_names[i].c_str();
+}
+
+// Plan-check engines only: write the (B,T) launch plan as data - a JSON description of every op (operands as placeholder
+// addresses, shapes, strides, epilogues), the placeholder allocation table and the fp32 source of every weight - so that a
+// test can re-evaluate the plan's arithmetic on the host (tests/plan_interp.py) and compare it with the oracle.
+// File layout: "WSPT1\n", uint64 JSON length, JSON, then the weight blobs (fp32) back to back; the JSON's "blobs" table
+// holds [address, float offset into the blob area, float count].
+int ws_engine_plan_trace(ws_engine* e, int B, int T, const char* path) {
+    if (!e || !path) { set_err("ws_engine_plan_trace: null argument"); return 1; }
+    if (!e->plan_check || !e->finalized) { set_err("ws_engine_plan_trace: needs a finalized plan-check engine"); return 1; }
+    Plan* p = get_plan(e, B, T);
+    if (!p) return 1;
+    std::string j = "{";
+    j += Builder::ti("B", B) + "," + Builder::ti("T", T) + "," + Builder::ti("feat_dim", e->feat_dim) + "," + Builder::ti("embed_dim", e->embed_dim) + "," +
+         Builder::ti("act_es", ws_esize(e->act_dt)) + "," + Builder::tp("feats_in", p->feats_in) + "," + Builder::tp("emb", p->emb) + ",\"model\":\"" + e->model +
+         "\",\"precision\":\"" + e->prec + "\",\"allocs\":[";
+    for (size_t i = 0; i < e->check_allocs.size(); ++i)
+        j += std::string(i ? "," : "") + "[" + std::to_string(e->check_allocs[i].first) + "," + std::to_string(e->check_allocs[i].second) + "]";
+    j += "],\"blobs\":[";
+    unsigned long long off = 0;
+    bool first = true;
+    for (auto& kv : e->check_blobs) {
+        j += std::string(first ? "" : ",") + "[" + std::to_string(kv.first) + "," + std::to_string(off) + "," + std::to_string(kv.second.size()) + "]";
+        off += kv.second.size();
+        first = false;
+    }
+    j += "],\"ops\":[";
+    for (size_t i = 0; i < p->ops.size(); ++i) {
+        std::string lab = p->op_names[i];
+        for (char& ch : lab) if (ch == '"' || ch == '\\') ch = ' ';
+        j += std::string(i ? "," : "") + "{\"label\":\"" + lab + "\",\"trace\":" + (p->op_traces[i].empty() ? std::string("null") : p->op_traces[i]) + "}";
+    }
+    j += "]}";
+    FILE* f = fopen(path, "wb");
+    if (!f) { set_err(std::string("ws_engine_plan_trace: cannot open ") + path); return 1; }
+    const unsigned long long n = j.size();
+    bool okw = fwrite("WSPT1\n", 1, 6, f) == 6 && fwrite(&n, 8, 1, f) == 1 && fwrite(j.data(), 1, j.size(), f) == j.size();
+    for (auto& kv : e->check_blobs)
+        okw = okw && (kv.second.empty() || fwrite(kv.second.data(), 4, kv.second.size(), f) == kv.second.size());
+    okw = (fclose(f) == 0) && okw;
+    if (!okw) { set_err(std::string("ws_engine_plan_trace: write failed: ") + path); return 1; }
+    return 0;
 }
 
 void ws_engine_destroy(ws_engine* e) {

@@ -43,6 +43,11 @@ struct PlanCheckScope {
     ~PlanCheckScope();
 };
 void* plan_check_alloc(size_t bytes);   // 256-byte aligned placeholder address
+// Plan trace (plan-check mode only, ws_engine_plan_trace): op factories leave a JSON description of the op they just built
+// (operands as placeholder addresses, shapes, strides, epilogue) and Builder::push() attaches it to the plan, so that a test
+// can re-evaluate the plan's arithmetic on the host and compare it with the oracle.  Outside plan-check mode these are no-ops.
+void set_op_trace(const std::string& json);
+bool take_op_trace(std::string* json);
 
 // channels-last activation view: element (b,f,t,c) at p[((b*F+f)*T+t)*ld + c]
 struct View {
@@ -103,9 +108,10 @@ bool make_astp_op(const View& x, const View& h, const void* W2, float* stats, Op
                   const int* lens = nullptr);
 
 // Halo-resident 3x3 pad-1 conv (ws_conv3x3.cu), strides 1 or 2 per axis: out = act(conv(x, W) + bias [+ res]).  x/out/res:
-// channels-last 16-bit views (out / res with the strided extents); W: [Cout][9*Cin] tap-major in the activation dtype.  Returns false with
+// channels-last 16-bit views (out / res with the strided extents); W: [Cout][9*Cin] tap-major in the activation dtype; relu: 0 none,
+// 1 ReLU, 2 Hardtanh(0, 20).  Returns false with
 // *unsupported = true when the shape is outside the kernel's envelope (the caller then uses make_conv_op).
-bool make_conv3x3_op(const View& x, const View& out, const void* W, const float* bias, const View* res, bool relu,
+bool make_conv3x3_op(const View& x, const View& out, const void* W, const float* bias, const View* res, int relu,
                      Op* op, bool* unsupported, int stride_f = 1, int stride_t = 1, const int* lens = nullptr);
 
 // Fused CAM++ dense layers (ws_cam_dense.cu).  cam_layer_fill builds one host-side layer descriptor (weights are device

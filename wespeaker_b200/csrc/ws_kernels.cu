@@ -346,6 +346,37 @@ __global__ void scale_residual_kernel(const void* __restrict__ x, long long x_ld
     }
 }
 
+// ERes2Net attentional feature fusion, the combine step (eres2net.py:97-100): att = 1 + t with t = tanh(local_att(x | y))
+// already applied by the producing conv's epilogue; out = x * att + y * (2 - att).  8 channels per thread, 16-byte accesses.
+template <int dt>
+__global__ void aff_combine_kernel(const void* __restrict__ x, long long x_ld, const void* __restrict__ y, long long y_ld,
+                                   const void* __restrict__ t, long long t_ld, void* __restrict__ out, float* __restrict__ lo,
+                                   long long out_ld, int C, long long nvec) {
+    const unsigned cv = (unsigned)C >> 3;
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned stride = gridDim.x * blockDim.x, n = (unsigned)nvec;   // launcher guarantees nvec < 2^31
+    for (; i < n; i += stride) {
+        const unsigned upos = i / cv;
+        const int c = (int)(i - upos * cv) * 8;
+        const long long pos = upos;
+        float a[8], b[8], g[8];
+        ws_ldv8(x, dt, pos * x_ld + c, a);
+        ws_ldv8(y, dt, pos * y_ld + c, b);
+        ws_ldv8(t, dt, pos * t_ld + c, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float att = 1.f + g[k];
+            a[k] = a[k] * att + b[k] * (2.f - att);
+        }
+        ws_stv8(out, dt, pos * out_ld + c, a);
+        if (lo != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = ws_tf32_lo(a[k]);
+            ws_stv8(lo, WS_F32, pos * out_ld + c, a);
+        }
+    }
+}
+
 // block (32, 8), 2 channels per thread; ONE pass over (x, logits) with an online softmax per (b, c): running max m and
 // sums rescaled by exp(m_old - m_new); the 8 T-slices are merged through shared memory.
 __global__ void __launch_bounds__(256) astp_stats_kernel(const void* __restrict__ x, const void* __restrict__ lg,
@@ -919,6 +950,18 @@ const char* ws_launch_scale_residual(const void* x, long long x_ld, const float*
     if (dt == WS_BF16) scale_residual_kernel<WS_BF16><<<g, 256, 0, s>>>(x, x_ld, gate, res, res_ld, out, lo, out_ld, T, C, nvec);
     else if (dt == WS_F16) scale_residual_kernel<WS_F16><<<g, 256, 0, s>>>(x, x_ld, gate, res, res_ld, out, lo, out_ld, T, C, nvec);
     else scale_residual_kernel<WS_F32><<<g, 256, 0, s>>>(x, x_ld, gate, res, res_ld, out, lo, out_ld, T, C, nvec);
+    return last_err();
+}
+
+const char* ws_launch_aff_combine(const void* x, long long x_ld, const void* y, long long y_ld, const void* t, long long t_ld,
+                                  void* out, float* lo, long long out_ld, int dt, long long npos, int C, cudaStream_t s) {
+    if (C % 8 != 0 || x_ld % 8 != 0 || y_ld % 8 != 0 || t_ld % 8 != 0 || out_ld % 8 != 0) return "aff_combine: C and the row pitches must be multiples of 8";
+    const long long nvec = npos * (C / 8);
+    if (nvec >= (1LL << 31)) return "aff_combine: tensor too large for 32-bit vector indices";
+    const int g = grid_for(nvec, 256);
+    if (dt == WS_BF16) aff_combine_kernel<WS_BF16><<<g, 256, 0, s>>>(x, x_ld, y, y_ld, t, t_ld, out, lo, out_ld, C, nvec);
+    else if (dt == WS_F16) aff_combine_kernel<WS_F16><<<g, 256, 0, s>>>(x, x_ld, y, y_ld, t, t_ld, out, lo, out_ld, C, nvec);
+    else aff_combine_kernel<WS_F32><<<g, 256, 0, s>>>(x, x_ld, y, y_ld, t, t_ld, out, lo, out_ld, C, nvec);
     return last_err();
 }
 

@@ -27,6 +27,9 @@ const char* ws_launch_linear_rows(const float* in, long long in_ld, const float*
 const char* ws_launch_scale_residual(const void* x, long long x_ld, const float* gate, const void* res,
                                      long long res_ld, void* out, float* lo, long long out_ld, int dt, int B, int T,
                                      int C, cudaStream_t s);
+// ERes2Net AFF combine (eres2net.py:97-100): out[pos][c] = x * (1 + t) + y * (2 - (1 + t)), t = the tanh'd attention map
+const char* ws_launch_aff_combine(const void* x, long long x_ld, const void* y, long long y_ld, const void* t, long long t_ld,
+                                  void* out, float* lo, long long out_ld, int dt, long long npos, int C, cudaStream_t s);
 // ASTP statistics (pooling_layers.py:138-144): softmax over T of logits, weighted mean / std of x
 const char* ws_launch_astp_stats(const void* x, const void* logits, int dt, int B, int T, int C, long long ld,
                                  float* out /*[B][2C]*/, cudaStream_t s, const int* lens = nullptr);

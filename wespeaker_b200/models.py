@@ -20,10 +20,11 @@ import numpy as np
 import torch
 
 from . import lib as _lib
-from .synthetic import CAMPP_NAMES, DEFAULT_MODEL_ARGS, ECAPA_NAMES, RESNET_NAMES, XVEC_NAMES, state_dict_spec
+from .synthetic import (CAMPP_NAMES, DEFAULT_MODEL_ARGS, ECAPA_NAMES, RES2NET_NAMES, RESNET_NAMES, XVEC_NAMES,
+                        state_dict_spec)
 
 _IncompatibleKeys = namedtuple("IncompatibleKeys", ["missing_keys", "unexpected_keys"])
-SUPPORTED_MODELS = tuple(ECAPA_NAMES) + tuple(RESNET_NAMES) + tuple(CAMPP_NAMES) + tuple(XVEC_NAMES)
+SUPPORTED_MODELS = tuple(ECAPA_NAMES) + tuple(RESNET_NAMES) + tuple(CAMPP_NAMES) + tuple(XVEC_NAMES) + tuple(RES2NET_NAMES)
 
 
 class B200SpeakerModel(torch.nn.Module):
@@ -152,6 +153,19 @@ class B200SpeakerModel(torch.nn.Module):
                        "ws_engine_set_tensor")
         _lib.check(L.ws_engine_finalize(h), "ws_engine_finalize")
 
+    def plan_trace(self, path: str, batch: int = 1, frames: int = 200):
+        """Write the (batch, frames) launch plan as data (ws_engine_plan_trace; no device, nothing computed): tests re-evaluate
+        it on the host against the oracle (tests/plan_interp.py)."""
+        L = _lib.load()
+        h = _lib.c_engine_p()
+        _lib.check(L.ws_engine_create_plan_check(self.model_name.encode(), self.precision.encode(), self.feat_dim,
+                                                 self.embed_dim, C.byref(h)), "ws_engine_create_plan_check")
+        try:
+            self._configure(L, h)
+            _lib.check(L.ws_engine_plan_trace(h, batch, frames, path.encode()), "ws_engine_plan_trace")
+        finally:
+            L.ws_engine_destroy(h)
+
     def plan_check(self, batch: int = 1, frames: int = 200):
         """Validate the loaded checkpoint against the engine's plan builder WITHOUT a device (ws_engine_create_plan_check:
         nothing is computed): missing / mis-shaped tensors, kernel envelopes and tensor-map alignment rules raise B200Error.
@@ -207,8 +221,8 @@ class B200SpeakerModel(torch.nn.Module):
 
     def forward(self, features: torch.Tensor):
         emb = self.embed(features)
-        if self.model_name in CAMPP_NAMES:
-            return emb  # campplus.py:409-413 returns a bare tensor
+        if self.model_name in CAMPP_NAMES or self.model_name in RES2NET_NAMES:
+            return emb  # campplus.py:409-413, res2net.py:199, eres2net.py:391 return a bare tensor
         # ecapa_tdnn.py:234 returns (out4, emb); resnet.py:204 returns (tensor(0.), embed_a).  Callers use [-1].
         return torch.tensor(0.0), emb
 
