@@ -66,6 +66,18 @@ class Memory:
         return self.strided(v["p"], es, (B, F, T, C), (F * T * ld, T * ld, ld, 1), write)
 
 
+ROUND = None   # None: exact re-evaluation; "bf16" / "fp16": emulate the plan's 16-bit storage (activations and conv weights
+               # rounded where the kernels round them) to PREDICT the 16-bit paths' distance from the oracle
+
+
+def rnd(x, es):
+    if ROUND is None or es != 2:
+        return x
+    import torch
+    dt = torch.bfloat16 if ROUND == "bf16" else torch.float16
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dt).to(torch.float32).numpy().astype(np.float64)
+
+
 def act(x, code):
     if code == 0:
         return x
@@ -99,7 +111,7 @@ def run_conv(mem, tr):
         if tr[k]:
             raise NotImplementedError("conv epilogue feature " + k)
     B, F, T, Cout, K = tr["B"], tr["F"], tr["T"], tr["Cout"], tr["Ktot"]
-    W = mem.vec(tr["W"], Cout * K).reshape(Cout, K)
+    W = rnd(mem.vec(tr["W"], Cout * K).reshape(Cout, K), es)
     srcs = [mem.strided(s["p"], es, (s["B"], s["F"], s["T"], s["C"]), (s["sB"], s["sF"], s["sT"], 1)) for s in tr["src"]]
     acc = np.zeros((B, F, T, Cout))
     for si, c0, dt, df, wk, nch in tr["taps"]:
@@ -113,7 +125,7 @@ def run_conv(mem, tr):
     if tr["res"]:
         acc = acc + mem.view(dict(p=tr["res"], B=B, F=F, T=T, C=Cout, ld=tr["res_ld"]), es)
     acc = act(acc, tr["act2"])
-    mem.view(dict(p=tr["out"], B=B, F=F, T=T, C=Cout, ld=tr["out_ld"]), es, write=True)[...] = acc
+    mem.view(dict(p=tr["out"], B=B, F=F, T=T, C=Cout, ld=tr["out_ld"]), es, write=True)[...] = rnd(acc, es)
 
 
 def run_conv3x3(mem, tr):
@@ -123,7 +135,7 @@ def run_conv3x3(mem, tr):
     x = mem.view(tr["x"], es)
     o = tr["out"]
     Cin, Cout, sf, st = tr["x"]["C"], o["C"], tr["sf"], tr["st"]
-    W = mem.vec(tr["W"], Cout * 9 * Cin).reshape(Cout, 9, Cin)
+    W = rnd(mem.vec(tr["W"], Cout * 9 * Cin).reshape(Cout, 9, Cin), es)
     Fo, To = o["F"], o["T"]
     assert Fo == (x.shape[1] - 1) // sf + 1 and To == (x.shape[2] - 1) // st + 1
     acc = np.zeros((o["B"], Fo, To, Cout))
@@ -136,7 +148,7 @@ def run_conv3x3(mem, tr):
     if tr["res"] is not None:
         acc = acc + mem.view(tr["res"], es)
     acc = {0: acc, 1: np.maximum(acc, 0.0), 2: np.clip(acc, 0.0, 20.0)}[tr["relu"]]
-    mem.view(o, es, write=True)[...] = acc
+    mem.view(o, es, write=True)[...] = rnd(acc, es)
 
 
 def run_stem(mem, tr, meta):
@@ -152,7 +164,7 @@ def run_stem(mem, tr, meta):
         for jt in range(3):
             acc += shifted(x, jf - 1, jt - 1, Fd, T) * w9[:, jf * 3 + jt]
     acc = np.maximum(acc + mem.vec(tr["shift"], C), 0.0)
-    mem.view(o, tr["es"], write=True)[...] = acc
+    mem.view(o, tr["es"], write=True)[...] = rnd(acc, tr["es"])
 
 
 def run_tstats(mem, tr):
@@ -188,14 +200,14 @@ def run_aff_combine(mem, tr):
     es = tr["es"]
     x, y, t = mem.view(tr["x"], es), mem.view(tr["y"], es), mem.view(tr["t"], es)
     att = 1.0 + t
-    mem.view(tr["out"], es, write=True)[...] = x * att + y * (2.0 - att)
+    mem.view(tr["out"], es, write=True)[...] = rnd(x * att + y * (2.0 - att), es)
 
 
 def run_convert(mem, tr):
     n = tr["n"]
     mem.array(tr["out"], tr["es"])  # materialise with the right element size
     arr, off = mem.array(tr["out"], tr["es"])
-    arr[off:off + n] = mem.vec(tr["in"], n)
+    arr[off:off + n] = rnd(mem.vec(tr["in"], n), tr["es"])
 
 
 def run_plan(path, feats):
