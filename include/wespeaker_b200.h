@@ -25,7 +25,8 @@ const char* ws_last_error(void);
  *      (wespeaker/models/speaker_model.py:31-62, wespeaker/utils/checkpoint.py:20-85, wespeaker/bin/extract.py:68-79,133)
  *      and is the B200 back-end for `SpeakerModel::ExtractEmbedding` (runtime/core/speaker/speaker_model.h:25-32).
  * model_name: ECAPA_TDNN_c512 | ECAPA_TDNN_GLOB_c512 | ECAPA_TDNN_c1024 | ECAPA_TDNN_GLOB_c1024 | ResNet18 |
- *             ResNet34 | CAMPPlus.
+ *             ResNet34 | CAMPPlus; SURVEY section 8(f) rank 4: ResNet50 | ResNet101 | ResNet152 | ResNet221 | ResNet293 |
+ *             XVEC | Res2Net34_Base | Res2Net34_Large | ERes2Net34_Base | ERes2Net34_Large | ERes2Net34_aug.
  * precision:  "fp32" (exact IEEE fp32 FFMA path, parity <= 1e-4), "tf32x3" (tcgen05 with 3xTF32 error compensation,
  *             fp32-grade accuracy), "tf32", "bf16", "fp16" (tcgen05 tensor cores). */
 int ws_engine_create(const char* model_name, const char* precision, int feat_dim, int embed_dim, int device,
