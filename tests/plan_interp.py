@@ -5,7 +5,8 @@ activations - against the oracle on the CPU; the CUDA kernels that execute the s
 
 Memory model: every placeholder allocation becomes a flat float64 array indexed in ELEMENTS (address offset / element size of
 the tensor's dtype in the plan); values are never rounded, so a bf16 plan and an fp32 plan both reproduce the oracle to
-floating-point accuracy.  Ops the interpreter does not model (fused ECAPA / CAM++ kernels) raise NotImplementedError."""
+floating-point accuracy.  The fused kernels (Res2 chain, ASTP tail, CAM++ dense block, SE gate) are re-evaluated from their
+documented contracts (ws_host.h); length-masked plans are not modelled (NotImplementedError)."""
 import json
 import struct
 
@@ -107,10 +108,7 @@ def shifted(src, df, dt, F, T):
 
 def run_conv(mem, tr):
     es = tr["es"]
-    for k in ("rowbias", "gate", "out2", "add2", "colsum"):
-        if tr[k]:
-            raise NotImplementedError("conv epilogue feature " + k)
-    B, F, T, Cout, K = tr["B"], tr["F"], tr["T"], tr["Cout"], tr["Ktot"]
+    B, F, T, Cout, K = tr["B"], tr["F"], tr["T"], tr["Cout"], tr["Ktot"]   # (colsum, the fused SE squeeze, is a side output)
     W = rnd(mem.vec(tr["W"], Cout * K).reshape(Cout, K), es)
     srcs = [mem.strided(s["p"], es, (s["B"], s["F"], s["T"], s["C"]), (s["sB"], s["sF"], s["sT"], 1)) for s in tr["src"]]
     acc = np.zeros((B, F, T, Cout))
@@ -119,13 +117,23 @@ def run_conv(mem, tr):
         acc += x @ W[:, wk:wk + nch].T
     if tr["bias"]:
         acc += mem.vec(tr["bias"], Cout)
+    if tr["rowbias"]:      # per-utterance bias row (ECAPA global-context attention)
+        acc += mem.strided(tr["rowbias"], 4, (B, Cout), (tr["rowbias_ld"], 1))[:, None, None, :]
     acc = act(acc, tr["act1"])
     if tr["scale"]:
         acc = acc * mem.vec(tr["scale"], Cout) + mem.vec(tr["shift"], Cout)
+    if tr["gate"]:         # CAM context mask: gate[b][t / gate_seg][c]
+        nseg, gl = tr["gate_nseg"], tr["gate_ld"]
+        g = mem.strided(tr["gate"], 4, (B, nseg, Cout), (nseg * gl, gl, 1))
+        acc = acc * g[:, np.arange(T) // tr["gate_seg"], :][:, None]
     if tr["res"]:
         acc = acc + mem.view(dict(p=tr["res"], B=B, F=F, T=T, C=Cout, ld=tr["res_ld"]), es)
     acc = act(acc, tr["act2"])
-    mem.view(dict(p=tr["out"], B=B, F=F, T=T, C=Cout, ld=tr["out_ld"]), es, write=True)[...] = rnd(acc, es)
+    acc = rnd(acc, es)
+    mem.view(dict(p=tr["out"], B=B, F=F, T=T, C=Cout, ld=tr["out_ld"]), es, write=True)[...] = acc
+    if tr["out2"]:         # Res2 chain: s_{i+1} = sp_i + x_{i+1}
+        add2 = mem.view(dict(p=tr["add2"], B=B, F=F, T=T, C=Cout, ld=tr["add2_ld"]), es)
+        mem.view(dict(p=tr["out2"], B=B, F=F, T=T, C=Cout, ld=tr["out2_ld"]), es, write=True)[...] = rnd(acc + add2, es)
 
 
 def run_conv3x3(mem, tr):
@@ -210,6 +218,151 @@ def run_convert(mem, tr):
     arr[off:off + n] = rnd(mem.vec(tr["in"], n), tr["es"])
 
 
+def _dil_conv1d(x, W, dil):
+    """x (B,T,Cin), W (Cout,3,Cin) tap-major, zero padding `dil` -> (B,T,Cout): sum_j x[t + (j-1)*dil] @ W[:, j].T"""
+    B, T, _ = x.shape
+    out = np.zeros((B, T, W.shape[0]))
+    for j in range(3):
+        off = (j - 1) * dil
+        xs = shifted(x[:, None], 0, off, 1, T)[:, 0]
+        out += xs @ W[:, j].T
+    return out
+
+
+def run_res2_fused(mem, tr):
+    """ws_host.h make_res2_op: 7 dependent dilated k=3 convs on w8-channel groups (ecapa_tdnn.py:29-78):
+    sp_i = bn(relu(conv(s_i) + bias_i)), s_0 = x_0, s_{i+1} = sp_i + x_{i+1}; out groups 0..6 = sp_0..sp_6."""
+    if tr["lens"]:
+        raise NotImplementedError("masked res2")
+    es, w8, dil = tr["es"], tr["w8"], tr["dil"]
+    x = mem.view(tr["x"], es)[:, 0]                      # (B,T,8*w8)
+    out = mem.view(tr["out"], es, write=True)
+    W7 = rnd(mem.vec(tr["W7"], 7 * w8 * 3 * w8).reshape(7, w8, 3, w8), es)
+    bias, scale, shift = (mem.vec(tr[k], 7 * w8).reshape(7, w8) for k in ("bias", "scale", "shift"))
+    s = x[..., :w8]
+    for i in range(7):
+        sp = rnd(np.maximum(_dil_conv1d(s, W7[i], dil) + bias[i], 0.0) * scale[i] + shift[i], es)
+        out[:, 0, :, i * w8:(i + 1) * w8] = sp
+        if i < 6:
+            s = rnd(sp + x[..., (i + 1) * w8:(i + 2) * w8], es)
+
+
+def run_se_gate(mem, tr):
+    """gate[b][c] = sigmoid(W2 relu(W1 mean_T(x[b]) + b1) + b2); W2t is W2 transposed to [H][C] (ecapa_tdnn.py:113-126)."""
+    if tr["lens"]:
+        raise NotImplementedError("masked se_gate")
+    x = mem.view(tr["x"], tr["es"])[:, 0]
+    B, T, C = x.shape
+    H = tr["H"]
+    W1 = mem.vec(tr["W1"], H * C).reshape(H, C)
+    W2t = mem.vec(tr["W2t"], H * C).reshape(H, C)
+    hid = np.maximum(x.mean(axis=1) @ W1.T + mem.vec(tr["b1"], H), 0.0)
+    mem.strided(tr["gate"], 4, (B, C), (C, 1), write=True)[...] = act(hid @ W2t + mem.vec(tr["b2"], C), 3)
+
+
+def run_scale_residual(mem, tr):
+    es = tr["es"]
+    x, res = mem.view(tr["x"], es), mem.view(tr["res"], es)
+    B, _, T, C = x.shape
+    gate = mem.strided(tr["gate"], 4, (B, C), (C, 1))
+    mem.view(tr["out"], es, write=True)[...] = rnd(x * gate[:, None, None, :] + res, es)
+
+
+def _astp(x, logits):
+    """pooling_layers.py:140-144: softmax over T, weighted mean and sqrt(clamp(E[x^2] - mean^2, 1e-7))."""
+    a = np.exp(logits - logits.max(axis=1, keepdims=True))
+    a /= a.sum(axis=1, keepdims=True)
+    mean = (a * x).sum(axis=1)
+    var = (a * x * x).sum(axis=1) - mean * mean
+    return np.concatenate([mean, np.sqrt(np.maximum(var, 1e-7))], axis=1)
+
+
+def run_astp_fused(mem, tr):
+    """ws_host.h make_astp_op: logits = h @ W2^T (linear2's bias cancels in the softmax over time)."""
+    if tr["lens"]:
+        raise NotImplementedError("masked astp")
+    es = tr["es"]
+    x, h = mem.view(tr["x"], es)[:, 0], mem.view(tr["h"], es)[:, 0]
+    B, T, C = x.shape
+    W2 = rnd(mem.vec(tr["W2"], C * 128).reshape(C, 128), es)
+    mem.strided(tr["stats"], 4, (B, 2 * C), (2 * C, 1), write=True)[...] = _astp(x, h @ W2.T)
+
+
+def run_astp_stats(mem, tr):
+    if tr["lens"]:
+        raise NotImplementedError("masked astp")
+    es = tr["es"]
+    x, lg = mem.view(tr["x"], es)[:, 0], mem.view(tr["logits"], es)[:, 0]
+    B, T, C = x.shape
+    mem.strided(tr["stats"], 4, (B, 2 * C), (2 * C, 1), write=True)[...] = _astp(x, lg)
+
+
+def run_bnrelu(mem, tr):
+    es, C = tr["es"], tr["C"]
+    x = mem.view(tr["x"], es)[..., :C]
+    mem.view(tr["out"], es, write=True)[..., :C] = rnd(np.maximum(x * mem.vec(tr["scale"], C) + mem.vec(tr["shift"], C), 0.0), es)
+
+
+def _cam_context(h, seg_len):
+    """campplus.py:108-135: mean over T + per-segment means (avg_pool1d, ceil_mode: the last segment averages its own frames),
+    one context vector per segment: (B, nseg, C)."""
+    B, T, C = h.shape
+    nseg = (T + seg_len - 1) // seg_len
+    seg = np.stack([h[:, s * seg_len:min(T, (s + 1) * seg_len)].mean(axis=1) for s in range(nseg)], axis=1)
+    return h.mean(axis=1)[:, None, :] + seg
+
+
+def run_cam_gate(mem, tr):
+    es, H, G, L = tr["es"], tr["H"], tr["G"], tr["seg_len"]
+    h = mem.view(tr["x"], es)[:, 0]
+    B, T, C = h.shape
+    ctx = _cam_context(h, L)
+    W1 = mem.vec(tr["W1"], H * C).reshape(H, C)
+    W2 = mem.vec(tr["W2"], G * H).reshape(G, H)
+    hid = np.maximum(ctx @ W1.T + mem.vec(tr["b1"], H), 0.0)
+    nseg = ctx.shape[1]
+    mem.strided(tr["gate"], 4, (B, nseg, G), (nseg * G, G, 1), write=True)[...] = act(hid @ W2.T + mem.vec(tr["b2"], G), 3)
+
+
+def run_seg_means(mem, tr):
+    es, L = tr["es"], tr["seg_len"]
+    h = mem.view(tr["x"], es)[:, 0]
+    B, T, C = h.shape
+    nseg = (T + L - 1) // L
+    mem.strided(tr["mean"], 4, (B, C), (C, 1), write=True)[...] = h.mean(axis=1)
+    seg = np.stack([h[:, s * L:min(T, (s + 1) * L)].mean(axis=1) for s in range(nseg)], axis=1)
+    mem.strided(tr["segmean"], 4, (B, nseg, C), (nseg * C, C, 1), write=True)[...] = seg
+
+
+def run_cam_dense(mem, tr):
+    """ws_host.h make_cam_dense_op / campplus.py:86-201, per layer: h = relu(W1 relu(bn1(x[:, :cin])) + bias2) (BN2 folded into
+    W1), context mask m = sigmoid(W2c relu(W1c (mean_T(h) + segmean(h)) + b1c) + b2c) per 100-frame segment,
+    x[:, cin:cin+32] = (k3 dilated conv of h) * m."""
+    if tr["lens"]:
+        raise NotImplementedError("masked cam_dense")
+    es, L = tr["es"], tr["seg_len"]
+    X = mem.view(tr["X"], es, write=True)
+    B, _, T, _ = X.shape
+    for ly in tr["layers"]:
+        cin, dil = ly["cin"], ly["dil"]
+        xin = rnd(np.maximum(X[:, 0, :, :cin] * mem.vec(ly["bn1_scale"], cin) + mem.vec(ly["bn1_shift"], cin), 0.0), es)
+        W1 = rnd(mem.vec(ly["W1"], 128 * cin).reshape(128, cin), es)
+        h = rnd(np.maximum(xin @ W1.T + mem.vec(ly["bias2"], 128), 0.0), es)
+        ctx = _cam_context(h, L)                                           # (B,nseg,128)
+        w1c_t = mem.vec(ly["w1c_t"], 128 * 64).reshape(128, 64)
+        w2c_t = mem.vec(ly["w2c_t"], 64 * 32).reshape(64, 32)
+        m = act(np.maximum(ctx @ w1c_t + mem.vec(ly["b1c"], 64), 0.0) @ w2c_t + mem.vec(ly["b2c"], 32), 3)   # (B,nseg,32)
+        Wl = rnd(mem.vec(ly["Wl"], 32 * 3 * 128).reshape(32, 3, 128), es)
+        y = _dil_conv1d(h, Wl, dil)
+        seg_of_t = np.arange(T) // L
+        X[:, 0, :, cin:cin + 32] = rnd(y * m[:, seg_of_t, :], es)
+
+
+EXTRA = {"res2_fused": run_res2_fused, "se_gate": run_se_gate, "scale_residual": run_scale_residual, "astp_fused": run_astp_fused,
+         "astp_stats": run_astp_stats, "bnrelu": run_bnrelu, "cam_gate": run_cam_gate, "seg_means": run_seg_means,
+         "cam_dense": run_cam_dense}
+
+
 def run_plan(path, feats):
     """feats (B,T,feat_dim) float -> embeddings (B,embed_dim) float64 by re-evaluating the traced plan on the host."""
     meta, blob = load_trace(path)
@@ -237,6 +390,8 @@ def run_plan(path, feats):
             run_aff_combine(mem, tr)
         elif kind == "convert":
             run_convert(mem, tr)
+        elif kind in EXTRA:
+            EXTRA[kind](mem, tr)
         else:
             raise NotImplementedError(kind)
     return mem.vec(meta["emb"], B * E).reshape(B, E).copy(), meta

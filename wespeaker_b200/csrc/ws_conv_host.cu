@@ -61,7 +61,7 @@ static std::string conv_trace(const ConvSpec& s) {
     const WsEpi& e = s.epi;
     j += "],\"W\":" + jp(s.W) + "," + jv("Ktot", s.Ktot) + "," + jv("Cout", s.Cout) + "," + jv("B", s.B) + "," + jv("F", s.F) + "," + jv("T", s.T) +
          ",\"bias\":" + jp(e.bias) + ",\"rowbias\":" + jp(e.rowbias) + "," + jv("rowbias_ld", e.rowbias_ld) + "," + jv("act1", e.act1) + ",\"scale\":" + jp(e.scale) +
-         ",\"shift\":" + jp(e.shift) + ",\"gate\":" + jp(e.gate) + ",\"res\":" + jp(e.res) + "," + jv("res_ld", e.res_ld) + "," + jv("act2", e.act2) + ",\"out\":" + jp(e.out) +
+         ",\"shift\":" + jp(e.shift) + ",\"gate\":" + jp(e.gate) + "," + jv("gate_ld", e.gate_ld) + "," + jv("gate_seg", e.gate_seg) + "," + jv("gate_nseg", e.gate_nseg) + ",\"res\":" + jp(e.res) + "," + jv("res_ld", e.res_ld) + "," + jv("act2", e.act2) + ",\"out\":" + jp(e.out) +
          "," + jv("out_ld", e.out_ld) + ",\"out2\":" + jp(e.out2) + "," + jv("out2_ld", e.out2_ld) + ",\"add2\":" + jp(e.add2) + "," + jv("add2_ld", e.add2_ld) +
          ",\"colsum\":" + jp(e.colsum) + "}";
     return j;
@@ -521,6 +521,9 @@ bool make_res2_op(const View& x, const View& out, const void* W7, const float* b
     const long long units = (long long)x.B * q->ntile;
     q->grid = (int)(units < slots ? units : slots);
     *op = [q](cudaStream_t s) { return ws_res2_launch(q.get(), s); };
+    if (plan_check_mode())
+        set_op_trace("{\"kind\":\"res2_fused\",\"es\":2,\"x\":" + view_json(x) + ",\"out\":" + view_json(out) + ",\"W7\":" + jp(W7) + ",\"bias\":" + jp(bias) +
+                     ",\"scale\":" + jp(scale) + ",\"shift\":" + jp(shift) + "," + jv("w8", w8) + "," + jv("dil", dil) + ",\"lens\":" + jp(lens) + "}");
     {
         char buf[160];
         snprintf(buf, sizeof buf, "res2_fused B=%d T=%d C=%d", x.B, x.T, x.C);
@@ -598,6 +601,9 @@ bool make_astp_op(const View& x, const View& h, const void* W2, float* stats, Op
         return true;
     }
     *op = [q](cudaStream_t s) { return ws_astp_launch(q.get(), s); };
+    if (plan_check_mode())
+        set_op_trace("{\"kind\":\"astp_fused\",\"es\":2,\"x\":" + view_json(x) + ",\"h\":" + view_json(h) + ",\"W2\":" + jp(W2) + ",\"stats\":" + jp(stats) +
+                     ",\"lens\":" + jp(lens) + "}");
     {
         char buf[160];
         snprintf(buf, sizeof buf, "astp_fused B=%d T=%d C=%d g=%d grid=%d", x.B, x.T, x.C, q->g, q->grid);

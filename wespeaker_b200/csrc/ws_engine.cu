@@ -504,6 +504,8 @@ bool build_ecapa(Builder& b) {
             const int dt = e.act_dt;
             const float* cs_in = se_colsum;
             const int* l0 = b.lens(0);
+            set_op_trace("{\"kind\":\"se_gate\"," + Builder::ti("es", ws_esize(dt)) + "," + Builder::tview("x", tc) + "," + Builder::tp("W1", w1d) + "," + Builder::tp("b1", b1d) + "," +
+                         Builder::tp("W2t", w2d) + "," + Builder::tp("b2", b2d) + "," + Builder::ti("H", 128) + "," + Builder::tp("gate", segate) + "," + Builder::tp("lens", l0) + "}");
             b.push([=](cudaStream_t s) { return ws_launch_se_gate(tc.p, dt, B, T, C, tc.ld, w1d, b1d, w2d, b2d, 128, segate, cs_in, s, l0); }, "se_gate");
         } else {
             b.tstats(tC, nullptr, nullptr, semean, C, -1);
@@ -515,6 +517,8 @@ bool build_ecapa(Builder& b) {
         {
             View o = cat.ch((L - 2) * C, C), xi = xin, tc = tC;
             const int dt = e.act_dt;
+            set_op_trace("{\"kind\":\"scale_residual\"," + Builder::ti("es", ws_esize(dt)) + "," + Builder::tview("x", tc) + "," + Builder::tp("gate", segate) + "," +
+                         Builder::tview("res", xi) + "," + Builder::tview("out", o) + "}");
             b.push([=](cudaStream_t s) {
                 return ws_launch_scale_residual(tc.p, tc.ld, segate, xi.p, xi.ld, o.p, (float*)o.plo, o.ld, dt, B, T, C, s);
             }, "scale_residual");
@@ -578,6 +582,8 @@ bool build_ecapa(Builder& b) {
             ep2.bias = b.w.vec("pool.linear2.bias");
             b.conv_simple(hid, logits, W2d, 1, 1, 1, 1, 0, 0, 1, 1, ep2);
             View fr = frame, lg = logits;
+            set_op_trace("{\"kind\":\"astp_stats\"," + Builder::ti("es", ws_esize(fr.dt)) + "," + Builder::tview("x", fr) + "," + Builder::tview("logits", lg) + "," +
+                         Builder::tp("stats", stats) + "," + Builder::tp("lens", l0) + "}");
             b.push([=](cudaStream_t s) { return ws_launch_astp_stats(fr.p, lg.p, fr.dt, B, T, 1536, fr.ld, stats, s, l0); }, "astp_stats");
         }
     }
@@ -1349,6 +1355,7 @@ bool build_campplus(Builder& b) {
         bool fused_done = false;
         if (cam_fused) {
             std::vector<WsCamLayer> hl((size_t)nl[bl]);
+            std::vector<std::string> hl_trace((size_t)nl[bl]);   // plan-check engines: what each layer descriptor points at
             bool okl = true;
             for (int j = 1; j <= nl[bl] && okl; ++j) {
                 const std::string p = "xvector.block" + std::to_string(bl + 1) + ".tdnnd" + std::to_string(j);
@@ -1366,10 +1373,20 @@ bool build_campplus(Builder& b) {
                     for (int c = 0; c < bnc; ++c) w1ct[(size_t)c * (bnc / 2) + o] = c1w->v[(size_t)o * bnc + c];
                 for (int g = 0; g < growth; ++g)
                     for (int o = 0; o < bnc / 2; ++o) w2ct[(size_t)o * growth + g] = c2w->v[(size_t)g * (bnc / 2) + o];
-                okl = cam_layer_fill(&hl[(size_t)j - 1], e.act_dt, b.w.act("w:" + p + ".linear1", w1), b.w.act("w:" + p + ".local", wl),
-                                     b.w.f32("bns:" + p + ".n1", s1), b.w.f32("bnh:" + p + ".n1", h1), b.w.f32("bnh:" + p + ".n2", h2),
-                                     b.w.f32("w1ct:" + p, w1ct), b.w.vec(p + ".cam_layer.linear1.bias"), b.w.f32("w2ct:" + p, w2ct),
-                                     b.w.vec(p + ".cam_layer.linear2.bias"), cin, dil[bl]);
+                const void* W1d = b.w.act("w:" + p + ".linear1", w1);
+                const void* Wld = b.w.act("w:" + p + ".local", wl);
+                const float* s1d = b.w.f32("bns:" + p + ".n1", s1);
+                const float* h1d = b.w.f32("bnh:" + p + ".n1", h1);
+                const float* h2d = b.w.f32("bnh:" + p + ".n2", h2);
+                const float* w1cd = b.w.f32("w1ct:" + p, w1ct);
+                const float* b1cd = b.w.vec(p + ".cam_layer.linear1.bias");
+                const float* w2cd = b.w.f32("w2ct:" + p, w2ct);
+                const float* b2cd = b.w.vec(p + ".cam_layer.linear2.bias");
+                okl = cam_layer_fill(&hl[(size_t)j - 1], e.act_dt, W1d, Wld, s1d, h1d, h2d, w1cd, b1cd, w2cd, b2cd, cin, dil[bl]);
+                if (plan_check_mode())
+                    hl_trace[(size_t)j - 1] = "{" + Builder::tp("W1", W1d) + "," + Builder::tp("Wl", Wld) + "," + Builder::tp("bn1_scale", s1d) + "," + Builder::tp("bn1_shift", h1d) +
+                                              "," + Builder::tp("bias2", h2d) + "," + Builder::tp("w1c_t", w1cd) + "," + Builder::tp("b1c", b1cd) + "," + Builder::tp("w2c_t", w2cd) + "," +
+                                              Builder::tp("b2c", b2cd) + "," + Builder::ti("cin", cin) + "," + Builder::ti("dil", dil[bl]) + "}";
             }
             if (!okl || !b.good()) { b.ok = false; break; }
             const WsCamLayer* ldev = (const WsCamLayer*)b.w.upload("camlayers:" + std::to_string(bl), hl.data(), hl.size() * sizeof(WsCamLayer));
@@ -1379,7 +1396,16 @@ bool build_campplus(Builder& b) {
             for (int j = 0; j < nl[bl]; j += whole ? nl[bl] : 1) {
                 Op op;
                 bool unsupported = false;
-                if (make_cam_dense_op(X[bl], ldev, j, whole ? nl[bl] : j + 1, &op, &unsupported, b.lens(1))) b.push(std::move(op));
+                if (make_cam_dense_op(X[bl], ldev, j, whole ? nl[bl] : j + 1, &op, &unsupported, b.lens(1))) {
+                    if (plan_check_mode()) {   // semantic description of the fused launch: layers [j, j1) over the concat buffer
+                        const int j1 = whole ? nl[bl] : j + 1;
+                        std::string tr = "{\"kind\":\"cam_dense\"," + Builder::ti("es", ws_esize(e.act_dt)) + "," + Builder::tview("X", X[bl]) + "," + Builder::tp("lens", b.lens(1)) +
+                                         "," + Builder::ti("seg_len", 100) + ",\"layers\":[";
+                        for (int k = j; k < j1; ++k) tr += std::string(k > j ? "," : "") + hl_trace[(size_t)k];
+                        set_op_trace(tr + "]}");
+                    }
+                    b.push(std::move(op));
+                }
                 else if (unsupported && j == 0) { fused_done = false; break; }
                 else { b.ok = false; break; }
             }
@@ -1400,6 +1426,8 @@ bool build_campplus(Builder& b) {
             View sv = scratch; sv.C = cin; sv.ld = cin;
             const float* s1d = b.w.f32("bns:" + p + ".n1", s1);
             const float* h1d = b.w.f32("bnh:" + p + ".n1", h1);
+            set_op_trace("{\"kind\":\"bnrelu\"," + Builder::ti("es", ws_esize(dt)) + "," + Builder::tview("x", xs) + "," + Builder::tp("scale", s1d) + "," + Builder::tp("shift", h1d) + "," +
+                         Builder::tview("out", sv) + "," + Builder::ti("C", cin) + "}");
             b.push([=](cudaStream_t st) { return ws_launch_bnrelu(xs.p, xs.ld, s1d, h1d, sv.p, (float*)sv.plo, sv.ld, dt, npos, cin, st); }, "bnrelu");
             // linear1 (1x1, no bias) + nonlinear2 (BN folded) + ReLU -> hid
             WsEpi e1{};
@@ -1415,10 +1443,15 @@ bool build_campplus(Builder& b) {
                 const float* b2c = b.w.vec(p + ".cam_layer.linear2.bias");
                 const size_t cam_smem = (size_t)((bnc / 2) * bnc + nseg * bnc + 16 * bnc + nseg * (bnc / 2) + bnc) * 4;
                 if (cam_smem <= 48 * 1024) {
+                    set_op_trace("{\"kind\":\"cam_gate\"," + Builder::ti("es", ws_esize(dt)) + "," + Builder::tview("x", hv) + "," + Builder::ti("seg_len", 100) + "," + Builder::tp("W1", w1c) + "," +
+                                 Builder::tp("b1", b1c) + "," + Builder::tp("W2", w2c) + "," + Builder::tp("b2", b2c) + "," + Builder::ti("H", bnc / 2) + "," + Builder::ti("G", growth) + "," +
+                                 Builder::tp("gate", cgate) + "}");
                     b.push([=](cudaStream_t st) {
                         return ws_launch_cam_gate(hv.p, dt, B, Tp, bnc, hv.ld, 100, w1c, b1c, w2c, b2c, bnc / 2, growth, cgate, st);
                     }, "cam_gate");
                 } else {  // very long utterances: unfused path
+                    set_op_trace("{\"kind\":\"seg_means\"," + Builder::ti("es", ws_esize(dt)) + "," + Builder::tview("x", hv) + "," + Builder::ti("seg_len", 100) + "," + Builder::tp("mean", cmean) + "," +
+                                 Builder::tp("segmean", csegm) + "}");
                     b.push([=](cudaStream_t st) { return ws_launch_seg_means(hv.p, dt, B, Tp, bnc, hv.ld, 100, cmean, csegm, st); }, "seg_means");
                     b.linear(csegm, bnc, cmean, bnc, nseg, w1c, b1c, chid, bnc / 2, B * nseg, bnc, bnc / 2, WS_ACT_RELU);
                     b.linear(chid, bnc / 2, nullptr, 0, 1, w2c, b2c, cgate, growth, B * nseg, bnc / 2, growth, WS_ACT_SIGMOID);
@@ -1440,6 +1473,8 @@ bool build_campplus(Builder& b) {
         const float* sd_ = b.w.f32("bns:" + tp, s);
         const float* hd_ = b.w.f32("bnh:" + tp, h);
         const int cc = cmax[bl];
+        set_op_trace("{\"kind\":\"bnrelu\"," + Builder::ti("es", ws_esize(dt)) + "," + Builder::tview("x", xs) + "," + Builder::tp("scale", sd_) + "," + Builder::tp("shift", hd_) + "," +
+                     Builder::tview("out", sv) + "," + Builder::ti("C", cc) + "}");
         b.push([=](cudaStream_t st) { return ws_launch_bnrelu(xs.p, xs.ld, sd_, hd_, sv.p, (float*)sv.plo, sv.ld, dt, npos, cc, st); }, "bnrelu");
         WsEpi et{};
         View dst = (bl < 2) ? X[bl + 1].ch(0, cmax[bl] / 2) : Xf;
