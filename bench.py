@@ -51,6 +51,15 @@ WORKLOADS = {
     "ecapa1024_tf32x3_b256": ("ECAPA_TDNN_c1024", "tf32x3", 256, 32320, 5.141),
 }
 DEFAULT_WORKLOAD = "ecapa1024_bf16_b256"
+# Not BASELINE configs: reported beside them in "extras" (N = 1 only).  Batch 1 is how the reference extracts every test set
+# (examples/voxceleb/v2/local/extract_vox.sh:31: one whole utterance per forward); the last two are SURVEY section 8(f) rank-4
+# families on the existing operators.  (model, precision, batch, samples per utterance)
+EXTRA_WORKLOADS = {
+    "ecapa512_tf32x3_b1": ("ECAPA_TDNN_c512", "tf32x3", 1, 32320),
+    "ecapa512_bf16_b1": ("ECAPA_TDNN_c512", "bf16", 1, 32320),
+    "res2net34_fp16_b64": ("Res2Net34_Base", "fp16", 64, 32320),
+    "eres2net34_fp16_b64": ("ERes2Net34_Base", "fp16", 64, 32320),
+}
 METRIC = "utterances/s (2s@16kHz) embedding extraction"
 DTYPE_NAME = {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3", "bf16": "bf16", "fp16": "f16"}
 # bars for `parity_rel_l2` (max over the checked utterances of |e - e_ref|_2 / |e_ref|_2), as in tests/test_gpu_parity.py
@@ -665,6 +674,19 @@ def main():
         configs["campplus_bf16_varlen"] = varlen_leg(args.steps, args.warmup, dev, rank, world, parallel, peaks, sampler)
         if not args.no_plda:
             configs["plda_1Mx100k"] = plda_leg(dev, rank, world, parallel, peaks)
+    extras = None
+    if not args.no_configs and world == 1:
+        extras = {}
+        for name, (m, pr, b, ns) in EXTRA_WORKLOADS.items():
+            try:   # an extra must never cost the line its contract fields
+                r = model_leg(name, m, pr, b, ns, 0.0, args.steps, args.warmup, dev, rank, world, parallel, peaks, sampler, parity_n=min(2, b))
+                for k in ("step_tflops_per_gpu", "step_frac_of_sustained"):
+                    r.pop(k, None)
+                if b == 1:
+                    r["latency_ms_per_utt"] = r["ms_per_step"]
+                extras[name] = r
+            except Exception as ex:
+                extras[name] = {"workload": name, "error": repr(ex)[:300]}
     if sampler:
         last = sampler.stop()
         if clocks is None:     # nvidia-smi fallback: one window over the whole run
@@ -711,7 +733,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": B * nsamples * 2, "d2h_bytes_per_step": B * embed_dim * 4,
                 "api": "B200SpeakerModel.extract_stream(pinned int16 PCM host batches): H2D + fbank + CMN + forward + D2H per step, copy/compute overlapped over 4 slots; best of 3 windows of K steps"},
         "gpu_launches": int(launches_per_step * args.steps),
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity, "sustained": sustained, "configs": configs,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity, "sustained": sustained, "configs": configs, "extras": extras,
     }
     if configs and "plda_1Mx100k" in configs:
         line["plda"] = configs["plda_1Mx100k"]

@@ -71,7 +71,28 @@ ROUND = None   # None: exact re-evaluation; "bf16" / "fp16": emulate the plan's 
                # rounded where the kernels round them) to PREDICT the 16-bit paths' distance from the oracle
 
 
+def _tf32_trunc(a):
+    return (np.ascontiguousarray(a, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def tf32x3_matmul(x, Wt):
+    """The engine's 3xTF32 product x @ Wt as the tensor core sees it (ROUND = "tf32x3" or "tf32x3_trunc_lo"): operands are
+    truncated to tf32; x_lo * W_hi + x_hi * W_lo + x_hi * W_hi with lo = the residual rounded to the nearest tf32 (the engine's
+    ws_tf32_lo) or, for comparison, left to the hardware's truncation."""
+    def split(a):
+        a32 = np.ascontiguousarray(a, dtype=np.float32)
+        hi = _tf32_trunc(a32)
+        d = a32 - hi
+        lo = ((d.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32) if ROUND == "tf32x3" else _tf32_trunc(d)
+        return hi.astype(np.float64), lo.astype(np.float64)
+    xh, xl = split(x)
+    wh, wl = split(Wt)
+    return xl @ wh + xh @ wl + xh @ wh
+
+
 def rnd(x, es):
+    if ROUND in ("tf32x3", "tf32x3_trunc_lo"):
+        return np.asarray(x, np.float32).astype(np.float64) if es == 4 else x   # fp32 storage
     if ROUND is None or es != 2:
         return x
     import torch
@@ -114,7 +135,7 @@ def run_conv(mem, tr):
     acc = np.zeros((B, F, T, Cout))
     for si, c0, dt, df, wk, nch in tr["taps"]:
         x = shifted(srcs[si][..., c0:c0 + nch], df, dt, F, T)
-        acc += x @ W[:, wk:wk + nch].T
+        acc += tf32x3_matmul(x, W[:, wk:wk + nch].T) if ROUND in ("tf32x3", "tf32x3_trunc_lo") and es == 4 else x @ W[:, wk:wk + nch].T
     if tr["bias"]:
         acc += mem.vec(tr["bias"], Cout)
     if tr["rowbias"]:      # per-utterance bias row (ECAPA global-context attention)
