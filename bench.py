@@ -720,6 +720,22 @@ def main():
         cpu = {"value": nst * pool.utts_per_step / cdt, "unit": "utt/s", "cores": pool.active * pool.threads, "kind": "port",
                "sample": f"{nst} pool steps in {cdt:.1f} s; " + pool.describe(nsamples)}
         pool.close()
+        try:
+            # the reference-faithful mode: one whole utterance per forward, as the reference extracts every test set
+            # (examples/voxceleb/v2/local/extract_vox.sh:31: batch size 1); one process, 8 torch threads, ~3 s
+            th0 = torch.get_num_threads()
+            torch.set_num_threads(min(8, os.cpu_count() or 1))
+            one = _cpu_path(model_name, nsamples, 1)
+            one()
+            n1, t1 = 0, time.perf_counter()
+            while time.perf_counter() - t1 < 3.0:
+                one(); n1 += 1
+            d1 = time.perf_counter() - t1
+            torch.set_num_threads(th0)
+            cpu["batch1"] = {"value": n1 / d1, "unit": "utt/s", "latency_ms_per_utt": 1e3 * d1 / n1, "cores": min(8, os.cpu_count() or 1),
+                             "sample": f"{n1} utterances one at a time in {d1:.1f} s, one process"}
+        except Exception as ex:
+            cpu["batch1"] = {"error": repr(ex)[:200]}
     act_mb = B * L_frames * (1536 * 2 + 128 + (1024 if '1024' in model_name else 512) * 7) * (4 if prec in ("fp32", "tf32", "tf32x3") else 2) / 1e6
     line = {
         "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
