@@ -17,9 +17,10 @@ from wespeaker_b200 import synthetic as syn
 from wespeaker_b200.models import from_synthetic
 
 
-def _run(name, prec, B, T, opts=None, seed=5, round_as=None):
+def _run(name, prec, B, T, opts=None, seed=5, round_as=None, model_args=None):
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    m = from_synthetic(name, precision=prec)
+    model_args = model_args or {}
+    m = from_synthetic(name, precision=prec, **model_args)
     for k, v in (opts or {}).items():
         m.set_option(k, v)
     import tempfile
@@ -32,7 +33,7 @@ def _run(name, prec, B, T, opts=None, seed=5, round_as=None):
             emb, meta = plan_interp.run_plan(path, feats)
         finally:
             plan_interp.ROUND = None
-    ref = models_torch.forward(name, syn.make_state_dict(name, 0), feats).numpy()
+    ref = models_torch.forward(name, syn.make_state_dict(name, 0, **model_args), feats, **model_args).numpy()
     rel = np.linalg.norm(emb - ref, axis=1) / np.linalg.norm(ref, axis=1)
     return rel.max(), {op["trace"]["kind"] for op in meta["ops"]}
 
@@ -65,3 +66,14 @@ def test_16bit_storage_roundings_explain_the_16bit_distance(name, prec, B, T, ba
     16-bit deviation is the arithmetic of 16-bit storage, not a property of the kernels."""
     rel, _ = _run(name, prec, B, T, None, seed=23, round_as=prec)
     assert rel < bar and 0.5 * gpu_measured < rel < 2.0 * gpu_measured, (rel, gpu_measured)
+
+
+@pytest.mark.parametrize("name,prec,B,T,model_args", [
+    ("ResNet34", "fp16", 1, 64, dict(two_emb_layer=True)),          # seg_bn_1 (affine=False) folded into seg_2
+    ("ECAPA_TDNN_c512", "bf16", 1, 99, dict(emb_bn=True)),           # bn2 folded into the embedding linear
+    ("ERes2Net34_Base", "fp16", 1, 48, dict(two_emb_layer=True)),
+    ("ResNet221", "bf16", 1, 40, {}),                                # 73 Bottleneck blocks
+])
+def test_model_arg_variants_and_deep_plans(name, prec, B, T, model_args):
+    rel, _ = _run(name, prec, B, T, model_args=model_args)
+    assert rel < 5e-6, rel
