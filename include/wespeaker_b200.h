@@ -103,7 +103,7 @@ int ws_engine_profile_ops(ws_engine* e, int B, int T, int iters, float* ms_out, 
 const char* ws_engine_plan_op_name(ws_engine* e, int B, int T, int i, double* flops_out);   /* label + FLOPs of op i */
 /* plan-check engines only: write the (B,T) launch plan as data (JSON op descriptions + placeholder allocation table + fp32
  * weight sources) so that a test can re-evaluate the plan's arithmetic on the host (tests/plan_interp.py) */
-int ws_engine_plan_trace(ws_engine* e, int B, int T, const char* path);
+int ws_engine_plan_trace(ws_engine* e, int B, int T, int masked, const char* path);   /* masked: the length-masked plan of (B,T) */
 /* number of this library's kernels launched by the most recent forward/extract call */
 long long ws_engine_last_launches(const ws_engine* e);
 void ws_engine_destroy(ws_engine* e);

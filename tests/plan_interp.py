@@ -6,7 +6,8 @@ activations - against the oracle on the CPU; the CUDA kernels that execute the s
 Memory model: every placeholder allocation becomes a flat float64 array indexed in ELEMENTS (address offset / element size of
 the tensor's dtype in the plan); values are never rounded, so a bf16 plan and an fp32 plan both reproduce the oracle to
 floating-point accuracy.  The fused kernels (Res2 chain, ASTP tail, CAM++ dense block, SE gate) are re-evaluated from their
-documented contracts (ws_host.h); length-masked plans are not modelled (NotImplementedError)."""
+documented contracts (ws_host.h).  Length-masked plans are modelled for the 2-D families (stem / 3x3 conv / zero_tail / TSTP
+over each utterance's own frames); the masked fused ECAPA / CAM++ kernels raise NotImplementedError."""
 import json
 import struct
 
@@ -159,8 +160,6 @@ def run_conv(mem, tr):
 
 def run_conv3x3(mem, tr):
     es = tr["es"]
-    if tr["lens"]:
-        raise NotImplementedError("masked conv3x3")
     x = mem.view(tr["x"], es)
     o = tr["out"]
     Cin, Cout, sf, st = tr["x"]["C"], o["C"], tr["sf"], tr["st"]
@@ -177,39 +176,42 @@ def run_conv3x3(mem, tr):
     if tr["res"] is not None:
         acc = acc + mem.view(tr["res"], es)
     acc = {0: acc, 1: np.maximum(acc, 0.0), 2: np.clip(acc, 0.0, 20.0)}[tr["relu"]]
+    if tr["lens"]:      # length-masked batch: output rows behind an utterance's end are stored as zeros
+        acc = acc * (np.arange(To)[None, :] < mem.vec(tr["lens"], o["B"])[:, None])[:, None, :, None]
     mem.view(o, es, write=True)[...] = rnd(acc, es)
 
 
 def run_stem(mem, tr, meta):
-    if tr["lens"]:
-        raise NotImplementedError("masked stem")
     o = tr["out"]
     B, Fd, T, C = o["B"], o["F"], o["T"], o["C"]
     feats = mem.vec(tr["feats"], B * T * Fd).reshape(B, T, Fd)
+    valid = np.ones((B, T), bool)
+    if tr["lens"]:      # frames behind an utterance's end are padding: read as zeros, written as zeros
+        valid = np.arange(T)[None, :] < mem.vec(tr["lens"], B)[:, None]
+        feats = feats * valid[:, :, None]
     w9 = mem.vec(tr["w9"], C * 9).reshape(C, 9)
     x = feats.transpose(0, 2, 1)[..., None]                                # (B,F,T,1)
     acc = np.zeros((B, Fd, T, C))
     for jf in range(3):
         for jt in range(3):
             acc += shifted(x, jf - 1, jt - 1, Fd, T) * w9[:, jf * 3 + jt]
-    acc = np.maximum(acc + mem.vec(tr["shift"], C), 0.0)
+    acc = np.maximum(acc + mem.vec(tr["shift"], C), 0.0) * valid[:, None, :, None]
     mem.view(o, tr["es"], write=True)[...] = rnd(acc, tr["es"])
 
 
 def run_tstats(mem, tr):
-    if tr["lens"]:
-        raise NotImplementedError("masked tstats")
     x = mem.view(tr["x"], tr["es"])
     B, F, T, C = x.shape
     if tr["pre_scale"]:
         x = np.maximum(x * mem.vec(tr["pre_scale"], C) + mem.vec(tr["pre_shift"], C), 0.0)
     out_ld, so = tr["out_ld"], tr["std_off"]
     out = mem.strided(tr["out"], 4, (B, out_ld), (out_ld, 1), write=True)
-    mean = x.mean(axis=2)                                                  # (B,F,C) -> index c*F + f
-    out[:, :C * F] = mean.transpose(0, 2, 1).reshape(B, C * F)
-    if so >= 0:
-        std = np.sqrt(x.var(axis=2, ddof=1) + 1e-7)
-        out[:, so:so + C * F] = std.transpose(0, 2, 1).reshape(B, C * F)
+    lens = mem.vec(tr["lens"], B).astype(int) if tr["lens"] else np.full(B, T)   # statistics over each utterance's own frames
+    for b in range(B):
+        xb = x[b, :, :lens[b]]
+        out[b, :C * F] = xb.mean(axis=1).T.reshape(C * F)                       # (F,C) -> index c*F + f
+        if so >= 0:
+            out[b, so:so + C * F] = np.sqrt(xb.var(axis=1, ddof=1) + 1e-7).T.reshape(C * F)
 
 
 def run_linear(mem, tr):
@@ -379,19 +381,39 @@ def run_cam_dense(mem, tr):
         X[:, 0, :, cin:cin + 32] = rnd(y * m[:, seg_of_t, :], es)
 
 
-EXTRA = {"res2_fused": run_res2_fused, "se_gate": run_se_gate, "scale_residual": run_scale_residual, "astp_fused": run_astp_fused,
+def run_lens_derive(mem, tr):
+    """frames per utterance behind each stride-2 level: level 0 clamped to [1, T], level k + 1 = (level k - 1) // 2 + 1"""
+    B, T, levels = tr["B"], tr["T"], tr["levels"]
+    lens = mem.strided(tr["lens"], 4, (levels, B), (B, 1), write=True)
+    lens[0] = np.clip(lens[0], 1, T)
+    for k in range(1, levels):
+        lens[k] = (lens[k - 1] - 1) // 2 + 1
+
+
+def run_zero_tail(mem, tr):
+    x = mem.view(tr["x"], tr["es"], write=True)
+    B, F, T, C = x.shape
+    x *= (np.arange(T)[None, :] < mem.vec(tr["lens"], B)[:, None])[:, None, :, None]
+
+
+EXTRA = {"lens_derive": run_lens_derive, "zero_tail": run_zero_tail, "res2_fused": run_res2_fused, "se_gate": run_se_gate, "scale_residual": run_scale_residual, "astp_fused": run_astp_fused,
          "astp_stats": run_astp_stats, "bnrelu": run_bnrelu, "cam_gate": run_cam_gate, "seg_means": run_seg_means,
          "cam_dense": run_cam_dense}
 
 
-def run_plan(path, feats):
-    """feats (B,T,feat_dim) float -> embeddings (B,embed_dim) float64 by re-evaluating the traced plan on the host."""
+def run_plan(path, feats, n_frames=None):
+    """feats (B,T,feat_dim) float -> embeddings (B,embed_dim) float64 by re-evaluating the traced plan on the host.
+    n_frames: per-utterance frame counts of a length-masked plan (ws_engine_forward_masked)."""
     meta, blob = load_trace(path)
     B, T, Fd, E = meta["B"], meta["T"], meta["feat_dim"], meta["embed_dim"]
     assert feats.shape == (B, T, Fd)
     mem = Memory(meta, blob)
     arr, off = mem.array(meta["feats_in"], 4)
     arr[off:off + B * T * Fd] = np.asarray(feats, np.float64).reshape(-1)
+    assert (n_frames is not None) == bool(meta["lens"]), "n_frames goes with a masked plan"
+    if n_frames is not None:
+        arr, off = mem.array(meta["lens"], 4)
+        arr[off:off + B] = np.asarray(n_frames, np.float64)
     for op in meta["ops"]:
         tr = op["trace"]
         if tr is None:

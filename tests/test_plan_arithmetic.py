@@ -77,3 +77,28 @@ def test_16bit_storage_roundings_explain_the_16bit_distance(name, prec, B, T, ba
 def test_model_arg_variants_and_deep_plans(name, prec, B, T, model_args):
     rel, _ = _run(name, prec, B, T, model_args=model_args)
     assert rel < 5e-6, rel
+
+
+@pytest.mark.parametrize("name,prec", [("ResNet34", "fp16"), ("ResNet18", "fp32"), ("ResNet50", "bf16"), ("Res2Net34_Base", "fp16"),
+                                       ("ERes2Net34_Base", "fp16"), ("ERes2Net34_Base", "tf32x3")])
+def test_length_masked_plans_equal_each_utterance_alone(name, prec, tmp_path):
+    """The length-masked plan of the 2-D families (ws_engine_forward_masked): where the builder zeroes the rows behind an
+    utterance's end, which stride level's frame counts every op gets, statistics over the utterance's own frames.  Four
+    utterances of 21..90 frames padded with large garbage into one (4, 90) batch, re-evaluated on the host, must equal the
+    ORACLE run on each utterance alone, unpadded."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    B, T = 4, 90
+    lens = np.array([90, 37, 64, 21])
+    g = np.random.default_rng(1)
+    feats = syn.make_feats(B, T, 80, seed=9)
+    for b in range(B):
+        feats[b, lens[b]:] = 50.0 * g.standard_normal((T - lens[b], 80))
+    m = from_synthetic(name, precision=prec)
+    path = str(tmp_path / "plan.bin")
+    m.plan_trace(path, B, T, masked=True)
+    emb, meta = plan_interp.run_plan(path, feats, n_frames=lens)
+    assert any(op["trace"]["kind"] == "zero_tail" for op in meta["ops"]) and meta["ops"][0]["trace"]["kind"] == "lens_derive"
+    sd = syn.make_state_dict(name, 0)
+    for b in range(B):
+        ref = models_torch.forward(name, sd, feats[b:b + 1, :lens[b]]).numpy()[0]
+        assert np.linalg.norm(emb[b] - ref) / np.linalg.norm(ref) < 5e-6, (name, b)

@@ -138,6 +138,33 @@ def test_gpu_batch_of_64_matches_oracle_and_single_utterances():
         assert rel_l2(emb[sel], alone).max() <= 5e-3   # other tile shapes / kernels: fp16 rounding flips only
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,prec,tol", [("Res2Net34_Base", "fp16", 0.0), ("ERes2Net34_Base", "fp16", 0.0), ("ERes2Net34_Base", "tf32x3", 0.0),
+                                           ("Res2Net34_Base", "fp32", 0.0)])
+def test_gpu_length_masked_batch_equals_unpadded_utterances(name, prec, tol):
+    """ws_engine_forward_masked for these families: utterances of different lengths padded (with large garbage) to a common T
+    in ONE batch give what each gives alone - the same kernels see the same rows, so bitwise - and match the oracle run per
+    utterance.  (The plan's arithmetic is also re-evaluated on the host: tests/test_plan_arithmetic.py.)"""
+    lens = [200, 137, 163, 101, 301, 64]
+    g = torch.Generator().manual_seed(5)
+    feats = [torch.from_numpy(syn.make_feats(1, n, 80, seed=40 + i))[0] for i, n in enumerate(lens)]
+    x = 50.0 * torch.randn(len(lens), max(lens), 80, generator=g)
+    for i, f in enumerate(feats):
+        x[i, : lens[i]] = f
+    m = from_synthetic(name, 0, precision=prec)
+    got = m.embed_padded(x.to(DEV), lens).cpu().numpy()
+    sd = syn.make_state_dict(name, 0)
+    worst_self, worst_ref = 0.0, 0.0
+    for i, f in enumerate(feats):
+        alone = m.embed(f[None].to(DEV)).cpu().numpy()[0]
+        ref = models_torch.forward(name, sd, f[None]).numpy()[0]
+        worst_self = max(worst_self, float(rel_l2(got[i], alone)))
+        worst_ref = max(worst_ref, float(rel_l2(got[i], ref)))
+    print(f"masked batch {name} {prec}: vs alone {worst_self:.2e}, vs oracle {worst_ref:.2e}")
+    assert np.isfinite(got).all() and worst_self <= max(tol, 1e-6)
+    assert worst_ref <= (1e-4 if prec in ("fp32", "tf32x3") else 1e-2)
+
+
 def _conv_slices(prec, use_tc, kf, act1, act2, with_res, seed, B=2, F=12, T=70, Cin=32, Cout=32, xtot=96, x0=32, otot=64, o0=32, gain=1.0):
     """ws_conv on CHANNEL SLICES of wider buffers (x_ld = xtot, out_ld = otot), as the Res2Net plans use it; returns
     (kernel output, fp64 reference on the rounded operands)."""

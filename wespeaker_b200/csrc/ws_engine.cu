@@ -300,6 +300,7 @@ struct Builder {
         if (!p.masked) return;
         const View x = v;
         const int* l = lens(level);
+        set_op_trace("{\"kind\":\"zero_tail\"," + ti("es", ws_esize(x.dt)) + "," + tview("x", x) + "," + tp("lens", l) + "}");
         push([=](cudaStream_t s) { return ws_launch_zero_tail(x.p, (float*)x.plo, x.dt, x.B, x.F, x.T, x.C, x.ld, l, s); }, "zero_tail");
     }
     void conv(const ConvSpec& s_in) {
@@ -971,7 +972,7 @@ static bool aff(Builder& b, const std::string& p, const View& x, const View& y, 
 // 3x3 pad-1 conv (+ folded BN shift) -> act over `in` (and, when in2 != nullptr, over in + in2 with the weights repeated):
 // the halo-resident kernel where it applies, else the generic conv-GEMM.  act: WS_ACT_RELU20 or WS_ACT_NONE.
 static bool res2_conv3x3(Builder& b, const std::string& id, const View& in, const View* in2, const View& out, const std::vector<float>& w9,
-                         const std::vector<float>& bias, int act, int stride) {
+                         const std::vector<float>& bias, int act, int stride, int lvl) {   // lvl: stride level of `out` (length-masked plans)
     const int Cin = in.C, Cout = out.C;
     if ((int)w9.size() != Cout * 9 * Cin || (int)bias.size() != Cout) { set_err(id + ": 3x3 weight shape mismatch"); b.ok = false; return false; }
     const float* bd = b.w.f32("b:" + id, bias);
@@ -980,7 +981,7 @@ static bool res2_conv3x3(Builder& b, const std::string& id, const View& in, cons
         if (b.e.use_tc >= 2 && b.e.act_dt != WS_F32 && b.e.opt("conv3x3", 1) != 0 && (stride == 1 || b.e.opt("conv3x3_strided", 1) != 0)) {
             Op op;
             bool unsupported = false;
-            if (make_conv3x3_op(in, out, W, bd, nullptr, act == WS_ACT_RELU20 ? 2 : 0, &op, &unsupported, stride, stride, nullptr)) {
+            if (make_conv3x3_op(in, out, W, bd, nullptr, act == WS_ACT_RELU20 ? 2 : 0, &op, &unsupported, stride, stride, b.lens(lvl))) {
                 b.push(std::move(op));
                 return b.good();
             }
@@ -990,6 +991,7 @@ static bool res2_conv3x3(Builder& b, const std::string& id, const View& in, cons
         ep.bias = bd;
         ep.act1 = act;
         b.conv_simple(in, out, W, 3, 3, 1, 1, 1, 1, stride, stride, ep);
+        b.zero_tail(out, lvl);
         return b.good();
     }
     // two summed inputs: K = [9 taps over in | 9 taps over in2], weight rows repeated
@@ -1009,6 +1011,7 @@ static bool res2_conv3x3(Builder& b, const std::string& id, const View& in, cons
     cs.epi.act1 = act;
     fill_epi_out(cs.epi, out);
     b.conv(cs);
+    b.zero_tail(out, lvl);
     return b.good();
 }
 
@@ -1017,7 +1020,11 @@ struct Res2Bufs {   // per-stage scratch, sized for the stage's largest tensor o
 };
 
 // one residual block; kind 0 = BasicBlockRes2Net, 1 = BasicBlockERes2Net, 2 = BasicBlockERes2Net_diff_AFF
-static View res2_block(Builder& b, const Res2Cfg& c, const std::string& p, const View& x, int planes, int stride, int kind, Res2Bufs& bf, View obuf) {
+// Length-masked plans (lvl = stride level of the block's output): the rows behind an utterance's end are zeroed wherever a
+// 3x3 conv is about to read across time (A after conv1, every chain output, and the stage outputs that ERes2Net's bottom-up
+// fusion reads through stride-2 3x3 convs); the 1x1 convs and AFF never mix time, and AFF of two zero rows is zero.
+static View res2_block(Builder& b, const Res2Cfg& c, const std::string& p, const View& x, int planes, int stride, int kind, Res2Bufs& bf, View obuf,
+                       int lvl, bool zero_out_tail) {
     View none;
     const int w = (int)std::floor(planes * (c.base_width / 64.0)), wp = res2_pad(w), s = c.scale, cout = planes * c.expansion, cin = x.C;
     const int nconv = kind == 0 ? s - 1 : s;            // chain convs
@@ -1040,6 +1047,7 @@ static View res2_block(Builder& b, const Res2Cfg& c, const std::string& p, const
         e1.bias = b.w.f32("b:" + p + ".bn1", b1p);
         e1.act1 = WS_ACT_RELU20;
         b.conv_simple(x, A, b.w.act("w:" + p + ".conv1", w1p), 1, 1, 1, 1, 0, 0, stride, stride, e1);
+        b.zero_tail(A, lvl);
         if (!b.good()) return none;
     }
     for (int i = 0; i < nconv; ++i) {
@@ -1055,14 +1063,14 @@ static View res2_block(Builder& b, const Res2Cfg& c, const std::string& p, const
         for (int j = 0; j < w; ++j) bcp[j] = sh[j];
         const View dst = cat.ch(i * wp, wp), spx = A.ch(i * wp, wp);
         if (i == 0) {
-            if (!res2_conv3x3(b, ck, spx, nullptr, dst, wcp, bcp, WS_ACT_RELU20, 1)) return none;
+            if (!res2_conv3x3(b, ck, spx, nullptr, dst, wcp, bcp, WS_ACT_RELU20, 1, lvl)) return none;
         } else if (kind == 2) {
             View fz = bf.fz; fz.B = x.B; fz.F = Fo; fz.T = To; fz.C = wp; fz.ld = wp;
             if (!aff(b, p + ".fuse_models." + std::to_string(i - 1), cat.ch((i - 1) * wp, wp), spx, w, bf.hid, bf.att, fz)) return none;
-            if (!res2_conv3x3(b, ck, fz, nullptr, dst, wcp, bcp, WS_ACT_RELU20, 1)) return none;
+            if (!res2_conv3x3(b, ck, fz, nullptr, dst, wcp, bcp, WS_ACT_RELU20, 1, lvl)) return none;
         } else {
             const View prev = cat.ch((i - 1) * wp, wp);
-            if (!res2_conv3x3(b, ck, prev, &spx, dst, wcp, bcp, WS_ACT_RELU20, 1)) return none;
+            if (!res2_conv3x3(b, ck, prev, &spx, dst, wcp, bcp, WS_ACT_RELU20, 1, lvl)) return none;
         }
     }
     // conv3 (1x1) + bn3 over [concat chunks | (Res2Net) last chunk of A] (+ the strided 1x1 shortcut conv as one more K range,
@@ -1103,13 +1111,13 @@ static View res2_block(Builder& b, const Res2Cfg& c, const std::string& p, const
     cs.epi.act2 = WS_ACT_RELU20;
     fill_epi_out(cs.epi, o);
     b.conv(cs);
+    if (zero_out_tail) b.zero_tail(o, lvl);   // a stage output the fusion path's stride-2 3x3 conv / AFF will read
     return b.good() ? o : none;
 }
 
 bool build_res2net(Builder& b, const Res2Cfg& c) {
     ws_engine& e = b.e;
     const int B = b.p.B, T = b.p.T, Fd = e.feat_dim, E = e.embed_dim, m = c.m;
-    if (b.p.masked) { set_err("length-masked batches are not implemented for Res2Net / ERes2Net"); return false; }
     if (m != 32 && m != 64) { set_err("Res2Net / ERes2Net: m_channels must be 32 or 64"); return false; }
     View stem_buf = b.act(B, Fd, T, m);
     if (!b.good()) return false;
@@ -1138,7 +1146,8 @@ bool build_res2net(Builder& b, const Res2Cfg& c) {
         if (!b.good()) return false;
         for (int bi = 0; bi < e.num_blocks[li - 1] && b.good(); ++bi) {
             const std::string p = "layer" + std::to_string(li) + "." + std::to_string(bi);
-            View o = res2_block(b, c, p, cur, planes, bi == 0 ? stride : 1, kind, bf, bf.xo[bi & 1]);
+            View o = res2_block(b, c, p, cur, planes, bi == 0 ? stride : 1, kind, bf, bf.xo[bi & 1], li - 1,
+                                c.fuse && bi == e.num_blocks[li - 1] - 1);
             if (!b.good() || o.p == nullptr) return false;
             cur = o;
         }
@@ -1161,7 +1170,7 @@ bool build_res2net(Builder& b, const Res2Cfg& c) {
             View d = b.act(B, nx.F, nx.T, C2), hid = b.act(B, nx.F, nx.T, std::max(32, (C2 / 4 + 31) / 32 * 32)), att = b.act(B, nx.F, nx.T, C2),
                  fo = b.act(B, nx.F, nx.T, C2);
             if (!b.good()) return false;
-            if (!res2_conv3x3(b, dk, f, nullptr, d, wd, std::vector<float>((size_t)C2, 0.f), WS_ACT_NONE, 2)) return false;
+            if (!res2_conv3x3(b, dk, f, nullptr, d, wd, std::vector<float>((size_t)C2, 0.f), WS_ACT_NONE, 2, k + 1)) return false;
             if (!aff(b, names[k], nx, d, C2, hid, att, fo)) return false;
             f = fo;
         }
@@ -1513,7 +1522,10 @@ Plan* get_plan(ws_engine* e, int B, int T, bool masked = false) {
     if (masked) {
         p->lens = (int*)b.raw((size_t)4 * B * sizeof(int));
         int* l = p->lens;
-        if (b.good()) b.push([=](cudaStream_t s) { return ws_launch_lens_derive(l, B, T, 4, s); }, "lens_derive");
+        if (b.good()) {
+            set_op_trace("{\"kind\":\"lens_derive\"," + Builder::tp("lens", l) + "," + Builder::ti("B", B) + "," + Builder::ti("T", T) + "," + Builder::ti("levels", 4) + "}");
+            b.push([=](cudaStream_t s) { return ws_launch_lens_derive(l, B, T, 4, s); }, "lens_derive");
+        }
     }
     p->feats_in = b.f32((size_t)B * T * e->feat_dim);
     p->emb = b.f32((size_t)B * e->embed_dim);
@@ -2132,14 +2144,14 @@ const char* ws_engine_plan_op_name(ws_engine* e, int B, int T, int i, double* fl
 // test can re-evaluate the plan's arithmetic on the host (tests/plan_interp.py) and compare it with the oracle.
 // File layout: "WSPT1\n", uint64 JSON length, JSON, then the weight blobs (fp32) back to back; the JSON's "blobs" table
 // holds [address, float offset into the blob area, float count].
-int ws_engine_plan_trace(ws_engine* e, int B, int T, const char* path) {
+int ws_engine_plan_trace(ws_engine* e, int B, int T, int masked, const char* path) {
     if (!e || !path) { set_err("ws_engine_plan_trace: null argument"); return 1; }
     if (!e->plan_check || !e->finalized) { set_err("ws_engine_plan_trace: needs a finalized plan-check engine"); return 1; }
-    Plan* p = get_plan(e, B, T);
+    Plan* p = get_plan(e, B, T, masked != 0);
     if (!p) return 1;
     std::string j = "{";
     j += Builder::ti("B", B) + "," + Builder::ti("T", T) + "," + Builder::ti("feat_dim", e->feat_dim) + "," + Builder::ti("embed_dim", e->embed_dim) + "," +
-         Builder::ti("act_es", ws_esize(e->act_dt)) + "," + Builder::tp("feats_in", p->feats_in) + "," + Builder::tp("emb", p->emb) + ",\"model\":\"" + e->model +
+         Builder::ti("act_es", ws_esize(e->act_dt)) + "," + Builder::tp("feats_in", p->feats_in) + "," + Builder::tp("emb", p->emb) + "," + Builder::tp("lens", p->lens) + ",\"model\":\"" + e->model +
          "\",\"precision\":\"" + e->prec + "\",\"allocs\":[";
     for (size_t i = 0; i < e->check_allocs.size(); ++i)
         j += std::string(i ? "," : "") + "[" + std::to_string(e->check_allocs[i].first) + "," + std::to_string(e->check_allocs[i].second) + "]";

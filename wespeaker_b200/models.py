@@ -153,7 +153,7 @@ class B200SpeakerModel(torch.nn.Module):
                        "ws_engine_set_tensor")
         _lib.check(L.ws_engine_finalize(h), "ws_engine_finalize")
 
-    def plan_trace(self, path: str, batch: int = 1, frames: int = 200):
+    def plan_trace(self, path: str, batch: int = 1, frames: int = 200, masked: bool = False):
         """Write the (batch, frames) launch plan as data (ws_engine_plan_trace; no device, nothing computed): tests re-evaluate
         it on the host against the oracle (tests/plan_interp.py)."""
         L = _lib.load()
@@ -162,7 +162,7 @@ class B200SpeakerModel(torch.nn.Module):
                                                  self.embed_dim, C.byref(h)), "ws_engine_create_plan_check")
         try:
             self._configure(L, h)
-            _lib.check(L.ws_engine_plan_trace(h, batch, frames, path.encode()), "ws_engine_plan_trace")
+            _lib.check(L.ws_engine_plan_trace(h, batch, frames, int(masked), path.encode()), "ws_engine_plan_trace")
         finally:
             L.ws_engine_destroy(h)
 
