@@ -102,3 +102,38 @@ def test_length_masked_plans_equal_each_utterance_alone(name, prec, tmp_path):
     for b in range(B):
         ref = models_torch.forward(name, sd, feats[b:b + 1, :lens[b]]).numpy()[0]
         assert np.linalg.norm(emb[b] - ref) / np.linalg.norm(ref) < 5e-6, (name, b)
+
+
+def test_tf32x3_error_is_the_truncating_accumulation_not_the_split(tmp_path):
+    """tools/tf32x3_error_budget.py in small: on the 3xTF32 plan of ECAPA-TDNN-512 the operand split alone (x_lo*W + x*W_lo + x*W
+    with tf32-truncated operands, exact accumulation) stays at fp32 level, while truncating every fp32 accumulate of a K = 8 MMA
+    step - what tensor cores do - lands where the B200 measures the path (2.3e-5 at 200 frames)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("tf32x3_error_budget", os.path.join(root, "tools", "tf32x3_error_budget.py"))
+    eb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(eb)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    name, T = "ECAPA_TDNN_c512", 64
+    m = from_synthetic(name, precision="tf32x3")
+    path = str(tmp_path / "plan.bin")
+    m.plan_trace(path, 1, T)
+    feats = syn.make_feats(1, T, 80, seed=17 * T)
+    ref = models_torch.forward(name, syn.make_state_dict(name, 0), torch.from_numpy(feats).double()).numpy()
+
+    def rel(emb):
+        return float(np.linalg.norm(emb - ref) / np.linalg.norm(ref))
+    orig = plan_interp.run_conv
+    try:
+        plan_interp.ROUND = "tf32x3_trunc_lo"
+        split = rel(plan_interp.run_plan(path, feats)[0])
+        plan_interp.ROUND = None
+        plan_interp.run_conv = eb.make_run_conv(eb.rn32)
+        rn = rel(plan_interp.run_plan(path, feats)[0])
+        plan_interp.run_conv = eb.make_run_conv(eb.rz32)
+        rz = rel(plan_interp.run_plan(path, feats)[0])
+    finally:
+        plan_interp.run_conv = orig
+        plan_interp.ROUND = None
+    assert split < 6e-6 and rn < 6e-6, (split, rn)
+    assert 5 * split < rz < 1e-4, (split, rz)
