@@ -6,8 +6,8 @@ activations - against the oracle on the CPU; the CUDA kernels that execute the s
 Memory model: every placeholder allocation becomes a flat float64 array indexed in ELEMENTS (address offset / element size of
 the tensor's dtype in the plan); values are never rounded, so a bf16 plan and an fp32 plan both reproduce the oracle to
 floating-point accuracy.  The fused kernels (Res2 chain, ASTP tail, CAM++ dense block, SE gate) are re-evaluated from their
-documented contracts (ws_host.h).  Length-masked plans are modelled for the 2-D families (stem / 3x3 conv / zero_tail / TSTP
-over each utterance's own frames); the masked fused ECAPA / CAM++ kernels raise NotImplementedError."""
+documented contracts (ws_host.h).  Length-masked plans are modelled too: rows behind an utterance's end are conv padding and
+every statistic runs over the utterance's own frames."""
 import json
 import struct
 
@@ -252,34 +252,44 @@ def _dil_conv1d(x, W, dil):
     return out
 
 
+def _lens(mem, tr, B, T):
+    """frames per utterance of a length-masked op (clamped to [1, T]); T for every utterance in ordinary plans"""
+    if not tr["lens"]:
+        return np.full(B, T, dtype=int)
+    return np.clip(mem.vec(tr["lens"], B).astype(int), 1, T)
+
+
 def run_res2_fused(mem, tr):
     """ws_host.h make_res2_op: 7 dependent dilated k=3 convs on w8-channel groups (ecapa_tdnn.py:29-78):
     sp_i = bn(relu(conv(s_i) + bias_i)), s_0 = x_0, s_{i+1} = sp_i + x_{i+1}; out groups 0..6 = sp_0..sp_6."""
-    if tr["lens"]:
-        raise NotImplementedError("masked res2")
     es, w8, dil = tr["es"], tr["w8"], tr["dil"]
-    x = mem.view(tr["x"], es)[:, 0]                      # (B,T,8*w8)
+    xall = mem.view(tr["x"], es)[:, 0]                   # (B,T,8*w8)
     out = mem.view(tr["out"], es, write=True)
     W7 = rnd(mem.vec(tr["W7"], 7 * w8 * 3 * w8).reshape(7, w8, 3, w8), es)
     bias, scale, shift = (mem.vec(tr[k], 7 * w8).reshape(7, w8) for k in ("bias", "scale", "shift"))
-    s = x[..., :w8]
-    for i in range(7):
-        sp = rnd(np.maximum(_dil_conv1d(s, W7[i], dil) + bias[i], 0.0) * scale[i] + shift[i], es)
-        out[:, 0, :, i * w8:(i + 1) * w8] = sp
-        if i < 6:
-            s = rnd(sp + x[..., (i + 1) * w8:(i + 2) * w8], es)
+    B, T, _ = xall.shape
+    lens = _lens(mem, tr, B, T)
+    for b in range(B):       # length-masked: rows behind the utterance's end are conv padding = the utterance alone
+        x = xall[b:b + 1, :lens[b]]
+        s = x[..., :w8]
+        out[b, 0, lens[b]:, :7 * w8] = 0.0
+        for i in range(7):
+            sp = rnd(np.maximum(_dil_conv1d(s, W7[i], dil) + bias[i], 0.0) * scale[i] + shift[i], es)
+            out[b, 0, :lens[b], i * w8:(i + 1) * w8] = sp[0]
+            if i < 6:
+                s = rnd(sp + x[..., (i + 1) * w8:(i + 2) * w8], es)
 
 
 def run_se_gate(mem, tr):
     """gate[b][c] = sigmoid(W2 relu(W1 mean_T(x[b]) + b1) + b2); W2t is W2 transposed to [H][C] (ecapa_tdnn.py:113-126)."""
-    if tr["lens"]:
-        raise NotImplementedError("masked se_gate")
     x = mem.view(tr["x"], tr["es"])[:, 0]
     B, T, C = x.shape
     H = tr["H"]
     W1 = mem.vec(tr["W1"], H * C).reshape(H, C)
     W2t = mem.vec(tr["W2t"], H * C).reshape(H, C)
-    hid = np.maximum(x.mean(axis=1) @ W1.T + mem.vec(tr["b1"], H), 0.0)
+    lens = _lens(mem, tr, B, T)
+    mean = np.stack([x[b, :lens[b]].mean(axis=0) for b in range(B)])
+    hid = np.maximum(mean @ W1.T + mem.vec(tr["b1"], H), 0.0)
     mem.strided(tr["gate"], 4, (B, C), (C, 1), write=True)[...] = act(hid @ W2t + mem.vec(tr["b2"], C), 3)
 
 
@@ -302,22 +312,24 @@ def _astp(x, logits):
 
 def run_astp_fused(mem, tr):
     """ws_host.h make_astp_op: logits = h @ W2^T (linear2's bias cancels in the softmax over time)."""
-    if tr["lens"]:
-        raise NotImplementedError("masked astp")
     es = tr["es"]
     x, h = mem.view(tr["x"], es)[:, 0], mem.view(tr["h"], es)[:, 0]
     B, T, C = x.shape
     W2 = rnd(mem.vec(tr["W2"], C * 128).reshape(C, 128), es)
-    mem.strided(tr["stats"], 4, (B, 2 * C), (2 * C, 1), write=True)[...] = _astp(x, h @ W2.T)
+    lens = _lens(mem, tr, B, T)
+    st = mem.strided(tr["stats"], 4, (B, 2 * C), (2 * C, 1), write=True)
+    for b in range(B):
+        st[b] = _astp(x[b:b + 1, :lens[b]], h[b:b + 1, :lens[b]] @ W2.T)[0]
 
 
 def run_astp_stats(mem, tr):
-    if tr["lens"]:
-        raise NotImplementedError("masked astp")
     es = tr["es"]
     x, lg = mem.view(tr["x"], es)[:, 0], mem.view(tr["logits"], es)[:, 0]
     B, T, C = x.shape
-    mem.strided(tr["stats"], 4, (B, 2 * C), (2 * C, 1), write=True)[...] = _astp(x, lg)
+    lens = _lens(mem, tr, B, T)
+    st = mem.strided(tr["stats"], 4, (B, 2 * C), (2 * C, 1), write=True)
+    for b in range(B):
+        st[b] = _astp(x[b:b + 1, :lens[b]], lg[b:b + 1, :lens[b]])[0]
 
 
 def run_bnrelu(mem, tr):
@@ -361,24 +373,27 @@ def run_cam_dense(mem, tr):
     """ws_host.h make_cam_dense_op / campplus.py:86-201, per layer: h = relu(W1 relu(bn1(x[:, :cin])) + bias2) (BN2 folded into
     W1), context mask m = sigmoid(W2c relu(W1c (mean_T(h) + segmean(h)) + b1c) + b2c) per 100-frame segment,
     x[:, cin:cin+32] = (k3 dilated conv of h) * m."""
-    if tr["lens"]:
-        raise NotImplementedError("masked cam_dense")
     es, L = tr["es"], tr["seg_len"]
-    X = mem.view(tr["X"], es, write=True)
-    B, _, T, _ = X.shape
-    for ly in tr["layers"]:
-        cin, dil = ly["cin"], ly["dil"]
-        xin = rnd(np.maximum(X[:, 0, :, :cin] * mem.vec(ly["bn1_scale"], cin) + mem.vec(ly["bn1_shift"], cin), 0.0), es)
-        W1 = rnd(mem.vec(ly["W1"], 128 * cin).reshape(128, cin), es)
-        h = rnd(np.maximum(xin @ W1.T + mem.vec(ly["bias2"], 128), 0.0), es)
-        ctx = _cam_context(h, L)                                           # (B,nseg,128)
-        w1c_t = mem.vec(ly["w1c_t"], 128 * 64).reshape(128, 64)
-        w2c_t = mem.vec(ly["w2c_t"], 64 * 32).reshape(64, 32)
-        m = act(np.maximum(ctx @ w1c_t + mem.vec(ly["b1c"], 64), 0.0) @ w2c_t + mem.vec(ly["b2c"], 32), 3)   # (B,nseg,32)
-        Wl = rnd(mem.vec(ly["Wl"], 32 * 3 * 128).reshape(32, 3, 128), es)
-        y = _dil_conv1d(h, Wl, dil)
-        seg_of_t = np.arange(T) // L
-        X[:, 0, :, cin:cin + 32] = rnd(y * m[:, seg_of_t, :], es)
+    Xall = mem.view(tr["X"], es, write=True)
+    B, _, Tmax, _ = Xall.shape
+    lens = _lens(mem, tr, B, Tmax)
+    for b in range(B):       # one utterance at a time over its own frames (what the one-CTA-per-utterance kernel does)
+        T = lens[b]
+        X = Xall[b:b + 1, :, :T]
+        for ly in tr["layers"]:
+            cin, dil = ly["cin"], ly["dil"]
+            xin = rnd(np.maximum(X[:, 0, :, :cin] * mem.vec(ly["bn1_scale"], cin) + mem.vec(ly["bn1_shift"], cin), 0.0), es)
+            W1 = rnd(mem.vec(ly["W1"], 128 * cin).reshape(128, cin), es)
+            h = rnd(np.maximum(xin @ W1.T + mem.vec(ly["bias2"], 128), 0.0), es)
+            ctx = _cam_context(h, L)                                           # (1,nseg,128)
+            w1c_t = mem.vec(ly["w1c_t"], 128 * 64).reshape(128, 64)
+            w2c_t = mem.vec(ly["w2c_t"], 64 * 32).reshape(64, 32)
+            m = act(np.maximum(ctx @ w1c_t + mem.vec(ly["b1c"], 64), 0.0) @ w2c_t + mem.vec(ly["b2c"], 32), 3)   # (1,nseg,32)
+            Wl = rnd(mem.vec(ly["Wl"], 32 * 3 * 128).reshape(32, 3, 128), es)
+            y = _dil_conv1d(h, Wl, dil)
+            seg_of_t = np.arange(T) // L
+            X[:, 0, :, cin:cin + 32] = rnd(y * m[:, seg_of_t, :], es)
+            Xall[b, 0, T:, cin:cin + 32] = 0.0
 
 
 def run_lens_derive(mem, tr):

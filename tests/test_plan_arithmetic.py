@@ -79,16 +79,22 @@ def test_model_arg_variants_and_deep_plans(name, prec, B, T, model_args):
     assert rel < 5e-6, rel
 
 
-@pytest.mark.parametrize("name,prec", [("ResNet34", "fp16"), ("ResNet18", "fp32"), ("ResNet50", "bf16"), ("Res2Net34_Base", "fp16"),
-                                       ("ERes2Net34_Base", "fp16"), ("ERes2Net34_Base", "tf32x3")])
-def test_length_masked_plans_equal_each_utterance_alone(name, prec, tmp_path):
-    """The length-masked plan of the 2-D families (ws_engine_forward_masked): where the builder zeroes the rows behind an
-    utterance's end, which stride level's frame counts every op gets, statistics over the utterance's own frames.  Four
-    utterances of 21..90 frames padded with large garbage into one (4, 90) batch, re-evaluated on the host, must equal the
-    ORACLE run on each utterance alone, unpadded."""
+@pytest.mark.parametrize("name,prec,lens", [
+    ("ResNet34", "fp16", [90, 37, 64, 21]), ("ResNet18", "fp32", [90, 37, 64, 21]), ("ResNet50", "bf16", [90, 37, 64, 21]),
+    ("Res2Net34_Base", "fp16", [90, 37, 64, 21]), ("ERes2Net34_Base", "fp16", [90, 37, 64, 21]), ("ERes2Net34_Base", "tf32x3", [90, 37, 64, 21]),
+    ("ECAPA_TDNN_c512", "bf16", [200, 137, 64, 256]),        # fused Res2 chain / ASTP tail / SE gate over each utterance's own frames
+    ("ECAPA_TDNN_c1024", "bf16", [301, 137]),                # tiled Res2 chain (T > 256)
+    ("ECAPA_TDNN_GLOB_c512", "fp32", [90, 37, 64, 21]),      # global-context statistics per utterance
+    ("CAMPPlus", "bf16", [455, 137, 200, 301]),              # context segments (ceil mode) of each utterance's own length
+])
+def test_length_masked_plans_equal_each_utterance_alone(name, prec, lens, tmp_path):
+    """The length-masked plans (ws_engine_forward_masked): where the builder zeroes the rows behind an utterance's end, which
+    stride level's frame counts every op gets, statistics over the utterance's own frames.  Utterances of different lengths
+    padded with large garbage into one batch, re-evaluated on the host, must equal the ORACLE run on each utterance alone,
+    unpadded."""
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    B, T = 4, 90
-    lens = np.array([90, 37, 64, 21])
+    lens = np.array(lens)
+    B, T = len(lens), int(lens.max())
     g = np.random.default_rng(1)
     feats = syn.make_feats(B, T, 80, seed=9)
     for b in range(B):
