@@ -103,7 +103,9 @@ def test_length_masked_plans_equal_each_utterance_alone(name, prec, lens, tmp_pa
     path = str(tmp_path / "plan.bin")
     m.plan_trace(path, B, T, masked=True)
     emb, meta = plan_interp.run_plan(path, feats, n_frames=lens)
-    assert any(op["trace"]["kind"] == "zero_tail" for op in meta["ops"]) and meta["ops"][0]["trace"]["kind"] == "lens_derive"
+    assert meta["ops"][0]["trace"]["kind"] == "lens_derive"
+    if name != "CAMPPlus":      # (CAM++'s 16-bit kernels all take the frame counts themselves)
+        assert any(op["trace"]["kind"] == "zero_tail" for op in meta["ops"])
     sd = syn.make_state_dict(name, 0)
     for b in range(B):
         ref = models_torch.forward(name, sd, feats[b:b + 1, :lens[b]]).numpy()[0]
