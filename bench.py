@@ -368,6 +368,11 @@ def model_leg(name, model_name, prec, B, nsamples, gflop_utt, steps, warmup, dev
            "value": value, "unit": "utt/s", "ms_per_step": ms / steps, "launches_per_step": int(launches),
            "step_tflops_per_gpu": value / world * gflop_utt / 1e3,
            "step_frac_of_sustained": value / world * gflop_utt / 1e3 / peaks["tf_sustained"]}
+    if prec == "tf32x3":
+        # the algorithmic FLOPs are executed three times at the tf32 rate (half the bf16 rate the peak was measured at): the
+        # same number against peak / 6 is the fraction of what a 3xTF32 GEMM could reach on this machine
+        res["step_frac_of_3xtf32_sustained"] = 6.0 * res["step_frac_of_sustained"]
+        res["note"] = "3 error-compensated tf32 passes: tensor ceiling = the measured bf16 sustained peak / 6"
     if rank == 0:
         emb, feats = model.extract_from_wav(wavs[0], return_feats=True)   # the timed batch (full B: same kernels / tiles)
         sel = [int(round(j * (B - 1) / max(1, parity_n - 1))) for j in range(parity_n)]
