@@ -685,7 +685,7 @@ def main():
         for name, (m, pr, b, ns) in EXTRA_WORKLOADS.items():
             try:   # an extra must never cost the line its contract fields
                 r = model_leg(name, m, pr, b, ns, 0.0, args.steps, args.warmup, dev, rank, world, parallel, peaks, sampler, parity_n=min(2, b))
-                for k in ("step_tflops_per_gpu", "step_frac_of_sustained"):
+                for k in ("step_tflops_per_gpu", "step_frac_of_sustained", "step_frac_of_3xtf32_sustained", "note"):
                     r.pop(k, None)
                 if b == 1:
                     r["latency_ms_per_utt"] = r["ms_per_step"]
